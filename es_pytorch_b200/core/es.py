@@ -1,0 +1,160 @@
+"""One ES generation (mirror of src/core/es.py): ``step``, ``test_params``,
+``_share_results``, ``approx_grad`` with the reference signatures and return layouts.
+
+Two evaluation paths behind ``test_params``:
+  * ``fit_fn`` is a ``BatchedRollout``  -> the whole rank's pairs are drawn, perturbed,
+    rolled out and scored by the fused device pipeline (``DeviceGeneration.evaluate``);
+  * any other callable -> the reference's per-perturbation loop (es.py:67-74); each
+    ``policy.pheno`` / ``run_model`` call still runs its arithmetic on the device.
+``approx_grad`` always runs rank-weights -> reconstruction -> optimizer on the device, each
+process summing only its own shard of pairs followed by one allreduce.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Tuple
+
+import numpy as np
+import torch
+
+from .. import dist
+from ..engine import get_engine
+from ..generation import DeviceGeneration
+from ..gym.training_result import TrainingResult
+from ..nn.obstat import ObStat
+from ..utils.rankers import CenteredRanker, Ranker
+from ..utils.reporters import Reporter, StdoutReporter
+from .noisetable import NoiseTable
+from .policy import Policy
+
+
+def step(cfg, comm, policy: Policy, nt: NoiseTable, env, fit_fn: Callable, rs: np.random.RandomState = None,
+         ranker: Ranker = None, reporter: Reporter = None) -> Tuple[TrainingResult, ObStat]:
+    """Runs a single generation of ES (es.py:23-51); returns the noiseless result and the
+    generation's observation statistics."""
+    rs = np.random.RandomState() if rs is None else rs
+    ranker = CenteredRanker() if ranker is None else ranker
+    reporter = StdoutReporter(comm) if reporter is None else reporter
+    assert cfg.general.policies_per_gen % comm.size == 0 and (cfg.general.policies_per_gen / comm.size) % 2 == 0
+    eps_per_proc = int((cfg.general.policies_per_gen / comm.size) / 2)
+
+    gen_obstat = ObStat(env.observation_space.shape, 0)
+    pos_res, neg_res, inds, steps = test_params(comm, eps_per_proc, policy, nt, gen_obstat, fit_fn, rs)
+
+    reporter.print(f'n dupes: {len(inds) - len(set(inds))}')
+
+    ranker.rank(pos_res, neg_res, inds)
+    approx_grad(policy, ranker, nt, policy.flat_params, cfg.general.batch_size, cfg.policy.l2coeff)
+    noiseless_result = fit_fn(policy.pheno(np.zeros(len(policy))), False)
+    reporter.log_gen(ranker.fits, noiseless_result, policy, steps)
+
+    return noiseless_result, gen_obstat
+
+
+def _device_generation(fit_fn, policy: Policy, nt: NoiseTable, streams) -> DeviceGeneration:
+    eng = get_engine()
+    gen = fit_fn._gen
+    theta = policy.theta_dev(eng)
+    if gen is None or gen.theta is not theta or gen.n_streams != len(streams) or gen.table is not nt.device_table(eng):
+        env = fit_fn.env
+        obs_dev, rew_dev = env.device_arrays(eng)
+        T = fit_fn.max_steps
+        archive = None if fit_fn.archive is None else eng.to_device(fit_fn.archive, torch.float64)
+        gen = DeviceGeneration(nt.device_table(eng), theta, policy._module.layer_sizes(), obs_dev[:T + 1].contiguous(),
+                               rew_dev[:T].contiguous(), streams, policy.std, 0.0, policy.optim,
+                               ob_clip=policy._module.ob_clip, pos_scale=env.pos_scale,
+                               coins_per_eval=fit_fn.coins_per_eval, save_obs_chance=fit_fn.save_obs_chance,
+                               archive=archive, nov_k=fit_fn.nov_k, rollout_mode=fit_fn.rollout_mode, engine=eng)
+        fit_fn._gen = gen
+    else:
+        gen.load_states(streams)
+    gen.sigma = float(policy.std)                       # scripts decay the noise std between generations
+    gen.save_obs_chance = fit_fn.save_obs_chance
+    if fit_fn.archive is not None and (gen.archive is None or gen.archive.shape[0] != len(fit_fn.archive)):
+        gen.archive = eng.to_device(fit_fn.archive, torch.float64)
+    gen.set_obstat(policy._module._obmean, policy._module._obstd)
+    return gen
+
+
+def _test_params_batched(comm, n: int, policy: Policy, nt: NoiseTable, gen_obstat: ObStat, fit_fn, rs):
+    if not policy._module.is_tanh_mlp():
+        raise NotImplementedError('the fused rollout evaluates tanh MLPs (FeedForward with torch.nn.Tanh)')
+    streams = fit_fn.rank_streams if fit_fn.rank_streams is not None else [rs]
+    gen = _device_generation(fit_fn, policy, nt, streams)
+    fpos, fneg = gen.evaluate(n)
+    # one device->host hop for everything the reference API returns as ndarrays
+    pos = fpos.cpu().numpy().reshape(gen.K, gen.n_obj)
+    neg = fneg.cpu().numpy().reshape(gen.K, gen.n_obj)
+    idx_local = gen.idx.cpu().numpy()
+    gen.store_states(streams)
+    if comm.size > 1:
+        inds = np.concatenate(dist.world().allgather_object(idx_local)).astype(np.float64)
+    else:
+        inds = idx_local.astype(np.float64)
+    if gen.extra_words:
+        cnt = gen.gen_count.cpu().numpy()
+        gen_obstat.inc(gen.gen_sum.cpu().numpy(), gen.gen_sumsq.cpu().numpy(), float(cnt[0]))
+    steps = 2 * gen.K * (fit_fn.max_steps - 1)          # run_model returns the last loop index (gym_runner.py:50,67)
+    return pos, neg, inds, steps
+
+
+def test_params(comm, n: int, policy: Policy, nt: NoiseTable, gen_obstat: ObStat, fit_fn: Callable,
+                rs: np.random.RandomState) -> Tuple[np.ndarray, np.ndarray, np.ndarray, int]:
+    """Tests ``n`` antithetic perturbation pairs per rank and returns the positive / negative
+    results of ALL ranks plus the noise indices (es.py:54-81):
+    (pos[K, n_obj], neg[K, n_obj], inds[K], steps), rank-major, float64."""
+    if getattr(fit_fn, 'is_batched_rollout', False):
+        return _test_params_batched(comm, n, policy, nt, gen_obstat, fit_fn, rs)
+
+    results_pos, results_neg, inds = [], [], []
+    for _ in range(n):
+        idx, noise = nt.sample(rs)
+        inds.append(idx)
+        results_pos.append(fit_fn(policy.pheno(noise)))
+        results_neg.append(fit_fn(policy.pheno(-noise)))
+        gen_obstat.inc(*results_pos[-1].ob_sum_sq_cnt)
+        gen_obstat.inc(*results_neg[-1].ob_sum_sq_cnt)
+
+    n_objectives = len(results_pos[0].result)
+    results = _share_results(comm, [tr.result for tr in results_pos], [tr.result for tr in results_neg], inds)
+    gen_obstat.mpi_inc(comm)
+    steps = sum([tr.steps for tr in results_pos + results_neg])
+    if comm.size > 1:
+        steps = int(sum(dist.world().allgather_object(steps)))
+    return results[:, 0:n_objectives], results[:, n_objectives:2 * n_objectives], results[:, -1], steps
+
+
+def _share_results(comm, fits_pos: List[List[float]], fits_neg: List[List[float]], inds: List[int]) -> np.ndarray:
+    """Share results and noise inds with all processes: rows ``f+... f-... idx`` (float64),
+    ranks concatenated in order (es.py:84-95; the reference's Alltoall of tiled rows is an
+    allgather)."""
+    rows = np.array([list(fp) + list(fn) + [i] for fp, fn, i in zip(fits_pos, fits_neg, inds)], dtype=np.float64)
+    objectives = len(fits_pos[0])
+    rows = rows.reshape(-1, 1 + 2 * objectives)
+    if comm.size == 1:
+        return rows
+    t = torch.from_numpy(rows)
+    backend = torch.distributed.get_backend()
+    if backend == 'nccl':
+        t = t.cuda()
+    out = torch.empty((comm.size,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+    dist.world().allgather_into(out, t)
+    return out.cpu().numpy().reshape(-1, 1 + 2 * objectives)
+
+
+def approx_grad(policy: Policy, ranker: Ranker, nt: NoiseTable, params: np.ndarray, batch_size: int, l2coeff: float):
+    """Approximates the gradient and updates the policy (es.py:98-101):
+    grad = scale_noise(ranked_fits, noise_inds) / n_fits_ranked;  theta += optim.step(l2coeff*theta - grad).
+    Each process reconstructs the partial sum of its own shard of pairs; one allreduce."""
+    if params is not policy.flat_params:
+        raise NotImplementedError('approx_grad updates policy.flat_params in place; pass it as `params`')
+    eng = get_engine()
+    comm = dist.world()
+    K = len(ranker.noise_inds)
+    k0, k1 = dist.shard_bounds(K, comm.size, comm.rank) if K % comm.size == 0 else (0, K if comm.rank == 0 else 0)
+    w = eng.to_device(np.ascontiguousarray(ranker.ranked_fits[k0:k1], dtype=np.float32))
+    idx = eng.to_device(np.ascontiguousarray(ranker.noise_inds[k0:k1]).astype(np.int64))
+    theta = policy.theta_dev(eng)
+    gsum = eng.grad_reconstruct(nt.device_table(eng), idx, w, len(policy))
+    comm.allreduce_sum(gsum)
+    policy.optim.apply_fused(eng, theta, gsum, float(ranker.n_fits_ranked), float(l2coeff))
+    policy.sync_host()

@@ -1,0 +1,248 @@
+// api.cu -- extern "C" surface of libes_b200.so (declared in include/es_b200.h):
+// argument validation, context/scratch management, dispatch to the kernels.
+#include <stdarg.h>
+#include <stdlib.h>
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void es_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int es_ctx_scratch(es_ctx* ctx, size_t bytes, void** out) {
+    if (bytes > ctx->scratch_bytes) {
+        // growing is rare (first call per shape); it synchronises the device, which is
+        // fine outside the steady state.
+        if (ctx->scratch) ES_CHECK_CUDA(cudaFree(ctx->scratch));
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+        size_t want = bytes + (bytes >> 2) + 4096;
+        cudaError_t e = cudaMalloc(&ctx->scratch, want);
+        if (e != cudaSuccess) {
+            es_set_error("scratch cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            return ES_ERR_NOMEM;
+        }
+        ctx->scratch_bytes = want;
+    }
+    *out = ctx->scratch;
+    return ES_OK;
+}
+
+int es_ctx_counters(es_ctx* ctx, size_t n, unsigned** out) {
+    if (n > ctx->n_counters) {
+        if (ctx->counters) ES_CHECK_CUDA(cudaFree(ctx->counters));
+        ctx->counters = nullptr;
+        ctx->n_counters = 0;
+        size_t want = n * 2 + 64;
+        cudaError_t e = cudaMalloc((void**)&ctx->counters, want * sizeof(unsigned));
+        if (e != cudaSuccess) {
+            es_set_error("counter cudaMalloc failed: %s", cudaGetErrorString(e));
+            return ES_ERR_NOMEM;
+        }
+        ES_CHECK_CUDA(cudaMemset(ctx->counters, 0, want * sizeof(unsigned)));
+        ctx->n_counters = want;
+    }
+    *out = ctx->counters;
+    return ES_OK;
+}
+
+extern "C" {
+
+int es_abi_version(void) { return 1; }
+
+const char* es_last_error(void) { return g_err; }
+
+int es_ctx_create(int device, es_ctx** out) {
+    ES_REQUIRE(out != nullptr, "es_ctx_create: out is NULL");
+    int n = 0;
+    ES_CHECK_CUDA(cudaGetDeviceCount(&n));
+    ES_REQUIRE(device >= 0 && device < n, "es_ctx_create: device %d out of range (%d devices)", device, n);
+    ES_CHECK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    ES_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        es_set_error("es_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                     prop.major, prop.minor);
+        return ES_ERR_UNSUPPORTED;
+    }
+    es_ctx* c = (es_ctx*)calloc(1, sizeof(es_ctx));
+    if (!c) return ES_ERR_NOMEM;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    *out = c;
+    return ES_OK;
+}
+
+int es_ctx_destroy(es_ctx* ctx) {
+    if (!ctx) return ES_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->counters) cudaFree(ctx->counters);
+    free(ctx);
+    return ES_OK;
+}
+
+int64_t es_launch_count(const es_ctx* ctx) { return ctx ? ctx->launches : -1; }
+int es_sm_count(const es_ctx* ctx) { return ctx ? ctx->sm_count : -1; }
+
+#define ES_ENTER(ctx)                                                        \
+    ES_REQUIRE((ctx) != nullptr, "%s: ctx is NULL", __func__);               \
+    ES_CHECK_CUDA(cudaSetDevice((ctx)->device))
+
+int es_draw_indices(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int n_streams, int n_per_stream,
+                    uint64_t upper_bound, int extra_words, int64_t* idx_out, uint32_t* extra_out, void* stream) {
+    ES_ENTER(ctx);
+    ES_REQUIRE(mt_key && mt_pos && idx_out, "es_draw_indices: NULL pointer");
+    ES_REQUIRE(n_streams >= 0 && n_per_stream >= 0, "es_draw_indices: negative count");
+    ES_REQUIRE(extra_words >= 0 && extra_words <= 7, "es_draw_indices: extra_words must be in [0,7]");
+    // NoiseTable.sample_idx raises ValueError when upper_bound <= 0 (noisetable.py:39)
+    ES_REQUIRE(upper_bound >= 1, "es_draw_indices: upper_bound must be >= 1 (network too large for noise table)");
+    if (upper_bound - 1 >= 0xFFFFFFFFull) {
+        es_set_error("es_draw_indices: ranges >= 2^32 use numpy's 64-bit draw path, not implemented");
+        return ES_ERR_UNSUPPORTED;
+    }
+    if (n_streams == 0 || n_per_stream == 0) return ES_OK;
+    return es_impl_draw_indices(ctx, mt_key, mt_pos, n_streams, n_per_stream, upper_bound, extra_words, idx_out,
+                                extra_out, (cudaStream_t)stream);
+}
+
+int es_perturb(es_ctx* ctx, const float* theta, const float* table, int64_t table_len, const int64_t* idx, int n_idx,
+               int P, float sigma, float* out_pos, float* out_neg, void* stream) {
+    ES_ENTER(ctx);
+    ES_REQUIRE(theta && table && idx && out_pos, "es_perturb: NULL pointer");
+    ES_REQUIRE(n_idx >= 0 && P > 0 && table_len > P, "es_perturb: bad sizes");
+    if (n_idx == 0) return ES_OK;
+    return es_impl_perturb(ctx, theta, table, table_len, idx, n_idx, P, sigma, out_pos, out_neg, (cudaStream_t)stream);
+}
+
+int es_normalise_obs(es_ctx* ctx, const float* obs, const double* mean, const double* std, double clip, int rows,
+                     int obs_dim, float* out, void* stream) {
+    ES_ENTER(ctx);
+    ES_REQUIRE(obs && mean && std && out, "es_normalise_obs: NULL pointer");
+    ES_REQUIRE(rows >= 0 && obs_dim > 0, "es_normalise_obs: bad sizes");
+    if (rows == 0) return ES_OK;
+    return es_impl_normalise_obs(ctx, obs, mean, std, clip, rows, obs_dim, out, (cudaStream_t)stream);
+}
+
+int es_obs_colsum(es_ctx* ctx, const float* obs, int rows, int obs_dim, float* sum_out, float* sumsq_out, void* stream) {
+    ES_ENTER(ctx);
+    ES_REQUIRE(obs && sum_out && sumsq_out, "es_obs_colsum: NULL pointer");
+    ES_REQUIRE(rows >= 0 && obs_dim > 0, "es_obs_colsum: bad sizes");
+    return es_impl_obs_colsum(ctx, obs, rows, obs_dim, sum_out, sumsq_out, (cudaStream_t)stream);
+}
+
+int es_obstat_accumulate(es_ctx* ctx, double* sum, double* sumsq, const float* s, const float* ssq, int obs_dim,
+                         int n_rollouts, void* stream) {
+    ES_ENTER(ctx);
+    ES_REQUIRE(sum && sumsq && s && ssq, "es_obstat_accumulate: NULL pointer");
+    ES_REQUIRE(obs_dim > 0 && n_rollouts >= 0, "es_obstat_accumulate: bad sizes");
+    if (n_rollouts == 0) return ES_OK;
+    return es_impl_obstat_accumulate(ctx, sum, sumsq, s, ssq, obs_dim, n_rollouts, (cudaStream_t)stream);
+}
+
+int es_obstat_accumulate_coins(es_ctx* ctx, double* sum, double* sumsq, double* count_io, const float* s,
+                               const float* ssq, int obs_dim, int rows_per_rollout, const uint32_t* coin_words,
+                               int n_coins, double chance, void* stream) {
+    ES_ENTER(ctx);
+    ES_REQUIRE(sum && sumsq && count_io && s && ssq && (coin_words || n_coins == 0),
+               "es_obstat_accumulate_coins: NULL pointer");
+    ES_REQUIRE(obs_dim > 0 && n_coins >= 0 && rows_per_rollout >= 0, "es_obstat_accumulate_coins: bad sizes");
+    return es_impl_obstat_accumulate_coins(ctx, sum, sumsq, count_io, s, ssq, obs_dim, rows_per_rollout, coin_words,
+                                           n_coins, chance, (cudaStream_t)stream);
+}
+
+int es_rollout_openloop(es_ctx* ctx, const float* table, int64_t table_len, const int64_t* idx, int n_pairs,
+                        const float* theta, int P, float sigma, const int* layer_sizes, int n_layers, const float* obsn,
+                        const float* rew_vec, int T, float pos_scale, double* fit_pos, double* fit_neg, int fit_stride,
+                        float* behv_pos, float* behv_neg, int mode, void* stream) {
+    ES_ENTER(ctx);
+    ES_REQUIRE(table && idx && theta && layer_sizes && obsn && rew_vec && fit_pos && fit_neg,
+               "es_rollout_openloop: NULL pointer");
+    ES_REQUIRE(n_layers >= 1 && n_layers <= ES_MAX_LAYERS, "es_rollout_openloop: n_layers must be in [1,%d]",
+               ES_MAX_LAYERS);
+    ES_REQUIRE(n_pairs >= 0 && T >= 1 && fit_stride >= 1, "es_rollout_openloop: bad sizes");
+    ES_REQUIRE((behv_pos == nullptr) == (behv_neg == nullptr), "es_rollout_openloop: behv_pos/behv_neg must both be set or NULL");
+    int64_t count = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        ES_REQUIRE(layer_sizes[l] > 0 && layer_sizes[l + 1] > 0, "es_rollout_openloop: layer size <= 0");
+        count += (int64_t)layer_sizes[l] * layer_sizes[l + 1] + layer_sizes[l + 1];
+    }
+    ES_REQUIRE(count == P, "es_rollout_openloop: layer sizes give %lld params, P=%d", (long long)count, P);
+    ES_REQUIRE(table_len > P, "es_rollout_openloop: table smaller than the network");
+    if (n_pairs == 0) return ES_OK;
+    if (mode == ES_ROLLOUT_F32)
+        return es_impl_rollout_f32(ctx, table, table_len, idx, n_pairs, theta, P, sigma, layer_sizes, n_layers, obsn,
+                                   rew_vec, T, pos_scale, fit_pos, fit_neg, fit_stride, behv_pos, behv_neg,
+                                   (cudaStream_t)stream);
+    if (mode == ES_ROLLOUT_TC)
+        return es_impl_rollout_tc(ctx, table, table_len, idx, n_pairs, theta, P, sigma, layer_sizes, n_layers, obsn,
+                                  rew_vec, T, pos_scale, fit_pos, fit_neg, fit_stride, behv_pos, behv_neg,
+                                  (cudaStream_t)stream);
+    es_set_error("es_rollout_openloop: unknown mode %d", mode);
+    return ES_ERR_INVALID;
+}
+
+int es_novelty(es_ctx* ctx, const float* behv, int n, const double* archive, int A, int k, double* out, int out_stride,
+               void* stream) {
+    ES_ENTER(ctx);
+    ES_REQUIRE(behv && archive && out, "es_novelty: NULL pointer");
+    ES_REQUIRE(n >= 0 && A >= 1 && k >= 1 && out_stride >= 1, "es_novelty: bad sizes");
+    ES_REQUIRE((k < A ? k : A) <= 64, "es_novelty: min(k, archive size) > 64 not supported");
+    if (n == 0) return ES_OK;
+    return es_impl_novelty(ctx, behv, n, archive, A, k, out, out_stride, (cudaStream_t)stream);
+}
+
+int es_centered_rank(es_ctx* ctx, const double* fpos, const double* fneg, int K, int n_obj, float w0, float w1,
+                     int k_begin, int k_count, float* weights_out, int32_t* ranks_out, void* stream) {
+    ES_ENTER(ctx);
+    ES_REQUIRE(fpos && fneg && weights_out, "es_centered_rank: NULL pointer");
+    // MultiObjectiveRanker asserts exactly two columns (rankers.py:114)
+    ES_REQUIRE(n_obj == 1 || n_obj == 2, "es_centered_rank: n_obj must be 1 or 2");
+    ES_REQUIRE(K >= 1 && k_begin >= 0 && k_count >= 0 && k_begin + k_count <= K, "es_centered_rank: bad shard");
+    if (k_count == 0) return ES_OK;
+    return es_impl_centered_rank(ctx, fpos, fneg, K, n_obj, w0, w1, k_begin, k_count, weights_out, ranks_out,
+                                 (cudaStream_t)stream);
+}
+
+int es_grad_reconstruct(es_ctx* ctx, const float* table, int64_t table_len, const int64_t* idx, const float* weights,
+                        int n_idx, int P, float* out, void* stream) {
+    ES_ENTER(ctx);
+    ES_REQUIRE(table && out, "es_grad_reconstruct: NULL pointer");
+    ES_REQUIRE(n_idx >= 0 && P > 0 && table_len > P, "es_grad_reconstruct: bad sizes");
+    ES_REQUIRE(n_idx == 0 || (idx && weights), "es_grad_reconstruct: NULL idx/weights");
+    if (n_idx == 0) {
+        ES_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)P * sizeof(float), (cudaStream_t)stream));
+        return ES_OK;
+    }
+    return es_impl_grad_reconstruct(ctx, table, table_len, idx, weights, n_idx, P, out, (cudaStream_t)stream);
+}
+
+int es_adam_step(es_ctx* ctx, float* theta, float* m, float* v, const float* gsum, float n_ranked, float l2coeff,
+                 float neg_a, float beta1, float one_minus_beta1, float beta2, float one_minus_beta2, float epsilon,
+                 int P, void* stream) {
+    ES_ENTER(ctx);
+    ES_REQUIRE(theta && m && v && gsum && P > 0, "es_adam_step: bad arguments");
+    return es_impl_adam(ctx, theta, m, v, gsum, n_ranked, l2coeff, neg_a, beta1, one_minus_beta1, beta2,
+                        one_minus_beta2, epsilon, P, (cudaStream_t)stream);
+}
+
+int es_sgd_step(es_ctx* ctx, float* theta, float* v, const float* gsum, float n_ranked, float l2coeff, float neg_lr,
+                float momentum, float one_minus_momentum, int P, void* stream) {
+    ES_ENTER(ctx);
+    ES_REQUIRE(theta && v && gsum && P > 0, "es_sgd_step: bad arguments");
+    return es_impl_sgd(ctx, theta, v, gsum, n_ranked, l2coeff, neg_lr, momentum, one_minus_momentum, P,
+                       (cudaStream_t)stream);
+}
+
+int es_simple_step(es_ctx* ctx, float* theta, const float* gsum, float n_ranked, float l2coeff, float lr, int P,
+                   void* stream) {
+    ES_ENTER(ctx);
+    ES_REQUIRE(theta && gsum && P > 0, "es_simple_step: bad arguments");
+    return es_impl_simple(ctx, theta, gsum, n_ranked, l2coeff, lr, P, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+// common.cuh -- shared host/device helpers for libes_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/es_b200.h"
+
+#ifndef __CUDA_ARCH_LIST__
+#endif
+
+struct es_ctx {
+    int device;
+    int sm_count;
+    int64_t launches;
+    // scratch owned by the ctx (grown on demand, never shrunk)
+    void* scratch;          // generic scratch (reconstruct partials, rank keys, ...)
+    size_t scratch_bytes;
+    unsigned* counters;     // small zero-initialised counter array (last-block detection)
+    size_t n_counters;
+};
+
+void es_set_error(const char* fmt, ...);
+
+#define ES_CHECK_CUDA(expr)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            es_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,              \
+                         cudaGetErrorString(_e));                                        \
+            return ES_ERR_CUDA;                                                          \
+        }                                                                                \
+    } while (0)
+
+#define ES_REQUIRE(cond, ...)                                                            \
+    do {                                                                                 \
+        if (!(cond)) {                                                                   \
+            es_set_error(__VA_ARGS__);                                                   \
+            return ES_ERR_INVALID;                                                       \
+        }                                                                                \
+    } while (0)
+
+// after a kernel launch: count it and surface launch-configuration errors
+#define ES_LAUNCHED(ctx)                                                                 \
+    do {                                                                                 \
+        (ctx)->launches++;                                                               \
+        ES_CHECK_CUDA(cudaGetLastError());                                               \
+    } while (0)
+
+int es_ctx_scratch(es_ctx* ctx, size_t bytes, void** out);
+int es_ctx_counters(es_ctx* ctx, size_t n, unsigned** out);
+
+static inline int es_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- entry points implemented one per .cu file (called from api.cu) -------------------------
+int es_impl_draw_indices(es_ctx*, uint32_t*, int32_t*, int, int, uint64_t, int, int64_t*, uint32_t*, cudaStream_t);
+int es_impl_perturb(es_ctx*, const float*, const float*, int64_t, const int64_t*, int, int, float, float*, float*,
+                    cudaStream_t);
+int es_impl_normalise_obs(es_ctx*, const float*, const double*, const double*, double, int, int, float*, cudaStream_t);
+int es_impl_obs_colsum(es_ctx*, const float*, int, int, float*, float*, cudaStream_t);
+int es_impl_obstat_accumulate(es_ctx*, double*, double*, const float*, const float*, int, int, cudaStream_t);
+int es_impl_obstat_accumulate_coins(es_ctx*, double*, double*, double*, const float*, const float*, int, int,
+                                    const uint32_t*, int, double, cudaStream_t);
+int es_impl_rollout_f32(es_ctx*, const float*, int64_t, const int64_t*, int, const float*, int, float, const int*, int,
+                        const float*, const float*, int, float, double*, double*, int, float*, float*, cudaStream_t);
+int es_impl_rollout_tc(es_ctx*, const float*, int64_t, const int64_t*, int, const float*, int, float, const int*, int,
+                       const float*, const float*, int, float, double*, double*, int, float*, float*, cudaStream_t);
+int es_impl_novelty(es_ctx*, const float*, int, const double*, int, int, double*, int, cudaStream_t);
+int es_impl_centered_rank(es_ctx*, const double*, const double*, int, int, float, float, int, int, float*, int32_t*,
+                          cudaStream_t);
+int es_impl_grad_reconstruct(es_ctx*, const float*, int64_t, const int64_t*, const float*, int, int, float*,
+                             cudaStream_t);
+int es_impl_adam(es_ctx*, float*, float*, float*, const float*, float, float, float, float, float, float, float, float,
+                 int, cudaStream_t);
+int es_impl_sgd(es_ctx*, float*, float*, const float*, float, float, float, float, float, int, cudaStream_t);
+int es_impl_simple(es_ctx*, float*, const float*, float, float, float, int, cudaStream_t);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float es_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int es_warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif

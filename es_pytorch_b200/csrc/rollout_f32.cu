@@ -1,0 +1,211 @@
+// rollout_f32.cu -- fused perturb + MLP rollout + fitness, float32 CUDA-core path.
+//
+// One CTA evaluates one perturbed policy (blockIdx.x = 2*pair + sign) over the whole
+// open-loop episode:
+//   W = theta +- sigma*table[idx : idx+P]      (src/core/policy.py:61-64; built straight into
+//                                               shared memory, theta' never touches HBM)
+//   a_t = tanh(W3 tanh(W2 tanh(W1 x_t + b1) + b2) + b3)   (src/nn/nn.py:35-36,46)
+//   r_t = <a_t, c_t> float32;  fitness = sum_t r_t in float64, step order
+//                                               (src/gym/training_result.py:28,62-64)
+//   pos += pos_scale * a_t[0..2]                (synthetic env position integrator)
+// This is the device-side precision reference for the tensor-core path and the general
+// fallback (any layer sizes whose weights fit in shared memory).
+//
+// Shared-memory layout: weight rows are padded to a pitch with (pitch/4) odd so that the
+// 128-bit reads of 32 different output rows at the same k hit 32 different bank groups;
+// activations for a tile of RF_TM time steps ping-pong between two buffers.
+#include "common.cuh"
+
+constexpr int RF_THREADS = 256;
+constexpr int RF_WARPS = RF_THREADS / 32;
+constexpr int RF_TM = 32;   // time steps per tile
+constexpr int RF_RT = 8;    // time steps per thread (register tile)
+
+struct RfDesc {
+    int n_layers;
+    int in[ES_MAX_LAYERS], out[ES_MAX_LAYERS];
+    int in4[ES_MAX_LAYERS];      // in rounded up to a multiple of 4
+    int pitch[ES_MAX_LAYERS];    // shared-memory row pitch of W_l (floats)
+    int w_off[ES_MAX_LAYERS];    // offset of W_l / b_l in the flat parameter vector
+    int b_off[ES_MAX_LAYERS];
+    int sw_off[ES_MAX_LAYERS];   // offset of W_l / b_l in shared memory (floats)
+    int sb_off[ES_MAX_LAYERS];
+    int w_floats;                // total shared floats for weights + biases
+    int xpitch;                  // activation buffer pitch (floats), multiple of 4
+    int P;
+};
+
+__device__ __forceinline__ void rf_dense(const float* __restrict__ Wsm, const float* __restrict__ bsm, int in4, int pitch,
+                                         int out, const float* __restrict__ Xin, float* __restrict__ Xout, int xpitch) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_blocks = (out + 31) >> 5;
+    const int tasks = n_blocks * (RF_TM / RF_RT);
+    for (int task = warp; task < tasks; task += RF_WARPS) {
+        const int nb = task % n_blocks, tg = task / n_blocks;
+        const int n = nb * 32 + lane;
+        const bool valid = n < out;
+        const int nn = valid ? n : out - 1;
+        float acc[RF_RT];
+        const float bias = bsm[nn];
+#pragma unroll
+        for (int r = 0; r < RF_RT; ++r) acc[r] = bias;
+        const float4* __restrict__ wrow = reinterpret_cast<const float4*>(Wsm + (size_t)nn * pitch);
+        const float4* __restrict__ xrow = reinterpret_cast<const float4*>(Xin + (size_t)(tg * RF_RT) * xpitch);
+        const int xp4 = xpitch >> 2;
+        for (int k4 = 0; k4 < (in4 >> 2); ++k4) {
+            const float4 w = wrow[k4];
+#pragma unroll
+            for (int r = 0; r < RF_RT; ++r) {
+                const float4 x = xrow[r * xp4 + k4];
+                acc[r] = fmaf(x.x, w.x, acc[r]);
+                acc[r] = fmaf(x.y, w.y, acc[r]);
+                acc[r] = fmaf(x.z, w.z, acc[r]);
+                acc[r] = fmaf(x.w, w.w, acc[r]);
+            }
+        }
+        if (valid) {
+#pragma unroll
+            for (int r = 0; r < RF_RT; ++r) Xout[(size_t)(tg * RF_RT + r) * xpitch + n] = tanhf(acc[r]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RF_THREADS, 1)
+rollout_f32_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx, const float* __restrict__ theta,
+                   float sigma, const __grid_constant__ RfDesc d, const float* __restrict__ obsn,
+                   const float* __restrict__ rew_vec, int T, float pos_scale, double* __restrict__ fit_pos,
+                   double* __restrict__ fit_neg, int fit_stride, float* __restrict__ behv_pos,
+                   float* __restrict__ behv_neg) {
+    extern __shared__ __align__(16) float smem[];
+    float* Wsm = smem;                                  // [w_floats]
+    float* Xa = Wsm + d.w_floats;                       // [RF_TM][xpitch]
+    float* Xb = Xa + RF_TM * d.xpitch;                  // [RF_TM][xpitch]
+    float* s_rew = Xb + RF_TM * d.xpitch;               // [RF_TM]
+    __shared__ double s_fit;
+    __shared__ float s_pos[3];
+
+    const int pair = blockIdx.x >> 1;
+    const bool neg = blockIdx.x & 1;
+    const float* __restrict__ eps = table + idx[pair];
+
+    // ---- stage W = theta +- sigma*eps (zero the padding first) ----
+    for (int i = threadIdx.x; i < d.w_floats; i += RF_THREADS) Wsm[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * RF_TM * d.xpitch; i += RF_THREADS) Xa[i] = 0.f;
+    if (threadIdx.x == 0) { s_fit = 0.0; s_pos[0] = s_pos[1] = s_pos[2] = 0.f; }
+    __syncthreads();
+    for (int l = 0; l < d.n_layers; ++l) {
+        const int in = d.in[l], cnt = d.in[l] * d.out[l];
+        for (int i = threadIdx.x; i < cnt; i += RF_THREADS) {
+            const int n = i / in, k = i - n * in;
+            const float dlt = __fmul_rn(sigma, __ldg(eps + d.w_off[l] + i));     // std * noise
+            const float t = __ldg(theta + d.w_off[l] + i);
+            Wsm[d.sw_off[l] + n * d.pitch[l] + k] = __fadd_rn(t, neg ? -dlt : dlt);
+        }
+        for (int i = threadIdx.x; i < d.out[l]; i += RF_THREADS) {
+            const float dlt = __fmul_rn(sigma, __ldg(eps + d.b_off[l] + i));
+            Wsm[d.sb_off[l] + i] = __fadd_rn(__ldg(theta + d.b_off[l] + i), neg ? -dlt : dlt);
+        }
+    }
+    __syncthreads();
+
+    const int obs_dim = d.in[0];
+    const int act_dim = d.out[d.n_layers - 1];
+    for (int t0 = 0; t0 < T; t0 += RF_TM) {
+        const int rows = min(RF_TM, T - t0);
+        // observation tile -> Xa (rows beyond T are zero: computed and ignored)
+        // (columns [obs_dim, in4) are re-zeroed every tile: later layers reuse this buffer)
+        const int in40 = d.in4[0];
+        for (int i = threadIdx.x; i < RF_TM * in40; i += RF_THREADS) {
+            const int r = i / in40, k = i - r * in40;
+            Xa[r * d.xpitch + k] = (r < rows && k < obs_dim) ? __ldg(obsn + (size_t)(t0 + r) * obs_dim + k) : 0.f;
+        }
+        __syncthreads();
+        float* xin = Xa;
+        float* xout = Xb;
+        for (int l = 0; l < d.n_layers; ++l) {
+            // the padding columns [out, in4_next) of xout must read as zero in the next layer
+            if (l + 1 < d.n_layers && d.in4[l + 1] != d.out[l]) {
+                const int padw = d.in4[l + 1] - d.out[l];
+                for (int i = threadIdx.x; i < RF_TM * padw; i += RF_THREADS)
+                    xout[(i / padw) * d.xpitch + d.out[l] + (i % padw)] = 0.f;
+            }
+            rf_dense(Wsm + d.sw_off[l], Wsm + d.sb_off[l], d.in4[l], d.pitch[l], d.out[l], xin, xout, d.xpitch);
+            __syncthreads();
+            float* tmp = xin; xin = xout; xout = tmp;
+        }
+        // xin now holds the actions [RF_TM][act_dim]
+        if (threadIdx.x < rows) {
+            const int r = threadIdx.x;
+            const float* a = xin + r * d.xpitch;
+            const float* c = rew_vec + (size_t)(t0 + r) * act_dim;
+            float acc = 0.f;
+            for (int j = 0; j < act_dim; ++j) acc = __fadd_rn(acc, __fmul_rn(a[j], __ldg(c + j)));
+            s_rew[r] = acc;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double f = s_fit;
+            float p0 = s_pos[0], p1 = s_pos[1], p2 = s_pos[2];
+            for (int r = 0; r < rows; ++r) {
+                f += (double)s_rew[r];
+                const float* a = xin + r * d.xpitch;
+                p0 = __fadd_rn(p0, __fmul_rn(pos_scale, a[0 % act_dim]));
+                p1 = __fadd_rn(p1, __fmul_rn(pos_scale, a[1 % act_dim]));
+                p2 = __fadd_rn(p2, __fmul_rn(pos_scale, a[2 % act_dim]));
+            }
+            s_fit = f; s_pos[0] = p0; s_pos[1] = p1; s_pos[2] = p2;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        (neg ? fit_neg : fit_pos)[(size_t)pair * fit_stride] = s_fit;
+        float* b = neg ? behv_neg : behv_pos;
+        if (b) { b[pair * 3 + 0] = s_pos[0]; b[pair * 3 + 1] = s_pos[1]; b[pair * 3 + 2] = s_pos[2]; }
+    }
+}
+
+static int rf_round4(int x) { return (x + 3) & ~3; }
+
+int es_impl_rollout_f32(es_ctx* ctx, const float* table, int64_t table_len, const int64_t* idx, int n_pairs,
+                        const float* theta, int P, float sigma, const int* layer_sizes, int n_layers, const float* obsn,
+                        const float* rew_vec, int T, float pos_scale, double* fit_pos, double* fit_neg, int fit_stride,
+                        float* behv_pos, float* behv_neg, cudaStream_t stream) {
+    (void)table_len;
+    RfDesc d;
+    memset(&d, 0, sizeof(d));
+    d.n_layers = n_layers;
+    d.P = P;
+    int off = 0, soff = 0, xmax = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        d.in[l] = layer_sizes[l];
+        d.out[l] = layer_sizes[l + 1];
+        d.in4[l] = rf_round4(d.in[l]);
+        d.pitch[l] = ((d.in4[l] >> 2) & 1) ? d.in4[l] : d.in4[l] + 4;   // (pitch/4) odd -> conflict-free float4 rows
+        d.w_off[l] = off; off += d.in[l] * d.out[l];
+        d.b_off[l] = off; off += d.out[l];
+        d.sw_off[l] = soff; soff += d.out[l] * d.pitch[l];
+        if (d.in4[l] > xmax) xmax = d.in4[l];
+        if (rf_round4(d.out[l]) > xmax) xmax = rf_round4(d.out[l]);
+    }
+    for (int l = 0; l < n_layers; ++l) { d.sb_off[l] = soff; soff += rf_round4(d.out[l]); }
+    d.w_floats = rf_round4(soff);
+    d.xpitch = xmax;
+    const size_t smem = ((size_t)d.w_floats + 2 * (size_t)RF_TM * d.xpitch + RF_TM) * sizeof(float);
+    if (smem > 227 * 1024) {
+        es_set_error("es_rollout_openloop(F32): network needs %zu bytes of shared memory (> 227 KB)", smem);
+        return ES_ERR_UNSUPPORTED;
+    }
+    ES_REQUIRE(n_pairs <= (1 << 30), "es_rollout_openloop: too many pairs");
+    ES_CHECK_CUDA(cudaFuncSetAttribute(rollout_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rollout_f32_kernel<<<2 * n_pairs, RF_THREADS, smem, stream>>>(table, idx, theta, sigma, d, obsn, rew_vec, T, pos_scale,
+                                                                  fit_pos, fit_neg, fit_stride, behv_pos, behv_neg);
+    ES_LAUNCHED(ctx);
+    return ES_OK;
+}
+
+// Placeholder until the tcgen05 path lands: fail loudly, never fall back silently.
+int es_impl_rollout_tc(es_ctx*, const float*, int64_t, const int64_t*, int, const float*, int, float, const int*, int,
+                       const float*, const float*, int, float, double*, double*, int, float*, float*, cudaStream_t) {
+    es_set_error("es_rollout_openloop: ES_ROLLOUT_TC is not built in this revision");
+    return ES_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,183 @@
+"""One OpenAI-ES generation, resident on the GPU.
+
+``DeviceGeneration`` owns the HBM-resident state of the hot path (noise table, theta,
+optimizer moments, observation stream, per-rank MT19937 streams) and enqueues, on the
+current CUDA stream and without any host synchronisation, the kernel sequence that
+replaces ``es.test_params`` -> ``Ranker.rank`` -> ``es.approx_grad`` of the reference
+(src/core/es.py:54-101):
+
+    draw K indices            es_draw_indices        (noisetable.py:37-40, es.py:67-68)
+    normalise obs stream      es_normalise_obs       (nn.py:45)
+    theta +- sigma*eps, MLP rollout, fitness
+                              es_rollout_openloop    (policy.py:61-64, nn.py:42-50, gym_runner.py:33-67)
+    [novelty column]          es_novelty             (novelty.py:16-18)            NSRA only
+    [obs statistics]          es_obs_colsum + es_obstat_accumulate_coins           (es.py:73-74)
+    allgather fitness         NCCL (only when world size > 1)                       (es.py:84-95)
+    centered rank -> weights  es_centered_rank       (rankers.py:9-58,106-120)
+    sum_k w_k eps_k           es_grad_reconstruct    (utils.py:14-39)
+    allreduce partial grad    NCCL (only when world size > 1)
+    /2K, l2, Adam/SGD, theta  es_adam_step ...       (es.py:100-101, optimizers.py)
+
+Sharding: each process (GPU) owns ``n_streams`` virtual MPI ranks
+and evaluates their pairs; ranks are global (fitness allgather), the gradient partial is
+shard-local and summed by ONE allreduce; the optimizer step is replicated.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import dist
+from ._lib import ES_MT_N, ES_ROLLOUT_F32
+from .engine import Engine, get_engine
+from .nn.optimizers import Optimizer
+
+
+class DeviceGeneration:
+    def __init__(self, table: torch.Tensor, theta: torch.Tensor, layer_sizes: Sequence[int], obs_stream: torch.Tensor,
+                 rew_vec: torch.Tensor, rank_states: Sequence[np.random.RandomState], sigma: float, l2coeff: float,
+                 optim: Optimizer, ob_clip: float = 5.0, pos_scale: float = 0.05, coins_per_eval: int = 0,
+                 save_obs_chance: float = 0.0, archive: Optional[torch.Tensor] = None, nov_k: int = 10,
+                 moo_w: float = 1.0, rollout_mode: int = ES_ROLLOUT_F32, comm: Optional[dist.Comm] = None,
+                 engine: Optional[Engine] = None):
+        self.eng = engine or get_engine()
+        e = self.eng
+        self.comm = comm or dist.world()
+        self.table = table
+        self.theta = theta
+        self.P = theta.numel()
+        self.layer_sizes = [int(x) for x in layer_sizes]
+        self.obs_dim, self.act_dim = self.layer_sizes[0], self.layer_sizes[-1]
+        self.obs_stream = obs_stream                    # [T+1, obs_dim]
+        self.rew_vec = rew_vec                          # [T, act_dim]
+        self.T = rew_vec.shape[0]
+        assert obs_stream.shape == (self.T + 1, self.obs_dim)
+        self.sigma, self.l2coeff, self.optim = float(sigma), float(l2coeff), optim
+        self.ob_clip, self.pos_scale = float(ob_clip), float(pos_scale)
+        self.coins_per_eval, self.save_obs_chance = int(coins_per_eval), float(save_obs_chance)
+        self.archive, self.nov_k, self.moo_w = archive, int(nov_k), float(moo_w)
+        self.n_obj = 1 if archive is None else 2
+        self.rollout_mode = rollout_mode
+        assert self.coins_per_eval in (0, 1), 'fit_fns draw at most one save_obs coin per evaluation'
+
+        # per-rank MT19937 streams, resident on the device between generations
+        self.n_streams = len(rank_states)
+        self._gauss = [(s.get_state()[3], s.get_state()[4]) for s in rank_states]
+        key = np.stack([s.get_state()[1].astype(np.uint32) for s in rank_states]).view(np.int32)
+        pos = np.array([s.get_state()[2] for s in rank_states], dtype=np.int32)
+        self.mt_key = e.to_device(key)
+        self.mt_pos = e.to_device(pos)
+
+        f32, f64 = torch.float32, torch.float64
+        self.gsum = e.empty((self.P,), f32)
+        self.ob_mean = torch.zeros(self.obs_dim, dtype=f64, device=e.device)
+        self.ob_std = torch.ones(self.obs_dim, dtype=f64, device=e.device)
+        self.obsn = e.empty((self.T, self.obs_dim), f32)
+        # generation obs statistics (ObStat(shape, 0), es.py:41): sum, sumsq, [count, n_saved]
+        self.gen_sum = torch.zeros(self.obs_dim, dtype=f64, device=e.device)
+        self.gen_sumsq = torch.zeros(self.obs_dim, dtype=f64, device=e.device)
+        self.gen_count = torch.zeros(2, dtype=f64, device=e.device)
+        self._bufs_for = None
+
+    # ------------------------------------------------------------------------------------------
+    def _ensure_buffers(self, n_per_stream: int):
+        if self._bufs_for == n_per_stream:
+            return
+        e, i64, f32, f64 = self.eng, torch.int64, torch.float32, torch.float64
+        self.k_local = self.n_streams * n_per_stream
+        self.K = self.k_local * self.comm.size
+        self.k_begin = self.k_local * self.comm.rank
+        self.idx = e.empty((self.k_local,), i64)
+        self.extra_words = 4 * self.coins_per_eval       # 2 evaluations x coins x 2 words per double
+        self.extras = e.empty((self.k_local, self.extra_words), torch.int32) if self.extra_words else None
+        self.fit_local = e.empty((2, self.k_local, self.n_obj), f64)          # [pos|neg][k][obj]
+        self.fit_all = e.empty((self.comm.size, 2, self.k_local, self.n_obj), f64) if self.comm.size > 1 else None
+        self.fpos_all = e.empty((self.K, self.n_obj), f64) if self.comm.size > 1 else None
+        self.fneg_all = e.empty((self.K, self.n_obj), f64) if self.comm.size > 1 else None
+        self.behv = e.empty((2, self.k_local, 3), f32) if self.n_obj == 2 else None
+        self.weights = None
+        self._bufs_for = n_per_stream
+
+    def set_obstat(self, mean: np.ndarray, std: np.ndarray):
+        """Policy.update_obstat -> BaseNet.set_ob_mean_std (policy.py:69-71, nn.py:19-21)."""
+        self.ob_mean.copy_(torch.from_numpy(np.ascontiguousarray(mean, dtype=np.float64)), non_blocking=True)
+        self.ob_std.copy_(torch.from_numpy(np.ascontiguousarray(std, dtype=np.float64)), non_blocking=True)
+
+    # ------------------------------------------------------------------------------------------
+    def evaluate(self, n_per_stream: int):
+        """es.test_params on the device: draw, perturb+rollout, fitness (+novelty, obstat),
+        allgather.  Leaves fpos/fneg [K, n_obj] (global) and idx [k_local] on the device."""
+        e = self.eng
+        self._ensure_buffers(n_per_stream)
+        e.draw_indices(self.mt_key, self.mt_pos, n_per_stream, self.table.numel() - self.P, self.extra_words,
+                       self.idx, self.extras)
+        e.normalise_obs(self.obs_stream[:self.T], self.ob_mean, self.ob_std, self.ob_clip, self.obsn)
+        fp, fn = self.fit_local[0], self.fit_local[1]
+        e.rollout(self.table, self.idx, self.theta, self.sigma, self.layer_sizes, self.obsn, self.rew_vec,
+                  self.pos_scale, fp, fn, self.n_obj, None if self.behv is None else self.behv[0],
+                  None if self.behv is None else self.behv[1], self.rollout_mode)
+        if self.n_obj == 2:
+            # second objective column = novelty of the final (x, y) (training_result.py:95-97)
+            e.novelty(self.behv.view(-1, 3), self.archive, self.nov_k, self.fit_local.view(-1)[1:], 2)
+        self.gen_sum.zero_(); self.gen_sumsq.zero_(); self.gen_count.zero_()
+        if self.extra_words:
+            s, q = e.obs_colsum(self.obs_stream[1:self.T + 1])
+            e.obstat_accumulate_coins(self.gen_sum, self.gen_sumsq, self.gen_count, s, q, self.T,
+                                      self.extras.view(-1, 2), self.save_obs_chance)
+        if self.comm.size > 1:
+            self.comm.allgather_into(self.fit_all, self.fit_local)
+            # [rank][pos|neg][k][obj] -> rank-major [K][obj] per sign (es.py:93-95 ordering)
+            self.fpos_all.view(self.comm.size, self.k_local, self.n_obj).copy_(self.fit_all[:, 0])
+            self.fneg_all.view(self.comm.size, self.k_local, self.n_obj).copy_(self.fit_all[:, 1])
+            self.comm.allreduce_sum(self.gen_sum); self.comm.allreduce_sum(self.gen_sumsq)
+            self.comm.allreduce_sum(self.gen_count)
+            return self.fpos_all, self.fneg_all
+        return fp, fn
+
+    def update(self, fpos: torch.Tensor, fneg: torch.Tensor):
+        """Ranker.rank + es.approx_grad on the device (rankers.py:46-50, es.py:98-101)."""
+        e = self.eng
+        w0, w1 = (1.0, 0.0) if self.n_obj == 1 else (self.moo_w, 1 - self.moo_w)
+        self.weights = e.centered_rank(fpos, fneg, w0, w1, self.k_begin, self.k_local)
+        e.grad_reconstruct(self.table, self.idx, self.weights, self.P, self.gsum)
+        self.comm.allreduce_sum(self.gsum)
+        self.apply_optimizer(self.gsum, float(2 * self.K))
+
+    def apply_optimizer(self, gsum: torch.Tensor, n_ranked: float):
+        """grad = gsum/n_ranked; theta += optim.step(l2coeff*theta - grad)  (es.py:100-101)."""
+        self.optim.apply_fused(self.eng, self.theta, gsum, n_ranked, self.l2coeff)
+
+    def run(self, n_per_stream: int):
+        """One whole generation, fully asynchronous on the current stream."""
+        fpos, fneg = self.evaluate(n_per_stream)
+        self.update(fpos, fneg)
+
+    # ------------------------------------------------------------------------------------------
+    def load_states(self, rank_states: Sequence[np.random.RandomState]):
+        """Upload the callers' RandomState streams (they may have been advanced on the host)."""
+        assert len(rank_states) == self.n_streams
+        self._gauss = [(s.get_state()[3], s.get_state()[4]) for s in rank_states]
+        key = np.stack([s.get_state()[1].astype(np.uint32) for s in rank_states]).view(np.int32)
+        pos = np.array([s.get_state()[2] for s in rank_states], dtype=np.int32)
+        self.mt_key.copy_(torch.from_numpy(key), non_blocking=True)
+        self.mt_pos.copy_(torch.from_numpy(pos), non_blocking=True)
+
+    def store_states(self, rank_states: Sequence[np.random.RandomState]):
+        """Write the advanced streams back into the callers' RandomState objects (synchronises)."""
+        key = self.mt_key.cpu().numpy().view(np.uint32)
+        pos = self.mt_pos.cpu().numpy()
+        for r, rs in enumerate(rank_states):
+            rs.set_state(('MT19937', key[r], int(pos[r]), self._gauss[r][0], self._gauss[r][1]))
+
+    def rank_states(self) -> List[np.random.RandomState]:
+        """Download the MT19937 streams back into numpy RandomState objects (synchronises)."""
+        key = self.mt_key.cpu().numpy().view(np.uint32)
+        pos = self.mt_pos.cpu().numpy()
+        out = []
+        for r in range(self.n_streams):
+            rs = np.random.RandomState()
+            rs.set_state(('MT19937', key[r], int(pos[r]), self._gauss[r][0], self._gauss[r][1]))
+            out.append(rs)
+        return out

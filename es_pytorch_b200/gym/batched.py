@@ -1,0 +1,51 @@
+"""``BatchedRollout``: the fit_fn that lets ``es.test_params`` / ``es.step`` evaluate ALL of a
+rank's antithetic pairs in one fused launch.
+
+The reference's ``fit_fn`` is an opaque per-policy python callback (src/core/es.py:28,71-72),
+which forces one rollout per call.  A ``BatchedRollout`` is still callable like that (it is
+what ``es.step`` uses for the noiseless evaluation, es.py:48) but it also *describes* the
+evaluation -- env, episode length, how many ``rs.random()`` coins the script's fit_fn draws
+per evaluation, which TrainingResult adaptor it builds -- so the generation can run on the
+device with the same RNG consumption and the same results layout.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .. import _lib
+from .gym_runner import run_model
+from .training_result import NSRResult, RewardResult, TrainingResult
+
+
+class BatchedRollout:
+    is_batched_rollout = True
+
+    def __init__(self, env, max_steps: int, coins_per_eval: int = 1, save_obs_chance: float = 0.0,
+                 archive: Optional[np.ndarray] = None, nov_k: int = 10,
+                 rank_streams: Optional[Sequence[np.random.RandomState]] = None,
+                 rollout_mode: int = _lib.ES_ROLLOUT_F32):
+        if not getattr(env, 'is_synthetic_openloop', False):
+            raise TypeError('BatchedRollout needs the synthetic open-loop env (es_pytorch_b200.gym.synthetic_env)')
+        self.env = env
+        self.max_steps = min(int(max_steps), env.T)
+        self.coins_per_eval = int(coins_per_eval)
+        self.save_obs_chance = float(save_obs_chance)
+        self.archive = None if archive is None else np.asarray(archive, dtype=np.float64)
+        self.nov_k = int(nov_k)
+        self.rank_streams = list(rank_streams) if rank_streams is not None else None
+        self.rollout_mode = rollout_mode
+        self._gen = None            # cached DeviceGeneration (see core.es)
+
+    @property
+    def n_obj(self) -> int:
+        return 1 if self.archive is None else 2
+
+    def __call__(self, model, use_ac_noise=True) -> TrainingResult:
+        """Single-policy evaluation with the reference's fit_fn contract (no action noise)."""
+        rews, behv, obs, steps = run_model(model, self.env, self.max_steps, None)
+        no_obs = np.array([np.zeros(self.env.observation_space.shape)])
+        if self.archive is None:
+            return RewardResult(rews, behv, no_obs, steps)
+        return NSRResult(rews, behv[-3:], no_obs, steps, self.archive, self.nov_k)

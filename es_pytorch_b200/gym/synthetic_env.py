@@ -1,0 +1,123 @@
+"""Synthetic open-loop vector environment.
+
+Observations are a fixed stream shared by every policy (``obs_stream[t]`` is what the
+policy sees at step ``t``; ``obs_stream[t+1]`` is what ``step`` returns), the reward is
+``r_t = <a_t, rew_vec[t]>`` in float32 and the 'robot position' integrates the first
+three action components.  It offers the classic gym single-env API (``reset``/``step``,
+used by the per-perturbation compatibility path of ``gym_runner.run_model``) and, through
+``device_arrays``, the resident HBM copy that the batched rollout kernels read.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+
+# name fragments -> (obs_dim, act_dim) of the gym/pybullet tasks the reference's configs name
+KNOWN_SHAPES = {
+    'HalfCheetah': (17, 6),          # BASELINE.json config 2 ("HalfCheetah-shaped")
+    'Humanoid': (376, 17),           # BASELINE.json configs 3-5 ("Humanoid-shaped")
+    'Hopper': (15, 3),               # configs/simple_conf.json (HopperBulletEnv-v0)
+    'Walker2D': (22, 6),
+    'Ant': (28, 8),
+}
+
+
+class Box:
+    """Stand-in for gym.spaces.Box: shape/low/high/seed/sample are all the reference reads."""
+
+    def __init__(self, low, high, shape, dtype=np.float32):
+        self.shape = tuple(shape)
+        self.low = np.full(self.shape, low, dtype=dtype)
+        self.high = np.full(self.shape, high, dtype=dtype)
+        self.dtype = dtype
+        self._rs = np.random.RandomState()
+
+    def seed(self, seed=None):
+        self._rs = np.random.RandomState(seed)
+        return [seed]
+
+    def sample(self):
+        return self._rs.uniform(-1, 1, self.shape).astype(self.dtype)
+
+
+class _Robot:
+    """pybullet-gym style handle so position getters like ``env.robot.robot_body.pose().xyz()``
+    (src/gym/gym_runner.py:17-18) keep working on the synthetic env."""
+
+    def __init__(self, env):
+        self._env = env
+        self.robot_body = self
+
+    def pose(self):
+        return self
+
+    def xyz(self):
+        return tuple(float(x) for x in self._env.pos)
+
+    @property
+    def body_real_xyz(self):
+        return self.xyz()
+
+
+class SyntheticEnv:
+    is_synthetic_openloop = True
+
+    def __init__(self, obs_dim: int, act_dim: int, max_episode_steps: int = 1000, obs_seed: int = 11,
+                 rew_seed: int = 13, pos_scale: float = 0.05, name: str = 'Synthetic-v0'):
+        self.name = name
+        self.obs_dim, self.act_dim, self.T = int(obs_dim), int(act_dim), int(max_episode_steps)
+        self.pos_scale = float(pos_scale)
+        self.observation_space = Box(-np.inf, np.inf, (self.obs_dim,))
+        self.action_space = Box(-1.0, 1.0, (self.act_dim,))
+        self.obs_stream = np.random.RandomState(obs_seed).randn(self.T + 1, self.obs_dim).astype(np.float32)
+        self.rew_vec = np.random.RandomState(rew_seed).randn(self.T, self.act_dim).astype(np.float32)
+        self.robot = _Robot(self)
+        self.unwrapped = self
+        self.t = 0
+        self.pos = np.zeros(3, dtype=np.float32)
+        self._dev = None
+
+    # ---- gym API -------------------------------------------------------------------------
+    def seed(self, seed=None):
+        return [seed]
+
+    def reset(self):
+        self.t = 0
+        self.pos = np.zeros(3, dtype=np.float32)
+        return self.obs_stream[0].copy()
+
+    def step(self, action) -> Tuple[np.ndarray, float, bool, dict]:
+        if self.t >= self.T:
+            raise RuntimeError('step() called on a finished episode; call reset()')
+        a = np.asarray(action, dtype=np.float32).reshape(-1)
+        c = self.rew_vec[self.t]
+        acc = np.float32(0.0)
+        for j in range(self.act_dim):
+            acc = np.float32(acc + np.float32(a[j] * c[j]))
+        ps = np.float32(self.pos_scale)
+        for j in range(3):
+            self.pos[j] = np.float32(self.pos[j] + np.float32(ps * a[j % self.act_dim]))
+        self.t += 1
+        return self.obs_stream[self.t].copy(), float(acc), self.t >= self.T, {}
+
+    def render(self, *args, **kwargs):
+        return None
+
+    def close(self):
+        pass
+
+    # ---- device residency ----------------------------------------------------------------------
+    def device_arrays(self, engine):
+        """(obs_stream[T+1,obs] , rew_vec[T,act]) as float32 tensors in HBM (uploaded once)."""
+        if self._dev is None or self._dev[0].device != engine.device:
+            self._dev = (engine.to_device(self.obs_stream), engine.to_device(self.rew_vec))
+        return self._dev
+
+
+def make(name: str, **kwargs) -> SyntheticEnv:
+    """``gym.make`` replacement: any task name maps to a synthetic env of the matching shape."""
+    for frag, (o, a) in KNOWN_SHAPES.items():
+        if frag.lower() in name.lower():
+            return SyntheticEnv(o, a, name=name, **kwargs)
+    raise ValueError(f'no synthetic shape registered for env {name!r}; known: {sorted(KNOWN_SHAPES)}')

@@ -1,0 +1,164 @@
+/* es_b200.h -- C ABI of libes_b200.so: the B200 (sm_100a) OpenAI-ES generation step.
+ *
+ * The reference (sash-a/es_pytorch) is pure Python; its boundary for this path is
+ * the Python API of src.core / src.nn / src.utils.  Each entry point below replaces
+ * the arithmetic of one reference function (cited as file:line into the reference
+ * checkout); the Python mirror in es_pytorch_b200/ binds them with ctypes.
+ *
+ * Conventions
+ *   - every pointer marked "dev" is a device pointer owned by the caller (a torch
+ *     tensor's storage); the library never frees or retains it past the call;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     all work is enqueued asynchronously on it, nothing synchronises the device;
+ *   - return value: 0 = ok, negative = error (ES_ERR_*); es_last_error() returns a
+ *     thread-local message for the last failing call;
+ *   - one es_ctx per device and per host thread; the ctx owns scratch buffers only.
+ */
+#ifndef ES_B200_H
+#define ES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ES_OK                 0
+#define ES_ERR_INVALID       -1   /* bad argument                                   */
+#define ES_ERR_CUDA          -2   /* a CUDA runtime call failed                     */
+#define ES_ERR_UNSUPPORTED   -3   /* shape / mode not implemented by this build     */
+#define ES_ERR_NOMEM         -4
+
+#define ES_MAX_LAYERS         8
+#define ES_MT_N             624   /* MT19937 state words                            */
+
+typedef struct es_ctx es_ctx;
+
+/* ---- context ------------------------------------------------------------------ */
+int         es_ctx_create(int device, es_ctx** out);
+int         es_ctx_destroy(es_ctx* ctx);
+const char* es_last_error(void);
+int         es_abi_version(void);
+/* kernels launched through this ctx since creation (bench.py's "gpu_launches"). */
+int64_t     es_launch_count(const es_ctx* ctx);
+int         es_sm_count(const es_ctx* ctx);
+
+/* ---- a2: draw noise indices ------------------------------------------------------
+ * Replaces NoiseTable.sample_idx, src/core/noisetable.py:37-40, as called n times per
+ * rank from es.test_params, src/core/es.py:67-68: numpy's legacy
+ * RandomState.randint(0, upper_bound) = MT19937 + masked rejection, bit-exact.
+ * One independent stream per virtual MPI rank (src/utils/utils.py:63-65).  After each
+ * accepted index the next `extra_words` raw 32-bit outputs of the same stream are
+ * consumed and returned (4 = the two rs.random() save_obs coins of one antithetic
+ * pair, simple_example.py:38 / obj.py:54; 0 = index-only).
+ *   mt_key  dev uint32 [n_streams][624]  in/out  (RandomState.get_state()[1])
+ *   mt_pos  dev int32  [n_streams]       in/out  (get_state()[2], 0..624)
+ *   idx_out dev int64  [n_streams*n_per_stream]  rank-major (es.py:89-95 order)
+ *   extra_out dev uint32 [n_streams*n_per_stream][extra_words] or NULL            */
+int es_draw_indices(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int n_streams, int n_per_stream,
+                    uint64_t upper_bound, int extra_words, int64_t* idx_out, uint32_t* extra_out,
+                    void* stream);
+
+/* ---- a3: materialise theta +- sigma*eps -------------------------------------------
+ * Replaces Policy.pheno's arithmetic, src/core/policy.py:61-64 (two separately
+ * rounded float32 ops, no FMA).  out_neg may be NULL.  Used by the per-perturbation
+ * compatibility path and by parity tests; the fused rollout never writes theta' out.
+ *   out_pos/out_neg dev float [n_idx][P]                                            */
+int es_perturb(es_ctx* ctx, const float* theta, const float* table, int64_t table_len, const int64_t* idx,
+               int n_idx, int P, float sigma, float* out_pos, float* out_neg, void* stream);
+
+/* ---- a4: observation normalisation -------------------------------------------------
+ * clamp((o - mean) / std, +-clip) in float64, then float32: src/nn/nn.py:45.
+ *   obs dev float [rows][obs_dim]; mean/std dev double [obs_dim]; out dev float      */
+int es_normalise_obs(es_ctx* ctx, const float* obs, const double* mean, const double* std, double clip,
+                     int rows, int obs_dim, float* out, void* stream);
+
+/* ---- a3+a4+a5: fused perturb + batched MLP rollout + fitness ------------------------
+ * For every antithetic pair k: W+- = theta +- sigma*table[idx[k] : idx[k]+P]
+ * (policy.py:61-64), T steps of the FeedForward forward (Linear+tanh after every
+ * layer, src/nn/nn.py:35-36,46) on the pre-normalised open-loop observation stream,
+ * reward r_t = <a_t, rew_vec[t]> (float32), fitness = sum_t r_t accumulated in
+ * float64 in step order (python sum(rews), src/gym/training_result.py:28,62-64), and
+ * the synthetic env's position integrator pos += pos_scale * a_t[0..2].
+ *   layer_sizes  host int [n_layers+1]  (obs_dim, hidden..., act_dim)
+ *   obsn   dev float [T][obs_dim]   rew_vec dev float [T][act_dim]
+ *   fit_pos/fit_neg dev double [n_pairs*fit_stride]  (element k*fit_stride)
+ *   behv_pos/behv_neg dev float [n_pairs][3] or NULL (final x,y,z)
+ *   mode: ES_ROLLOUT_F32 = float32 CUDA-core path (parity reference on device),
+ *         ES_ROLLOUT_TC  = tcgen05 tensor-core path                 */
+#define ES_ROLLOUT_F32 0
+#define ES_ROLLOUT_TC  1
+int es_rollout_openloop(es_ctx* ctx, const float* table, int64_t table_len, const int64_t* idx, int n_pairs,
+                        const float* theta, int P, float sigma, const int* layer_sizes, int n_layers,
+                        const float* obsn, const float* rew_vec, int T, float pos_scale,
+                        double* fit_pos, double* fit_neg, int fit_stride, float* behv_pos, float* behv_neg,
+                        int mode, void* stream);
+
+/* ---- a13: novelty ---------------------------------------------------------------------
+ * mean of the k smallest euclidean distances (float64) between behv[e][0..1] and the
+ * archive rows: src/utils/novelty.py:16-18, src/gym/training_result.py:82-97.
+ *   behv dev float [n][3]; archive dev double [A][2]; out dev double, element e*out_stride */
+int es_novelty(es_ctx* ctx, const float* behv, int n, const double* archive, int A, int k, double* out,
+               int out_stride, void* stream);
+
+/* ---- a8/a9: centered rank -> antithetic weights -------------------------------------------
+ * Replaces Ranker.rank with CenteredRanker (src/utils/rankers.py:9-17,37-58) and, for
+ * n_obj == 2, MultiObjectiveRanker (rankers.py:106-120): ranks over all 2K fitnesses
+ * (pos then neg), y = float32(rank)/(2K-1) - 0.5, blend y0*w0 + y1*w1, weight[k] =
+ * y[k] - y[K+k].  Ranks are integer-exact; ties broken by position (stable).  Only the
+ * weights of pairs [k_begin, k_begin+k_count) are produced (a GPU's shard) but ranks
+ * are global over all K pairs.
+ *   fpos/fneg dev double [K][n_obj]; weights_out dev float [k_count]
+ *   ranks_out dev int32 [n_obj][2][k_count] or NULL (debug/parity: rank of pos/neg)   */
+int es_centered_rank(es_ctx* ctx, const double* fpos, const double* fneg, int K, int n_obj, float w0, float w1,
+                     int k_begin, int k_count, float* weights_out, int32_t* ranks_out, void* stream);
+
+/* ---- a10: gradient reconstruction ---------------------------------------------------------
+ * out[p] = sum_k weights[k] * table[idx[k] + p], p in [0,P): scale_noise/batch_noise,
+ * src/utils/utils.py:14-39.  HBM-bound: reads n_idx*P*4 bytes of the table once.
+ * Deterministic (fixed summation order for a given shape).                            */
+int es_grad_reconstruct(es_ctx* ctx, const float* table, int64_t table_len, const int64_t* idx,
+                        const float* weights, int n_idx, int P, float* out, void* stream);
+
+/* ---- a11/a12: gradient scaling + optimizer step ----------------------------------------------
+ * g = l2coeff*theta - gsum/n_ranked (src/core/es.py:100-101), then the optimizer step
+ * and theta += step (src/core/policy.py:73-74), all float32 with every operation
+ * rounded separately (numpy 1.18 casting of src/nn/optimizers.py:28-61).
+ * Adam: neg_a = float32(-lr*sqrt(1-b2^t)/(1-b1^t)) computed by the caller in float64.   */
+int es_adam_step(es_ctx* ctx, float* theta, float* m, float* v, const float* gsum, float n_ranked, float l2coeff,
+                 float neg_a, float beta1, float one_minus_beta1, float beta2, float one_minus_beta2,
+                 float epsilon, int P, void* stream);
+int es_sgd_step(es_ctx* ctx, float* theta, float* v, const float* gsum, float n_ranked, float l2coeff,
+                float neg_lr, float momentum, float one_minus_momentum, int P, void* stream);
+int es_simple_step(es_ctx* ctx, float* theta, const float* gsum, float n_ranked, float l2coeff, float lr, int P,
+                   void* stream);
+
+/* ---- a14: observation statistics (open-loop stream) ---------------------------------------------
+ * column sums of obs and obs^2 over rows, float32 sequential in row order
+ * (TrainingResult.ob_sum_sq_cnt, src/gym/training_result.py:17-21).
+ *   obs dev float [rows][obs_dim]; sum_out/sumsq_out dev float [obs_dim]               */
+int es_obs_colsum(es_ctx* ctx, const float* obs, int rows, int obs_dim, float* sum_out, float* sumsq_out,
+                  void* stream);
+
+/* gen_obstat.inc(sum, sumsq, cnt) repeated for the n_rollouts rollouts that saved their
+ * observations (ObStat.inc, src/nn/obstat.py:19-22, called per evaluation from
+ * src/core/es.py:73-74): sum += (double)s, sumsq += (double)ssq, n_rollouts times in
+ * order (float64 repeated addition is not n*s).  In the open-loop env every saved
+ * rollout contributes the same (s, ssq).
+ *   sum/sumsq dev double [obs_dim] in/out; s/ssq dev float [obs_dim]                    */
+int es_obstat_accumulate(es_ctx* ctx, double* sum, double* sumsq, const float* s, const float* ssq, int obs_dim,
+                         int n_rollouts, void* stream);
+/* Same, with the number of saving rollouts decided on the device from the save_obs coins
+ * drawn by es_draw_indices: rollout e saves iff double(coin_words[2e], coin_words[2e+1])
+ * < chance (numpy legacy random_sample: (a>>5, b>>6) -> 53-bit double; the coin is
+ * simple_example.py:38 / obj.py:54).  count_io[0] += rows_per_rollout per saving rollout
+ * (ObStat.count, obstat.py:22); count_io[1] = number of saving rollouts (out).
+ *   coin_words dev uint32 [n_coins][2]; count_io dev double [2]                          */
+int es_obstat_accumulate_coins(es_ctx* ctx, double* sum, double* sumsq, double* count_io, const float* s,
+                               const float* ssq, int obs_dim, int rows_per_rollout, const uint32_t* coin_words,
+                               int n_coins, double chance, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ES_B200_H */

@@ -1,0 +1,231 @@
+"""GPU parity of whole generations: the device pipeline (DeviceGeneration) and the
+reference-facing API (es.test_params / Ranker.rank / es.approx_grad / es.step) against the
+oracle's restatement of src/core/es.py:38-101 on the same seeds, plus size-independent
+properties at BASELINE.json's full sizes."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import es_oracle as orc
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'golden'))
+
+
+def _small(eng):
+    from make_golden import small_problem
+    dims, P, table, theta, env = small_problem()
+    return dims, P, table, theta, env
+
+
+def _mk_generation(eng, table, theta, env, streams, optim, **kw):
+    from es_pytorch_b200.generation import DeviceGeneration
+    sizes = kw.pop('sizes')
+    return DeviceGeneration(eng.to_device(table), eng.to_device(theta.copy()), sizes, eng.to_device(env.obs_stream),
+                            eng.to_device(env.rew_vec), streams, 0.02, 0.005, optim, ob_clip=5.0,
+                            pos_scale=env.pos_scale, engine=eng, **kw)
+
+
+def test_device_generation_matches_golden(eng, oracle_vectors):
+    """Two generations, 2 virtual ranks x 6 pairs, one save_obs coin per evaluation, Adam."""
+    from es_pytorch_b200.nn.optimizers import Adam
+    v = oracle_vectors
+    dims, P, table, theta, env = _small(eng)
+    streams = [np.random.RandomState(1000), np.random.RandomState(1001)]
+    gen = _mk_generation(eng, table, theta, env, streams, Adam(P, 0.01), sizes=[17, 64, 64, 6], coins_per_eval=1,
+                         save_obs_chance=0.0)
+    gen.set_obstat(v['obmean'], v['obstd'])
+    for g in range(2):
+        fpos, fneg = gen.evaluate(6)
+        assert np.array_equal(gen.idx.cpu().numpy(), v[f'gen{g}_inds'].astype(np.int64))     # indices bit-exact
+        scale = 40.0
+        assert np.abs(fpos.cpu().numpy() - v[f'gen{g}_pos']).max() <= 1e-5 * scale
+        assert np.abs(fneg.cpu().numpy() - v[f'gen{g}_neg']).max() <= 1e-5 * scale
+        gen.update(fpos, fneg)
+        assert np.array_equal(gen.weights.cpu().numpy(), v[f'gen{g}_w'])                       # rank weights bit-exact
+        # theta after the Adam step: gradient within 1e-5 rel -> theta within a few ulp of the step size
+        assert np.abs(gen.theta.cpu().numpy() - v[f'gen{g}_theta']).max() <= 2e-6
+    # the device streams are where numpy's would be after the same draws
+    ref = [np.random.RandomState(1000), np.random.RandomState(1001)]
+    for r in ref:
+        for _ in range(12):
+            r.randint(0, len(table) - P); r.random(); r.random()
+    for a, b in zip(gen.rank_states(), ref):
+        assert np.array_equal(a.get_state()[1], b.get_state()[1]) and a.get_state()[2] == b.get_state()[2]
+
+
+def test_device_generation_nsra_matches_golden(eng, oracle_vectors):
+    from es_pytorch_b200.nn.optimizers import Adam
+    v = oracle_vectors
+    dims, P, table, theta, env = _small(eng)
+    archive = np.random.RandomState(17).randn(16, 2)
+    gen = _mk_generation(eng, table, theta, env, [np.random.RandomState(1000), np.random.RandomState(1001)],
+                         Adam(P, 0.01), sizes=[17, 64, 64, 6], coins_per_eval=1,
+                         archive=eng.to_device(archive), nov_k=10, moo_w=0.5)
+    gen.set_obstat(v['obmean'], v['obstd'])
+    fpos, fneg = gen.evaluate(6)
+    fp, fn = fpos.cpu().numpy(), fneg.cpu().numpy()
+    assert np.abs(fp[:, 0] - v['nsra_pos'][:, 0]).max() <= 4e-4 and np.abs(fn[:, 0] - v['nsra_neg'][:, 0]).max() <= 4e-4
+    assert np.allclose(fp[:, 1], v['nsra_pos'][:, 1], rtol=1e-5) and np.allclose(fn[:, 1], v['nsra_neg'][:, 1], rtol=1e-5)
+    gen.update(fpos, fneg)
+    assert np.array_equal(gen.weights.cpu().numpy(), v['nsra_w'])
+    assert np.abs(gen.theta.cpu().numpy() - v['nsra_theta']).max() <= 2e-6
+
+
+def test_generation_vs_live_oracle_with_obstat(eng):
+    """Humanoid-shaped, 4 virtual ranks x 8 pairs, save_obs_chance 0.3 so the obs statistics path runs."""
+    from es_pytorch_b200.nn.optimizers import SGD
+    rs = np.random.RandomState(77)
+    obs_dim, act_dim, hidden, T = 376, 17, (64, 64), 25
+    dims = orc.layer_dims(obs_dim, hidden, act_dim)
+    P = orc.n_params(dims)
+    table = rs.randn(P + 400_000).astype(np.float32)
+    theta = (rs.randn(P) * 0.05).astype(np.float32)
+    env = orc.SyntheticEnvSpec(obs_dim, act_dim, T)
+    seeds = [1000, 1001, 1002, 1003]
+    gen = _mk_generation(eng, table, theta, env, [np.random.RandomState(s) for s in seeds], SGD(P, 0.01),
+                         sizes=[obs_dim, 64, 64, act_dim], coins_per_eval=1, save_obs_chance=0.3)
+    gen.run(8)
+    flat, opt = theta.copy(), orc.SGDOracle(P, 0.01)
+    res = orc.generation(table, flat, opt, 0.02, dims, env, seeds, 8, np.zeros(obs_dim), np.ones(obs_dim), 5.0, T, 500,
+                         0.005, coins_per_eval=1, batched=True)
+    # save_obs_chance only matters for obstat; replay it for the oracle
+    pos, neg, inds, steps, obstat = orc.es_test_params(table, theta, 0.02, dims, env, seeds, 8, np.zeros(obs_dim),
+                                                       np.ones(obs_dim), 5.0, T, coins_per_eval=1, save_obs_chance=0.3)
+    assert np.array_equal(gen.idx.cpu().numpy(), res['inds'].astype(np.int64))
+    assert np.array_equal(gen.weights.cpu().numpy(), res['weights'])
+    assert np.abs(gen.theta.cpu().numpy() - flat).max() <= 2e-6
+    assert obstat.count > 0
+    assert np.array_equal(gen.gen_sum.cpu().numpy(), obstat.sum) and np.array_equal(gen.gen_sumsq.cpu().numpy(), obstat.sumsq)
+    assert gen.gen_count.cpu().numpy()[0] == obstat.count
+
+
+# ---- the reference-facing API -----------------------------------------------------------------------------
+class _Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+def _api_objects(eng, table, theta, env_spec, hidden):
+    from es_pytorch_b200.core.noisetable import NoiseTable
+    from es_pytorch_b200.core.policy import Policy
+    from es_pytorch_b200.gym.synthetic_env import SyntheticEnv
+    from es_pytorch_b200.nn.nn import FeedForward
+    from es_pytorch_b200.nn.optimizers import Adam
+    env = SyntheticEnv(env_spec.obs_dim, env_spec.act_dim, env_spec.T)
+    assert np.array_equal(env.obs_stream, env_spec.obs_stream) and np.array_equal(env.rew_vec, env_spec.rew_vec)
+    net = FeedForward(list(hidden), torch.nn.Tanh(), env, 0.0, 5)
+    policy = Policy(net, 0.02, Adam(len(theta), 0.01))
+    policy.flat_params[...] = theta                        # parity harness passes theta in explicitly
+    policy.set_nn_params(policy.flat_params)
+    return env, net, policy, NoiseTable(len(theta), table)
+
+
+def test_api_step_batched_matches_oracle(eng, oracle_vectors):
+    """es.step with a BatchedRollout fit_fn == two oracle generations (same golden vectors as above)."""
+    from es_pytorch_b200 import dist
+    from es_pytorch_b200.core import es
+    from es_pytorch_b200.gym.batched import BatchedRollout
+    from es_pytorch_b200.utils.rankers import CenteredRanker
+    from es_pytorch_b200.utils.reporters import ReporterSet
+    v = oracle_vectors
+    dims, P, table, theta, spec = _small(eng)
+    env, net, policy, nt = _api_objects(eng, table, theta, spec, (64, 64))
+    net.set_ob_mean_std(v['obmean'], v['obstd'])
+    streams = [np.random.RandomState(1000), np.random.RandomState(1001)]
+    fit_fn = BatchedRollout(env, spec.T, coins_per_eval=1, save_obs_chance=0.0, rank_streams=streams)
+    cfg = _Cfg(general=_Cfg(policies_per_gen=12, batch_size=500), policy=_Cfg(l2coeff=0.005))
+    comm = dist.world()
+    ranker = CenteredRanker()
+    for g in range(2):
+        # 2 virtual ranks live in this one process: n = 6 pairs per stream
+        gen_obstat_shape = env.observation_space.shape
+        from es_pytorch_b200.nn.obstat import ObStat
+        gen_obstat = ObStat(gen_obstat_shape, 0)
+        pos, neg, inds, steps = es.test_params(comm, 6, policy, nt, gen_obstat, fit_fn, streams[0])
+        assert pos.shape == (12, 1) and pos.dtype == np.float64 and inds.dtype == np.float64
+        assert np.array_equal(inds, v[f'gen{g}_inds']) and steps == int(v[f'gen{g}_steps'])
+        ranked = ranker.rank(pos, neg, inds)
+        assert ranked.dtype == np.float32 and np.array_equal(ranked, v[f'gen{g}_w']) and ranker.n_fits_ranked == 24
+        es.approx_grad(policy, ranker, nt, policy.flat_params, 500, 0.005)
+        assert np.abs(policy.flat_params - v[f'gen{g}_theta']).max() <= 2e-6
+    # callers' RandomState objects were advanced exactly like the reference would have
+    ref = np.random.RandomState(1000)
+    for _ in range(12):
+        ref.randint(0, len(table) - P); ref.random(); ref.random()
+    assert np.array_equal(streams[0].get_state()[1], ref.get_state()[1])
+    # es.step end to end (one more generation): returns the noiseless TrainingResult and the generation ObStat
+    tr, ob = es.step(cfg, comm, policy, nt, env, BatchedRollout(env, spec.T, coins_per_eval=1, rank_streams=None),
+                     streams[0], CenteredRanker(), ReporterSet())
+    assert len(tr.result) == 1 and np.isfinite(tr.result[0]) and ob.count == 0
+
+
+def test_api_opaque_fit_fn_loop_matches_oracle(eng):
+    """The per-perturbation compatibility path (an opaque python fit_fn like simple_example.py:37-40)."""
+    from es_pytorch_b200 import dist
+    from es_pytorch_b200.core import es
+    from es_pytorch_b200.gym import gym_runner
+    from es_pytorch_b200.gym.training_result import RewardResult
+    from es_pytorch_b200.nn.obstat import ObStat
+    from es_pytorch_b200.utils.rankers import CenteredRanker
+    dims, P, table, theta, spec = _small(eng)
+    env, net, policy, nt = _api_objects(eng, table, theta, spec, (64, 64))
+    rs = np.random.RandomState(1000)
+
+    def r_fn(model):
+        save_obs = rs.random() < 0.0
+        rews, behv, obs, steps = gym_runner.run_model(model, env, 10000, rs)
+        return RewardResult(rews, behv, obs if save_obs else np.array([np.zeros(env.observation_space.shape)]), steps)
+
+    gen_obstat = ObStat(env.observation_space.shape, 0)
+    pos, neg, inds, steps = es.test_params(dist.world(), 5, policy, nt, gen_obstat, r_fn, rs)
+    opos, oneg, oinds, osteps, _ = orc.es_test_params(table, theta, 0.02, dims, spec, [1000], 5, np.zeros(17),
+                                                      np.ones(17), 5.0, 10000, coins_per_eval=1)
+    assert np.array_equal(inds, oinds) and steps == osteps
+    assert np.abs(pos - opos).max() <= 4e-4 and np.abs(neg - oneg).max() <= 4e-4
+    ranker = CenteredRanker()
+    ranker.rank(pos, neg, inds)
+    flat, opt = theta.copy(), orc.AdamOracle(P, 0.01)
+    w, n = orc.centered_ranker(opos, oneg)
+    orc.approx_grad(flat, opt, w, oinds, n, table, 500, 0.005)
+    es.approx_grad(policy, ranker, nt, policy.flat_params, 500, 0.005)
+    assert np.array_equal(ranker.ranked_fits, w)
+    assert np.abs(policy.flat_params - flat).max() <= 2e-6
+
+
+# ---- size-independent properties at BASELINE.json's full sizes ---------------------------------------------
+def test_full_size_properties(eng):
+    """Humanoid-shaped P=29393, K=10000 (config 3): properties that need no CPU replay."""
+    g = torch.Generator(device=eng.device).manual_seed(1)
+    P, K, L = 29393, 10000, 50_000_000
+    table = torch.randn(L, generator=g, device=eng.device, dtype=torch.float32)
+    idx = torch.randint(0, L - P, (K,), generator=g, device=eng.device, dtype=torch.int64)
+    fpos = torch.randn(K, generator=g, device=eng.device, dtype=torch.float64)
+    fneg = torch.randn(K, generator=g, device=eng.device, dtype=torch.float64)
+    w, ranks = eng.centered_rank(fpos, fneg, want_ranks=True)
+    r = ranks.view(-1).to(torch.int64)
+    assert int(r.sum().item()) == (2 * K) * (2 * K - 1) // 2 and int(r.min().item()) == 0       # a permutation
+    order = torch.argsort(torch.cat((fpos, fneg)))
+    assert torch.equal(r[order].cpu(), torch.arange(2 * K))                                         # sortedness
+    w_swapped = eng.centered_rank(fneg, fpos)
+    assert torch.equal(w_swapped, -w)                                                                # antisymmetry
+    # reconstruction is linear in the weights and a one-hot weight returns its slice
+    g1 = eng.grad_reconstruct(table, idx, w, P)
+    w2 = torch.rand(K, generator=g, device=eng.device, dtype=torch.float32)
+    g2 = eng.grad_reconstruct(table, idx, w2, P)
+    g12 = eng.grad_reconstruct(table, idx, w + w2, P)
+    scale = float(g12.abs().max().item())
+    assert float((g12 - (g1 + g2)).abs().max().item()) <= 1e-5 * scale
+    onehot = torch.zeros(K, device=eng.device, dtype=torch.float32)
+    onehot[K - 1] = 1.0
+    sl = eng.grad_reconstruct(table, idx, onehot, P)
+    assert torch.equal(sl, table[int(idx[K - 1].item()):int(idx[K - 1].item()) + P])
+    # float64 reference of the same sum on the device, chunked (plumbing only; not the product path)
+    ref = torch.zeros(P, dtype=torch.float64, device=eng.device)
+    ar = torch.arange(P, device=eng.device)
+    for c in range(0, K, 500):
+        rows = table[(idx[c:c + 500, None] + ar[None, :])].double()
+        ref += (w[c:c + 500, None].double() * rows).sum(0)
+    assert float((g1.double() - ref).abs().max().item()) <= 1e-5 * float(ref.abs().max().item())

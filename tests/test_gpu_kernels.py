@@ -1,0 +1,318 @@
+"""GPU parity: every kernel of libes_b200.so, called through the C ABI (ctypes engine),
+against the CPU oracle and the committed golden vectors.  Integer / index / rank results
+are bit-exact; float results carry their tolerance in the assert."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import es_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(eng, a, dtype=None):
+    return eng.to_device(np.ascontiguousarray(a), dtype)
+
+
+# ------------------------------------------------------------------------------------------- a2
+@pytest.mark.parametrize('tag', ['a', 'b', 'c', 'd'])
+def test_draw_indices_golden(eng, ref_vectors, tag):
+    v = ref_vectors
+    seed, n, ub, extra = [int(x) for x in v[f'mt_{tag}_cfg']]
+    key = dev(eng, v[f'mt_{tag}_key0'].astype(np.uint32).view(np.int32).reshape(1, -1))
+    pos = dev(eng, np.array([int(v[f'mt_{tag}_pos0'])], dtype=np.int32))
+    idx, ext = eng.draw_indices(key, pos, n, ub, extra)
+    assert np.array_equal(idx.cpu().numpy(), v[f'mt_{tag}_idx'])
+    if extra:
+        assert np.array_equal(ext.cpu().numpy().view(np.uint32), v[f'mt_{tag}_extra'])
+    assert np.array_equal(key.cpu().numpy().view(np.uint32).ravel(), v[f'mt_{tag}_key1'])
+    assert int(pos.item()) == int(v[f'mt_{tag}_pos1'])
+
+
+@pytest.mark.parametrize('extra', [0, 4])
+def test_draw_indices_streams_continue(eng, extra):
+    """8 virtual ranks, three consecutive generations: the device streams stay in lock step with numpy."""
+    R, n, ub = 8, 333, 250_000_000 - 29393
+    streams = [np.random.RandomState(1000 + r) for r in range(R)]
+    for s in streams[::2]:
+        s.randn(3)                         # arbitrary starting position / cached gaussian
+    key = dev(eng, np.stack([s.get_state()[1].astype(np.uint32) for s in streams]).view(np.int32))
+    pos = dev(eng, np.array([s.get_state()[2] for s in streams], dtype=np.int32))
+    for gen in range(3):
+        idx, ext = eng.draw_indices(key, pos, n, ub, extra)
+        ref_idx, ref_ext = [], []
+        for s in streams:
+            for _ in range(n):
+                ref_idx.append(int(s.randint(0, ub)))
+                ref_ext.append([int.from_bytes(s.bytes(4), 'little') for _ in range(extra)])
+        assert np.array_equal(idx.cpu().numpy(), np.array(ref_idx))
+        if extra:
+            assert np.array_equal(ext.cpu().numpy().view(np.uint32), np.array(ref_ext, dtype=np.uint32))
+    assert np.array_equal(key.cpu().numpy().view(np.uint32), np.stack([s.get_state()[1] for s in streams]))
+    assert pos.cpu().numpy().tolist() == [s.get_state()[2] for s in streams]
+
+
+def test_draw_indices_errors(eng):
+    from es_pytorch_b200._lib import EsLibraryError
+    key = dev(eng, np.zeros((1, 624), dtype=np.int32))
+    pos = dev(eng, np.array([624], dtype=np.int32))
+    with pytest.raises(EsLibraryError):           # network larger than the table (noisetable.py:39 ValueError)
+        eng.draw_indices(key, pos, 4, 0, 0)
+    with pytest.raises(EsLibraryError):
+        eng.draw_indices(key, pos, 4, 1 << 33, 0)
+
+
+# ------------------------------------------------------------------------------------------- a3
+def test_perturb_bit_exact(eng):
+    rs = np.random.RandomState(0)
+    P, L = 5702, 100_000
+    table = rs.randn(L).astype(np.float32)
+    theta = (rs.randn(P) * 0.1).astype(np.float32)
+    idx = np.array([0, 1, 17, L - P - 1, 4242], dtype=np.int64)
+    op, on = eng.perturb(dev(eng, theta), dev(eng, table), dev(eng, idx), 0.02)
+    for i, k in enumerate(idx):
+        noise = orc.table_get(table, int(k), P)
+        assert np.array_equal(op[i].cpu().numpy(), orc.pheno_params(theta, 0.02, noise))
+        assert np.array_equal(on[i].cpu().numpy(), orc.pheno_params(theta, 0.02, -noise))
+
+
+# ------------------------------------------------------------------------------------------- a4 / a14
+def test_normalise_and_colsum_bit_exact(eng, oracle_vectors):
+    rs = np.random.RandomState(1)
+    obs = (rs.randn(257, 376) * 3).astype(np.float32)
+    mean, std = rs.randn(376) * 0.2, 0.3 + rs.rand(376)
+    out = eng.normalise_obs(dev(eng, obs), dev(eng, mean), dev(eng, std), 5.0)
+    assert np.array_equal(out.cpu().numpy(), orc.normalise_obs(obs, mean, std, 5.0))
+    s, q = eng.obs_colsum(dev(eng, obs))
+    es, eq, _ = orc.ob_sum_sq_cnt(obs)
+    assert np.array_equal(s.cpu().numpy(), es) and np.array_equal(q.cpu().numpy(), eq)
+
+
+def test_obstat_accumulate_coins(eng):
+    rs = np.random.RandomState(2)
+    d, T, n = 17, 40, 500
+    s, q = rs.randn(d).astype(np.float32), rs.rand(d).astype(np.float32)
+    words = rs.randint(0, 1 << 32, size=(n, 2), dtype=np.uint64).astype(np.uint32)
+    chance = 0.07
+    osum = dev(eng, np.zeros(d)); osq = dev(eng, np.zeros(d)); cnt = dev(eng, np.zeros(2))
+    eng.obstat_accumulate_coins(osum, osq, cnt, dev(eng, s), dev(eng, q), T, dev(eng, words.view(np.int32)), chance)
+    ob = orc.ObStatOracle((d,), 0)
+    saved = 0
+    for a, b in words:
+        if orc.words_to_double(int(a), int(b)) < chance:
+            ob.inc(s, q, T)
+            saved += 1
+    assert saved > 5
+    assert np.array_equal(osum.cpu().numpy(), ob.sum) and np.array_equal(osq.cpu().numpy(), ob.sumsq)
+    assert cnt.cpu().numpy().tolist() == [float(ob.count), float(saved)]
+
+
+# ------------------------------------------------------------------------------------------- a4 + a5
+def _rollout_case(eng, obs_dim, act_dim, hidden, T, n_pairs, seed=0, sigma=0.02, with_stats=True):
+    rs = np.random.RandomState(seed)
+    dims = orc.layer_dims(obs_dim, hidden, act_dim)
+    P = orc.n_params(dims)
+    L = P + 50_000
+    table = rs.randn(L).astype(np.float32)
+    theta = (rs.randn(P) * 0.1).astype(np.float32)
+    env = orc.SyntheticEnvSpec(obs_dim, act_dim, T)
+    mean = rs.randn(obs_dim) * 0.1 if with_stats else np.zeros(obs_dim)
+    std = 0.5 + rs.rand(obs_dim) if with_stats else np.ones(obs_dim)
+    idx = rs.randint(0, L - P, size=n_pairs).astype(np.int64)
+    idx[0] = 0
+    idx[-1] = L - P - 1
+    obsn = eng.normalise_obs(dev(eng, env.obs_stream[:T]), dev(eng, mean), dev(eng, std), 5.0)
+    fit = torch.zeros(2, n_pairs, dtype=torch.float64, device=eng.device)
+    behv = torch.zeros(2, n_pairs, 3, dtype=torch.float32, device=eng.device)
+    eng.rollout(dev(eng, table), dev(eng, idx), dev(eng, theta), sigma, [obs_dim] + list(hidden) + [act_dim], obsn,
+                dev(eng, env.rew_vec), env.pos_scale, fit[0], fit[1], 1, behv[0], behv[1])
+    fit, behv = fit.cpu().numpy(), behv.cpu().numpy()
+    for k in range(n_pairs):
+        noise = orc.table_get(table, int(idx[k]), P)
+        for s, nz in ((0, noise), (1, -noise)):
+            layers = orc.unflatten(orc.pheno_params(theta, sigma, nz), dims)
+            rews, b, _, _ = orc.run_model(env, layers, mean, std, 5.0, T, batched=True)
+            ref = orc.reward_result(rews)[0]
+            scale = max(1.0, np.abs(rews).sum())
+            # float32 forward, different summation order than torch-CPU: 1e-5 of the episode's |reward| mass
+            assert abs(fit[s, k] - ref) <= 1e-5 * scale, (k, s, fit[s, k], ref)
+            assert np.allclose(behv[s, k], b[-3:], rtol=1e-4, atol=1e-5)
+
+
+def test_rollout_f32_halfcheetah_shape(eng):
+    _rollout_case(eng, 17, 6, (64, 64), T=100, n_pairs=6)
+
+
+def test_rollout_f32_humanoid_shape(eng):
+    _rollout_case(eng, 376, 17, (64, 64), T=70, n_pairs=4, seed=3)
+
+
+def test_rollout_f32_odd_shapes(eng):
+    _rollout_case(eng, 15, 3, (33,), T=33, n_pairs=3, seed=4)           # ragged: nothing is a multiple of 4
+    _rollout_case(eng, 5, 1, (8, 8, 8), T=1, n_pairs=2, seed=5)         # single step, single action
+
+
+def test_rollout_sigma_zero_is_symmetric(eng):
+    rs = np.random.RandomState(9)
+    sizes = [17, 64, 64, 6]
+    P = orc.n_params(orc.layer_dims(17, (64, 64), 6))
+    env = orc.SyntheticEnvSpec(17, 6, 64)
+    table, theta = dev(eng, rs.randn(P + 1000).astype(np.float32)), dev(eng, (rs.randn(P) * .1).astype(np.float32))
+    idx = dev(eng, rs.randint(0, 1000, size=16).astype(np.int64))
+    fit = torch.zeros(2, 16, dtype=torch.float64, device=eng.device)
+    eng.rollout(table, idx, theta, 0.0, sizes, dev(eng, env.obs_stream[:64]), dev(eng, env.rew_vec), 0.05, fit[0], fit[1])
+    f = fit.cpu().numpy()
+    assert np.array_equal(f[0], f[1]) and np.all(f[0] == f[0][0])
+
+
+def test_rollout_too_large_fails_loudly(eng):
+    from es_pytorch_b200._lib import EsLibraryError
+    sizes = [15, 256, 256, 3]                       # configs/simple_conf.json: 283 kB of float32 weights
+    P = orc.n_params(orc.layer_dims(15, (256, 256), 3))
+    z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=eng.device)
+    fit = torch.zeros(2, 1, dtype=torch.float64, device=eng.device)
+    with pytest.raises(EsLibraryError, match='shared memory'):
+        eng.rollout(z(P + 10), torch.zeros(1, dtype=torch.int64, device=eng.device), z(P), 0.02, sizes, z(8, 15),
+                    z(8, 3), 0.05, fit[0], fit[1])
+
+
+# ------------------------------------------------------------------------------------------- a8 / a9
+@pytest.mark.parametrize('tag', ['a', 'b', 'c'])
+def test_rank_golden(eng, ref_vectors, tag):
+    v = ref_vectors
+    w = eng.centered_rank(dev(eng, v[f'rank1_{tag}_pos']), dev(eng, v[f'rank1_{tag}_neg']))
+    assert np.array_equal(w.cpu().numpy(), v[f'rank1_{tag}_w'])
+    for wtag, wt in (('w03', 0.3), ('w10', 1.0), ('w00', 0.0)):
+        w2 = eng.centered_rank(dev(eng, v[f'rank2_{tag}_pos']), dev(eng, v[f'rank2_{tag}_neg']), wt, 1 - wt)
+        assert np.array_equal(w2.cpu().numpy(), v[f'rank2_{tag}_{wtag}_w'])
+
+
+@pytest.mark.parametrize('K,n_obj', [(1, 1), (2, 2), (777, 1), (3000, 2), (10000, 1)])
+def test_rank_vs_oracle_and_shards(eng, K, n_obj):
+    rs = np.random.RandomState(K)
+    pos, neg = rs.randn(K, n_obj) * 10, rs.randn(K, n_obj) * 10
+    if K > 100:                                      # inject ties, signed zeros and infinities
+        pos[5] = pos[17]; neg[3] = pos[5]; pos[40] = 0.0; neg[41] = -0.0; pos[60] = np.inf; neg[61] = -np.inf
+    ref = orc.centered_ranker(pos, neg)[0] if n_obj == 1 else orc.moo_ranker(pos, neg, 0.37)[0]
+    w0, w1 = (1.0, 0.0) if n_obj == 1 else (0.37, 1 - 0.37)
+    fp, fn = dev(eng, pos), dev(eng, neg)
+    w, ranks = eng.centered_rank(fp, fn, w0, w1, want_ranks=True)
+    assert np.array_equal(w.cpu().numpy(), ref)
+    full = np.concatenate((pos, neg))
+    for c in range(n_obj):
+        r = ranks[c].cpu().numpy().ravel()
+        assert np.array_equal(r, orc.rank(full[:, c]))
+    # a GPU's shard gets exactly its slice of the global weights
+    if K >= 4:
+        b, cnt = K // 4, K // 2
+        ws = eng.centered_rank(fp, fn, w0, w1, k_begin=b, k_count=cnt)
+        assert np.array_equal(ws.cpu().numpy(), ref[b:b + cnt])
+
+
+def test_rank_integer_ties_and_nan(eng):
+    pos = np.array([[3.], [1.], [3.], [0.], [2.], [np.nan]])
+    neg = np.array([[1.], [3.], [2.], [2.], [-0.], [5.]])
+    w, ranks = eng.centered_rank(dev(eng, pos), dev(eng, neg), want_ranks=True)
+    x = np.concatenate((pos, neg)).ravel()
+    assert np.array_equal(ranks.cpu().numpy().ravel(), orc.rank(x))       # NaN last, ties by position
+    assert np.array_equal(w.cpu().numpy(), orc.centered_ranker(pos, neg)[0])
+
+
+# ------------------------------------------------------------------------------------------- a10
+def test_reconstruct_reference_known_answer(eng):
+    """test/utils/utils_test.py:24-40 (integer data: exact in any summation order)."""
+    evals, params = 100, 500
+    fits, inds, table = np.arange(evals), np.arange(evals), np.arange(2000)
+    expected = np.dot(fits, [[i + j for j in range(params)] for i in range(evals)])
+    out = eng.grad_reconstruct(dev(eng, table.astype(np.float32)), dev(eng, inds.astype(np.int64)),
+                               dev(eng, fits.astype(np.float32)), params)
+    assert np.array_equal(out.cpu().numpy(), expected.astype(np.float32))
+
+
+@pytest.mark.parametrize('K,P', [(1, 7), (37, 1023), (256, 5702), (1000, 29393), (5, 70659)])
+def test_reconstruct_vs_oracle(eng, K, P):
+    rs = np.random.RandomState(K + P)
+    L = P + 300_000
+    table = rs.randn(L).astype(np.float32)
+    idx = rs.randint(0, L - P, size=K).astype(np.int64)
+    idx[0] = L - P - 1                                   # last admissible slice (noisetable.py:34)
+    if K > 2:
+        idx[1] = idx[2]                                  # duplicate index (es.py:44 reports dupes)
+    w = (rs.rand(K).astype(np.float32) - 0.5) * 2
+    out = eng.grad_reconstruct(dev(eng, table), dev(eng, idx), dev(eng, w), P).cpu().numpy()
+    ref32 = np.asarray(orc.scale_noise(w, idx.astype(np.float64), table, P, 500), dtype=np.float32)
+    truth = orc.scale_noise_f64(w, idx, table, P)
+    scale = np.abs(truth).max()
+    assert np.abs(out - truth).max() <= 1e-5 * scale                 # north-star tolerance, vs float64 truth
+    assert np.abs(out - ref32).max() <= 1e-5 * scale                 # and vs the reference's float32 sgemv order
+    out2 = eng.grad_reconstruct(dev(eng, table), dev(eng, idx), dev(eng, w), P).cpu().numpy()
+    assert np.array_equal(out, out2)                                 # deterministic
+
+
+def test_reconstruct_empty_and_onehot(eng):
+    rs = np.random.RandomState(5)
+    P, L = 2000, 50_000
+    table = rs.randn(L).astype(np.float32)
+    t = dev(eng, table)
+    out = eng.grad_reconstruct(t, dev(eng, np.zeros(0, dtype=np.int64)), dev(eng, np.zeros(0, dtype=np.float32)), P)
+    assert not out.cpu().numpy().any()
+    idx = rs.randint(0, L - P, size=300).astype(np.int64)
+    w = np.zeros(300, dtype=np.float32)
+    w[123] = 1.0
+    out = eng.grad_reconstruct(t, dev(eng, idx), dev(eng, w), P).cpu().numpy()
+    assert np.array_equal(out, table[idx[123]:idx[123] + P])        # a one-hot weight returns the slice itself
+
+
+# ------------------------------------------------------------------------------------------- a11 / a12
+@pytest.mark.parametrize('kind', ['adam', 'sgd', 'simple'])
+def test_optimizer_steps_bit_exact(eng, kind):
+    from es_pytorch_b200.nn import optimizers as O
+    rs = np.random.RandomState(11)
+    P, K = 5702, 256
+    theta = (rs.randn(P) * 0.1).astype(np.float32)
+    mine = {'adam': O.Adam(P, 0.01), 'sgd': O.SGD(P, 0.02), 'simple': O.SimpleES(P, 0.03)}[kind]
+    ref = {'adam': orc.AdamOracle(P, 0.01), 'sgd': orc.SGDOracle(P, 0.02), 'simple': orc.SimpleESOracle(P, 0.03)}[kind]
+    th_dev, th_ref = dev(eng, theta), theta.copy()
+    for it in range(5):
+        gsum = (rs.randn(P) * 3).astype(np.float32)
+        mine.apply_fused(eng, th_dev, dev(eng, gsum), float(2 * K), 0.005)
+        grad = (gsum / np.float32(2 * K)).astype(np.float32)
+        g = ((np.float32(0.005) * th_ref).astype(np.float32) - grad).astype(np.float32)
+        th_ref += ref.step(g)
+        assert np.array_equal(th_dev.cpu().numpy(), th_ref), it
+    if kind == 'adam':
+        assert np.array_equal(mine.m, ref.m) and np.array_equal(mine.v, ref.v) and mine.t == ref.t == 5
+    # reference-style step(g) -> delta contract
+    g = rs.randn(P).astype(np.float32)
+    assert np.array_equal(mine.step(g), ref.step(g))
+
+
+def test_optimizers_golden(eng, ref_vectors):
+    from es_pytorch_b200.nn import optimizers as O
+    v = ref_vectors
+    sgd, ses, adam = O.SGD(40, 0.01), O.SimpleES(40, 0.01), O.Adam(40, 0.01)
+    for i, g in enumerate(v['sgd_g']):
+        assert np.array_equal(sgd.step(g), v['sgd_steps'][i])           # real reference module, bit-exact
+        assert np.array_equal(ses.step(g), v['simple_steps'][i])
+        assert np.allclose(adam.step(g), v['adam_steps_real_f64'][i], rtol=2e-6, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------- a13
+def test_novelty(eng):
+    rs = np.random.RandomState(21)
+    n, A = 500, 64
+    behv = rs.randn(n, 3).astype(np.float32)
+    archive = rs.randn(A, 2)
+    for k in (1, 10, 64, 100):
+        out = torch.zeros(n, dtype=torch.float64, device=eng.device)
+        eng.novelty(dev(eng, behv), dev(eng, archive), k, out)
+        ref = np.array([orc.novelty(behv[i, :2], archive, k) for i in range(n)])
+        assert np.allclose(out.cpu().numpy(), ref, rtol=1e-14, atol=0)
+    # reference known answers (test/utils/novelty_test.py:27-33)
+    b = dev(eng, np.zeros((1, 3), dtype=np.float32))
+    arch = dev(eng, np.array([[2., 2.], [1., 1.], [3., 3.]]))
+    for k, expect in ((1, np.sqrt(2)), (2, (np.sqrt(2) + np.sqrt(8)) / 2), (3, (np.sqrt(2) + np.sqrt(8) + np.sqrt(18)) / 3),
+                      (50, (np.sqrt(2) + np.sqrt(8) + np.sqrt(18)) / 3)):
+        out = torch.zeros(1, dtype=torch.float64, device=eng.device)
+        eng.novelty(b, arch, k, out)
+        assert out.item() == expect
