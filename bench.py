@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- perturbations/sec of a whole OpenAI-ES generation on B200 (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3                      # this repo's CUDA path
+    torchrun --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 3 --warmup 1               # the reference's CPU path on the host cores
+
+A "step" is one generation over synthetic input: draw K noise indices -> theta +- sigma*eps ->
+open-loop MLP rollouts (T steps) -> fitness -> [allgather] -> centered rank -> sum_k w_k eps_k ->
+[allreduce] -> /2K, l2, Adam -> theta'.  ``value`` = antithetic pairs (K) per second with every
+input resident in HBM; ``e2e`` = the same generation driven through the reference-facing API
+(es.test_params / Ranker.rank / es.approx_grad) with host ndarrays in and out.
+Weak scaling: every GPU owns ``--pairs-per-gpu`` pairs (8 virtual MPI-rank streams).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: Humanoid-shaped synthetic, K=10000 per GPU, sigma 0.02 (the config the
+    # metric's targets -- 60 % HBM on the reconstruction kernel -- are quoted on)
+    'humanoid': dict(obs=376, act=17, hidden=(64, 64), T=1000, pairs=10000, table=250_000_000),
+    # BASELINE.json configs[1]: HalfCheetah-shaped synthetic, K=256 (latency-bound; parity-size case)
+    'halfcheetah': dict(obs=17, act=6, hidden=(64, 64), T=1000, pairs=256, table=250_000_000),
+}
+VIRTUAL_RANKS_PER_GPU = 8
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='humanoid', choices=sorted(WORKLOADS))
+    ap.add_argument('--pairs-per-gpu', type=int, default=0)
+    ap.add_argument('--mode', default='auto', choices=['auto', 'f32', 'tc'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# the reference's CPU path (oracle/cpu_generation.py), timed on the host cores
+# --------------------------------------------------------------------------------------------------------------
+def run_reference(args, wl, n_gpus):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return                                              # rank 0 alone runs and prints it
+    from oracle.cpu_generation import CpuReference
+    K = (args.pairs_per_gpu or wl['pairs']) * n_gpus
+    ref = CpuReference(K, wl['obs'], wl['act'], wl['hidden'], wl['T'])
+    for _ in range(max(args.warmup, 1)):
+        ref.sample(1)
+    t, last = [], None
+    for _ in range(args.steps):
+        last = ref.sample(1)
+        t.append(last['t_generation_s'])
+    ref.close()
+    sec = statistics.mean(t)
+    value = K / sec
+    line = dict(metric='perturbations/sec (whole ES generation)', value=value, unit='antithetic pairs/s', n_gpus=n_gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
+                config=workload_config(args, wl, n_gpus, K),
+                cpu_baseline=dict(value=value, unit='antithetic pairs/s', cores=last['cores'], kind='port',
+                                  sample=last['sample'], evaluations_per_sec=2 * value,
+                                  breakdown_s=dict(rollouts=last['t_rollouts_s'], rank_reconstruct_adam=last['t_update_s']),
+                                  numpy=last['numpy'], torch=last['torch']),
+                e2e=dict(value=value, unit='antithetic pairs/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, wl, n_gpus, K):
+    return dict(workload=f"{args.workload}-shaped synthetic open-loop env: MLP {wl['obs']}-{'-'.join(map(str, wl['hidden']))}"
+                         f"-{wl['act']} tanh, T={wl['T']}, sigma=0.02, l2coeff=0.005, Adam lr=0.01, "
+                         f"noise table {wl['table']} float32",
+                pairs_total=K, pairs_per_gpu=K // n_gpus, evaluations_total=2 * K,
+                virtual_mpi_ranks_per_gpu=VIRTUAL_RANKS_PER_GPU, save_obs_coins_per_pair=2,
+                parallelism=f'perturbation shards x{n_gpus}, fitness allgather + one grad allreduce',
+                l2_policy='inputs larger than L2: every generation streams K*P*4 bytes of fresh noise slices '
+                          '(1.18 GB per GPU at K=10000, P=29393 vs 126 MB L2)')
+
+
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ''
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(nme)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['no samples'])
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), power_w_max=max(pw), samples=len(sm),
+                    reasons=sorted(reasons))
+
+
+def event_ms(pairs):
+    return [a.elapsed_time(b) for a, b in pairs]
+
+
+def run_ours(args, wl, n_gpus):
+    import numpy as np
+    import torch
+    import torch.distributed as td
+    from es_pytorch_b200 import _lib, dist
+    from es_pytorch_b200.core import es
+    from es_pytorch_b200.core.noisetable import NoiseTable
+    from es_pytorch_b200.core.policy import Policy
+    from es_pytorch_b200.engine import get_engine
+    from es_pytorch_b200.generation import DeviceGeneration
+    from es_pytorch_b200.gym.batched import BatchedRollout
+    from es_pytorch_b200.gym.synthetic_env import SyntheticEnv
+    from es_pytorch_b200.nn.nn import FeedForward
+    from es_pytorch_b200.nn.obstat import ObStat
+    from es_pytorch_b200.nn.optimizers import Adam
+    from es_pytorch_b200.utils.rankers import CenteredRanker
+
+    comm = dist.init_from_env('nccl' if int(os.environ.get('WORLD_SIZE', '1')) > 1 else None)
+    assert comm.size == n_gpus, f'--gpus {n_gpus} but WORLD_SIZE={comm.size}; launch with torchrun --nproc-per-node {n_gpus}'
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    eng = get_engine(local)
+    rank = comm.rank
+    mode = {'auto': _lib.ES_ROLLOUT_F32, 'f32': _lib.ES_ROLLOUT_F32, 'tc': _lib.ES_ROLLOUT_TC}[args.mode]
+
+    k_local = args.pairs_per_gpu or wl['pairs']
+    assert k_local % VIRTUAL_RANKS_PER_GPU == 0
+    n_per_stream = k_local // VIRTUAL_RANKS_PER_GPU
+    K = k_local * n_gpus
+    sizes = [wl['obs'], *wl['hidden'], wl['act']]
+    P = sum(i * o + o for i, o in zip(sizes[:-1], sizes[1:]))
+
+    # synthetic data (random-init weights of the named architecture, random table): identical on every rank
+    g = torch.Generator(device=eng.device).manual_seed(123)
+    table = torch.randn(wl['table'], generator=g, device=eng.device, dtype=torch.float32)
+    theta0 = (np.random.RandomState(7).randn(P) * 0.1).astype(np.float32)
+    env = SyntheticEnv(wl['obs'], wl['act'], wl['T'])
+    seeds = [1000 + rank * VIRTUAL_RANKS_PER_GPU + r for r in range(VIRTUAL_RANKS_PER_GPU)]
+    obs_dev, rew_dev = env.device_arrays(eng)
+
+    # ---------------- device-resident generation: `value` ----------------
+    gen = DeviceGeneration(table, eng.to_device(theta0.copy()), sizes, obs_dev, rew_dev,
+                           [np.random.RandomState(s) for s in seeds], 0.02, 0.005, Adam(P, 0.01), coins_per_eval=1,
+                           save_obs_chance=0.01, rollout_mode=mode, comm=comm, engine=eng)
+    for _ in range(args.warmup):
+        gen.run(n_per_stream)
+    gen.enable_timers(True)
+    sampler = ClockSampler(local)
+    comm.barrier(); torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launches
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        gen.run(n_per_stream)
+    t1.record()
+    torch.cuda.synchronize(); comm.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.launches - launches0
+    ms_total = torch.tensor([t0.elapsed_time(t1)], device=eng.device, dtype=torch.float64)
+    if n_gpus > 1:
+        td.all_reduce(ms_total, op=td.ReduceOp.MAX)
+    ms_step = float(ms_total.item()) / args.steps
+    kern = {k: statistics.mean(event_ms(v)) for k, v in gen.timers.items()}
+    gen.enable_timers(False)
+
+    # ---------------- the reference-facing API with host buffers: `e2e` ----------------
+    e2e = None
+    if not args.no_e2e:
+        net = FeedForward(list(wl['hidden']), torch.nn.Tanh(), env, 0.0, 5)
+        policy = Policy(net, 0.02, Adam(P, 0.01))
+        policy.flat_params[...] = theta0
+        nt = NoiseTable(P, table)
+        streams = [np.random.RandomState(s) for s in seeds]
+        fit_fn = BatchedRollout(env, wl['T'], coins_per_eval=1, save_obs_chance=0.01, rank_streams=streams,
+                                rollout_mode=mode)
+        fit_fn.stream_env_from_host = True
+        ranker = CenteredRanker()
+
+        def api_generation():
+            gen_obstat = ObStat(env.observation_space.shape, 0)
+            pos, neg, inds, steps = es.test_params(comm, n_per_stream, policy, nt, gen_obstat, fit_fn, streams[0])
+            policy.update_obstat(gen_obstat)
+            ranker.rank(pos, neg, inds)
+            es.approx_grad(policy, ranker, nt, policy.flat_params, 500, 0.005)
+            return pos
+
+        for _ in range(args.warmup):
+            api_generation()
+        comm.barrier(); torch.cuda.synchronize()
+        h0, d0 = eng.h2d_bytes, eng.d2h_bytes
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            api_generation()
+        torch.cuda.synchronize(); comm.barrier()
+        wall = torch.tensor([time.perf_counter() - w0], device=eng.device, dtype=torch.float64)
+        if n_gpus > 1:
+            td.all_reduce(wall, op=td.ReduceOp.MAX)
+        sec = float(wall.item()) / args.steps
+        e2e = dict(value=K / sec, unit='antithetic pairs/s', ms_per_step=sec * 1e3,
+                   h2d_bytes_per_step=(eng.h2d_bytes - h0) // args.steps,
+                   d2h_bytes_per_step=(eng.d2h_bytes - d0) // args.steps,
+                   path='es.test_params(BatchedRollout) -> CenteredRanker.rank -> es.approx_grad, numpy in/out; '
+                        'per step H2D: theta, obs/reward streams, MT19937 states, obs mean/std, fitness, weights, '
+                        'indices; D2H: fitness, indices, states, weights, theta')
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak, hbm_src = (peaks['hbm_gbs'], 'measured (MEASURED_PEAKS.json)') if 'hbm_gbs' in peaks else (6650.0, 'fallback')
+    tf_peak, tf_src = ((peaks['bf16_tflops_sustained'], 'measured sustained (MEASURED_PEAKS.json)')
+                       if 'bf16_tflops_sustained' in peaks else (1400.0, 'fallback'))
+    rec_bytes = k_local * P * 4
+    rec_gbs = rec_bytes / (kern['reconstruct'] * 1e-3) / 1e9
+    mac = sum(i * o for i, o in zip(sizes[:-1], sizes[1:]))
+    roll_flop = 2.0 * (2 * k_local) * wl['T'] * mac
+    roll_tfs = roll_flop / (kern['rollout'] * 1e-3) / 1e12
+    value = K / (ms_step * 1e-3)
+    line = dict(
+        metric='perturbations/sec (whole ES generation)', value=value, unit='antithetic pairs/s', n_gpus=n_gpus,
+        steps=args.steps, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling='weak',
+        vs_baseline=None, dtype='f32' if mode == _lib.ES_ROLLOUT_F32 else 'bf16 mma / f32 accumulate',
+        data='synthetic', impl='ours', evaluations_per_sec=2 * value,
+        config=workload_config(args, wl, n_gpus, K), clocks=clocks, gpu_launches=launches, e2e=e2e,
+        kernel_ms=kern,
+        # dominant kernel by time: the fused perturb+rollout
+        roofline=dict(kernel='rollout (es_rollout_openloop)', bound='tensor', achieved=roll_tfs, peak=tf_peak,
+                      unit='TFLOP/s', frac=roll_tfs / tf_peak, traffic=None, peak_source=tf_src,
+                      algorithmic_flops_per_launch=roll_flop, share_of_step=kern['rollout'] / ms_step,
+                      note='mode f32 runs on the CUDA cores (FFMA); reported against the tensor peak the '
+                           'tcgen05 path is judged by' if mode == _lib.ES_ROLLOUT_F32 else 'tcgen05 path'),
+        # the north-star's named HBM-bound kernel
+        roofline_reconstruct=dict(kernel='reconstruct_kernel (es_grad_reconstruct)', bound='hbm', achieved=rec_gbs,
+                                  peak=hbm_peak, unit='GB/s', frac=rec_gbs / hbm_peak, traffic=None,
+                                  peak_source=hbm_src, algorithmic_bytes_per_launch=rec_bytes,
+                                  share_of_step=kern['reconstruct'] / ms_step),
+    )
+    if not args.no_cpu_baseline and n_gpus == 1:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                              '--warmup', '1', '--workload', args.workload, '--gpus', '1'] +
+                             (['--pairs-per-gpu', str(args.pairs_per_gpu)] if args.pairs_per_gpu else []),
+                             capture_output=True, text=True, env={**os.environ, 'RANK': '0', 'WORLD_SIZE': '1'})
+        try:
+            ref = json.loads(out.stdout.strip().splitlines()[-1])
+            line['cpu_baseline'] = ref['cpu_baseline']
+        except Exception:
+            line['cpu_baseline'] = dict(value=None, unit='antithetic pairs/s', cores=None, kind='port',
+                                        sample='failed: ' + (out.stderr or out.stdout)[-300:])
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    wl = WORKLOADS[args.workload]
+    n_gpus = args.gpus
+    if args.impl == 'reference':
+        run_reference(args, wl, n_gpus)
+    else:
+        run_ours(args, wl, n_gpus)
+    try:
+        import torch.distributed as td
+        if td.is_available() and td.is_initialized():
+            td.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == '__main__':
+    main()

@@ -67,6 +67,11 @@ def _device_generation(fit_fn, policy: Policy, nt: NoiseTable, streams) -> Devic
         fit_fn._gen = gen
     else:
         gen.load_states(streams)
+        if getattr(fit_fn, 'stream_env_from_host', False):
+            # the env's observation / reward streams are this generation's inputs: copy them from the host again
+            env = fit_fn.env
+            eng.upload_into(gen.obs_stream, env.obs_stream[:gen.T + 1])
+            eng.upload_into(gen.rew_vec, env.rew_vec[:gen.T])
     gen.sigma = float(policy.std)                       # scripts decay the noise std between generations
     gen.save_obs_chance = fit_fn.save_obs_chance
     if fit_fn.archive is not None and (gen.archive is None or gen.archive.shape[0] != len(fit_fn.archive)):
@@ -82,17 +87,18 @@ def _test_params_batched(comm, n: int, policy: Policy, nt: NoiseTable, gen_obsta
     gen = _device_generation(fit_fn, policy, nt, streams)
     fpos, fneg = gen.evaluate(n)
     # one device->host hop for everything the reference API returns as ndarrays
-    pos = fpos.cpu().numpy().reshape(gen.K, gen.n_obj)
-    neg = fneg.cpu().numpy().reshape(gen.K, gen.n_obj)
-    idx_local = gen.idx.cpu().numpy()
+    eng = gen.eng
+    pos = eng.to_host(fpos).reshape(gen.K, gen.n_obj)
+    neg = eng.to_host(fneg).reshape(gen.K, gen.n_obj)
+    idx_local = eng.to_host(gen.idx)
     gen.store_states(streams)
     if comm.size > 1:
         inds = np.concatenate(dist.world().allgather_object(idx_local)).astype(np.float64)
     else:
         inds = idx_local.astype(np.float64)
     if gen.extra_words:
-        cnt = gen.gen_count.cpu().numpy()
-        gen_obstat.inc(gen.gen_sum.cpu().numpy(), gen.gen_sumsq.cpu().numpy(), float(cnt[0]))
+        cnt = eng.to_host(gen.gen_count)
+        gen_obstat.inc(eng.to_host(gen.gen_sum), eng.to_host(gen.gen_sumsq), float(cnt[0]))
     steps = 2 * gen.K * (fit_fn.max_steps - 1)          # run_model returns the last loop index (gym_runner.py:50,67)
     return pos, neg, inds, steps
 

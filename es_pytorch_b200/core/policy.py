@@ -47,13 +47,14 @@ class Policy:
         if self._theta_dev is None or self._theta_dev.device != engine.device:
             self._theta_dev = engine.to_device(self.flat_params, torch.float32)
         elif refresh:
-            self._theta_dev.copy_(torch.from_numpy(self.flat_params), non_blocking=True)
+            engine.upload_into(self._theta_dev, self.flat_params)
         return self._theta_dev
 
     def sync_host(self):
         """Copy theta back into ``flat_params`` in place (keeps aliases held by scripts valid)."""
         if self._theta_dev is not None:
-            self.flat_params[...] = self._theta_dev.cpu().numpy()
+            from ..engine import get_engine
+            self.flat_params[...] = get_engine(self._theta_dev.device.index).to_host(self._theta_dev)
 
     # -- checkpointing (policy.py:37-47) -------------------------------------------------------------
     @staticmethod

@@ -46,6 +46,8 @@ class Engine:
         h = C.c_void_p()
         check(self.lib.es_ctx_create(device_index, C.byref(h)), 'es_ctx_create')
         self._ctx = h
+        self.h2d_bytes = 0          # bytes copied host->device / device->host through this engine
+        self.d2h_bytes = 0
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -70,7 +72,21 @@ class Engine:
             t = torch.from_numpy(np.ascontiguousarray(a))
         if dtype is not None and t.dtype != dtype:
             t = t.to(dtype)
+        if not t.is_cuda:
+            self.h2d_bytes += t.numel() * t.element_size()
         return t.to(self.device, non_blocking=True).contiguous()
+
+    def upload_into(self, dst: torch.Tensor, src) -> torch.Tensor:
+        """Copy a host array into an existing device tensor (counts the bytes)."""
+        t = src if isinstance(src, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(src))
+        self.h2d_bytes += t.numel() * t.element_size()
+        dst.copy_(t.view(dst.shape) if t.numel() == dst.numel() else t, non_blocking=True)
+        return dst
+
+    def to_host(self, t: torch.Tensor) -> np.ndarray:
+        """Device tensor -> numpy (synchronises the stream; counts the bytes)."""
+        self.d2h_bytes += t.numel() * t.element_size()
+        return t.cpu().numpy()
 
     # ------------------------------------------------------------------ a2
     def draw_indices(self, mt_key: torch.Tensor, mt_pos: torch.Tensor, n_per_stream: int, upper_bound: int,

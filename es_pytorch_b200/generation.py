@@ -80,8 +80,31 @@ class DeviceGeneration:
         self.gen_sumsq = torch.zeros(self.obs_dim, dtype=f64, device=e.device)
         self.gen_count = torch.zeros(2, dtype=f64, device=e.device)
         self._bufs_for = None
+        self.timers = None          # optional {'name': [(start_event, end_event), ...]} filled by _timed()
 
     # ------------------------------------------------------------------------------------------
+    def enable_timers(self, on: bool = True):
+        """Bracket each kernel group with CUDA events on the launching stream (bench.py's roofline)."""
+        self.timers = {} if on else None
+
+    def _timed(self, name: str):
+        gen = self
+
+        class _T:
+            def __enter__(self_inner):
+                if gen.timers is not None:
+                    self_inner.a = torch.cuda.Event(enable_timing=True)
+                    self_inner.b = torch.cuda.Event(enable_timing=True)
+                    self_inner.a.record()
+                return self_inner
+
+            def __exit__(self_inner, *exc):
+                if gen.timers is not None:
+                    self_inner.b.record()
+                    gen.timers.setdefault(name, []).append((self_inner.a, self_inner.b))
+                return False
+        return _T()
+
     def _ensure_buffers(self, n_per_stream: int):
         if self._bufs_for == n_per_stream:
             return
@@ -102,8 +125,8 @@ class DeviceGeneration:
 
     def set_obstat(self, mean: np.ndarray, std: np.ndarray):
         """Policy.update_obstat -> BaseNet.set_ob_mean_std (policy.py:69-71, nn.py:19-21)."""
-        self.ob_mean.copy_(torch.from_numpy(np.ascontiguousarray(mean, dtype=np.float64)), non_blocking=True)
-        self.ob_std.copy_(torch.from_numpy(np.ascontiguousarray(std, dtype=np.float64)), non_blocking=True)
+        self.eng.upload_into(self.ob_mean, np.ascontiguousarray(mean, dtype=np.float64).reshape(-1))
+        self.eng.upload_into(self.ob_std, np.ascontiguousarray(std, dtype=np.float64).reshape(-1))
 
     # ------------------------------------------------------------------------------------------
     def evaluate(self, n_per_stream: int):
@@ -111,13 +134,15 @@ class DeviceGeneration:
         allgather.  Leaves fpos/fneg [K, n_obj] (global) and idx [k_local] on the device."""
         e = self.eng
         self._ensure_buffers(n_per_stream)
-        e.draw_indices(self.mt_key, self.mt_pos, n_per_stream, self.table.numel() - self.P, self.extra_words,
-                       self.idx, self.extras)
+        with self._timed('draw_indices'):
+            e.draw_indices(self.mt_key, self.mt_pos, n_per_stream, self.table.numel() - self.P, self.extra_words,
+                           self.idx, self.extras)
         e.normalise_obs(self.obs_stream[:self.T], self.ob_mean, self.ob_std, self.ob_clip, self.obsn)
         fp, fn = self.fit_local[0], self.fit_local[1]
-        e.rollout(self.table, self.idx, self.theta, self.sigma, self.layer_sizes, self.obsn, self.rew_vec,
-                  self.pos_scale, fp, fn, self.n_obj, None if self.behv is None else self.behv[0],
-                  None if self.behv is None else self.behv[1], self.rollout_mode)
+        with self._timed('rollout'):
+            e.rollout(self.table, self.idx, self.theta, self.sigma, self.layer_sizes, self.obsn, self.rew_vec,
+                      self.pos_scale, fp, fn, self.n_obj, None if self.behv is None else self.behv[0],
+                      None if self.behv is None else self.behv[1], self.rollout_mode)
         if self.n_obj == 2:
             # second objective column = novelty of the final (x, y) (training_result.py:95-97)
             e.novelty(self.behv.view(-1, 3), self.archive, self.nov_k, self.fit_local.view(-1)[1:], 2)
@@ -140,10 +165,14 @@ class DeviceGeneration:
         """Ranker.rank + es.approx_grad on the device (rankers.py:46-50, es.py:98-101)."""
         e = self.eng
         w0, w1 = (1.0, 0.0) if self.n_obj == 1 else (self.moo_w, 1 - self.moo_w)
-        self.weights = e.centered_rank(fpos, fneg, w0, w1, self.k_begin, self.k_local)
-        e.grad_reconstruct(self.table, self.idx, self.weights, self.P, self.gsum)
-        self.comm.allreduce_sum(self.gsum)
-        self.apply_optimizer(self.gsum, float(2 * self.K))
+        with self._timed('rank'):
+            self.weights = e.centered_rank(fpos, fneg, w0, w1, self.k_begin, self.k_local)
+        with self._timed('reconstruct'):
+            e.grad_reconstruct(self.table, self.idx, self.weights, self.P, self.gsum)
+        with self._timed('allreduce'):
+            self.comm.allreduce_sum(self.gsum)
+        with self._timed('optimizer'):
+            self.apply_optimizer(self.gsum, float(2 * self.K))
 
     def apply_optimizer(self, gsum: torch.Tensor, n_ranked: float):
         """grad = gsum/n_ranked; theta += optim.step(l2coeff*theta - grad)  (es.py:100-101)."""
@@ -161,13 +190,13 @@ class DeviceGeneration:
         self._gauss = [(s.get_state()[3], s.get_state()[4]) for s in rank_states]
         key = np.stack([s.get_state()[1].astype(np.uint32) for s in rank_states]).view(np.int32)
         pos = np.array([s.get_state()[2] for s in rank_states], dtype=np.int32)
-        self.mt_key.copy_(torch.from_numpy(key), non_blocking=True)
-        self.mt_pos.copy_(torch.from_numpy(pos), non_blocking=True)
+        self.eng.upload_into(self.mt_key, key)
+        self.eng.upload_into(self.mt_pos, pos)
 
     def store_states(self, rank_states: Sequence[np.random.RandomState]):
         """Write the advanced streams back into the callers' RandomState objects (synchronises)."""
-        key = self.mt_key.cpu().numpy().view(np.uint32)
-        pos = self.mt_pos.cpu().numpy()
+        key = self.eng.to_host(self.mt_key).view(np.uint32)
+        pos = self.eng.to_host(self.mt_pos)
         for r, rs in enumerate(rank_states):
             rs.set_state(('MT19937', key[r], int(pos[r]), self._gauss[r][0], self._gauss[r][1]))
 

@@ -37,6 +37,7 @@ class BatchedRollout:
         self.rank_streams = list(rank_streams) if rank_streams is not None else None
         self.rollout_mode = rollout_mode
         self._gen = None            # cached DeviceGeneration (see core.es)
+        self.stream_env_from_host = False   # True: re-upload the env's obs/reward streams every generation
 
     @property
     def n_obj(self) -> int:

@@ -57,7 +57,7 @@ class Ranker(ABC):
         self._pre_rank(fits_pos, fits_neg, noise_inds)
         fp = eng.to_device(_as_2d(fits_pos), torch.float64)
         fn = eng.to_device(_as_2d(fits_neg), torch.float64)
-        self.ranked_fits = self.rank_device(eng, fp, fn).cpu().numpy()
+        self.ranked_fits = eng.to_host(self.rank_device(eng, fp, fn))
         return self.ranked_fits
 
 
