@@ -165,7 +165,9 @@ def run_ours(args, wl, n_gpus):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     eng = get_engine(local)
     rank = comm.rank
-    mode = {'auto': _lib.ES_ROLLOUT_F32, 'f32': _lib.ES_ROLLOUT_F32, 'tc': _lib.ES_ROLLOUT_TC}[args.mode]
+    tc_ok = list(wl['hidden']) == [64, 64] and wl['act'] <= 32 and wl['obs'] <= 1023
+    mode = {'auto': _lib.ES_ROLLOUT_TC if tc_ok else _lib.ES_ROLLOUT_F32, 'f32': _lib.ES_ROLLOUT_F32,
+            'tc': _lib.ES_ROLLOUT_TC}[args.mode]
 
     k_local = args.pairs_per_gpu or wl['pairs']
     assert k_local % VIRTUAL_RANKS_PER_GPU == 0

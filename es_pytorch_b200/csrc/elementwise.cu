@@ -58,10 +58,18 @@ __global__ void colsum_kernel(const float* __restrict__ obs, int rows, int obs_d
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= obs_dim) return;
     float s = 0.f, q = 0.f;
-    for (int r = 0; r < rows; ++r) {
-        const float x = obs[(size_t)r * obs_dim + d];
-        s = __fadd_rn(s, x);
-        q = __fadd_rn(q, __fmul_rn(x, x));
+    constexpr int U = 16;                       // loads in flight per thread; the adds stay in row order
+    for (int r0 = 0; r0 < rows; r0 += U) {
+        float x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) x[u] = (r0 + u < rows) ? __ldg(obs + (size_t)(r0 + u) * obs_dim + d) : 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (r0 + u < rows) {
+                s = __fadd_rn(s, x[u]);
+                q = __fadd_rn(q, __fmul_rn(x[u], x[u]));
+            }
+        }
     }
     sum_out[d] = s;
     sumsq_out[d] = q;
@@ -92,28 +100,26 @@ int es_impl_obstat_accumulate(es_ctx* ctx, double* sum, double* sumsq, const flo
     return ES_OK;
 }
 
-__global__ void obstat_coins_kernel(double* __restrict__ sum, double* __restrict__ sumsq, double* __restrict__ count_io,
-                                    const float* __restrict__ s, const float* __restrict__ ssq, int obs_dim,
-                                    int rows_per_rollout, const uint32_t* __restrict__ coins, int n_coins, double chance) {
-    __shared__ int s_cnt[64];
+__global__ void coin_count_kernel(const uint32_t* __restrict__ coins, int n_coins, double chance, int* __restrict__ count) {
     int c = 0;
-    for (int e = threadIdx.x; e < n_coins; e += blockDim.x) {
-        const uint32_t a = coins[2 * e] >> 5, b = coins[2 * e + 1] >> 6;
-        const double u = ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;   // legacy random_sample
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_coins; e += gridDim.x * blockDim.x) {
+        const uint2 w = *reinterpret_cast<const uint2*>(coins + 2 * (size_t)e);
+        const double u = ((double)(w.x >> 5) * 67108864.0 + (double)(w.y >> 6)) / 9007199254740992.0;   // legacy random_sample
         c += (u < chance) ? 1 : 0;
     }
-    s_cnt[threadIdx.x] = c;
-    __syncthreads();
-    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
-        if (threadIdx.x < o) s_cnt[threadIdx.x] += s_cnt[threadIdx.x + o];
-        __syncthreads();
-    }
-    const int n = s_cnt[0];
+    c = es_warp_sum_i(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
+__global__ void obstat_coins_kernel(double* __restrict__ sum, double* __restrict__ sumsq, double* __restrict__ count_io,
+                                    const float* __restrict__ s, const float* __restrict__ ssq, int obs_dim,
+                                    int rows_per_rollout, const int* __restrict__ n_saved) {
+    const int n = *n_saved;
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d < obs_dim) {
         double a = sum[d], b = sumsq[d];
         const double sa = (double)s[d], sb = (double)ssq[d];
-        for (int i = 0; i < n; ++i) { a = __dadd_rn(a, sa); b = __dadd_rn(b, sb); }
+        for (int i = 0; i < n; ++i) { a = __dadd_rn(a, sa); b = __dadd_rn(b, sb); }      // obstat.py:20-21, n times in order
         sum[d] = a;
         sumsq[d] = b;
     }
@@ -128,8 +134,18 @@ __global__ void obstat_coins_kernel(double* __restrict__ sum, double* __restrict
 int es_impl_obstat_accumulate_coins(es_ctx* ctx, double* sum, double* sumsq, double* count_io, const float* s,
                                     const float* ssq, int obs_dim, int rows, const uint32_t* coins, int n_coins,
                                     double chance, cudaStream_t stream) {
-    obstat_coins_kernel<<<es_div_up(obs_dim, 64), 64, 0, stream>>>(sum, sumsq, count_io, s, ssq, obs_dim, rows, coins,
-                                                                   n_coins, chance);
+    unsigned* cnt = nullptr;
+    int rc = es_ctx_counters(ctx, 4096, &cnt);                    // slot 4095: coin counter (tickets use the low slots)
+    if (rc) return rc;
+    int* n_saved = (int*)(cnt + 4095);
+    ES_CHECK_CUDA(cudaMemsetAsync(n_saved, 0, sizeof(int), stream));
+    if (n_coins > 0) {
+        int blocks = es_div_up(n_coins, 256);
+        if (blocks > ctx->sm_count) blocks = ctx->sm_count;
+        coin_count_kernel<<<blocks, 256, 0, stream>>>(coins, n_coins, chance, n_saved);
+        ES_LAUNCHED(ctx);
+    }
+    obstat_coins_kernel<<<es_div_up(obs_dim, 64), 64, 0, stream>>>(sum, sumsq, count_io, s, ssq, obs_dim, rows, n_saved);
     ES_LAUNCHED(ctx);
     return ES_OK;
 }

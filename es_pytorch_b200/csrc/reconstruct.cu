@@ -134,7 +134,8 @@ int es_impl_grad_reconstruct(es_ctx* ctx, const float* table, int64_t table_len,
         int rc = es_ctx_scratch(ctx, (size_t)n_chunks * P * sizeof(float), &p);
         if (rc) return rc;
         partials = (float*)p;
-        rc = es_ctx_counters(ctx, (size_t)n_tiles, &tickets);
+        ES_REQUIRE(n_tiles < 4000, "es_grad_reconstruct: P too large for the ticket array");
+        rc = es_ctx_counters(ctx, 4096, &tickets);
         if (rc) return rc;
     }
     dim3 grid(n_tiles, n_chunks);

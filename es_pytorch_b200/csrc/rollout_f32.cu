@@ -202,10 +202,3 @@ int es_impl_rollout_f32(es_ctx* ctx, const float* table, int64_t table_len, cons
     ES_LAUNCHED(ctx);
     return ES_OK;
 }
-
-// Placeholder until the tcgen05 path lands: fail loudly, never fall back silently.
-int es_impl_rollout_tc(es_ctx*, const float*, int64_t, const int64_t*, int, const float*, int, float, const int*, int,
-                       const float*, const float*, int, float, double*, double*, int, float*, float*, cudaStream_t) {
-    es_set_error("es_rollout_openloop: ES_ROLLOUT_TC is not built in this revision");
-    return ES_ERR_UNSUPPORTED;
-}

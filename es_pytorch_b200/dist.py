@@ -41,7 +41,8 @@ class Comm:
         if self.size == 1:
             out.view(-1)[:local.numel()].copy_(local.view(-1))
             return out
-        td.all_gather_into_tensor(out, local, group=self.group)
+        # flat views: rank r's block lands at out[r] for any [size, *local.shape] output (NCCL and gloo alike)
+        td.all_gather_into_tensor(out.view(-1), local.contiguous().view(-1), group=self.group)
         return out
 
     def allreduce_sum(self, t: torch.Tensor) -> torch.Tensor:

@@ -89,6 +89,18 @@ def _worker(args):
     return dict(rank=rank, pairs=n_pairs, t_roll=t_roll, t_update=t_update)
 
 
+def host_cores() -> int:
+    """Cores this process may actually use: the affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0))
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()
+        if quota != 'max':
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return n
+
+
 class CpuReference:
     """Pool of one worker per host core sharing the table; ``sample()`` times one bounded
     sample of a K-pair generation and extrapolates (rollouts linear in pairs, update linear in K)."""
@@ -97,7 +109,7 @@ class CpuReference:
                  cores: int = 0, seed: int = 1000):
         import torch
         from oracle import es_oracle as orc
-        self.cores = cores or len(os.sched_getaffinity(0))
+        self.cores = cores or host_cores()
         self.K, self.seed = K, seed
         dims = orc.layer_dims(obs_dim, hidden, act_dim)
         P = orc.n_params(dims)

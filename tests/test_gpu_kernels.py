@@ -316,3 +316,58 @@ def test_novelty(eng):
         out = torch.zeros(1, dtype=torch.float64, device=eng.device)
         eng.novelty(b, arch, k, out)
         assert out.item() == expect
+
+
+# ------------------------------------------------------------------------------------------- tensor-core rollout
+def _tc_vs_f32(eng, obs, act, T, n_pairs, seed):
+    from es_pytorch_b200 import _lib
+    rs = np.random.RandomState(seed)
+    sizes = [obs, 64, 64, act]
+    P = orc.n_params(orc.layer_dims(obs, (64, 64), act))
+    L = P + 1_000_000
+    table, theta = dev(eng, rs.randn(L).astype(np.float32)), dev(eng, (rs.randn(P) * 0.1).astype(np.float32))
+    idx = dev(eng, rs.randint(0, L - P, size=n_pairs).astype(np.int64))
+    obsn = dev(eng, np.clip(rs.randn(T, obs), -5, 5).astype(np.float32))
+    rew = dev(eng, rs.randn(T, act).astype(np.float32))
+    res = {}
+    for mode in (_lib.ES_ROLLOUT_F32, _lib.ES_ROLLOUT_TC):
+        fit = torch.zeros(2, n_pairs, dtype=torch.float64, device=eng.device)
+        behv = torch.zeros(2, n_pairs, 3, dtype=torch.float32, device=eng.device)
+        eng.rollout(table, idx, theta, 0.02, sizes, obsn, rew, 0.05, fit[0], fit[1], 1, behv[0], behv[1], mode)
+        res[mode] = (fit.cpu().numpy(), behv.cpu().numpy())
+    return res[_lib.ES_ROLLOUT_F32], res[_lib.ES_ROLLOUT_TC]
+
+
+@pytest.mark.parametrize('obs,act,T,n_pairs', [(376, 17, 1000, 200), (17, 6, 1000, 256), (17, 6, 100, 8), (5, 1, 130, 3),
+                                               (63, 32, 129, 5), (64, 3, 128, 4)])
+def test_rollout_tc_matches_f32(eng, obs, act, T, n_pairs):
+    """bf16 tensor-core rollout vs the float32 CUDA-core rollout (itself checked against the oracle above).
+    Tolerance (bf16 operands, fp32 accumulate, tanh.approx): fitness within 3 % of the population's fitness
+    spread, antithetic differences f+ - f- within 3 % of their spread, ranks essentially unchanged."""
+    (f32, b32), (ftc, btc) = _tc_vs_f32(eng, obs, act, T, n_pairs, seed=obs + T)
+    spread = max(f32.std(), 1e-3 * np.sqrt(T))
+    assert np.abs(ftc - f32).max() <= 0.05 * spread + 0.02 * np.sqrt(T) * 0.05
+    d32, dtc = f32[0] - f32[1], ftc[0] - ftc[1]
+    assert np.sqrt(((dtc - d32) ** 2).mean()) <= 0.03 * max(d32.std(), 1e-3 * np.sqrt(T)) + 0.02
+    assert np.abs(btc - b32).max() <= 0.01 * 0.05 * T + 1e-3
+    if n_pairs >= 100:
+        r32, rtc = np.argsort(np.argsort(f32.ravel())), np.argsort(np.argsort(ftc.ravel()))
+        assert np.corrcoef(r32, rtc)[0, 1] > 0.9995
+
+
+def test_rollout_tc_sigma_zero_symmetric_and_unsupported_shape(eng):
+    from es_pytorch_b200 import _lib
+    from es_pytorch_b200._lib import EsLibraryError
+    rs = np.random.RandomState(3)
+    P = orc.n_params(orc.layer_dims(17, (64, 64), 6))
+    table, theta = dev(eng, rs.randn(P + 5000).astype(np.float32)), dev(eng, (rs.randn(P) * .1).astype(np.float32))
+    idx = dev(eng, rs.randint(0, 5000, size=200).astype(np.int64))
+    obsn, rew = dev(eng, rs.randn(256, 17).astype(np.float32)), dev(eng, rs.randn(256, 6).astype(np.float32))
+    fit = torch.zeros(2, 200, dtype=torch.float64, device=eng.device)
+    eng.rollout(table, idx, theta, 0.0, [17, 64, 64, 6], obsn, rew, 0.05, fit[0], fit[1], mode=_lib.ES_ROLLOUT_TC)
+    f = fit.cpu().numpy()
+    assert np.array_equal(f[0], f[1]) and np.all(f[0] == f[0][0])        # sigma = 0: every evaluation identical
+    with pytest.raises(EsLibraryError, match='tensor-core path'):
+        P2 = orc.n_params(orc.layer_dims(17, (32,), 6))
+        eng.rollout(table, idx, dev(eng, np.zeros(P2, dtype=np.float32)), 0.02, [17, 32, 6], obsn, rew, 0.05, fit[0], fit[1],
+                    mode=_lib.ES_ROLLOUT_TC)

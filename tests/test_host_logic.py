@@ -1,0 +1,235 @@
+"""CPU (no GPU): the C-ABI library loads and exports every symbol include/es_b200.h declares, the
+host-side mirror keeps the reference's API surface, the shims let the reference scripts import,
+and the multi-process plumbing (gloo, world_size 2) keeps the reference's result layout."""
+import importlib.util
+import os
+import re
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from oracle import es_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+COMPAT = os.path.join(ROOT, 'es_pytorch_b200', 'compat')
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from es_pytorch_b200 import _lib, build
+    build.build()
+    hdr = open(os.path.join(ROOT, 'include', 'es_b200.h')).read()
+    declared = set(re.findall(r'\b(es_[a-z0-9_]+)\s*\(', hdr))
+    declared.discard('es_ctx')
+    assert len(declared) >= 18
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f'{name} declared in include/es_b200.h but not exported'
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    assert lib.es_abi_version() == 1
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from es_pytorch_b200._lib import EsLibraryError
+    from es_pytorch_b200.engine import get_engine
+    with pytest.raises(EsLibraryError, match='no CPU path'):
+        get_engine()
+    from es_pytorch_b200.utils.rankers import CenteredRanker
+    with pytest.raises(EsLibraryError):
+        CenteredRanker().rank(np.zeros((2, 1)), np.ones((2, 1)), np.arange(2))
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'es_pytorch_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'oracle' not in src.replace('the oracle', '').replace('CPU oracle', ''), os.path.join(dirpath, f)
+
+
+def test_synthetic_env_matches_oracle_spec():
+    from es_pytorch_b200.gym.synthetic_env import SyntheticEnv, make
+    spec = orc.SyntheticEnvSpec(17, 6, 30)
+    env = SyntheticEnv(17, 6, 30)
+    assert np.array_equal(env.obs_stream, spec.obs_stream) and np.array_equal(env.rew_vec, spec.rew_vec)
+    rs = np.random.RandomState(0)
+    acts = rs.randn(30, 6).astype(np.float32)
+    ob = env.reset()
+    assert np.array_equal(ob, spec.obs_stream[0])
+    rews = []
+    for t in range(30):
+        ob, r, done, _ = env.step(acts[t])
+        rews.append(r)
+        assert np.array_equal(ob, spec.obs_stream[t + 1]) and done == (t == 29)
+    # same arithmetic as the oracle's run_model reward / position integrator
+    pos = np.zeros(3, dtype=np.float32)
+    for t in range(30):
+        acc = np.float32(0)
+        for j in range(6):
+            acc = np.float32(acc + np.float32(acts[t, j] * spec.rew_vec[t, j]))
+        assert rews[t] == float(acc)
+        for j in range(3):
+            pos[j] = np.float32(pos[j] + np.float32(np.float32(0.05) * acts[t, j]))
+    assert np.array_equal(env.pos, pos) and env.robot.robot_body.pose().xyz() == tuple(float(x) for x in pos)
+    with pytest.raises(RuntimeError):
+        env.step(acts[0])
+    assert make('HalfCheetahBulletEnv-v0').obs_dim == 17 and make('HumanoidBulletEnv-v0').act_dim == 17
+    with pytest.raises(ValueError):
+        make('NoSuchEnv-v0')
+
+
+def test_noisetable_api():
+    from es_pytorch_b200.core.noisetable import NoiseTable
+    nt = NoiseTable(50, np.arange(100))
+    assert len(nt) == 100 and (nt.get(3, 50) == np.arange(3, 53)).all() and (nt[7] == np.arange(7, 57)).all()
+    with pytest.raises(AssertionError):
+        nt.get(50, 50)                                   # noisetable.py:34: len > i + size
+    with pytest.raises(ValueError):
+        NoiseTable(100, np.arange(100)).sample_idx(np.random.RandomState(0), 100)   # noisetable.py:39
+    rs, ref = np.random.RandomState(5), np.random.RandomState(5)
+    idx, sl = nt.sample(rs)
+    assert idx == ref.randint(0, 50) and (sl == np.arange(idx, idx + 50)).all()
+    assert np.array_equal(NoiseTable.make_noise(5, 1), np.random.RandomState(1).randn(5).astype(np.float32))
+
+
+def test_obstat_api():
+    from es_pytorch_b200.nn.obstat import ObStat
+    a, b, ref = ObStat((4,), 1e-2), ObStat((4,), 0), orc.ObStatOracle((4,), 1e-2)
+    x = np.random.RandomState(0).randn(10, 4).astype(np.float32)
+    b.inc(x.sum(0), np.square(x).sum(0), 10)
+    a += b
+    r2 = orc.ObStatOracle((4,), 0)
+    r2.inc(x.sum(0), np.square(x).sum(0), 10)
+    ref.merge(r2)
+    assert np.array_equal(a.sum, ref.sum) and np.array_equal(a.mean, ref.mean) and np.array_equal(a.std, ref.std)
+
+
+def test_policy_flat_layout_and_pickle(tmp_path):
+    import pickle
+    import torch
+    from es_pytorch_b200.core.policy import Policy
+    from es_pytorch_b200.gym.synthetic_env import SyntheticEnv
+    from es_pytorch_b200.nn.nn import FeedForward
+    from es_pytorch_b200.nn.optimizers import Adam
+    env = SyntheticEnv(17, 6, 8)
+    net = FeedForward([64, 64], torch.nn.Tanh(), env, 0.0, 5)
+    pol = Policy(net, 0.02, Adam(5702, 0.01))
+    assert len(pol) == 5702 == orc.n_params(orc.layer_dims(17, (64, 64), 6)) and pol.flat_params.dtype == np.float32
+    assert net.layer_sizes() == [17, 64, 64, 6] and net.is_tanh_mlp()
+    # state_dict order = weight[out,in] row-major then bias (policy.py:33-35): oracle.unflatten reads it back
+    layers = orc.unflatten(pol.flat_params, orc.layer_dims(17, (64, 64), 6))
+    assert np.array_equal(layers[0][0], net.model[0].weight.detach().numpy())
+    assert np.array_equal(layers[2][1], net.model[4].bias.detach().numpy())
+    flat2 = np.random.RandomState(0).randn(5702).astype(np.float32)
+    pol.set_nn_params(flat2)
+    assert np.array_equal(Policy.get_flat(net), flat2)
+    # forward of the module == oracle forward (float64 normalise, tanh after every layer)
+    net.set_ob_mean_std(np.full(17, 0.1), np.full(17, 2.0))
+    ob = np.random.RandomState(1).randn(17).astype(np.float32)
+    got = net(torch.from_numpy(ob), rs=None).detach().numpy()
+    want = orc.mlp_forward(orc.unflatten(flat2, orc.layer_dims(17, (64, 64), 6)),
+                           orc.normalise_obs(ob, np.full(17, 0.1), np.full(17, 2.0), 5))
+    assert np.allclose(got, want, rtol=1e-6, atol=1e-7)
+    pol.save(str(tmp_path), 'x')
+    pol2 = Policy.load(os.path.join(str(tmp_path), 'policy-x'))
+    assert np.array_equal(pol2.flat_params, pol.flat_params) and pol2.optim.t == 0 and pol2.std == 0.02
+
+
+def test_reference_scripts_import_against_the_shims():
+    """simple_example.py / obj.py / nsra.py resolve every import against es_pytorch_b200/compat
+    (only where the reference checkout is mounted: the build container)."""
+    if not os.path.isdir('/root/reference'):
+        pytest.skip('reference checkout not present on this box')
+    code = textwrap.dedent('''
+        import importlib.util, sys
+        for s in ('simple_example', 'obj', 'nsra'):
+            spec = importlib.util.spec_from_file_location('ref_' + s, '/root/reference/%s.py' % s)
+            m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+        import src.core.es, es_pytorch_b200.core.es
+        assert src.core.es is es_pytorch_b200.core.es
+        from src.utils import utils
+        cfg = utils.load_config('/root/reference/configs/simple_conf.json')
+        assert cfg.general.policies_per_gen == 4800 and cfg.noise.std == 0.02
+        print('OK')
+    ''')
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + COMPAT)
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env)
+    assert out.returncode == 0 and 'OK' in out.stdout, out.stderr[-2000:]
+
+
+def test_shard_bounds():
+    from es_pytorch_b200.dist import shard_bounds
+    assert [shard_bounds(40000, 8, r) for r in (0, 7)] == [(0, 5000), (35000, 40000)]
+    with pytest.raises(ValueError):
+        shard_bounds(10, 3, 0)
+
+
+_GLOO_WORKER = '''
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch
+from es_pytorch_b200 import dist
+from es_pytorch_b200.core.es import _share_results
+from es_pytorch_b200.nn.obstat import ObStat
+comm = dist.init_from_env('gloo')
+assert comm.size == 2
+# test/es/es_runner_test.py:10-31 on two real processes
+evals, objectives = 5, 4
+pf = evals * comm.rank + 1
+inds = (np.arange(evals) + pf) * 10
+fp = [[i + i * 10 ** j if j != 0 else i for j in range(objectives)] for i in range(pf, pf + evals)]
+fn = (-np.array(fp)).tolist()
+res = _share_results(comm, fp, fn, inds)
+expected = []
+for i in range(1, evals * comm.size + 1):
+    p = [i + i * 10 ** j if j != 0 else i for j in range(objectives)]
+    expected.append(p + (-np.array(p)).tolist() + [i * 10])
+assert res.dtype == np.float64 and (res == expected).all()
+# test/utils/obstat_test.py:8-23
+ob = ObStat(5, 0)
+ob.inc(np.arange(5) * (comm.rank + 1), np.square(np.arange(5) * (comm.rank + 1)), 1)
+ob.mpi_inc(comm)
+es_, eq = np.zeros(5), np.zeros(5)
+for i in range(comm.size):
+    es_ += np.arange(5) * (i + 1); eq += np.square(np.arange(5) * (i + 1))
+assert (ob.sum == es_).all() and (ob.sumsq == eq).all() and ob.count == comm.size
+# the two collectives of the sharded generation: rank-major allgather, summed partial gradient
+loc = torch.full((3, 2), float(comm.rank))
+out = torch.empty(2, 3, 2)
+comm.allgather_into(out, loc)
+assert out[0].eq(0).all() and out[1].eq(1).all()
+g = torch.arange(4, dtype=torch.float32) * (comm.rank + 1)
+comm.allreduce_sum(g)
+assert torch.equal(g, torch.arange(4, dtype=torch.float32) * 3)
+assert comm.broadcast_object('seed-%d' % comm.rank, 0) == 'seed-0'
+# mpi4py shim over the same group
+sys.path.insert(0, {compat!r})
+from mpi4py import MPI
+c = MPI.COMM_WORLD
+assert c.rank == comm.rank and c.size == 2
+assert c.alltoall([c.rank * 10 + 1] * 2) == [1, 11] and c.scatter(['a', 'b']) == 'ab'[c.rank] and c.allreduce(c.rank + 1, MPI.SUM) == 3
+send = np.tile(np.arange(3, dtype=np.float64) + 10 * c.rank, 2)
+recv = np.empty(6)
+c.Alltoall(send, recv)
+assert (recv == np.concatenate([np.arange(3), np.arange(3) + 10])).all()
+print('RANK_OK', comm.rank)
+'''
+
+
+def test_two_process_gloo(tmp_path):
+    script = tmp_path / 'w.py'
+    script.write_text(_GLOO_WORKER.format(root=ROOT, compat=COMPAT))
+    import socket
+    with socket.socket() as sk:
+        sk.bind(('127.0.0.1', 0))
+        port = sk.getsockname()[1]
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                          '--master-addr', '127.0.0.1', '--master-port', str(port), str(script)],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
+    assert 'RANK_OK 0' in out.stdout and 'RANK_OK 1' in out.stdout
