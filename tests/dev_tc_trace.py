@@ -1,0 +1,38 @@
+"""Dev tool: cycle-stamp timeline of CTA 0 of the tensor-core rollout (ES_TC_TRACE)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from es_pytorch_b200.engine import get_engine
+from es_pytorch_b200 import _lib
+eng = get_engine(0)
+trace = torch.zeros(4 * 512, dtype=torch.int64, device=eng.device)
+os.environ['ES_TC_TRACE'] = hex(trace.data_ptr())
+rs = np.random.RandomState(0)
+obs, act, T, n_pairs = 376, 17, 1000, 148 * 3
+sizes = [obs, 64, 64, act]; P = sum(i*o+o for i, o in zip(sizes[:-1], sizes[1:]))
+L = 50_000_000
+g = torch.Generator(device=eng.device).manual_seed(1)
+table = torch.randn(L, generator=g, device=eng.device)
+theta = eng.to_device((rs.randn(P)*0.1).astype(np.float32))
+idx = torch.randint(0, L-P, (n_pairs,), generator=g, device=eng.device, dtype=torch.int64)
+obsn = eng.to_device(np.clip(rs.randn(T, obs), -5, 5).astype(np.float32)); rew = eng.to_device(rs.randn(T, act).astype(np.float32))
+fit = torch.zeros(2, n_pairs, dtype=torch.float64, device=eng.device)
+for _ in range(2):
+    trace.zero_()
+    eng.rollout(table, idx, theta, 0.02, sizes, obsn, rew, 0.05, fit[0], fit[1], mode=_lib.ES_ROLLOUT_TC)
+    torch.cuda.synchronize()
+t = trace.cpu().numpy().reshape(4, 512)
+t0 = t[t > 0].min()
+mma, epi = t[0], t[1]
+print('tile | MMA: L1 first-chunk, L1 done-issue, L2+ issue, L3+ issue | EPI: wait D1, got D1, H1N arrived, got D2+, got D2-, wait D3+, got D3+, got D3-')
+for g_ in range(24):
+    m = [(mma[4*g_+k]-t0) if mma[4*g_+k] else -1 for k in range(4)]
+    e = [(epi[8*g_+k]-t0) if epi[8*g_+k] else -1 for k in range(8)]
+    print(f'{g_:3d} | {m} | {e}')
+
+h1p, d2p = t[2], t[3]
+print('per-warp H1P arrival (relative to warp 0 got-D1) and got-D2+ for tiles 4..6; L2+ issue stamp')
+for g_ in (4, 5, 6):
+    base = epi[8*g_+1]
+    print(g_, 'H1P arrive', [int(h1p[16*g_+w]-base) for w in range(16)])
+    print(g_, 'got D2+   ', [int(d2p[16*g_+w]-base) for w in range(16)], ' L2+ issued', int(mma[4*g_+2]-base), ' D1 got', int(base - t0))
