@@ -3,42 +3,47 @@
 //
 // Same contract as rollout_f32.cu (reference: src/core/policy.py:61-64, src/nn/nn.py:35-46,
 // src/gym/gym_runner.py:50-54, src/gym/training_result.py:28) for the policy family the
-// BASELINE configs name: obs -> 64 -> 64 -> act (act <= 32, obs <= 1024), tanh after every layer.
+// BASELINE configs name: obs -> 64 -> 64 -> act (act <= 32, obs <= 1023), tanh after every layer.
 //
-// One CTA = one antithetic pair at a time (persistent over pairs), time on the MMA M dimension:
-//   per 128-step tile of the episode
-//     L1:  [U | V] (128 x 128, fp32, TMEM) = Xn_tile (128 x obs, bf16)  x  [theta1 ; sigma*eps1]^T
-//          z1+- = U +- V + b1+-            (U is common to both signs: its bf16 rounding cancels
-//                                            to first order in f+ - f-, V carries the perturbation)
-//     epi1: h1+- = tanh(z1+-) -> bf16 -> shared (K-major, 128B swizzle) = A operand of L2
-//     L2:  D2+- (128 x 64) = h1+- x (theta2 +- sigma*eps2)^T ;  epi2: h2+- = tanh(D2+- + b2+-)
-//     L3:  D3+- (128 x 32) = h2+- x (theta3 +- sigma*eps3)^T ;  epi3: a = tanh(D3 + b3),
-//          r_t = <a_t, c_t>, fitness += r_t, pos += a_t[0..2]
-// Warp roles (448 threads, warp-specialised, mbarrier pipelines only -- no CTA-wide barrier in the loop):
-//   warp 0      producer: cp.async.bulk of the observation stages (ring of TC_NST x 16 KB)
-//   warp 1      L1 MMA issuer (one elected lane) and TMEM owner.  D1 is double-buffered in TMEM, so
-//               L1 of tile m+1 runs on the tensor pipe while the epilogue works on tile m.
-//   warp 22     L2/L3 MMA issuer: the short per-sign MMAs are issued by their own thread the moment
-//               the epilogue publishes H (blocking mbarrier waits, no polling); issuing costs the
-//               thread ~10^2 cycles per instruction, so one thread for everything was the bottleneck.
-//   warps 2-17  epilogue (TMEM lane quarter = warp % 4, column quarter = (warp-2)/4; four warps per
-//               scheduler hide the MUFU / dependent-ALU latency): the + and - sign
-//               chains are interleaved, so waiting for L2+/L3+ is covered by the other sign's work.
-//   warps 18-21 builders: convert the NEXT pair's noise slice (float32, arbitrary 4-byte alignment in
-//               the table) into the bf16 / swizzled B operands as soon as the current pair's last L1
-//               (resp. last L3) has retired, one pair ahead of the MMA issuer.
+// One CTA = one antithetic pair at a time (persistent over pairs), time on the MMA M dimension,
+// per 128-step tile of the episode:
+//   z1+- = U +- V.   U = Xn . theta1^T + b1 does not depend on the pair: it is computed ONCE per generation
+//                    in float32 (rollout_tc_ubase_kernel) and read from L2 by the epilogue.
+//                    V (128 x 64, fp32, TMEM) = Xn_tile (128 x K, bf16) . (sigma*eps1)^T is the only per-pair
+//                    L1 MMA; the perturbation term is therefore carried at bf16 *relative* precision and the
+//                    unperturbed pre-activation at full float32 precision.  The sigma*eps_b1 bias rides in a
+//                    constant-1 column of the observation tile.
+//   epi1: h1+- = tanh(U +- V) -> bf16 -> shared (K-major, 128B swizzle) = A operand of L2
+//   L2:   D2+- (128 x 64) = h1+- . (theta2 +- sigma*eps2)^T ;  epi2: h2+- = tanh(D2+- + b2+-)
+//   L3:   D3+- (128 x 32) = h2+- . (theta3 +- sigma*eps3)^T ;  epi3: a = tanh(D3 + b3),
+//         r_t = <a_t, c_t>, fitness += r_t, pos += a_t[0..2]
 //
-// The observation stream is pre-tiled once per generation by rollout_tc_prep_kernel into the
-// exact shared-memory image of each (M-tile, K-chunk) stage, so a stage is ONE contiguous
-// 16 KB cp.async.bulk (no tensor map needed).
+// Warp roles (736 threads, warp-specialised; mbarrier pipelines only, no CTA-wide barrier in the loop):
+//   warp 0       producer: cp.async.bulk of the observation stages (ring of TC_NST x 16 KB)
+//   warp 1       L1 MMA issuer and TMEM owner (warp-uniform loop, one elected lane issues, so the
+//                descriptors live in uniform registers).  V is double-buffered in TMEM.
+//   warps 2-9    epilogue group 0, warps 10-17 epilogue group 1.  The groups take alternate tiles and own
+//                separate H buffers, TMEM regions and barriers, so one group's waits for its short L2/L3
+//                MMAs are filled by the other group's MUFU/ALU work.  Inside a group the + and - sign
+//                chains are interleaved.  TMEM lane quarter = warp % 4, column half = ((warp-2) % 8) / 4.
+//   warps 18-20  builders: convert the NEXT pair's noise slice (float32, arbitrary 4-byte alignment in
+//                the table, which rules out TMA/bulk copies of the slice itself) into the bf16 swizzled
+//                B operands as soon as the current pair's last L1 (resp. last L3) has retired.
+//   warps 21-22  L2/L3 MMA issuers, one per epilogue group (blocking mbarrier waits, no polling).
+// Per-pair fitness: every epilogue warp writes its partial sums to a scratch slot; the last of the 16 to
+// arrive (atomic ticket) adds them in warp order -> deterministic.
+//
+// The observation stream is pre-tiled once per generation by rollout_tc_prep_kernel into the exact
+// shared-memory image of each (M-tile, K-chunk) stage, so a stage is ONE contiguous 16 KB cp.async.bulk
+// (no tensor map needed).
 #include <cuda_bf16.h>
 #include <stdlib.h>
 #include "common.cuh"
 
 namespace {
 
-constexpr int TC_THREADS = 736;
-constexpr int TC_EPI_WARP0 = 2, TC_EPI_WARPS = 16, TC_BLD_WARP0 = 18, TC_BLD_WARPS = 4, TC_MMA2_WARP = 22;
+constexpr int TC_THREADS = 736;     // 23 warps
+constexpr int TC_EPI_WARP0 = 2, TC_GRP_WARPS = 8, TC_EPI_WARPS = 16, TC_BLD_WARP0 = 18, TC_BLD_WARPS = 3, TC_MMA2_WARP0 = 21;
 constexpr int TC_H = 64;            // hidden width (both hidden layers)
 constexpr int TC_MT = 128;          // time steps per M tile
 constexpr int TC_KC = 64;           // K elements per chunk (= 128 bytes of bf16 = one swizzle row)
@@ -225,16 +230,17 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int k /*0..63*/) {
     return (uint32_t)(row * 128 + ((((k >> 3) ^ (row & 7)) << 4) | ((k & 7) << 1)));
 }
 
-// Fill rows [row0, row0+64) of every K-chunk block of B1 with bf16(scale * w[n][k]) (k < obs), bf16(scale * bias[n])
-// in column `obs`, zero beyond.  A warp takes whole rows; a lane owns two adjacent columns per chunk, so global reads
-// are coalesced 256-byte runs (12 independent loads in flight per row) and every shared store is one conflict-free
-// 4-byte word of a swizzled 128-byte row.
-__device__ __forceinline__ void tc_build_l1_rows(uint8_t* b1_base, int row0, const float* __restrict__ w,
+// Fill rows [0, 64) of every K-chunk block (64 rows x 128 B = 8 KB) of B1 with bf16(scale * w[n][k]) (k < obs),
+// bf16(scale * bias[n]) in column `obs`, zero beyond.  A warp takes two rows per iteration; a lane owns two
+// adjacent columns per chunk, so global reads are coalesced 256-byte runs (16 independent loads in flight per lane,
+// addresses clamped instead of branching) and every shared store is one conflict-free 4-byte word of a swizzled row.
+constexpr int TC_B1_CHUNK_BYTES = TC_H * 128;          // 8 KB
+__device__ __forceinline__ void tc_build_l1_rows(uint8_t* b1_base, const float* __restrict__ w,
                                                  const float* __restrict__ bvec, float scale, int obs, int nkc, int warp,
                                                  int nwarps, int lane) {
-    constexpr int KB = 4;                                  // K chunks per batch; 2 rows per batch -> 16 loads in flight per lane
-    const int c0 = 2 * lane;                               // this lane's two columns inside a chunk
-    for (int n = 2 * warp; n < TC_H; n += 2 * nwarps) {    // two rows per iteration
+    constexpr int KB = 4;
+    const int c0 = 2 * lane;
+    for (int n = 2 * warp; n < TC_H; n += 2 * nwarps) {
         const float* __restrict__ wa = w + (size_t)n * obs;
         const float* __restrict__ wb = wa + obs;
         const float ba = __ldg(bvec + n), bb = __ldg(bvec + n + 1);
@@ -243,7 +249,6 @@ __device__ __forceinline__ void tc_build_l1_rows(uint8_t* b1_base, int row0, con
 #pragma unroll
             for (int j = 0; j < KB; ++j) {
                 const int k = (kc0 + j) * TC_KC + c0;
-                // clamp the address instead of branching: out-of-range columns are replaced after the load
                 const int k0 = min(k, obs - 1), k1 = min(k + 1, obs - 1);
                 xa0[j] = __ldg(wa + k0); xa1[j] = __ldg(wa + k1);
                 xb0[j] = __ldg(wb + k0); xb1[j] = __ldg(wb + k1);
@@ -254,9 +259,9 @@ __device__ __forceinline__ void tc_build_l1_rows(uint8_t* b1_base, int row0, con
                 if (kc < nkc) {
                     const float a0 = (k < obs) ? xa0[j] : ((k == obs) ? ba : 0.f), a1 = (k + 1 < obs) ? xa1[j] : ((k + 1 == obs) ? ba : 0.f);
                     const float b0 = (k < obs) ? xb0[j] : ((k == obs) ? bb : 0.f), b1 = (k + 1 < obs) ? xb1[j] : ((k + 1 == obs) ? bb : 0.f);
-                    const uint32_t off = kc * TC_STAGE_BYTES;
-                    *(uint32_t*)(b1_base + off + sw128_off(row0 + n, c0)) = pack_bf16x2(__fmul_rn(scale, a0), __fmul_rn(scale, a1));
-                    *(uint32_t*)(b1_base + off + sw128_off(row0 + n + 1, c0)) = pack_bf16x2(__fmul_rn(scale, b0), __fmul_rn(scale, b1));
+                    const uint32_t off = kc * TC_B1_CHUNK_BYTES;
+                    *(uint32_t*)(b1_base + off + sw128_off(n, c0)) = pack_bf16x2(__fmul_rn(scale, a0), __fmul_rn(scale, a1));
+                    *(uint32_t*)(b1_base + off + sw128_off(n + 1, c0)) = pack_bf16x2(__fmul_rn(scale, b0), __fmul_rn(scale, b1));
                 }
             }
         }
@@ -268,15 +273,19 @@ struct TcParams {
     const int64_t* idx;
     const float* theta;
     const __nv_bfloat16* xnt;     // [n_mtiles][nkc][16 KB stage image]
+    const float* ubase;           // float32 Xn . theta1^T + b1, float4 [n_mtiles][2 halves][8 chunks][128 rows]: a warp's load of one
+                                  // chunk is 32 consecutive float4 (coalesced), each thread still owns its row's 32 columns
+    const float* crt;             // reward vectors transposed per tile: [n_mtiles][32 cols][128 rows] (zero padded)
     const float* rew_vec;         // [T][act]
+    float* partial;               // [n_pairs][16 warps][8] per-pair partial sums
+    unsigned* tickets;            // [n_pairs] zeroed before launch
     double* fit_pos;
     double* fit_neg;
     float* behv_pos;
     float* behv_neg;
     int n_pairs, obs, act, T, nkc, n_mtiles, fit_stride;
     float sigma, pos_scale;
-    // flat parameter offsets
-    int w1, b1, w2, b2, w3, b3;
+    int w1, b1, w2, b2, w3, b3;   // flat parameter offsets
     long long* trace;             // optional cycle-stamp trace of CTA 0 (ES_TC_TRACE env), NULL in production
     int dev_noload;               // dev experiment: skip the observation-tile copies (results are garbage)
 };
@@ -284,7 +293,7 @@ struct TcParams {
 #define TC_TRACE(role, slot) do { if (p.trace && blockIdx.x == 0 && (slot) < 512) p.trace[(role) * 512 + (slot)] = clock64(); } while (0)
 
 struct TcSmemLayout {   // byte offsets from the 1024-aligned dynamic smem base
-    uint32_t b1, a_stage, w2p, w2n, w3p, w3n, hp, hn, bias, red, bars, total;
+    uint32_t b1, a_stage, w2p, w2n, w3p, w3n, h, bias, bars, total;
 };
 
 constexpr int TC_BIAS_FLOATS = 2 * TC_H + 2 * TC_ACT_PAD;        // b2+, b2-, b3+, b3- (one buffer)
@@ -292,40 +301,34 @@ constexpr int TC_BIAS_FLOATS = 2 * TC_H + 2 * TC_ACT_PAD;        // b2+, b2-, b3
 __host__ __device__ inline TcSmemLayout tc_layout(int nkc) {
     TcSmemLayout L;
     uint32_t o = 0;
-    L.b1 = o;       o += (uint32_t)nkc * TC_STAGE_BYTES;         // [nkc][128 rows x 128 B]: rows 0-63 theta1, 64-127 sigma*eps1
+    L.b1 = o;       o += (uint32_t)nkc * TC_B1_CHUNK_BYTES;      // [nkc][64 rows x 128 B]: sigma*eps1
     L.a_stage = o;  o += TC_NST * TC_STAGE_BYTES;
     L.w2p = o;      o += TC_H * 128;
     L.w2n = o;      o += TC_H * 128;
     L.w3p = o;      o += TC_ACT_PAD * 128;
     L.w3n = o;      o += TC_ACT_PAD * 128;
-    L.hp = o;       o += TC_MT * 128;
-    L.hn = o;       o += TC_MT * 128;
+    o = (o + 1023) & ~1023u;
+    L.h = o;        o += 4 * TC_MT * 128;                        // [group][sign] 16 KB each
     L.bias = o;     o += 2 * TC_BIAS_FLOATS * 4;                 // double-buffered by pair parity
-    L.red = o;      o += 2 * TC_EPI_WARPS * 8 * 4;               // per-pair reduction scratch, double-buffered
-    L.bars = o;     o += 256;
+    L.bars = o;     o += 512;
     L.total = o;
     return L;
 }
 
+// barrier indices; per-group sets are laid out [kind][group]
 enum { BAR_FULL = 0, BAR_EMPTY = TC_NST, BAR_D1_FULL = 2 * TC_NST, BAR_D1_FREE = BAR_D1_FULL + 2,
-       BAR_H1P = BAR_D1_FREE + 2, BAR_H1N, BAR_D2P, BAR_D2N, BAR_H2P, BAR_H2N, BAR_D3P, BAR_D3N,
-       BAR_EPS_READY, BAR_EPS_FREE, BAR_W_READY, BAR_W_FREE, BAR_COUNT };
-static_assert(BAR_COUNT * 8 + 16 <= 256, "barrier block too small");
+       BAR_H1P = BAR_D1_FREE + 2, BAR_H1N = BAR_H1P + 2, BAR_D2P = BAR_H1N + 2, BAR_D2N = BAR_D2P + 2,
+       BAR_H2P = BAR_D2N + 2, BAR_H2N = BAR_H2P + 2, BAR_D3P = BAR_H2N + 2, BAR_D3N = BAR_D3P + 2,
+       BAR_EPS_READY = BAR_D3N + 2, BAR_EPS_FREE, BAR_W_READY, BAR_W_FREE, BAR_COUNT };
+static_assert(BAR_COUNT * 8 + 16 <= 512, "barrier block too small");
 
 // Descriptors are precomputed once (64-bit); stepping 16 bf16 (32 B) along K inside a 128B-swizzled row is +2 in the
-// 16-byte-unit address field, stepping a whole 16 KB block is +1024.
-// one K chunk (64 columns) of an L1 tile: 4 UMMA k-steps
-__device__ __forceinline__ void tc_issue_l1_chunk(uint32_t d1, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, int kc) {
-    umma_bf16(d1, a_desc, b_desc, idesc, kc != 0);
-    umma_bf16(d1, a_desc + 2, b_desc + 2, idesc, 1);
-    umma_bf16(d1, a_desc + 4, b_desc + 4, idesc, 1);
-    umma_bf16(d1, a_desc + 6, b_desc + 6, idesc, 1);
-}
-__device__ __forceinline__ void tc_issue_small(uint32_t d, uint64_t h_desc, uint64_t w_desc, uint32_t idesc) {
-    umma_bf16(d, h_desc, w_desc, idesc, 0);
-    umma_bf16(d, h_desc + 2, w_desc + 2, idesc, 1);
-    umma_bf16(d, h_desc + 4, w_desc + 4, idesc, 1);
-    umma_bf16(d, h_desc + 6, w_desc + 6, idesc, 1);
+// 16-byte-unit address field.
+__device__ __forceinline__ void tc_issue_4k(uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc0) {
+    umma_bf16(d, a_desc, b_desc, idesc, acc0);
+    umma_bf16(d, a_desc + 2, b_desc + 2, idesc, 1);
+    umma_bf16(d, a_desc + 4, b_desc + 4, idesc, 1);
+    umma_bf16(d, a_desc + 6, b_desc + 6, idesc, 1);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_constant__ TcParams p) {
@@ -335,21 +338,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
     uint64_t* bars = (uint64_t*)(smem + L.bars);
     uint32_t* tmem_slot = (uint32_t*)(smem + L.bars + BAR_COUNT * 8);
     float* bias_all = (float*)(smem + L.bias);
-    float* red_all = (float*)(smem + L.red);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NMT = p.n_mtiles, NKC = p.nkc;
+    const int my_pairs = (p.n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // pairs of this CTA
+    const uint32_t total_tiles = (uint32_t)my_pairs * NMT;
 
     // ---- one-time setup -------------------------------------------------------------------------
     for (uint32_t i = tid * 16; i < L.bars; i += TC_THREADS * 16) *(uint4*)(smem + i) = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         for (int s = 0; s < TC_NST; ++s) { mbar_init(&bars[BAR_FULL + s], 1); mbar_init(&bars[BAR_EMPTY + s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&bars[BAR_D1_FULL + b], 1); mbar_init(&bars[BAR_D1_FREE + b], TC_EPI_WARPS); }
-        mbar_init(&bars[BAR_H1P], TC_EPI_WARPS); mbar_init(&bars[BAR_H1N], TC_EPI_WARPS);
-        mbar_init(&bars[BAR_H2P], TC_EPI_WARPS); mbar_init(&bars[BAR_H2N], TC_EPI_WARPS);
-        mbar_init(&bars[BAR_D2P], 1); mbar_init(&bars[BAR_D2N], 1); mbar_init(&bars[BAR_D3P], 1); mbar_init(&bars[BAR_D3N], 1);
+        for (int gq = 0; gq < 2; ++gq) {
+            mbar_init(&bars[BAR_D1_FULL + gq], 1); mbar_init(&bars[BAR_D1_FREE + gq], TC_GRP_WARPS);
+            mbar_init(&bars[BAR_H1P + gq], TC_GRP_WARPS); mbar_init(&bars[BAR_H1N + gq], TC_GRP_WARPS);
+            mbar_init(&bars[BAR_H2P + gq], TC_GRP_WARPS); mbar_init(&bars[BAR_H2N + gq], TC_GRP_WARPS);
+            mbar_init(&bars[BAR_D2P + gq], 1); mbar_init(&bars[BAR_D2N + gq], 1);
+            mbar_init(&bars[BAR_D3P + gq], 1); mbar_init(&bars[BAR_D3N + gq], 1);
+        }
         mbar_init(&bars[BAR_EPS_READY], TC_BLD_WARPS); mbar_init(&bars[BAR_W_READY], TC_BLD_WARPS);
-        mbar_init(&bars[BAR_EPS_FREE], 1); mbar_init(&bars[BAR_W_FREE], 1);
+        mbar_init(&bars[BAR_EPS_FREE], 1); mbar_init(&bars[BAR_W_FREE], 2);
         fence_barrier_init();
     }
     __syncthreads();                    // zero fill + barrier init visible to everyone
@@ -358,204 +365,210 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tm_d1[2] = {tmem, tmem + 128};
-    const uint32_t tm_d2p = tmem + 256, tm_d2n = tmem + 320, tm_d3p = tmem + 384, tm_d3n = tmem + 416;
-
+    // TMEM columns: V buffers 0-63 / 64-127; group g: D2+ 128+128g, D2- +64; D3+ 384+64g, D3- +32
     if (warp == 0) {
         // ===================== producer: observation tiles =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x)
+            for (int i = 0; i < my_pairs; ++i)
                 for (int m = 0; m < NMT; ++m)
                     for (int kc = 0; kc < NKC; ++kc) {
                         mbar_wait(&bars[BAR_EMPTY + stage], phase ^ 1);
                         if (p.dev_noload) { mbar_arrive(&bars[BAR_FULL + stage]); }
                         else {
-                        mbar_expect_tx(&bars[BAR_FULL + stage], TC_STAGE_BYTES);
-                        bulk_g2s(smem + L.a_stage + stage * TC_STAGE_BYTES,
-                                 (const uint8_t*)p.xnt + ((size_t)m * NKC + kc) * TC_STAGE_BYTES, TC_STAGE_BYTES,
-                                 &bars[BAR_FULL + stage]);
+                            mbar_expect_tx(&bars[BAR_FULL + stage], TC_STAGE_BYTES);
+                            bulk_g2s(smem + L.a_stage + stage * TC_STAGE_BYTES,
+                                     (const uint8_t*)p.xnt + ((size_t)m * NKC + kc) * TC_STAGE_BYTES, TC_STAGE_BYTES,
+                                     &bars[BAR_FULL + stage]);
                         }
                         if (++stage == TC_NST) { stage = 0; phase ^= 1; }
                     }
         }
     } else if (warp == 1) {
         // ===================== L1 MMA issuer (whole warp runs the loop; one elected lane issues) =====================
-        {
-            const uint32_t id_l1 = umma_idesc_bf16(TC_MT, 2 * TC_H);
-            const uint64_t a_desc0 = umma_desc_sw128(smem_u32(smem + L.a_stage)), b_desc0 = umma_desc_sw128(smem_u32(smem + L.b1));
-            uint32_t stage = 0, phase = 0, g = 0, i = 0;
-            for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x, ++i) {
-                mbar_wait(&bars[BAR_EPS_READY], i & 1);
-                for (int m = 0; m < NMT; ++m, ++g) {
-                    const uint32_t buf = g & 1, use = g >> 1;
-                    mbar_wait(&bars[BAR_D1_FREE + buf], (use & 1) ^ 1);       // epilogue has drained this D1 buffer
+        const uint32_t id_l1 = umma_idesc_bf16(TC_MT, TC_H);
+        const uint64_t a_desc0 = umma_desc_sw128(smem_u32(smem + L.a_stage)), b_desc0 = umma_desc_sw128(smem_u32(smem + L.b1));
+        uint32_t stage = 0, phase = 0, g = 0;
+        for (int i = 0; i < my_pairs; ++i) {
+            mbar_wait(&bars[BAR_EPS_READY], i & 1);
+            for (int m = 0; m < NMT; ++m, ++g) {
+                const uint32_t buf = g & 1, use = g >> 1;
+                mbar_wait(&bars[BAR_D1_FREE + buf], (use & 1) ^ 1);           // the group has drained this V buffer
+                tc_fence_after();
+                if (lane == 0) TC_TRACE(0, 4 * g + 0);
+                for (int kc = 0; kc < NKC; ++kc) {
+                    mbar_wait(&bars[BAR_FULL + stage], phase);
                     tc_fence_after();
-                    if (lane == 0) TC_TRACE(0, 4 * g + 0);
-                    for (int kc = 0; kc < NKC; ++kc) {
-                        mbar_wait(&bars[BAR_FULL + stage], phase);
-                        tc_fence_after();
-                        const uint64_t ad = a_desc0 + (uint64_t)stage * (TC_STAGE_BYTES >> 4);
-                        const uint64_t bd = b_desc0 + (uint64_t)kc * (TC_STAGE_BYTES >> 4);
-                        if (elect_one()) {
-                            tc_issue_l1_chunk(tm_d1[buf], ad, bd, id_l1, kc);
-                            umma_commit(&bars[BAR_EMPTY + stage]);           // stage reusable once these MMAs retire
-                            if (kc == NKC - 1) umma_commit(&bars[BAR_D1_FULL + buf]);
-                        }
-                        __syncwarp();
-                        // pace the stream: the tensor pipe runs MMAs in issue order, so a queue of L1 chunks would delay
-                        // the short L2/L3 MMAs (issued by warp TC_MMA2_WARP) that the epilogue is waiting for.  Keep at
-                        // most one chunk (4 MMAs) in flight: wait until this chunk has retired (its EMPTY commit fired).
-                        mbar_wait(&bars[BAR_EMPTY + stage], phase);
-                        if (++stage == TC_NST) { stage = 0; phase ^= 1; }
+                    const uint64_t ad = a_desc0 + (uint64_t)stage * (TC_STAGE_BYTES >> 4);
+                    const uint64_t bd = b_desc0 + (uint64_t)kc * (TC_B1_CHUNK_BYTES >> 4);
+                    if (elect_one()) {
+                        tc_issue_4k(tmem + buf * TC_H, ad, bd, id_l1, kc != 0);
+                        umma_commit(&bars[BAR_EMPTY + stage]);               // stage reusable once these MMAs retire
+                        if (kc == NKC - 1) umma_commit(&bars[BAR_D1_FULL + buf]);
                     }
-                    if (lane == 0) TC_TRACE(0, 4 * g + 1);
+                    __syncwarp();
+                    if (++stage == TC_NST) { stage = 0; phase ^= 1; }
                 }
-                if (elect_one()) umma_commit(&bars[BAR_EPS_FREE]);           // the pair's last L1 is in flight
-                __syncwarp();
+                if (lane == 0) TC_TRACE(0, 4 * g + 1);
             }
+            if (elect_one()) umma_commit(&bars[BAR_EPS_FREE]);               // the pair's last L1 is in flight
+            __syncwarp();
         }
-    } else if (warp == TC_MMA2_WARP) {
-        // ===================== L2 / L3 MMA issuer (warp-uniform loop, elected lane issues) =====================
-        {
-            const uint32_t id_l2 = umma_idesc_bf16(TC_MT, TC_H), id_l3 = umma_idesc_bf16(TC_MT, TC_ACT_PAD);
-            const uint64_t hp = umma_desc_sw128(smem_u32(smem + L.hp)), hn = umma_desc_sw128(smem_u32(smem + L.hn));
-            const uint64_t w2p = umma_desc_sw128(smem_u32(smem + L.w2p)), w2n = umma_desc_sw128(smem_u32(smem + L.w2n));
-            const uint64_t w3p = umma_desc_sw128(smem_u32(smem + L.w3p)), w3n = umma_desc_sw128(smem_u32(smem + L.w3n));
-            uint32_t g = 0, i = 0;
-            for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x, ++i) {
-                mbar_wait(&bars[BAR_W_READY], i & 1);
-                for (int m = 0; m < NMT; ++m, ++g) {
-                    const uint32_t par = g & 1;
-                    mbar_wait(&bars[BAR_H1P], par); tc_fence_after();
-                    if (elect_one()) { tc_issue_small(tm_d2p, hp, w2p, id_l2); umma_commit(&bars[BAR_D2P]); }
-                    __syncwarp();
-                    if (lane == 0) TC_TRACE(0, 4 * g + 2);
-                    mbar_wait(&bars[BAR_H1N], par); tc_fence_after();
-                    if (elect_one()) { tc_issue_small(tm_d2n, hn, w2n, id_l2); umma_commit(&bars[BAR_D2N]); }
-                    __syncwarp();
-                    mbar_wait(&bars[BAR_H2P], par); tc_fence_after();
-                    if (elect_one()) { tc_issue_small(tm_d3p, hp, w3p, id_l3); umma_commit(&bars[BAR_D3P]); }
-                    __syncwarp();
-                    if (lane == 0) TC_TRACE(0, 4 * g + 3);
-                    mbar_wait(&bars[BAR_H2N], par); tc_fence_after();
-                    if (elect_one()) { tc_issue_small(tm_d3n, hn, w3n, id_l3); umma_commit(&bars[BAR_D3N]); }
-                    __syncwarp();
-                }
-                if (elect_one()) umma_commit(&bars[BAR_W_FREE]);             // fires when the pair's last L3 retires
+    } else if (warp >= TC_MMA2_WARP0) {
+        // ===================== L2 / L3 MMA issuer of one epilogue group =====================
+        const uint32_t eg = warp - TC_MMA2_WARP0;
+        const uint32_t id_l2 = umma_idesc_bf16(TC_MT, TC_H), id_l3 = umma_idesc_bf16(TC_MT, TC_ACT_PAD);
+        const uint64_t hp = umma_desc_sw128(smem_u32(smem + L.h + (eg * 2 + 0) * TC_MT * 128));
+        const uint64_t hn = umma_desc_sw128(smem_u32(smem + L.h + (eg * 2 + 1) * TC_MT * 128));
+        const uint64_t w2p = umma_desc_sw128(smem_u32(smem + L.w2p)), w2n = umma_desc_sw128(smem_u32(smem + L.w2n));
+        const uint64_t w3p = umma_desc_sw128(smem_u32(smem + L.w3p)), w3n = umma_desc_sw128(smem_u32(smem + L.w3n));
+        const uint32_t d2p = tmem + 128 + eg * 128, d2n = d2p + 64, d3p = tmem + 384 + eg * 64, d3n = d3p + 32;
+        uint32_t k = 0;                                                       // tiles handled by this group so far
+        for (int i = 0; i < my_pairs; ++i) {
+            mbar_wait(&bars[BAR_W_READY], i & 1);
+            tc_fence_after();
+            for (uint32_t g = (uint32_t)i * NMT; g < (uint32_t)(i + 1) * NMT; ++g) {
+                if ((g & 1) != eg) continue;
+                const uint32_t par = k & 1;
+                ++k;
+                mbar_wait(&bars[BAR_H1P + eg], par); tc_fence_after();
+                if (elect_one()) { tc_issue_4k(d2p, hp, w2p, id_l2, 0); umma_commit(&bars[BAR_D2P + eg]); }
+                __syncwarp();
+                if (lane == 0) TC_TRACE(0, 4 * g + 2);
+                mbar_wait(&bars[BAR_H1N + eg], par); tc_fence_after();
+                if (elect_one()) { tc_issue_4k(d2n, hn, w2n, id_l2, 0); umma_commit(&bars[BAR_D2N + eg]); }
+                __syncwarp();
+                mbar_wait(&bars[BAR_H2P + eg], par); tc_fence_after();
+                if (elect_one()) { tc_issue_4k(d3p, hp, w3p, id_l3, 0); umma_commit(&bars[BAR_D3P + eg]); }
+                __syncwarp();
+                if (lane == 0) TC_TRACE(0, 4 * g + 3);
+                mbar_wait(&bars[BAR_H2N + eg], par); tc_fence_after();
+                if (elect_one()) { tc_issue_4k(d3n, hn, w3n, id_l3, 0); umma_commit(&bars[BAR_D3N + eg]); }
                 __syncwarp();
             }
+            if (elect_one()) umma_commit(&bars[BAR_W_FREE]);                 // this group's L2/L3 of the pair are in flight
+            __syncwarp();
         }
     } else if (warp < TC_BLD_WARP0) {
-        // ===================== epilogue warps =====================
-        const int we = warp - TC_EPI_WARP0;
-        const int q = warp & 3, hq = we >> 2;                 // TMEM lane quarter, column quarter (16 columns)
+        // ===================== epilogue warps (two groups on alternate tiles) =====================
+        const int ew = warp - TC_EPI_WARP0;                   // 0..15
+        const uint32_t eg = ew >> 3;                          // group
+        const int we = ew & 7;
+        const int q = warp & 3, h = we >> 2;                  // TMEM lane quarter, column half (32 columns)
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        const uint32_t hp_row = smem_u32(smem + L.hp + row * 128);
-        const uint32_t hn_row = smem_u32(smem + L.hn + row * 128);
+        const uint32_t hp_row = smem_u32(smem + L.h + (eg * 2 + 0) * TC_MT * 128 + row * 128);
+        const uint32_t hn_row = smem_u32(smem + L.h + (eg * 2 + 1) * TC_MT * 128 + row * 128);
         const int sw = row & 7;
-        const uint32_t ch0 = (uint32_t)(((2 * hq) ^ sw) << 4), ch1 = (uint32_t)(((2 * hq + 1) ^ sw) << 4);   // this warp's two 16-byte chunks
-        const bool has_act = hq * 8 < p.act;                  // L3: this warp owns action columns 8hq..8hq+7
-        uint32_t g = 0, i = 0;
-        for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x, ++i) {
+        const uint32_t tm_v = tmem + eg * TC_H + lane_base + h * 32;
+        const uint32_t tm_d2p = tmem + 128 + eg * 128 + lane_base + h * 32, tm_d2n = tm_d2p + 64;
+        const uint32_t tm_d3p = tmem + 384 + eg * 64 + lane_base + h * 16, tm_d3n = tm_d3p + 32;
+        const bool has_act = h * 16 < p.act;                  // L3: this warp owns action columns 16h..16h+15
+        const int j1 = 1 % p.act, j2 = 2 % p.act;
+        uint32_t k = 0;                                       // tiles handled by this group so far
+        for (int i = 0; i < my_pairs; ++i) {
+            const int pair = blockIdx.x + i * gridDim.x;
             const uint32_t bias = smem_u32(bias_all + (i & 1) * TC_BIAS_FLOATS);
-            const uint32_t b2p = bias + hq * 64, b2n = bias + TC_H * 4 + hq * 64;
-            const uint32_t b3p = bias + 2 * TC_H * 4 + hq * 32, b3n = bias + (2 * TC_H + TC_ACT_PAD) * 4 + hq * 32;
+            const uint32_t b2p = bias + h * 128, b2n = bias + TC_H * 4 + h * 128;
+            const uint32_t b3p = bias + 2 * TC_H * 4 + h * 64, b3n = bias + (2 * TC_H + TC_ACT_PAD) * 4 + h * 64;
             float fitp = 0.f, fitn = 0.f, pp0 = 0.f, pp1 = 0.f, pp2 = 0.f, pn0 = 0.f, pn1 = 0.f, pn2 = 0.f;
-            for (int m = 0; m < NMT; ++m, ++g) {
-                const uint32_t par = g & 1, buf = g & 1, use = g >> 1;
+            bool bias_ready = false;
+            for (uint32_t g = (uint32_t)i * NMT; g < (uint32_t)(i + 1) * NMT; ++g) {
+                if ((g & 1) != eg) continue;
+                const uint32_t par = k & 1;
+                ++k;
+                const int m = (int)(g - (uint32_t)i * NMT);
                 const int t = m * TC_MT + row;
-                // reward coefficients of this warp's action columns: issue the loads before any waiting
-                float cr[8];
-                {
-                    const float* __restrict__ crow = p.rew_vec + (size_t)(t < p.T ? t : 0) * p.act;
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) cr[jj] = (hq * 8 + jj < p.act) ? __ldg(crow + hq * 8 + jj) : 0.f;
-                }
-                // ---- epi1: z1+- = U +- V (bias folded into the MMA) ----
-                if (we == 0 && lane == 0) TC_TRACE(1, 8 * g + 0);
-                mbar_wait(&bars[BAR_D1_FULL + buf], use & 1);
-                if (we == 0 && lane == 0) TC_TRACE(1, 8 * g + 1);
+                const float4* __restrict__ up = reinterpret_cast<const float4*>(p.ubase) + ((size_t)(m * 2 + h) * 8) * TC_MT + row;
+                if (ew == 0 && lane == 0) TC_TRACE(1, 8 * g + 0);
+                mbar_wait(&bars[BAR_D1_FULL + eg], par);
+                if (ew == 0 && lane == 0) TC_TRACE(1, 8 * g + 1);
                 tc_fence_after();
-                uint32_t u[16], v[16];
-                tmem_ld16(tm_d1[buf] + lane_base + hq * 16, u);
-                tmem_ld16(tm_d1[buf] + lane_base + TC_H + hq * 16, v);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars[BAR_D1_FREE + buf]);   // U, V are in registers: the buffer may be refilled
-                {
-                    uint32_t w[8];
+                // ---- epi1: h1+ = tanh(U + V), then h1- = tanh(U - V) (V is re-read from TMEM: cheaper than 32 registers) ----
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        float z0, z1;
-                        add2(z0, z1, u[2 * e], u[2 * e + 1], v[2 * e], v[2 * e + 1]);
-                        w[e] = tanh2_pack(z0, z1);
-                    }
-                    sts128(hp_row + ch0, w[0], w[1], w[2], w[3]);
-                    sts128(hp_row + ch1, w[4], w[5], w[6], w[7]);
-                    warp_arrive_after_smem_writes(&bars[BAR_H1P], lane);
-                    if (lane == 0) TC_TRACE(2, 16 * g + we);
+                for (int sgn = 0; sgn < 2; ++sgn) {
+                    const uint32_t hrow = sgn ? hn_row : hp_row;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        float z0, z1;
-                        sub2(z0, z1, u[2 * e], u[2 * e + 1], v[2 * e], v[2 * e + 1]);
-                        w[e] = tanh2_pack(z0, z1);
+                    for (int c2 = 0; c2 < 2; ++c2) {
+                        // unperturbed pre-activation (float32; coalesced float4 loads, L1/L2 resident) and the perturbation V
+                        float4 ub[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) ub[c] = __ldg(up + (c2 * 4 + c) * TC_MT);
+                        uint32_t v[16];
+                        tmem_ld16(tm_v + c2 * 16, v);
+                        tmem_ld_wait();
+                        uint32_t w[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 u4 = ub[e >> 1];
+                            const float u0 = (e & 1) ? u4.z : u4.x, u1 = (e & 1) ? u4.w : u4.y;
+                            float z0, z1;
+                            if (sgn) sub2(z0, z1, __float_as_uint(u0), __float_as_uint(u1), v[2 * e], v[2 * e + 1]);
+                            else     add2(z0, z1, __float_as_uint(u0), __float_as_uint(u1), v[2 * e], v[2 * e + 1]);
+                            w[e] = tanh2_pack(z0, z1);
+                        }
+                        sts128(hrow + (((h * 4 + c2 * 2) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+                        sts128(hrow + (((h * 4 + c2 * 2 + 1) ^ sw) << 4), w[4], w[5], w[6], w[7]);
                     }
-                    sts128(hn_row + ch0, w[0], w[1], w[2], w[3]);
-                    sts128(hn_row + ch1, w[4], w[5], w[6], w[7]);
-                    warp_arrive_after_smem_writes(&bars[BAR_H1N], lane);
+                    if (sgn) {                                        // V fully consumed: the buffer may be refilled
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars[BAR_D1_FREE + eg]);
+                    }
+                    warp_arrive_after_smem_writes(&bars[(sgn ? BAR_H1N : BAR_H1P) + eg], lane);
                 }
-                if (we == 0 && lane == 0) TC_TRACE(1, 8 * g + 2);
-                if (m == 0) mbar_wait(&bars[BAR_W_READY], i & 1);      // biases of this pair are in place
+                if (ew == 0 && lane == 0) TC_TRACE(1, 8 * g + 2);
+                if (!bias_ready) { mbar_wait(&bars[BAR_W_READY], i & 1); bias_ready = true; }   // biases of this pair are in place
                 // ---- epi2 (+ then -): h2 = tanh(D2 + b2), overwrites this warp's part of H ----
 #pragma unroll
                 for (int sgn = 0; sgn < 2; ++sgn) {
-                    mbar_wait(&bars[sgn ? BAR_D2N : BAR_D2P], par);
-                    if (we == 0 && lane == 0) TC_TRACE(1, 8 * g + 3 + sgn);
-                    if (lane == 0 && sgn == 0) TC_TRACE(3, 16 * g + we);
+                    mbar_wait(&bars[(sgn ? BAR_D2N : BAR_D2P) + eg], par);
+                    if (ew == 0 && lane == 0) TC_TRACE(1, 8 * g + 3 + sgn);
                     tc_fence_after();
-                    uint32_t d[16];
-                    tmem_ld16((sgn ? tm_d2n : tm_d2p) + lane_base + hq * 16, d);
-                    tmem_ld_wait();
                     const uint32_t b2 = sgn ? b2n : b2p;
                     const uint32_t hrow = sgn ? hn_row : hp_row;
-                    uint32_t w[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float2 bb = lds64f(b2 + e * 8);
-                        float z0, z1;
-                        add2(z0, z1, d[2 * e], d[2 * e + 1], __float_as_uint(bb.x), __float_as_uint(bb.y));
-                        w[e] = tanh2_pack(z0, z1);
+                    for (int c2 = 0; c2 < 2; ++c2) {
+                        uint32_t d[16];
+                        tmem_ld16((sgn ? tm_d2n : tm_d2p) + c2 * 16, d);
+                        tmem_ld_wait();
+                        uint32_t w[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float2 bb = lds64f(b2 + (c2 * 16 + 2 * e) * 4);
+                            float z0, z1;
+                            add2(z0, z1, d[2 * e], d[2 * e + 1], __float_as_uint(bb.x), __float_as_uint(bb.y));
+                            w[e] = tanh2_pack(z0, z1);
+                        }
+                        sts128(hrow + (((h * 4 + c2 * 2) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+                        sts128(hrow + (((h * 4 + c2 * 2 + 1) ^ sw) << 4), w[4], w[5], w[6], w[7]);
                     }
-                    sts128(hrow + ch0, w[0], w[1], w[2], w[3]);
-                    sts128(hrow + ch1, w[4], w[5], w[6], w[7]);
                     tc_fence_before();
-                    warp_arrive_after_smem_writes(&bars[sgn ? BAR_H2N : BAR_H2P], lane);
+                    warp_arrive_after_smem_writes(&bars[(sgn ? BAR_H2N : BAR_H2P) + eg], lane);
                 }
-                // ---- epi3 (+ then -): a = tanh(D3 + b3); reward and position (columns 8hq..8hq+7) ----
+                // ---- epi3 (+ then -): a = tanh(D3 + b3); reward and position (action columns 16h..16h+15) ----
+                const float* __restrict__ ccol = p.crt + ((size_t)m * TC_ACT_PAD + h * 16) * TC_MT + row;   // coalesced, L1/L2 resident
 #pragma unroll
                 for (int sgn = 0; sgn < 2; ++sgn) {
-                    if (we == 0 && lane == 0 && sgn == 0) TC_TRACE(1, 8 * g + 5);
-                    mbar_wait(&bars[sgn ? BAR_D3N : BAR_D3P], par);
-                    if (we == 0 && lane == 0) TC_TRACE(1, 8 * g + 6 + sgn);
+                    if (ew == 0 && lane == 0 && sgn == 0) TC_TRACE(1, 8 * g + 5);
+                    mbar_wait(&bars[(sgn ? BAR_D3N : BAR_D3P) + eg], par);
+                    if (ew == 0 && lane == 0) TC_TRACE(1, 8 * g + 6 + sgn);
                     if (has_act) {
                         tc_fence_after();
-                        uint32_t d[8];
-                        tmem_ld8((sgn ? tm_d3n : tm_d3p) + lane_base + hq * 8, d);
+                        uint32_t d[16];
+                        tmem_ld16(sgn ? tm_d3n : tm_d3p, d);
                         tmem_ld_wait();
                         const uint32_t b3 = sgn ? b3n : b3p;
                         float r = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
 #pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) {
-                            const int j = hq * 8 + jj;
+                        for (int jj = 0; jj < 16; ++jj) {
+                            const int j = h * 16 + jj;
                             if (j < p.act) {
                                 const float a = tanh_fast(__uint_as_float(d[jj]) + lds32f(b3 + jj * 4));
-                                r = fmaf(a, cr[jj], r);
+                                r = fmaf(a, __ldg(ccol + jj * TC_MT), r);
                                 if (j == 0) q0 += a;
-                                if (j == 1 % p.act) q1 += a;
-                                if (j == 2 % p.act) q2 += a;
+                                if (j == j1) q1 += a;
+                                if (j == j2) q2 += a;
                             }
                         }
                         if (t < p.T) {
@@ -566,77 +579,80 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
                     }
                 }
             }
-            // ---- per-pair reduction over the epilogue threads ----
+            // ---- flush this warp's partial sums of the pair; the last of the 16 warps adds them in warp order ----
             float vals[8] = {fitp, fitn, pp0, pp1, pp2, pn0, pn1, pn2};
 #pragma unroll
-            for (int k = 0; k < 8; ++k) vals[k] = es_warp_sum(vals[k]);
-            float* red = red_all + (i & 1) * TC_EPI_WARPS * 8;
+            for (int kk = 0; kk < 8; ++kk) vals[kk] = es_warp_sum(vals[kk]);
             if (lane == 0) {
+                float* slot = p.partial + ((size_t)pair * TC_EPI_WARPS + ew) * 8;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) red[we * 8 + k] = vals[k];
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");     // epilogue warps only
-            if (we == 0 && lane == 0) {
-                float tot[8];
+                for (int kk = 0; kk < 8; ++kk) __stcg(slot + kk, vals[kk]);
+                __threadfence();
+                if (atomicAdd(p.tickets + pair, 1u) == TC_EPI_WARPS - 1) {
+                    __threadfence();
+                    float tot[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    float sacc = 0.f;
+                    for (int kk = 0; kk < 8; ++kk) tot[kk] = 0.f;
+                    const float* all = p.partial + (size_t)pair * TC_EPI_WARPS * 8;
+                    for (int w = 0; w < TC_EPI_WARPS; ++w)
 #pragma unroll
-                    for (int w = 0; w < TC_EPI_WARPS; ++w) sacc += red[w * 8 + k];
-                    tot[k] = sacc;
-                }
-                p.fit_pos[(size_t)pair * p.fit_stride] = (double)tot[0];
-                p.fit_neg[(size_t)pair * p.fit_stride] = (double)tot[1];
-                if (p.behv_pos) {
-                    p.behv_pos[pair * 3 + 0] = p.pos_scale * tot[2]; p.behv_pos[pair * 3 + 1] = p.pos_scale * tot[3];
-                    p.behv_pos[pair * 3 + 2] = p.pos_scale * tot[4];
-                    p.behv_neg[pair * 3 + 0] = p.pos_scale * tot[5]; p.behv_neg[pair * 3 + 1] = p.pos_scale * tot[6];
-                    p.behv_neg[pair * 3 + 2] = p.pos_scale * tot[7];
+                        for (int kk = 0; kk < 8; ++kk) tot[kk] += __ldcg(all + w * 8 + kk);
+                    p.fit_pos[(size_t)pair * p.fit_stride] = (double)tot[0];
+                    p.fit_neg[(size_t)pair * p.fit_stride] = (double)tot[1];
+                    if (p.behv_pos) {
+                        p.behv_pos[pair * 3 + 0] = p.pos_scale * tot[2]; p.behv_pos[pair * 3 + 1] = p.pos_scale * tot[3];
+                        p.behv_pos[pair * 3 + 2] = p.pos_scale * tot[4];
+                        p.behv_neg[pair * 3 + 0] = p.pos_scale * tot[5]; p.behv_neg[pair * 3 + 1] = p.pos_scale * tot[6];
+                        p.behv_neg[pair * 3 + 2] = p.pos_scale * tot[7];
+                    }
                 }
             }
         }
-    } else if (warp < TC_MMA2_WARP) {
+    } else {
         // ===================== builder warps: next pair's B operands =====================
         const int bw = warp - TC_BLD_WARP0, btid = tid - TC_BLD_WARP0 * 32;
         constexpr int BT = TC_BLD_WARPS * 32;
-        // theta1 half of B1 (rows 0..63 of every K chunk) is the same for every pair; column `obs` carries the bias
-        tc_build_l1_rows(smem + L.b1, 0, p.theta + p.w1, p.theta + p.b1, 1.0f, p.obs, NKC, bw, TC_BLD_WARPS, lane);
-        uint32_t i = 0;
         const float sg = p.sigma;
-        for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x, ++i) {
+        for (int i = 0; i < my_pairs; ++i) {
+            const int pair = blockIdx.x + i * gridDim.x;
             const float* __restrict__ eps = p.table + p.idx[pair];
             if (i > 0) mbar_wait(&bars[BAR_EPS_FREE], (i - 1) & 1);      // previous pair's last L1 has retired
-            tc_build_l1_rows(smem + L.b1, TC_H, eps + p.w1, eps + p.b1, sg, p.obs, NKC, bw, TC_BLD_WARPS, lane);
+            tc_build_l1_rows(smem + L.b1, eps + p.w1, eps + p.b1, sg, p.obs, NKC, bw, TC_BLD_WARPS, lane);
             warp_arrive_after_smem_writes(&bars[BAR_EPS_READY], lane);
-            if (pair + (int)gridDim.x < p.n_pairs) {                     // pull the next slice into L2 early
+            if (i + 1 < my_pairs) {                                      // pull the next slice into L2 early
                 const char* nxt = (const char*)(p.table + p.idx[pair + gridDim.x]);
                 const int lines = (p.b3 + p.act) * 4 / 128 + 2;
                 for (int l = btid; l < lines; l += BT) prefetch_l2(nxt + (size_t)l * 128);
             }
             // W2+-, W3+-, biases: loads first (registers), shared stores after the previous pair's last L3 retired
-            constexpr int NB2 = (TC_H * TC_H / 2 + BT - 1) / BT;          // 16 column pairs per thread
-            float e0[NB2], e1[NB2], t0[NB2], t1[NB2];
+            constexpr int NB2 = (TC_H * TC_H / 2 + BT - 1) / BT;          // column pairs per thread
+            constexpr int WB = 8;                                         // loads batched 8 pairs at a time (32 registers)
+            for (int b0 = 0; b0 < NB2; b0 += WB) {
+                float e0[WB], e1[WB], t0[WB], t1[WB];
 #pragma unroll
-            for (int b = 0; b < NB2; ++b) {
-                const int k2 = 2 * (btid + b * BT);
-                e0[b] = __ldg(eps + p.w2 + k2); e1[b] = __ldg(eps + p.w2 + k2 + 1);
-                t0[b] = __ldg(p.theta + p.w2 + k2); t1[b] = __ldg(p.theta + p.w2 + k2 + 1);
-            }
-            if (i > 0) mbar_wait(&bars[BAR_W_FREE], (i - 1) & 1);
+                for (int b = 0; b < WB; ++b) {
+                    const int k2 = min(2 * (btid + (b0 + b) * BT), TC_H * TC_H - 2);
+                    e0[b] = __ldg(eps + p.w2 + k2); e1[b] = __ldg(eps + p.w2 + k2 + 1);
+                    t0[b] = __ldg(p.theta + p.w2 + k2); t1[b] = __ldg(p.theta + p.w2 + k2 + 1);
+                }
+                if (b0 == 0 && i > 0) mbar_wait(&bars[BAR_W_FREE], (i - 1) & 1);   // previous pair's last L3 has retired
 #pragma unroll
-            for (int b = 0; b < NB2; ++b) {
-                const int k2 = 2 * (btid + b * BT);
-                const int n = k2 >> 6, k = k2 & 63;
-                const float d0 = __fmul_rn(sg, e0[b]), d1 = __fmul_rn(sg, e1[b]);
-                *(uint32_t*)(smem + L.w2p + sw128_off(n, k)) = pack_bf16x2(__fadd_rn(t0[b], d0), __fadd_rn(t1[b], d1));
-                *(uint32_t*)(smem + L.w2n + sw128_off(n, k)) = pack_bf16x2(__fadd_rn(t0[b], -d0), __fadd_rn(t1[b], -d1));
+                for (int b = 0; b < WB; ++b) {
+                    const int k2 = 2 * (btid + (b0 + b) * BT);
+                    if (b0 + b < NB2 && k2 < TC_H * TC_H) {
+                        const int n = k2 >> 6, kk = k2 & 63;
+                        const float d0 = __fmul_rn(sg, e0[b]), d1 = __fmul_rn(sg, e1[b]);
+                        *(uint32_t*)(smem + L.w2p + sw128_off(n, kk)) = pack_bf16x2(__fadd_rn(t0[b], d0), __fadd_rn(t1[b], d1));
+                        *(uint32_t*)(smem + L.w2n + sw128_off(n, kk)) = pack_bf16x2(__fadd_rn(t0[b], -d0), __fadd_rn(t1[b], -d1));
+                    }
+                }
             }
             for (int k2 = 2 * btid; k2 < p.act * TC_H; k2 += 2 * BT) {    // W3+- (rows >= act stay zero)
-                const int n = k2 >> 6, k = k2 & 63;
+                const int n = k2 >> 6, kk = k2 & 63;
                 const float d0 = __fmul_rn(sg, __ldg(eps + p.w3 + k2)), d1 = __fmul_rn(sg, __ldg(eps + p.w3 + k2 + 1));
                 const float x0 = __ldg(p.theta + p.w3 + k2), x1 = __ldg(p.theta + p.w3 + k2 + 1);
-                *(uint32_t*)(smem + L.w3p + sw128_off(n, k)) = pack_bf16x2(__fadd_rn(x0, d0), __fadd_rn(x1, d1));
-                *(uint32_t*)(smem + L.w3n + sw128_off(n, k)) = pack_bf16x2(__fadd_rn(x0, -d0), __fadd_rn(x1, -d1));
+                *(uint32_t*)(smem + L.w3p + sw128_off(n, kk)) = pack_bf16x2(__fadd_rn(x0, d0), __fadd_rn(x1, d1));
+                *(uint32_t*)(smem + L.w3n + sw128_off(n, kk)) = pack_bf16x2(__fadd_rn(x0, -d0), __fadd_rn(x1, -d1));
             }
             {
                 float* bias = bias_all + (i & 1) * TC_BIAS_FLOATS;
@@ -674,6 +690,33 @@ __global__ void rollout_tc_prep_kernel(const float* __restrict__ obsn, int T, in
     }
 }
 
+// U[t][n] = b1[n] + sum_k Xn[t][k] * theta1[n][k] in float32, k ascending (rows t >= T are zero): one block per row.
+// Output layout (float index): (((m*2 + h)*8 + c)*128 + row)*4 + e  for column n = 32h + 4c + e, t = 128m + row.
+__global__ void __launch_bounds__(TC_H) rollout_tc_ubase_kernel(const float* __restrict__ obsn, const float* __restrict__ theta,
+                                                                 int w1, int b1, int T, int obs, float* __restrict__ ubase) {
+    extern __shared__ float s_x[];
+    const int t = blockIdx.x, n = threadIdx.x;
+    const int m = t / TC_MT, row = t % TC_MT, h = n >> 5, c = (n & 31) >> 2, e = n & 3;
+    float* out = ubase + ((((size_t)(m * 2 + h) * 8 + c) * TC_MT + row) * 4 + e);
+    if (t >= T) { *out = 0.f; return; }
+    for (int k = n; k < obs; k += TC_H) s_x[k] = obsn[(size_t)t * obs + k];
+    __syncthreads();
+    const float* __restrict__ w = theta + w1 + (size_t)n * obs;
+    float acc = __ldg(theta + b1 + n);
+    for (int k = 0; k < obs; ++k) acc = fmaf(s_x[k], __ldg(w + k), acc);
+    *out = acc;
+}
+
+// reward vectors transposed per tile: crt[(m*32 + j)*128 + row] = rew_vec[128m + row][j] (0 beyond T / act)
+__global__ void rollout_tc_crt_kernel(const float* __restrict__ rew_vec, int T, int act, int n_mtiles, float* __restrict__ crt) {
+    const int total = n_mtiles * TC_ACT_PAD * TC_MT;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int row = i % TC_MT, j = (i / TC_MT) % TC_ACT_PAD, m = i / (TC_MT * TC_ACT_PAD);
+        const int t = m * TC_MT + row;
+        crt[i] = (t < T && j < act) ? rew_vec[(size_t)t * act + j] : 0.f;
+    }
+}
+
 }  // namespace
 
 int es_impl_rollout_tc(es_ctx* ctx, const float* table, int64_t table_len, const int64_t* idx, int n_pairs,
@@ -688,6 +731,7 @@ int es_impl_rollout_tc(es_ctx* ctx, const float* table, int64_t table_len, const
         return ES_ERR_UNSUPPORTED;
     }
     TcParams p;
+    memset(&p, 0, sizeof(p));
     p.table = table; p.idx = idx; p.theta = theta; p.rew_vec = rew_vec;
     p.fit_pos = fit_pos; p.fit_neg = fit_neg; p.behv_pos = behv_pos; p.behv_neg = behv_neg;
     p.n_pairs = n_pairs; p.obs = layer_sizes[0]; p.act = layer_sizes[3]; p.T = T; p.fit_stride = fit_stride;
@@ -696,27 +740,42 @@ int es_impl_rollout_tc(es_ctx* ctx, const float* table, int64_t table_len, const
     p.n_mtiles = es_div_up(T, TC_MT);
     p.w1 = 0; p.b1 = p.obs * TC_H; p.w2 = p.b1 + TC_H; p.b2 = p.w2 + TC_H * TC_H; p.w3 = p.b2 + TC_H;
     p.b3 = p.w3 + TC_H * p.act;
-
     p.trace = nullptr;
     p.dev_noload = getenv("ES_TC_NOLOAD") ? 1 : 0;
     if (const char* e = getenv("ES_TC_TRACE")) p.trace = (long long*)strtoull(e, nullptr, 0);   // device pointer, dev tooling only
+
     const TcSmemLayout L = tc_layout(p.nkc);
     const size_t smem = (size_t)L.total + 1024;       // + alignment slack
     if (smem > 227 * 1024) {
         es_set_error("es_rollout_openloop(TC): obs_dim %d needs %zu bytes of shared memory (> 227 KB)", p.obs, smem);
         return ES_ERR_UNSUPPORTED;
     }
-    // pre-tiled bf16 observation stream lives in the ctx scratch (768 KB for T=1000, obs=376)
+    // scratch: pre-tiled bf16 observation stream | float32 U base | per-pair partial sums | tickets
     const size_t xnt_bytes = (size_t)p.n_mtiles * p.nkc * TC_STAGE_BYTES;
+    const size_t ub_bytes = (size_t)p.n_mtiles * TC_MT * TC_H * sizeof(float);
+    const size_t crt_bytes = (size_t)p.n_mtiles * TC_ACT_PAD * TC_MT * sizeof(float);
+    const size_t part_bytes = (size_t)n_pairs * TC_EPI_WARPS * 8 * sizeof(float);
+    const size_t tick_bytes = ((size_t)n_pairs * sizeof(unsigned) + 255) & ~(size_t)255;
     void* scratch = nullptr;
-    int rc = es_ctx_scratch(ctx, xnt_bytes, &scratch);
+    int rc = es_ctx_scratch(ctx, xnt_bytes + ub_bytes + crt_bytes + part_bytes + tick_bytes, &scratch);
     if (rc) return rc;
     p.xnt = (const __nv_bfloat16*)scratch;
+    float* ubase = (float*)((char*)scratch + xnt_bytes);
+    p.ubase = ubase;
+    float* crt = (float*)((char*)scratch + xnt_bytes + ub_bytes);
+    p.crt = crt;
+    p.partial = (float*)((char*)scratch + xnt_bytes + ub_bytes + crt_bytes);
+    p.tickets = (unsigned*)((char*)scratch + xnt_bytes + ub_bytes + crt_bytes + part_bytes);
+    ES_CHECK_CUDA(cudaMemsetAsync(p.tickets, 0, tick_bytes, stream));
     {
         const size_t total = xnt_bytes / 2;
         int blocks = es_div_up((int64_t)total, 256);
         if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
         rollout_tc_prep_kernel<<<blocks, 256, 0, stream>>>(obsn, T, p.obs, p.nkc, p.n_mtiles, (__nv_bfloat16*)scratch);
+        ES_LAUNCHED(ctx);
+        rollout_tc_ubase_kernel<<<p.n_mtiles * TC_MT, TC_H, p.obs * sizeof(float), stream>>>(obsn, theta, p.w1, p.b1, T, p.obs, ubase);
+        ES_LAUNCHED(ctx);
+        rollout_tc_crt_kernel<<<es_div_up(p.n_mtiles * TC_ACT_PAD * TC_MT, 256), 256, 0, stream>>>(rew_vec, T, p.act, p.n_mtiles, crt);
         ES_LAUNCHED(ctx);
     }
     ES_CHECK_CUDA(cudaFuncSetAttribute(rollout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
