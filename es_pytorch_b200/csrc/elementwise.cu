@@ -53,31 +53,46 @@ int es_impl_normalise_obs(es_ctx* ctx, const float* obs, const double* mean, con
 }
 
 // ---- a14: float32 column sums in row order (src/gym/training_result.py:17-21) --------------------
-__global__ void colsum_kernel(const float* __restrict__ obs, int rows, int obs_dim, float* __restrict__ sum_out,
-                              float* __restrict__ sumsq_out) {
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= obs_dim) return;
+// block = 64 columns x 4 row-lanes; tiles of 64 rows are staged in shared memory with coalesced loads (the next tile is
+// prefetched into registers while the current one is summed); the sums themselves stay float32 in row order.
+constexpr int CS_COLS = 64, CS_ROWS = 64;
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ obs, int rows, int obs_dim,
+                                                     float* __restrict__ sum_out, float* __restrict__ sumsq_out) {
+    __shared__ float tile[CS_ROWS][CS_COLS + 1];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;          // column, row lane (0..3)
+    const int d = blockIdx.x * CS_COLS + tx;
+    const bool col_ok = d < obs_dim;
     float s = 0.f, q = 0.f;
-    constexpr int U = 16;                       // loads in flight per thread; the adds stay in row order
-    for (int r0 = 0; r0 < rows; r0 += U) {
-        float x[U];
+    float pre[CS_ROWS / 4];
+    auto load = [&](int r0) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) x[u] = (r0 + u < rows) ? __ldg(obs + (size_t)(r0 + u) * obs_dim + d) : 0.f;
+        for (int u = 0; u < CS_ROWS / 4; ++u) {
+            const int r = r0 + ty + 4 * u;
+            pre[u] = (col_ok && r < rows) ? __ldg(obs + (size_t)r * obs_dim + d) : 0.f;
+        }
+    };
+    load(0);
+    for (int r0 = 0; r0 < rows; r0 += CS_ROWS) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (r0 + u < rows) {
-                s = __fadd_rn(s, x[u]);
-                q = __fadd_rn(q, __fmul_rn(x[u], x[u]));
+        for (int u = 0; u < CS_ROWS / 4; ++u) tile[ty + 4 * u][tx] = pre[u];
+        __syncthreads();
+        if (r0 + CS_ROWS < rows) load(r0 + CS_ROWS);
+        if (ty == 0) {
+            const int n = min(CS_ROWS, rows - r0);
+            for (int r = 0; r < n; ++r) {
+                const float x = tile[r][tx];
+                s = __fadd_rn(s, x);
+                q = __fadd_rn(q, __fmul_rn(x, x));
             }
         }
+        __syncthreads();
     }
-    sum_out[d] = s;
-    sumsq_out[d] = q;
+    if (ty == 0 && col_ok) { sum_out[d] = s; sumsq_out[d] = q; }
 }
 
 int es_impl_obs_colsum(es_ctx* ctx, const float* obs, int rows, int obs_dim, float* sum_out, float* sumsq_out,
                        cudaStream_t stream) {
-    colsum_kernel<<<es_div_up(obs_dim, 64), 64, 0, stream>>>(obs, rows, obs_dim, sum_out, sumsq_out);
+    colsum_kernel<<<es_div_up(obs_dim, CS_COLS), 256, 0, stream>>>(obs, rows, obs_dim, sum_out, sumsq_out);
     ES_LAUNCHED(ctx);
     return ES_OK;
 }

@@ -88,23 +88,31 @@ mt_draw_kernel(uint32_t* __restrict__ mt_key, int32_t* __restrict__ mt_pos, int 
         __syncwarp();
 
         const int avail = MT_N - pos;
-        const int C = (avail + 31) >> 5;  // words per lane
+        const int C = (avail + 31) >> 5;  // words per lane (<= 20)
         const int b = pos + lane * C;
         const int e = min(MT_N, b + C);
+        const int len = max(0, e - b);
 
-        // (1) this lane's transition function
+        // accept bits of this lane's chunk, in a register: bit i <=> word b+i passes the masked rejection test
+        uint32_t am = 0;
+        for (int i = 0; i < len; ++i) am |= (uint32_t)((tw[b + i] & mask) <= rng) << i;
+
+        // (1) this lane's transition function, from the bit mask alone: skip s words, then repeatedly jump to the
+        //     next accept bit and skip `extra` words after it
         MtFn f;
 #pragma unroll
         for (int s = 0; s < MT_MAXS; ++s) {
-            int st = s, cn = 0;
+            int cur = s, cn = 0, st = 0;
             if (s < S) {
-                for (int i = b; i < e; ++i) {
-                    if (st == 0) {
-                        if ((tw[i] & mask) <= rng) { ++cn; st = extra; }
-                    } else {
-                        --st;
-                    }
+                while (cur < len) {
+                    const uint32_t m = am >> cur;
+                    if (m == 0) { cur = len; break; }
+                    cur += __ffs(m) + extra;          // accepted word at cur + ffs - 1, then `extra` words to skip
+                    ++cn;
                 }
+                st = cur - len;                       // words still to skip in the next chunk (0 = seeking)
+            } else {
+                st = s;
             }
             f.st[s] = (unsigned char)st;
             f.cn[s] = (unsigned short)cn;
@@ -137,21 +145,27 @@ mt_draw_kernel(uint32_t* __restrict__ mt_key, int32_t* __restrict__ mt_pos, int 
         }
         const int blk_state = src[31].st[state];
         const int blk_count = src[31].cn[state];
-        // (4) replay; stop where the machine is seeking and everything requested is out
+        // (4) replay with the mask; stop where the machine is seeking and everything requested is out
         int stop = MT_N;  // first unconsumed position if the stream ends inside this lane's chunk
-        for (int i = b; i < e; ++i) {
-            if (st == 0) {
-                if (base >= n_per_stream) { stop = i; break; }
-                const uint32_t v = tw[i] & mask;
-                if (v <= rng) {
-                    out[base] = (int64_t)v;
-                    ++base;
-                    st = extra;
+        {
+            int cur = 0;
+            // leading extra words of the previous lane's last draw
+            while (st > 0 && cur < len) {
+                if (xout && base - 1 < n_per_stream) xout[(size_t)(base - 1) * extra + (extra - st)] = tw[b + cur];
+                --st; ++cur;
+            }
+            while (cur < len) {                       // st == 0 here
+                if (base >= n_per_stream) { stop = b + cur; break; }
+                const uint32_t m = am >> cur;
+                if (m == 0) { cur = len; break; }
+                cur += __ffs(m) - 1;                  // position of the accepted word
+                out[base] = (int64_t)(tw[b + cur] & mask);
+                ++base; ++cur;
+                st = extra;
+                while (st > 0 && cur < len) {
+                    if (xout && base - 1 < n_per_stream) xout[(size_t)(base - 1) * extra + (extra - st)] = tw[b + cur];
+                    --st; ++cur;
                 }
-            } else {
-                // extra word (extra - st) of draw base-1
-                if (xout && base - 1 < n_per_stream) xout[(size_t)(base - 1) * extra + (extra - st)] = tw[i];
-                --st;
             }
         }
         // a lane whose chunk starts after the end also reports its start

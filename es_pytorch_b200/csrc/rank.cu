@@ -3,20 +3,24 @@
 //  src/utils/rankers.py:9-17,37-58,106-120).
 //
 // rank(x_i) = #{j : x_j < x_i} + #{j < i : x_j == x_i}  over x = concat(pos, neg)
-// which equals ``ranks[argsort(x, kind='stable')] = arange`` -- integer-exact, and the
-// count form shards: a GPU ranks only its own 2*k_count elements against all 2K keys.
-// Keys are the float64 fitnesses mapped to order-preserving uint64 (-0.0 == +0.0 and
-// NaNs last, like numpy's sort), so the O(n * n_local) inner loop is integer compares.
-//   1. rank_keys_kernel      fitness -> keys[n_obj][2K]
-//   2. rank_count_kernel     counts (int atomics: order-independent -> deterministic)
-//   3. rank_finalize_kernel  y = float32(rank)/(2K-1) - 0.5, blend, weight = y+ - y-
-// The float32 ops are the reference's, one IEEE operation each (no contraction).
+// which equals ``ranks[argsort(x, kind='stable')] = arange`` -- integer-exact.
+// The float64 fitnesses are mapped to order-preserving uint64 keys (-0.0 == +0.0, NaNs last, like numpy's sort) and
+// ranked exactly in O(n) expected work with a monotone value bucketing (any non-decreasing bucket function is
+// correct; balance only affects speed):
+//   1. rank_keys_kernel     keys[n_obj][2K] + min/max of the finite values
+//   2. rank_hist_kernel     bucket histogram (RK_BUCKETS linear buckets over [min, max]; -inf first, +inf/NaN last)
+//   3. rank_scan_kernel     exclusive scan of the histogram (one block per objective)
+//   4. rank_scatter_kernel  (key, index) pairs grouped by bucket
+//   5. rank_local_kernel    rank = bucket start + #{(key_j, j) < (key_i, i) inside the bucket}, only for the
+//                           elements of this GPU's shard [k_begin, k_begin+k_count) -- ranks are global
+//   6. rank_finalize_kernel y = float32(rank)/(2K-1) - 0.5, blend, weight = y+ - y-
+// The float32 ops are the reference's, one IEEE operation each (no contraction).  Steps 1-4 are replicated on every
+// GPU (O(2K)), step 5 is O(shard * bucket occupancy): the cost no longer grows with the number of GPUs.
 #include "common.cuh"
 
 constexpr int RK_THREADS = 256;
-constexpr int RK_EPT = 4;          // elements ranked per thread
-constexpr int RK_JTILE = 1024;     // keys staged in shared memory per step
-constexpr int RK_JCHUNK = 1024;    // keys per CTA along j (grid.y = 2K / RK_JCHUNK)
+constexpr int RK_BUCKETS = 8192;        // linear value buckets (+2 edge buckets)
+constexpr int RK_NB = RK_BUCKETS + 2;
 
 __device__ __forceinline__ unsigned long long rk_key(double x) {
     if (x != x) return 0xFFFFFFFFFFFFFFFFull;     // NaN sorts last
@@ -24,14 +28,109 @@ __device__ __forceinline__ unsigned long long rk_key(double x) {
     if ((b << 1) == 0ull) b = 0ull;               // -0.0 -> +0.0 (they compare equal)
     return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
+__device__ __forceinline__ double rk_unkey(unsigned long long k) {
+    const unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+struct RkStats { unsigned long long kmin, kmax; };    // keys of the smallest / largest finite value (per objective)
+
+__device__ __forceinline__ double rk_value(const double* __restrict__ fpos, const double* __restrict__ fneg, int K,
+                                           int n_obj, int c, int e) {
+    return (e < K) ? fpos[(size_t)e * n_obj + c] : fneg[(size_t)(e - K) * n_obj + c];
+}
 
 __global__ void rank_keys_kernel(const double* __restrict__ fpos, const double* __restrict__ fneg, int K, int n_obj,
-                                 unsigned long long* __restrict__ keys) {
+                                 unsigned long long* __restrict__ keys, RkStats* __restrict__ stats) {
     const int n = 2 * K;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * n_obj; i += gridDim.x * blockDim.x) {
-        const int c = i / n, e = i - c * n;
-        const double x = (e < K) ? fpos[(size_t)e * n_obj + c] : fneg[(size_t)(e - K) * n_obj + c];
-        keys[i] = rk_key(x);
+    const int c = blockIdx.y;
+    unsigned long long lo = 0xFFFFFFFFFFFFFFFFull, hi = 0ull;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const double x = rk_value(fpos, fneg, K, n_obj, c, e);
+        const unsigned long long k = rk_key(x);
+        keys[(size_t)c * n + e] = k;
+        if (isfinite(x)) { lo = min(lo, k); hi = max(hi, k); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (lo != 0xFFFFFFFFFFFFFFFFull) atomicMin(&stats[c].kmin, lo);
+        if (hi != 0ull) atomicMax(&stats[c].kmax, hi);
+    }
+}
+
+// monotone (non-decreasing in x) bucket index in [0, RK_NB)
+__device__ __forceinline__ int rk_bucket(unsigned long long key, double mn, double scale) {
+    if (key == 0xFFFFFFFFFFFFFFFFull) return RK_NB - 1;              // NaN
+    const double x = rk_unkey(key);
+    if (x == -INFINITY) return 0;
+    if (x == INFINITY) return RK_NB - 1;
+    int b = (int)((x - mn) * scale);
+    b = b < 0 ? 0 : (b > RK_BUCKETS - 1 ? RK_BUCKETS - 1 : b);
+    return 1 + b;
+}
+__device__ __forceinline__ void rk_range(const RkStats& st, double& mn, double& scale) {
+    if (st.kmin > st.kmax) { mn = 0.0; scale = 0.0; return; }          // no finite value
+    mn = rk_unkey(st.kmin);
+    const double mx = rk_unkey(st.kmax), span = mx - mn;
+    scale = (span > 0.0 && isfinite(span)) ? (double)RK_BUCKETS / span : 0.0;
+    if (!isfinite(scale)) scale = 0.0;
+}
+
+__global__ void rank_hist_kernel(const unsigned long long* __restrict__ keys, int n, const RkStats* __restrict__ stats,
+                                 unsigned* __restrict__ hist) {
+    const int c = blockIdx.y;
+    double mn, scale;
+    rk_range(stats[c], mn, scale);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+        atomicAdd(&hist[(size_t)c * RK_NB + rk_bucket(keys[(size_t)c * n + e], mn, scale)], 1u);
+}
+
+// one block per objective: start[b] = sum_{b' < b} hist[b'];  cursor[b] = 0
+__global__ void __launch_bounds__(1024) rank_scan_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ start,
+                                                         unsigned* __restrict__ cursor) {
+    __shared__ unsigned s_part[1024];
+    const int c = blockIdx.x, t = threadIdx.x;
+    constexpr int PER = (RK_NB + 1023) / 1024;
+    unsigned loc[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int b = t * PER + i;
+        loc[i] = (b < RK_NB) ? hist[(size_t)c * RK_NB + b] : 0u;
+        sum += loc[i];
+    }
+    s_part[t] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const unsigned v = (t >= o) ? s_part[t - o] : 0u;
+        __syncthreads();
+        s_part[t] += v;
+        __syncthreads();
+    }
+    unsigned run = s_part[t] - sum;                                      // exclusive prefix of this thread's buckets
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int b = t * PER + i;
+        if (b < RK_NB) { start[(size_t)c * RK_NB + b] = run; cursor[(size_t)c * RK_NB + b] = 0u; }
+        run += loc[i];
+    }
+}
+
+__global__ void rank_scatter_kernel(const unsigned long long* __restrict__ keys, int n, const RkStats* __restrict__ stats,
+                                    const unsigned* __restrict__ start, unsigned* __restrict__ cursor,
+                                    unsigned long long* __restrict__ skeys, int* __restrict__ sidx) {
+    const int c = blockIdx.y;
+    double mn, scale;
+    rk_range(stats[c], mn, scale);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const unsigned long long k = keys[(size_t)c * n + e];
+        const int b = rk_bucket(k, mn, scale);
+        const unsigned at = start[(size_t)c * RK_NB + b] + atomicAdd(&cursor[(size_t)c * RK_NB + b], 1u);
+        skeys[(size_t)c * n + at] = k;
+        sidx[(size_t)c * n + at] = e;
     }
 }
 
@@ -41,51 +140,25 @@ __device__ __forceinline__ int rk_global_index(int e, int K, int k_begin, int k_
     return (e < k_count) ? (k_begin + e) : (K + k_begin + (e - k_count));
 }
 
-__global__ void __launch_bounds__(RK_THREADS)
-rank_count_kernel(const unsigned long long* __restrict__ keys, int K, int k_begin, int k_count,
-                  int* __restrict__ ranks /*[n_obj][2*k_count]*/) {
-    __shared__ unsigned long long s_keys[RK_JTILE];
-    const int n = 2 * K;
-    const int n_local = 2 * k_count;
-    const int c = blockIdx.z;
-    const unsigned long long* kc = keys + (size_t)c * n;
-
-    unsigned long long mykey[RK_EPT];
-    int myidx[RK_EPT];
-    int cnt[RK_EPT];
-    const int e0 = (blockIdx.x * RK_THREADS + threadIdx.x) * RK_EPT;
-#pragma unroll
-    for (int r = 0; r < RK_EPT; ++r) {
-        const int e = e0 + r;
-        cnt[r] = 0;
-        if (e < n_local) {
-            myidx[r] = rk_global_index(e, K, k_begin, k_count);
-            mykey[r] = kc[myidx[r]];
-        } else {
-            myidx[r] = -1;          // counts nothing: no j satisfies j < -1, key 0 has nothing below
-            mykey[r] = 0ull;
+__global__ void rank_local_kernel(const unsigned long long* __restrict__ keys, int K, int k_begin, int k_count,
+                                  const RkStats* __restrict__ stats, const unsigned* __restrict__ hist,
+                                  const unsigned* __restrict__ start, const unsigned long long* __restrict__ skeys,
+                                  const int* __restrict__ sidx, int* __restrict__ ranks /*[n_obj][2*k_count]*/) {
+    const int n = 2 * K, n_local = 2 * k_count, c = blockIdx.y;
+    double mn, scale;
+    rk_range(stats[c], mn, scale);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_local; e += gridDim.x * blockDim.x) {
+        const int gi = rk_global_index(e, K, k_begin, k_count);
+        const unsigned long long k = keys[(size_t)c * n + gi];
+        const int b = rk_bucket(k, mn, scale);
+        const unsigned s0 = start[(size_t)c * RK_NB + b], cnt = hist[(size_t)c * RK_NB + b];
+        int r = (int)s0;
+        for (unsigned j = 0; j < cnt; ++j) {
+            const unsigned long long kj = skeys[(size_t)c * n + s0 + j];
+            const int ij = sidx[(size_t)c * n + s0 + j];
+            r += (kj < k) || (kj == k && ij < gi);
         }
-    }
-
-    const int j_begin = blockIdx.y * RK_JCHUNK;
-    const int j_end = min(n, j_begin + RK_JCHUNK);
-    for (int jt = j_begin; jt < j_end; jt += RK_JTILE) {
-        const int m = min(RK_JTILE, j_end - jt);
-        __syncthreads();
-        for (int t = threadIdx.x; t < m; t += RK_THREADS) s_keys[t] = kc[jt + t];
-        __syncthreads();
-#pragma unroll 4
-        for (int t = 0; t < m; ++t) {
-            const unsigned long long kj = s_keys[t];
-            const int j = jt + t;
-#pragma unroll
-            for (int r = 0; r < RK_EPT; ++r) cnt[r] += (kj < mykey[r]) || (kj == mykey[r] && j < myidx[r]);
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < RK_EPT; ++r) {
-        const int e = e0 + r;
-        if (e < n_local && cnt[r]) atomicAdd(&ranks[(size_t)c * n_local + e], cnt[r]);
+        ranks[(size_t)c * n_local + e] = r;
     }
 }
 
@@ -116,31 +189,47 @@ __global__ void rank_finalize_kernel(const int* __restrict__ ranks, int K, int n
 int es_impl_centered_rank(es_ctx* ctx, const double* fpos, const double* fneg, int K, int n_obj, float w0, float w1,
                           int k_begin, int k_count, float* weights_out, int32_t* ranks_out, cudaStream_t stream) {
     const size_t n = 2 * (size_t)K, n_local = 2 * (size_t)k_count;
-    const size_t key_bytes = n * n_obj * sizeof(unsigned long long);
-    const size_t rank_bytes = n_local * n_obj * sizeof(int);
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t key_b = al(n * n_obj * 8), skey_b = key_b, sidx_b = al(n * n_obj * 4);
+    const size_t tab_b = al((size_t)RK_NB * n_obj * 4), stat_b = al(sizeof(RkStats) * n_obj);
+    const size_t rank_b = al(n_local * n_obj * 4);
     void* scratch = nullptr;
-    int rc = es_ctx_scratch(ctx, key_bytes + rank_bytes, &scratch);
+    int rc = es_ctx_scratch(ctx, key_b + skey_b + sidx_b + 3 * tab_b + stat_b + rank_b, &scratch);
     if (rc) return rc;
-    unsigned long long* keys = (unsigned long long*)scratch;
-    int* ranks = (int*)((char*)scratch + key_bytes);
+    char* base = (char*)scratch;
+    unsigned long long* keys = (unsigned long long*)base;   base += key_b;
+    unsigned long long* skeys = (unsigned long long*)base;  base += skey_b;
+    int* sidx = (int*)base;                                 base += sidx_b;
+    unsigned* hist = (unsigned*)base;                       base += tab_b;
+    unsigned* start = (unsigned*)base;                      base += tab_b;
+    unsigned* cursor = (unsigned*)base;                     base += tab_b;
+    RkStats* stats = (RkStats*)base;                        base += stat_b;
+    int* ranks = (int*)base;
 
-    ES_CHECK_CUDA(cudaMemsetAsync(ranks, 0, rank_bytes, stream));
+    // kmin = all ones / kmax = 0 ("no finite value yet"), histogram = 0
+    ES_CHECK_CUDA(cudaMemsetAsync(hist, 0, tab_b, stream));
+    ES_CHECK_CUDA(cudaMemsetAsync(stats, 0xFF, stat_b, stream));
+    for (int c = 0; c < n_obj; ++c)
+        ES_CHECK_CUDA(cudaMemsetAsync(&stats[c].kmax, 0, sizeof(unsigned long long), stream));
+    int blocks = es_div_up((int64_t)n, RK_THREADS);
+    if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
+    dim3 grid(blocks, n_obj);
+    rank_keys_kernel<<<grid, RK_THREADS, 0, stream>>>(fpos, fneg, K, n_obj, keys, stats);
+    ES_LAUNCHED(ctx);
+    rank_hist_kernel<<<grid, RK_THREADS, 0, stream>>>(keys, (int)n, stats, hist);
+    ES_LAUNCHED(ctx);
+    rank_scan_kernel<<<n_obj, 1024, 0, stream>>>(hist, start, cursor);
+    ES_LAUNCHED(ctx);
+    rank_scatter_kernel<<<grid, RK_THREADS, 0, stream>>>(keys, (int)n, stats, start, cursor, skeys, sidx);
+    ES_LAUNCHED(ctx);
     {
-        int blocks = es_div_up((int64_t)n * n_obj, RK_THREADS);
-        if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-        rank_keys_kernel<<<blocks, RK_THREADS, 0, stream>>>(fpos, fneg, K, n_obj, keys);
+        int lb = es_div_up((int64_t)n_local, 128);
+        if (lb > ctx->sm_count * 16) lb = ctx->sm_count * 16;
+        rank_local_kernel<<<dim3(lb, n_obj), 128, 0, stream>>>(keys, K, k_begin, k_count, stats, hist, start, skeys, sidx, ranks);
         ES_LAUNCHED(ctx);
     }
-    {
-        dim3 grid(es_div_up((int64_t)n_local, RK_THREADS * RK_EPT), es_div_up((int64_t)n, RK_JCHUNK), n_obj);
-        ES_REQUIRE(grid.y <= 65535, "es_centered_rank: K too large for this kernel");
-        rank_count_kernel<<<grid, RK_THREADS, 0, stream>>>(keys, K, k_begin, k_count, ranks);
-        ES_LAUNCHED(ctx);
-    }
-    {
-        rank_finalize_kernel<<<es_div_up(k_count, RK_THREADS), RK_THREADS, 0, stream>>>(ranks, K, n_obj, w0, w1, k_count,
-                                                                                       weights_out, ranks_out);
-        ES_LAUNCHED(ctx);
-    }
+    rank_finalize_kernel<<<es_div_up(k_count, RK_THREADS), RK_THREADS, 0, stream>>>(ranks, K, n_obj, w0, w1, k_count,
+                                                                                   weights_out, ranks_out);
+    ES_LAUNCHED(ctx);
     return ES_OK;
 }

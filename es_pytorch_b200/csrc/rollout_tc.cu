@@ -342,7 +342,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NMT = p.n_mtiles, NKC = p.nkc;
     const int my_pairs = (p.n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // pairs of this CTA
-    const uint32_t total_tiles = (uint32_t)my_pairs * NMT;
 
     // ---- one-time setup -------------------------------------------------------------------------
     for (uint32_t i = tid * 16; i < L.bars; i += TC_THREADS * 16) *(uint4*)(smem + i) = make_uint4(0, 0, 0, 0);

@@ -48,7 +48,7 @@ for g in range(2):
 th = gen.theta.clone(); allth = torch.empty(comm.size, P, device=eng.device)
 comm.allgather_into(allth, th)
 assert torch.equal(allth[0], allth[comm.size - 1])
-print('MULTI_OK', comm.rank)
+os.write(1, ('MULTI_OK_%d\\n' % comm.rank).encode())
 '''
 
 
@@ -63,4 +63,4 @@ def test_two_gpu_generation(tmp_path):
                           '--master-addr', '127.0.0.1', '--master-port', str(port), str(script)],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
-    assert 'MULTI_OK 0' in out.stdout and 'MULTI_OK 1' in out.stdout
+    assert 'MULTI_OK_0' in out.stdout and 'MULTI_OK_1' in out.stdout

@@ -217,7 +217,7 @@ send = np.tile(np.arange(3, dtype=np.float64) + 10 * c.rank, 2)
 recv = np.empty(6)
 c.Alltoall(send, recv)
 assert (recv == np.concatenate([np.arange(3), np.arange(3) + 10])).all()
-print('RANK_OK', comm.rank)
+os.write(1, ('RANK_OK_%d\\n' % comm.rank).encode())
 '''
 
 
@@ -232,4 +232,4 @@ def test_two_process_gloo(tmp_path):
                           '--master-addr', '127.0.0.1', '--master-port', str(port), str(script)],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
-    assert 'RANK_OK 0' in out.stdout and 'RANK_OK 1' in out.stdout
+    assert 'RANK_OK_0' in out.stdout and 'RANK_OK_1' in out.stdout
