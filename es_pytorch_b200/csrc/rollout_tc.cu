@@ -18,7 +18,7 @@
 //   L3:   D3+- (128 x 32) = h2+- . (theta3 +- sigma*eps3)^T ;  epi3: a = tanh(D3 + b3),
 //         r_t = <a_t, c_t>, fitness += r_t, pos += a_t[0..2]
 //
-// Warp roles (736 threads, warp-specialised; mbarrier pipelines only, no CTA-wide barrier in the loop):
+// Warp roles (800 threads, warp-specialised; mbarrier pipelines only, no CTA-wide barrier in the loop):
 //   warp 0       producer: cp.async.bulk of the observation stages (ring of TC_NST x 16 KB)
 //   warp 1       L1 MMA issuer and TMEM owner (warp-uniform loop, one elected lane issues, so the
 //                descriptors live in uniform registers).  V is double-buffered in TMEM.
@@ -26,10 +26,13 @@
 //                separate H buffers, TMEM regions and barriers, so one group's waits for its short L2/L3
 //                MMAs are filled by the other group's MUFU/ALU work.  Inside a group the + and - sign
 //                chains are interleaved.  TMEM lane quarter = warp % 4, column half = ((warp-2) % 8) / 4.
-//   warps 18-20  builders: convert the NEXT pair's noise slice (float32, arbitrary 4-byte alignment in
-//                the table, which rules out TMA/bulk copies of the slice itself) into the bf16 swizzled
-//                B operands as soon as the current pair's last L1 (resp. last L3) has retired.
-//   warps 21-22  L2/L3 MMA issuers, one per epilogue group (blocking mbarrier waits, no polling).
+//   warps 18-21  builders: while pair i computes, convert pair i+1's noise slice (float32, arbitrary 4-byte
+//                alignment in the table, which rules out TMA/bulk copies of the slice itself) into a bf16,
+//                pre-swizzled IMAGE of the B operands in an L2-resident scratch (the loads are latency-bound:
+//                ~3k cycles per row pair).  When pair i's last L1 (resp. last L3) has retired, the image is
+//                moved into shared memory with a few cp.async.bulk copies (~2k cycles instead of ~15k).
+//   warps 22-23  L2/L3 MMA issuers, one per epilogue group (blocking mbarrier waits, no polling).
+//   warp 24      copier: moves a finished operand image into shared memory (2-slot ring with the builders).
 // Per-pair fitness: every epilogue warp writes its partial sums to a scratch slot; the last of the 16 to
 // arrive (atomic ticket) adds them in warp order -> deterministic.
 //
@@ -42,8 +45,9 @@
 
 namespace {
 
-constexpr int TC_THREADS = 736;     // 23 warps
-constexpr int TC_EPI_WARP0 = 2, TC_GRP_WARPS = 8, TC_EPI_WARPS = 16, TC_BLD_WARP0 = 18, TC_BLD_WARPS = 3, TC_MMA2_WARP0 = 21;
+constexpr int TC_THREADS = 800;     // 25 warps
+constexpr int TC_EPI_WARP0 = 2, TC_GRP_WARPS = 8, TC_EPI_WARPS = 16, TC_BLD_WARP0 = 18, TC_BLD_WARPS = 4, TC_MMA2_WARP0 = 22,
+              TC_COPY_WARP = 24;
 constexpr int TC_H = 64;            // hidden width (both hidden layers)
 constexpr int TC_MT = 128;          // time steps per M tile
 constexpr int TC_KC = 64;           // K elements per chunk (= 128 bytes of bf16 = one swizzle row)
@@ -236,11 +240,12 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int k /*0..63*/) {
 // addresses clamped instead of branching) and every shared store is one conflict-free 4-byte word of a swizzled row.
 constexpr int TC_B1_CHUNK_BYTES = TC_H * 128;          // 8 KB
 __device__ __forceinline__ void tc_build_l1_rows(uint8_t* b1_base, const float* __restrict__ w,
-                                                 const float* __restrict__ bvec, float scale, int obs, int nkc, int warp,
-                                                 int nwarps, int lane) {
-    constexpr int KB = 4;
+                                                 const float* __restrict__ bvec, float scale, int obs, int nkc,
+                                                 int pair_begin, int pair_end, int worker, int nworkers, int lane) {
+    constexpr int KB = 8;                                  // K chunks per batch: 32 independent loads in flight per lane
     const int c0 = 2 * lane;
-    for (int n = 2 * warp; n < TC_H; n += 2 * nwarps) {
+    for (int rp = pair_begin + worker; rp < pair_end; rp += nworkers) {     // row pair (2rp, 2rp+1)
+        const int n = 2 * rp;
         const float* __restrict__ wa = w + (size_t)n * obs;
         const float* __restrict__ wb = wa + obs;
         const float ba = __ldg(bvec + n), bb = __ldg(bvec + n + 1);
@@ -268,6 +273,10 @@ __device__ __forceinline__ void tc_build_l1_rows(uint8_t* b1_base, const float* 
     }
 }
 
+// split of the 32 row pairs of sigma*eps1 between the builder warps (start early) and the epilogue warps (join when
+// they have finished the current pair's tiles and would otherwise idle until the next pair's first L1)
+constexpr int TC_BLD_ROWPAIRS = 16;
+
 struct TcParams {
     const float* table;
     const int64_t* idx;
@@ -277,6 +286,7 @@ struct TcParams {
                                   // chunk is 32 consecutive float4 (coalesced), each thread still owns its row's 32 columns
     const float* crt;             // reward vectors transposed per tile: [n_mtiles][32 cols][128 rows] (zero padded)
     const float* rew_vec;         // [T][act]
+    uint8_t* images;              // [gridDim.x][2][image bytes]: pre-swizzled bf16 operand images built one pair ahead
     float* partial;               // [n_pairs][16 warps][8] per-pair partial sums
     unsigned* tickets;            // [n_pairs] zeroed before launch
     double* fit_pos;
@@ -309,17 +319,34 @@ __host__ __device__ inline TcSmemLayout tc_layout(int nkc) {
     L.w3n = o;      o += TC_ACT_PAD * 128;
     o = (o + 1023) & ~1023u;
     L.h = o;        o += 4 * TC_MT * 128;                        // [group][sign] 16 KB each
-    L.bias = o;     o += 2 * TC_BIAS_FLOATS * 4;                 // double-buffered by pair parity
+    L.bias = o;     o += 2 * 1024;                               // double-buffered by pair parity (1 KB blocks)
     L.bars = o;     o += 512;
     L.total = o;
     return L;
 }
 
+// operand image in global scratch: [B1: nkc x 8 KB][W2+ 8 KB][W2- 8 KB][W3+ 4 KB][W3- 4 KB][bias 1 KB]
+struct TcImage { uint32_t b1, w2p, w2n, w3p, w3n, bias, total; };
+__host__ __device__ inline TcImage tc_image(int nkc) {
+    TcImage I;
+    uint32_t o = 0;
+    I.b1 = o;   o += (uint32_t)nkc * TC_B1_CHUNK_BYTES;
+    I.w2p = o;  o += TC_H * 128;
+    I.w2n = o;  o += TC_H * 128;
+    I.w3p = o;  o += TC_ACT_PAD * 128;
+    I.w3n = o;  o += TC_ACT_PAD * 128;
+    I.bias = o; o += 1024;
+    I.total = o;
+    return I;
+}
+static_assert(TC_BIAS_FLOATS * 4 <= 1024, "bias block");
+
 // barrier indices; per-group sets are laid out [kind][group]
 enum { BAR_FULL = 0, BAR_EMPTY = TC_NST, BAR_D1_FULL = 2 * TC_NST, BAR_D1_FREE = BAR_D1_FULL + 2,
        BAR_H1P = BAR_D1_FREE + 2, BAR_H1N = BAR_H1P + 2, BAR_D2P = BAR_H1N + 2, BAR_D2N = BAR_D2P + 2,
        BAR_H2P = BAR_D2N + 2, BAR_H2N = BAR_H2P + 2, BAR_D3P = BAR_H2N + 2, BAR_D3N = BAR_D3P + 2,
-       BAR_EPS_READY = BAR_D3N + 2, BAR_EPS_FREE, BAR_W_READY, BAR_W_FREE, BAR_COUNT };
+       BAR_EPS_READY = BAR_D3N + 2, BAR_EPS_FREE, BAR_W_READY, BAR_W_FREE, BAR_IMG_READY, BAR_IMG_FREE = BAR_IMG_READY + 2,
+       BAR_COUNT = BAR_IMG_FREE + 2 };
 static_assert(BAR_COUNT * 8 + 16 <= 512, "barrier block too small");
 
 // Descriptors are precomputed once (64-bit); stepping 16 bf16 (32 B) along K inside a 128B-swizzled row is +2 in the
@@ -354,8 +381,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
             mbar_init(&bars[BAR_D2P + gq], 1); mbar_init(&bars[BAR_D2N + gq], 1);
             mbar_init(&bars[BAR_D3P + gq], 1); mbar_init(&bars[BAR_D3N + gq], 1);
         }
-        mbar_init(&bars[BAR_EPS_READY], TC_BLD_WARPS); mbar_init(&bars[BAR_W_READY], TC_BLD_WARPS);
+        mbar_init(&bars[BAR_EPS_READY], 1); mbar_init(&bars[BAR_W_READY], 1);      // expect_tx arrivals of the bulk copies
         mbar_init(&bars[BAR_EPS_FREE], 1); mbar_init(&bars[BAR_W_FREE], 2);
+        for (int b = 0; b < 2; ++b) { mbar_init(&bars[BAR_IMG_READY + b], TC_BLD_WARPS); mbar_init(&bars[BAR_IMG_FREE + b], 1); }
         fence_barrier_init();
     }
     __syncthreads();                    // zero fill + barrier init visible to everyone
@@ -413,6 +441,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
             if (elect_one()) umma_commit(&bars[BAR_EPS_FREE]);               // the pair's last L1 is in flight
             __syncwarp();
         }
+    } else if (warp == TC_COPY_WARP) {
+        // ===================== copier: operand image -> shared memory =====================
+        if (lane == 0) {
+            const TcImage I = tc_image(NKC);
+            const uint8_t* my_images = p.images + (size_t)blockIdx.x * 2 * I.total;
+            for (int i = 0; i < my_pairs; ++i) {
+                const uint32_t b = i & 1, u = i >> 1;
+                const uint8_t* img = my_images + (size_t)b * I.total;
+                mbar_wait(&bars[BAR_IMG_READY + b], u & 1);                // builders have finished image i
+                if (i > 0) mbar_wait(&bars[BAR_EPS_FREE], (i - 1) & 1);    // previous pair's last L1 has retired
+                mbar_expect_tx(&bars[BAR_EPS_READY], NKC * TC_B1_CHUNK_BYTES);
+                for (int kc = 0; kc < NKC; ++kc)
+                    bulk_g2s(smem + L.b1 + kc * TC_B1_CHUNK_BYTES, img + I.b1 + kc * TC_B1_CHUNK_BYTES, TC_B1_CHUNK_BYTES,
+                             &bars[BAR_EPS_READY]);
+                if (i > 0) mbar_wait(&bars[BAR_W_FREE], (i - 1) & 1);      // previous pair's last L3 has retired
+                mbar_expect_tx(&bars[BAR_W_READY], 2 * TC_H * 128 + 2 * TC_ACT_PAD * 128 + 1024);
+                bulk_g2s(smem + L.w2p, img + I.w2p, 2 * TC_H * 128 + 2 * TC_ACT_PAD * 128, &bars[BAR_W_READY]);   // W2+,W2-,W3+,W3- contiguous
+                bulk_g2s((uint8_t*)bias_all + (i & 1) * 1024, img + I.bias, 1024, &bars[BAR_W_READY]);
+                mbar_wait(&bars[BAR_EPS_READY], i & 1);                    // landed: the image slot may be rewritten
+                mbar_wait(&bars[BAR_W_READY], i & 1);
+                mbar_arrive(&bars[BAR_IMG_FREE + b]);
+            }
+        }
     } else if (warp >= TC_MMA2_WARP0) {
         // ===================== L2 / L3 MMA issuer of one epilogue group =====================
         const uint32_t eg = warp - TC_MMA2_WARP0;
@@ -467,7 +518,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
         uint32_t k = 0;                                       // tiles handled by this group so far
         for (int i = 0; i < my_pairs; ++i) {
             const int pair = blockIdx.x + i * gridDim.x;
-            const uint32_t bias = smem_u32(bias_all + (i & 1) * TC_BIAS_FLOATS);
+            const uint32_t bias = smem_u32(bias_all + (i & 1) * 256);
             const uint32_t b2p = bias + h * 128, b2n = bias + TC_H * 4 + h * 128;
             const uint32_t b3p = bias + 2 * TC_H * 4 + h * 64, b3n = bias + (2 * TC_H + TC_ACT_PAD) * 4 + h * 64;
             float fitp = 0.f, fitn = 0.f, pp0 = 0.f, pp1 = 0.f, pp2 = 0.f, pn0 = 0.f, pn1 = 0.f, pn2 = 0.f;
@@ -608,24 +659,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
             }
         }
     } else {
-        // ===================== builder warps: next pair's B operands =====================
+        // ===================== builder warps: operand images one pair ahead =====================
         const int bw = warp - TC_BLD_WARP0, btid = tid - TC_BLD_WARP0 * 32;
         constexpr int BT = TC_BLD_WARPS * 32;
+        const TcImage I = tc_image(NKC);
         const float sg = p.sigma;
-        for (int i = 0; i < my_pairs; ++i) {
-            const int pair = blockIdx.x + i * gridDim.x;
-            const float* __restrict__ eps = p.table + p.idx[pair];
-            if (i > 0) mbar_wait(&bars[BAR_EPS_FREE], (i - 1) & 1);      // previous pair's last L1 has retired
-            tc_build_l1_rows(smem + L.b1, eps + p.w1, eps + p.b1, sg, p.obs, NKC, bw, TC_BLD_WARPS, lane);
-            warp_arrive_after_smem_writes(&bars[BAR_EPS_READY], lane);
-            if (i + 1 < my_pairs) {                                      // pull the next slice into L2 early
-                const char* nxt = (const char*)(p.table + p.idx[pair + gridDim.x]);
-                const int lines = (p.b3 + p.act) * 4 / 128 + 2;
-                for (int l = btid; l < lines; l += BT) prefetch_l2(nxt + (size_t)l * 128);
+        uint8_t* my_images = p.images + (size_t)blockIdx.x * 2 * I.total;
+        // build image j into buffer j&1 (pure global writes, no dependence on the MMA pipeline)
+        auto build_image = [&](int j) {
+            const int pair = blockIdx.x + j * gridDim.x;
+            {   // slot j&1 must have been drained by the copier (use j>>1 of this slot)
+                const uint32_t u = (uint32_t)j >> 1;
+                if (bw == 0 && lane == 0) TC_TRACE(3, 4 * j + 0);
+                mbar_wait(&bars[BAR_IMG_FREE + (j & 1)], (u & 1) ^ 1);
+                if (bw == 0 && lane == 0) TC_TRACE(3, 4 * j + 1);
             }
-            // W2+-, W3+-, biases: loads first (registers), shared stores after the previous pair's last L3 retired
+            const float* __restrict__ eps = p.table + p.idx[pair];
+            uint8_t* img = my_images + (size_t)(j & 1) * I.total;
+            tc_build_l1_rows(img + I.b1, eps + p.w1, eps + p.b1, sg, p.obs, NKC, 0, TC_H / 2, bw, TC_BLD_WARPS, lane);
+            if (bw == 0 && lane == 0) TC_TRACE(3, 4 * j + 2);
             constexpr int NB2 = (TC_H * TC_H / 2 + BT - 1) / BT;          // column pairs per thread
-            constexpr int WB = 8;                                         // loads batched 8 pairs at a time (32 registers)
+            constexpr int WB = 8;
             for (int b0 = 0; b0 < NB2; b0 += WB) {
                 float e0[WB], e1[WB], t0[WB], t1[WB];
 #pragma unroll
@@ -634,37 +688,72 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
                     e0[b] = __ldg(eps + p.w2 + k2); e1[b] = __ldg(eps + p.w2 + k2 + 1);
                     t0[b] = __ldg(p.theta + p.w2 + k2); t1[b] = __ldg(p.theta + p.w2 + k2 + 1);
                 }
-                if (b0 == 0 && i > 0) mbar_wait(&bars[BAR_W_FREE], (i - 1) & 1);   // previous pair's last L3 has retired
 #pragma unroll
                 for (int b = 0; b < WB; ++b) {
                     const int k2 = 2 * (btid + (b0 + b) * BT);
                     if (b0 + b < NB2 && k2 < TC_H * TC_H) {
                         const int n = k2 >> 6, kk = k2 & 63;
                         const float d0 = __fmul_rn(sg, e0[b]), d1 = __fmul_rn(sg, e1[b]);
-                        *(uint32_t*)(smem + L.w2p + sw128_off(n, kk)) = pack_bf16x2(__fadd_rn(t0[b], d0), __fadd_rn(t1[b], d1));
-                        *(uint32_t*)(smem + L.w2n + sw128_off(n, kk)) = pack_bf16x2(__fadd_rn(t0[b], -d0), __fadd_rn(t1[b], -d1));
+                        *(uint32_t*)(img + I.w2p + sw128_off(n, kk)) = pack_bf16x2(__fadd_rn(t0[b], d0), __fadd_rn(t1[b], d1));
+                        *(uint32_t*)(img + I.w2n + sw128_off(n, kk)) = pack_bf16x2(__fadd_rn(t0[b], -d0), __fadd_rn(t1[b], -d1));
                     }
                 }
             }
-            for (int k2 = 2 * btid; k2 < p.act * TC_H; k2 += 2 * BT) {    // W3+- (rows >= act stay zero)
-                const int n = k2 >> 6, kk = k2 & 63;
-                const float d0 = __fmul_rn(sg, __ldg(eps + p.w3 + k2)), d1 = __fmul_rn(sg, __ldg(eps + p.w3 + k2 + 1));
-                const float x0 = __ldg(p.theta + p.w3 + k2), x1 = __ldg(p.theta + p.w3 + k2 + 1);
-                *(uint32_t*)(smem + L.w3p + sw128_off(n, kk)) = pack_bf16x2(__fadd_rn(x0, d0), __fadd_rn(x1, d1));
-                *(uint32_t*)(smem + L.w3n + sw128_off(n, kk)) = pack_bf16x2(__fadd_rn(x0, -d0), __fadd_rn(x1, -d1));
+            {   // W3+- (rows >= act are zero): all loads first, then the stores
+                constexpr int NB3 = (TC_ACT_PAD * TC_H / 2 + BT - 1) / BT;
+                float d0[NB3], d1[NB3], x0[NB3], x1[NB3];
+#pragma unroll
+                for (int b = 0; b < NB3; ++b) {
+                    const int k2 = 2 * (btid + b * BT);
+                    const bool live = k2 < p.act * TC_H;
+                    const int kq = live ? k2 : 0;
+                    d0[b] = __ldg(eps + p.w3 + kq); d1[b] = __ldg(eps + p.w3 + kq + 1);
+                    x0[b] = __ldg(p.theta + p.w3 + kq); x1[b] = __ldg(p.theta + p.w3 + kq + 1);
+                }
+#pragma unroll
+                for (int b = 0; b < NB3; ++b) {
+                    const int k2 = 2 * (btid + b * BT);
+                    if (k2 < TC_ACT_PAD * TC_H) {
+                        const int n = k2 >> 6, kk = k2 & 63;
+                        uint32_t vp = 0, vn = 0;
+                        if (k2 < p.act * TC_H) {
+                            const float e0 = __fmul_rn(sg, d0[b]), e1 = __fmul_rn(sg, d1[b]);
+                            vp = pack_bf16x2(__fadd_rn(x0[b], e0), __fadd_rn(x1[b], e1));
+                            vn = pack_bf16x2(__fadd_rn(x0[b], -e0), __fadd_rn(x1[b], -e1));
+                        }
+                        *(uint32_t*)(img + I.w3p + sw128_off(n, kk)) = vp;
+                        *(uint32_t*)(img + I.w3n + sw128_off(n, kk)) = vn;
+                    }
+                }
             }
             {
-                float* bias = bias_all + (i & 1) * TC_BIAS_FLOATS;
+                float* bias = (float*)(img + I.bias);
                 if (btid < TC_H) {
                     const float d = __fmul_rn(sg, __ldg(eps + p.b2 + btid)), t = __ldg(p.theta + p.b2 + btid);
                     bias[btid] = __fadd_rn(t, d); bias[TC_H + btid] = __fadd_rn(t, -d);
-                } else if (btid - TC_H < p.act) {
-                    const int j = btid - TC_H;
-                    const float d = __fmul_rn(sg, __ldg(eps + p.b3 + j)), t = __ldg(p.theta + p.b3 + j);
-                    bias[2 * TC_H + j] = __fadd_rn(t, d); bias[2 * TC_H + TC_ACT_PAD + j] = __fadd_rn(t, -d);
+                } else if (btid - TC_H < TC_ACT_PAD) {
+                    const int j2 = btid - TC_H;
+                    float vp = 0.f, vn = 0.f;
+                    if (j2 < p.act) {
+                        const float d = __fmul_rn(sg, __ldg(eps + p.b3 + j2)), t = __ldg(p.theta + p.b3 + j2);
+                        vp = __fadd_rn(t, d); vn = __fadd_rn(t, -d);
+                    }
+                    bias[2 * TC_H + j2] = vp; bias[2 * TC_H + TC_ACT_PAD + j2] = vn;
                 }
             }
-            warp_arrive_after_smem_writes(&bars[BAR_W_READY], lane);
+            __threadfence();                                             // image visible device-wide (L2)
+            asm volatile("fence.proxy.async;" ::: "memory");             // ... and to the async proxy that will copy it
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[BAR_IMG_READY + (j & 1)]);
+            if (bw == 0 && lane == 0) TC_TRACE(3, 4 * j + 3);
+        };
+        for (int j = 0; j < my_pairs; ++j) {
+            build_image(j);
+            if (j + 1 < my_pairs) {                                      // L2 prefetch of the next slice
+                const char* nxt = (const char*)(p.table + p.idx[blockIdx.x + (j + 1) * gridDim.x]);
+                const int lines = (p.b3 + p.act) * 4 / 128 + 2;
+                for (int l = btid; l < lines; l += BT) prefetch_l2(nxt + (size_t)l * 128);
+            }
         }
     }
 
@@ -754,9 +843,11 @@ int es_impl_rollout_tc(es_ctx* ctx, const float* table, int64_t table_len, const
     const size_t ub_bytes = (size_t)p.n_mtiles * TC_MT * TC_H * sizeof(float);
     const size_t crt_bytes = (size_t)p.n_mtiles * TC_ACT_PAD * TC_MT * sizeof(float);
     const size_t part_bytes = (size_t)n_pairs * TC_EPI_WARPS * 8 * sizeof(float);
+    const int grid = n_pairs < ctx->sm_count ? n_pairs : ctx->sm_count;
+    const size_t img_bytes = (size_t)grid * 2 * tc_image(p.nkc).total;
     const size_t tick_bytes = ((size_t)n_pairs * sizeof(unsigned) + 255) & ~(size_t)255;
     void* scratch = nullptr;
-    int rc = es_ctx_scratch(ctx, xnt_bytes + ub_bytes + crt_bytes + part_bytes + tick_bytes, &scratch);
+    int rc = es_ctx_scratch(ctx, xnt_bytes + ub_bytes + crt_bytes + part_bytes + tick_bytes + img_bytes, &scratch);
     if (rc) return rc;
     p.xnt = (const __nv_bfloat16*)scratch;
     float* ubase = (float*)((char*)scratch + xnt_bytes);
@@ -765,6 +856,7 @@ int es_impl_rollout_tc(es_ctx* ctx, const float* table, int64_t table_len, const
     p.crt = crt;
     p.partial = (float*)((char*)scratch + xnt_bytes + ub_bytes + crt_bytes);
     p.tickets = (unsigned*)((char*)scratch + xnt_bytes + ub_bytes + crt_bytes + part_bytes);
+    p.images = (uint8_t*)scratch + xnt_bytes + ub_bytes + crt_bytes + part_bytes + tick_bytes;
     ES_CHECK_CUDA(cudaMemsetAsync(p.tickets, 0, tick_bytes, stream));
     {
         const size_t total = xnt_bytes / 2;
@@ -778,7 +870,6 @@ int es_impl_rollout_tc(es_ctx* ctx, const float* table, int64_t table_len, const
         ES_LAUNCHED(ctx);
     }
     ES_CHECK_CUDA(cudaFuncSetAttribute(rollout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = n_pairs < ctx->sm_count ? n_pairs : ctx->sm_count;
     rollout_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
     ES_LAUNCHED(ctx);
     return ES_OK;

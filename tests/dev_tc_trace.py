@@ -30,9 +30,6 @@ for g_ in range(24):
     e = [(epi[8*g_+k]-t0) if epi[8*g_+k] else -1 for k in range(8)]
     print(f'{g_:3d} | {m} | {e}')
 
-h1p, d2p = t[2], t[3]
-print('per-warp H1P arrival (relative to warp 0 got-D1) and got-D2+ for tiles 4..6; L2+ issue stamp')
-for g_ in (4, 5, 6):
-    base = epi[8*g_+1]
-    print(g_, 'H1P arrive', [int(h1p[16*g_+w]-base) for w in range(16)])
-    print(g_, 'got D2+   ', [int(d2p[16*g_+w]-base) for w in range(16)], ' L2+ issued', int(mma[4*g_+2]-base), ' D1 got', int(base - t0))
+
+print('builder warp 0 per image j: [start, slot free, L1 rows done, image ready]')
+for j in range(3): print(j, [int(t[3][4*j+k]-t0) if t[3][4*j+k] else -1 for k in range(4)])
