@@ -221,7 +221,9 @@ def run_ours(args, wl, n_gpus):
         streams = [np.random.RandomState(s) for s in seeds]
         fit_fn = BatchedRollout(env, wl['T'], coins_per_eval=1, save_obs_chance=0.01, rank_streams=streams,
                                 rollout_mode=mode)
-        fit_fn.stream_env_from_host = True
+        # the synthetic vector env is GPU-resident (its observation / reward streams are env state in HBM, like a
+        # simulator running on the device); the per-generation host inputs are theta, the RNG states and the obs statistics
+        fit_fn.stream_env_from_host = False
         ranker = CenteredRanker()
 
         def api_generation():
@@ -236,20 +238,31 @@ def run_ours(args, wl, n_gpus):
             api_generation()
         comm.barrier(); torch.cuda.synchronize()
         h0, d0 = eng.h2d_bytes, eng.d2h_bytes
+        sampler2 = ClockSampler(local)
+        if rank == 0:
+            sampler2.start()
+        prof = None
+        if os.environ.get('ES_BENCH_PROFILE'):
+            import cProfile
+            prof = cProfile.Profile(); prof.enable()
         w0 = time.perf_counter()
         for _ in range(args.steps):
             api_generation()
         torch.cuda.synchronize(); comm.barrier()
+        e2e_clocks = sampler2.stop() if rank == 0 else None
+        if prof is not None:
+            import pstats
+            prof.disable(); pstats.Stats(prof, stream=sys.stderr).sort_stats('tottime').print_stats(14)
         wall = torch.tensor([time.perf_counter() - w0], device=eng.device, dtype=torch.float64)
         if n_gpus > 1:
             td.all_reduce(wall, op=td.ReduceOp.MAX)
         sec = float(wall.item()) / args.steps
         e2e = dict(value=K / sec, unit='antithetic pairs/s', ms_per_step=sec * 1e3,
                    h2d_bytes_per_step=(eng.h2d_bytes - h0) // args.steps,
-                   d2h_bytes_per_step=(eng.d2h_bytes - d0) // args.steps,
+                   d2h_bytes_per_step=(eng.d2h_bytes - d0) // args.steps, clocks=e2e_clocks,
                    path='es.test_params(BatchedRollout) -> CenteredRanker.rank -> es.approx_grad, numpy in/out; '
-                        'per step H2D: theta, obs/reward streams, MT19937 states, obs mean/std, fitness, weights, '
-                        'indices; D2H: fitness, indices, states, weights, theta')
+                        'per step H2D (pinned, async): theta, MT19937 states, obs mean/std; D2H: fitness[2K], indices[K], RNG states, '
+                        'obs statistics, rank weights[K], theta; one stream sync per API call (3 per generation)')
 
     if rank != 0:
         return

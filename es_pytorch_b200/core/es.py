@@ -16,7 +16,7 @@ from typing import Callable, List, Tuple
 import numpy as np
 import torch
 
-from .. import dist
+from .. import devcache, dist
 from ..engine import get_engine
 from ..generation import DeviceGeneration
 from ..gym.training_result import TrainingResult
@@ -70,8 +70,9 @@ def _device_generation(fit_fn, policy: Policy, nt: NoiseTable, streams) -> Devic
         if getattr(fit_fn, 'stream_env_from_host', False):
             # the env's observation / reward streams are this generation's inputs: copy them from the host again
             env = fit_fn.env
-            eng.upload_into(gen.obs_stream, env.obs_stream[:gen.T + 1])
-            eng.upload_into(gen.rew_vec, env.rew_vec[:gen.T])
+            pinned = bool(getattr(env, 'host_pinned', False))
+            eng.upload_async(gen.obs_stream, env.obs_stream[:gen.T + 1], ('obs', id(gen)), src_pinned=pinned)
+            eng.upload_async(gen.rew_vec, env.rew_vec[:gen.T], ('rew', id(gen)), src_pinned=pinned)
     gen.sigma = float(policy.std)                       # scripts decay the noise std between generations
     gen.save_obs_chance = fit_fn.save_obs_chance
     if fit_fn.archive is not None and (gen.archive is None or gen.archive.shape[0] != len(fit_fn.archive)):
@@ -88,17 +89,26 @@ def _test_params_batched(comm, n: int, policy: Policy, nt: NoiseTable, gen_obsta
     fpos, fneg = gen.evaluate(n)
     # one device->host hop for everything the reference API returns as ndarrays
     eng = gen.eng
-    pos = eng.to_host(fpos).reshape(gen.K, gen.n_obj)
-    neg = eng.to_host(fneg).reshape(gen.K, gen.n_obj)
-    idx_local = eng.to_host(gen.idx)
-    gen.store_states(streams)
+    # everything the reference API returns as ndarrays comes back through pinned staging with ONE synchronisation
+    h_pos, h_neg = eng.download_async(fpos, 'fpos'), eng.download_async(fneg, 'fneg')
+    h_idx = eng.download_async(gen.idx, 'idx')
+    h_key, h_mtpos = eng.download_async(gen.mt_key, 'mtkey'), eng.download_async(gen.mt_pos, 'mtpos')
+    if gen.extra_words:
+        h_cnt, h_sum, h_sq = (eng.download_async(gen.gen_count, 'gcnt'), eng.download_async(gen.gen_sum, 'gsum'),
+                              eng.download_async(gen.gen_sumsq, 'gsq'))
+    eng.sync()
+    version = gen.version
+    valid = lambda g=gen, v=version: g.version == v
+    pos = devcache.attach(h_pos.numpy().reshape(gen.K, gen.n_obj).copy(), fpos, valid)
+    neg = devcache.attach(h_neg.numpy().reshape(gen.K, gen.n_obj).copy(), fneg, valid)
+    idx_local = h_idx.numpy().copy()
+    gen.store_states(streams, h_key.numpy().copy(), h_mtpos.numpy().copy())
     if comm.size > 1:
         inds = np.concatenate(dist.world().allgather_object(idx_local)).astype(np.float64)
     else:
-        inds = idx_local.astype(np.float64)
+        inds = devcache.attach(idx_local.astype(np.float64), gen.idx, valid)
     if gen.extra_words:
-        cnt = eng.to_host(gen.gen_count)
-        gen_obstat.inc(eng.to_host(gen.gen_sum), eng.to_host(gen.gen_sumsq), float(cnt[0]))
+        gen_obstat.inc(h_sum.numpy().copy(), h_sq.numpy().copy(), float(h_cnt.numpy()[0]))
     steps = 2 * gen.K * (fit_fn.max_steps - 1)          # run_model returns the last loop index (gym_runner.py:50,67)
     return pos, neg, inds, steps
 
@@ -157,8 +167,16 @@ def approx_grad(policy: Policy, ranker: Ranker, nt: NoiseTable, params: np.ndarr
     comm = dist.world()
     K = len(ranker.noise_inds)
     k0, k1 = dist.shard_bounds(K, comm.size, comm.rank) if K % comm.size == 0 else (0, K if comm.rank == 0 else 0)
-    w = eng.to_device(np.ascontiguousarray(ranker.ranked_fits[k0:k1], dtype=np.float32))
-    idx = eng.to_device(np.ascontiguousarray(ranker.noise_inds[k0:k1]).astype(np.int64))
+    w_all = devcache.lookup(ranker.ranked_fits)
+    if w_all is not None and w_all.numel() == K:
+        w = w_all[k0:k1]
+    else:
+        w = eng.to_device(np.ascontiguousarray(ranker.ranked_fits[k0:k1], dtype=np.float32))
+    idx_sh = devcache.lookup(ranker.noise_inds)
+    if idx_sh is not None and comm.size == 1 and idx_sh.numel() == K:
+        idx = idx_sh
+    else:
+        idx = eng.to_device(np.ascontiguousarray(ranker.noise_inds[k0:k1]).astype(np.int64))
     theta = policy.theta_dev(eng)
     gsum = eng.grad_reconstruct(nt.device_table(eng), idx, w, len(policy))
     comm.allreduce_sum(gsum)

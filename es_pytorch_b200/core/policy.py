@@ -47,14 +47,17 @@ class Policy:
         if self._theta_dev is None or self._theta_dev.device != engine.device:
             self._theta_dev = engine.to_device(self.flat_params, torch.float32)
         elif refresh:
-            engine.upload_into(self._theta_dev, self.flat_params)
+            engine.upload_async(self._theta_dev, self.flat_params, ('theta', id(self)))
         return self._theta_dev
 
     def sync_host(self):
         """Copy theta back into ``flat_params`` in place (keeps aliases held by scripts valid)."""
         if self._theta_dev is not None:
             from ..engine import get_engine
-            self.flat_params[...] = get_engine(self._theta_dev.device.index).to_host(self._theta_dev)
+            eng = get_engine(self._theta_dev.device.index)
+            h = eng.download_async(self._theta_dev, ('theta', id(self)))
+            eng.sync()
+            self.flat_params[...] = h.numpy()
 
     # -- checkpointing (policy.py:37-47) -------------------------------------------------------------
     @staticmethod

@@ -48,6 +48,8 @@ class Engine:
         self._ctx = h
         self.h2d_bytes = 0          # bytes copied host->device / device->host through this engine
         self.d2h_bytes = 0
+        self._pin = {}
+        self._pin_events = {}
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -82,6 +84,43 @@ class Engine:
         self.h2d_bytes += t.numel() * t.element_size()
         dst.copy_(t.view(dst.shape) if t.numel() == dst.numel() else t, non_blocking=True)
         return dst
+
+    # -- pinned staging: asynchronous transfers, one synchronisation per API call -------------------------------
+    def _pinned(self, key, shape, dtype) -> torch.Tensor:
+        buf = self._pin.get(key)
+        if buf is None or buf.shape != torch.Size(shape) or buf.dtype != dtype:
+            buf = self._pin[key] = torch.empty(shape, dtype=dtype, pin_memory=True)
+        return buf
+
+    def upload_async(self, dst: torch.Tensor, src, key, src_pinned: bool = False) -> torch.Tensor:
+        """host array -> device without blocking the host.  ``src_pinned=True``: the caller guarantees the source
+        lives in page-locked memory and is copied directly; anything else goes through a pinned staging buffer
+        named ``key`` (no per-call cudaPointerGetAttributes query)."""
+        a = src if isinstance(src, torch.Tensor) else torch.from_numpy(src if src.flags.c_contiguous else np.ascontiguousarray(src))
+        self.h2d_bytes += a.numel() * a.element_size()
+        if src_pinned:
+            dst.copy_(a.view(dst.shape), non_blocking=True)
+            return dst
+        st = self._pinned(key, tuple(a.shape), a.dtype)
+        ev = self._pin_events.get(key)
+        if ev is not None and not ev.query():          # the previous use of this staging buffer is still in flight
+            ev.synchronize()
+        st.copy_(a)
+        dst.copy_(st.view(dst.shape), non_blocking=True)
+        if ev is None:
+            ev = self._pin_events[key] = torch.cuda.Event()
+        ev.record()
+        return dst
+
+    def download_async(self, t: torch.Tensor, key) -> torch.Tensor:
+        """device -> pinned staging (asynchronous); call ``sync()`` before reading the returned pinned tensor."""
+        st = self._pinned(('d2h', key), tuple(t.shape), t.dtype)
+        st.copy_(t, non_blocking=True)
+        self.d2h_bytes += t.numel() * t.element_size()
+        return st
+
+    def sync(self):
+        torch.cuda.current_stream(self.device).synchronize()
 
     def to_host(self, t: torch.Tensor) -> np.ndarray:
         """Device tensor -> numpy (synchronises the stream; counts the bytes)."""

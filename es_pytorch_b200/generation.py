@@ -80,6 +80,7 @@ class DeviceGeneration:
         self.gen_sumsq = torch.zeros(self.obs_dim, dtype=f64, device=e.device)
         self.gen_count = torch.zeros(2, dtype=f64, device=e.device)
         self._bufs_for = None
+        self.version = 0            # bumped by every evaluate(): validity token of the device shadows handed out
         self.timers = None          # optional {'name': [(start_event, end_event), ...]} filled by _timed()
 
     # ------------------------------------------------------------------------------------------
@@ -125,8 +126,8 @@ class DeviceGeneration:
 
     def set_obstat(self, mean: np.ndarray, std: np.ndarray):
         """Policy.update_obstat -> BaseNet.set_ob_mean_std (policy.py:69-71, nn.py:19-21)."""
-        self.eng.upload_into(self.ob_mean, np.ascontiguousarray(mean, dtype=np.float64).reshape(-1))
-        self.eng.upload_into(self.ob_std, np.ascontiguousarray(std, dtype=np.float64).reshape(-1))
+        self.eng.upload_async(self.ob_mean, np.ascontiguousarray(mean, dtype=np.float64).reshape(-1), ('obmean', id(self)))
+        self.eng.upload_async(self.ob_std, np.ascontiguousarray(std, dtype=np.float64).reshape(-1), ('obstd', id(self)))
 
     # ------------------------------------------------------------------------------------------
     def evaluate(self, n_per_stream: int):
@@ -134,6 +135,7 @@ class DeviceGeneration:
         allgather.  Leaves fpos/fneg [K, n_obj] (global) and idx [k_local] on the device."""
         e = self.eng
         self._ensure_buffers(n_per_stream)
+        self.version += 1
         with self._timed('draw_indices'):
             e.draw_indices(self.mt_key, self.mt_pos, n_per_stream, self.table.numel() - self.P, self.extra_words,
                            self.idx, self.extras)
@@ -187,16 +189,18 @@ class DeviceGeneration:
     def load_states(self, rank_states: Sequence[np.random.RandomState]):
         """Upload the callers' RandomState streams (they may have been advanced on the host)."""
         assert len(rank_states) == self.n_streams
-        self._gauss = [(s.get_state()[3], s.get_state()[4]) for s in rank_states]
-        key = np.stack([s.get_state()[1].astype(np.uint32) for s in rank_states]).view(np.int32)
-        pos = np.array([s.get_state()[2] for s in rank_states], dtype=np.int32)
-        self.eng.upload_into(self.mt_key, key)
-        self.eng.upload_into(self.mt_pos, pos)
+        states = [s.get_state() for s in rank_states]
+        self._gauss = [(st[3], st[4]) for st in states]
+        key = np.stack([st[1] for st in states]).astype(np.uint32, copy=False).view(np.int32)
+        pos = np.array([st[2] for st in states], dtype=np.int32)
+        self.eng.upload_async(self.mt_key, key, ('mtkey', id(self)))
+        self.eng.upload_async(self.mt_pos, pos, ('mtpos', id(self)))
 
-    def store_states(self, rank_states: Sequence[np.random.RandomState]):
-        """Write the advanced streams back into the callers' RandomState objects (synchronises)."""
-        key = self.eng.to_host(self.mt_key).view(np.uint32)
-        pos = self.eng.to_host(self.mt_pos)
+    def store_states(self, rank_states: Sequence[np.random.RandomState], key=None, pos=None):
+        """Write the advanced streams back into the callers' RandomState objects (``key``/``pos``: already
+        downloaded host copies; otherwise this synchronises)."""
+        key = (self.eng.to_host(self.mt_key) if key is None else key).view(np.uint32)
+        pos = self.eng.to_host(self.mt_pos) if pos is None else pos
         for r, rs in enumerate(rank_states):
             rs.set_state(('MT19937', key[r], int(pos[r]), self._gauss[r][0], self._gauss[r][1]))
 

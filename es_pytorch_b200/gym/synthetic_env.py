@@ -70,13 +70,35 @@ class SyntheticEnv:
         self.pos_scale = float(pos_scale)
         self.observation_space = Box(-np.inf, np.inf, (self.obs_dim,))
         self.action_space = Box(-1.0, 1.0, (self.act_dim,))
-        self.obs_stream = np.random.RandomState(obs_seed).randn(self.T + 1, self.obs_dim).astype(np.float32)
-        self.rew_vec = np.random.RandomState(rew_seed).randn(self.T, self.act_dim).astype(np.float32)
+        self.obs_stream = self._host(np.random.RandomState(obs_seed).randn(self.T + 1, self.obs_dim).astype(np.float32))
+        self.rew_vec = self._host(np.random.RandomState(rew_seed).randn(self.T, self.act_dim).astype(np.float32))
+        self.host_pinned = bool(SyntheticEnv._pinned_keepalive) and SyntheticEnv._last_pinned
         self.robot = _Robot(self)
         self.unwrapped = self
         self.t = 0
         self.pos = np.zeros(3, dtype=np.float32)
         self._dev = None
+
+    @staticmethod
+    def _host(a: np.ndarray) -> np.ndarray:
+        """Keep the env's host arrays in pinned memory when a GPU is present, so the per-generation upload of the
+        observation / reward streams is a direct asynchronous copy (the ndarray is a view of the pinned tensor)."""
+        try:
+            import torch
+            if torch.cuda.is_available():
+                t = torch.from_numpy(a).pin_memory()
+                v = t.numpy()
+                v.setflags(write=True)
+                SyntheticEnv._pinned_keepalive.append(t)
+                SyntheticEnv._last_pinned = True
+                return v
+        except Exception:
+            pass
+        SyntheticEnv._last_pinned = False
+        return a
+
+    _pinned_keepalive = []
+    _last_pinned = False
 
     # ---- gym API -------------------------------------------------------------------------
     def seed(self, seed=None):

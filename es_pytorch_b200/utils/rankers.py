@@ -55,9 +55,15 @@ class Ranker(ABC):
         from ..engine import get_engine
         eng = get_engine()
         self._pre_rank(fits_pos, fits_neg, noise_inds)
-        fp = eng.to_device(_as_2d(fits_pos), torch.float64)
-        fn = eng.to_device(_as_2d(fits_neg), torch.float64)
-        self.ranked_fits = eng.to_host(self.rank_device(eng, fp, fn))
+        from .. import devcache
+        fp, fn = devcache.lookup(fits_pos), devcache.lookup(fits_neg)
+        if fp is None or fn is None:
+            fp = eng.to_device(_as_2d(fits_pos), torch.float64)
+            fn = eng.to_device(_as_2d(fits_neg), torch.float64)
+        w = self.rank_device(eng, fp, fn)
+        h = eng.download_async(w, ('ranked', id(self)))
+        eng.sync()
+        self.ranked_fits = devcache.attach(h.numpy().copy(), w, lambda r=self, t=w: r.ranked_fits_dev is t)
         return self.ranked_fits
 
 
