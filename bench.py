@@ -34,6 +34,8 @@ WORKLOADS = {
     'halfcheetah': dict(obs=17, act=6, hidden=(64, 64), T=1000, pairs=256, table=250_000_000),
 }
 VIRTUAL_RANKS_PER_GPU = 8
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (default workload)
+NCU_TRAFFIC = {'rollout': 1.132196e9 + 98.094592e6, 'reconstruct': 1.076947e9 + 4.036608e6}
 
 
 def parse():
@@ -238,9 +240,8 @@ def run_ours(args, wl, n_gpus):
             api_generation()
         comm.barrier(); torch.cuda.synchronize()
         h0, d0 = eng.h2d_bytes, eng.d2h_bytes
-        sampler2 = ClockSampler(local)
-        if rank == 0:
-            sampler2.start()
+        # (clocks are sampled during the device-resident timed region above; polling nvidia-smi during this
+        #  host-synchronous loop perturbs it: every query stalls the API path for tens of ms on these hosts)
         prof = None
         if os.environ.get('ES_BENCH_PROFILE'):
             import cProfile
@@ -249,7 +250,6 @@ def run_ours(args, wl, n_gpus):
         for _ in range(args.steps):
             api_generation()
         torch.cuda.synchronize(); comm.barrier()
-        e2e_clocks = sampler2.stop() if rank == 0 else None
         if prof is not None:
             import pstats
             prof.disable(); pstats.Stats(prof, stream=sys.stderr).sort_stats('tottime').print_stats(14)
@@ -259,7 +259,7 @@ def run_ours(args, wl, n_gpus):
         sec = float(wall.item()) / args.steps
         e2e = dict(value=K / sec, unit='antithetic pairs/s', ms_per_step=sec * 1e3,
                    h2d_bytes_per_step=(eng.h2d_bytes - h0) // args.steps,
-                   d2h_bytes_per_step=(eng.d2h_bytes - d0) // args.steps, clocks=e2e_clocks,
+                   d2h_bytes_per_step=(eng.d2h_bytes - d0) // args.steps,
                    path='es.test_params(BatchedRollout) -> CenteredRanker.rank -> es.approx_grad, numpy in/out; '
                         'per step H2D (pinned, async): theta, MT19937 states, obs mean/std; D2H: fitness[2K], indices[K], RNG states, '
                         'obs statistics, rank weights[K], theta; one stream sync per API call (3 per generation)')
@@ -281,6 +281,7 @@ def run_ours(args, wl, n_gpus):
     roll_flop = 2.0 * (2 * k_local) * wl['T'] * mac
     roll_tfs = roll_flop / (kern['rollout'] * 1e-3) / 1e12
     value = K / (ms_step * 1e-3)
+    default_wl = args.workload == 'humanoid' and not args.pairs_per_gpu and mode == _lib.ES_ROLLOUT_TC
     line = dict(
         metric='perturbations/sec (whole ES generation)', value=value, unit='antithetic pairs/s', n_gpus=n_gpus,
         steps=args.steps, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling='weak',
@@ -290,13 +291,19 @@ def run_ours(args, wl, n_gpus):
         kernel_ms=kern,
         # dominant kernel by time: the fused perturb+rollout
         roofline=dict(kernel='rollout (es_rollout_openloop)', bound='tensor', achieved=roll_tfs, peak=tf_peak,
-                      unit='TFLOP/s', frac=roll_tfs / tf_peak, traffic=None, peak_source=tf_src,
+                      unit='TFLOP/s', frac=roll_tfs / tf_peak, traffic=NCU_TRAFFIC['rollout'] if default_wl else None,
+                      traffic_source='profiles/r1_f_rollout_tc_ncu_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum, 1 launch)',
+                      peak_source=tf_src,
                       algorithmic_flops_per_launch=roll_flop, share_of_step=kern['rollout'] / ms_step,
                       note='mode f32 runs on the CUDA cores (FFMA); reported against the tensor peak the '
-                           'tcgen05 path is judged by' if mode == _lib.ES_ROLLOUT_F32 else 'tcgen05 path'),
+                           'tcgen05 path is judged by' if mode == _lib.ES_ROLLOUT_F32 else
+                           'tcgen05 path; the kernel is bound by the tanh/convert epilogue on the XU pipe (2.9 G tanh per '
+                           'generation, ncu: XU 42 %, tensor 19 %), not by the tensor pipe: see profiles/README.md'),
         # the north-star's named HBM-bound kernel
         roofline_reconstruct=dict(kernel='reconstruct_kernel (es_grad_reconstruct)', bound='hbm', achieved=rec_gbs,
-                                  peak=hbm_peak, unit='GB/s', frac=rec_gbs / hbm_peak, traffic=None,
+                                  peak=hbm_peak, unit='GB/s', frac=rec_gbs / hbm_peak,
+                                  traffic=NCU_TRAFFIC['reconstruct'] if default_wl else None,
+                                  traffic_source='profiles/r1_f_reconstruct_ncu_raw.csv',
                                   peak_source=hbm_src, algorithmic_bytes_per_launch=rec_bytes,
                                   share_of_step=kern['reconstruct'] / ms_step),
     )
