@@ -9,8 +9,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libes_b200.so')
+# ES_B200_LIB: development override used by tools/ to time kernel variants built next to the product library
+LIB_PATH = os.environ.get('ES_B200_LIB') or os.path.join(_HERE, 'libes_b200.so')
 
+ES_RANK_CENTERED, ES_RANK_DOUBLE_POSITIVE, ES_RANK_SEMI_CENTERED, ES_RANK_MAX_NORMALIZED = 0, 1, 2, 3
 ES_ROLLOUT_F32 = 0
 ES_ROLLOUT_TC = 1
 ES_MT_N = 624
@@ -32,6 +34,8 @@ SIGNATURES = {
                                    _f32, _vp, _vp, _i32, _vp, _vp, _i32, _vp]),
     'es_novelty': (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _i32, _vp]),
     'es_centered_rank': (_i32, [_vp, _vp, _vp, _i32, _i32, _f32, _f32, _i32, _i32, _vp, _vp, _vp]),
+    'es_rank_transform': (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f64, _f64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _vp, _vp]),
     'es_grad_reconstruct': (_i32, [_vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp]),
     'es_adam_step': (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _i32, _vp]),
     'es_sgd_step': (_i32, [_vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _i32, _vp]),

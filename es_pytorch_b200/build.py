@@ -49,6 +49,19 @@ def nvcc_path() -> str:
     return 'nvcc'
 
 
+def build_variant(name: str, defines) -> str:
+    """Development: the same sources with extra -D flags -> es_pytorch_b200/libes_b200_<name>.so (load it with
+    ES_B200_LIB=<path>; used by tools/ to time kernel variants side by side)."""
+    out = os.path.join(HERE, f'libes_b200_{name}.so')
+    cmd = [nvcc_path()] + NVCC_FLAGS + [f'-D{d}' for d in defines] + ['-o', out] + \
+          [os.path.join(CSRC, s) for s in _sources()]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source into es_pytorch_b200/libes_b200.so (no-op when up to date)."""
     digest = _digest()

@@ -204,8 +204,30 @@ int es_centered_rank(es_ctx* ctx, const double* fpos, const double* fneg, int K,
     ES_REQUIRE(n_obj == 1 || n_obj == 2, "es_centered_rank: n_obj must be 1 or 2");
     ES_REQUIRE(K >= 1 && k_begin >= 0 && k_count >= 0 && k_begin + k_count <= K, "es_centered_rank: bad shard");
     if (k_count == 0) return ES_OK;
-    return es_impl_centered_rank(ctx, fpos, fneg, K, n_obj, w0, w1, k_begin, k_count, weights_out, ranks_out,
-                                 (cudaStream_t)stream);
+    return es_impl_rank_transform(ctx, fpos, fneg, K, n_obj, ES_RANK_CENTERED, (double)w0, (double)w1, 0, k_begin, k_count,
+                                  nullptr, weights_out, nullptr, ranks_out, nullptr, nullptr, nullptr,
+                                  (cudaStream_t)stream);
+}
+
+int es_rank_transform(es_ctx* ctx, const double* fpos, const double* fneg, int K, int n_obj, int kind, double w0,
+                      double w1, int elite_n, int k_begin, int k_count, const int64_t* noise_idx, float* weights_out,
+                      double* weights64_out, int32_t* ranks_out, double* elite_vals_out, int32_t* elite_fit_out,
+                      int64_t* elite_idx_out, void* stream) {
+    ES_ENTER(ctx);
+    ES_REQUIRE(fpos && fneg && weights_out, "es_rank_transform: NULL pointer");
+    ES_REQUIRE(kind >= ES_RANK_CENTERED && kind <= ES_RANK_MAX_NORMALIZED, "es_rank_transform: unknown kind");
+    ES_REQUIRE(n_obj == 1 || n_obj == 2, "es_rank_transform: n_obj must be 1 or 2");   // rankers.py:114
+    ES_REQUIRE(K >= 1 && k_begin >= 0 && k_count >= 0 && k_begin + k_count <= K, "es_rank_transform: bad shard");
+    ES_REQUIRE(elite_n >= 0 && elite_n <= 2 * K, "es_rank_transform: elite_n out of range");
+    if (elite_n > 0) {
+        // EliteRanker(MultiObjectiveRanker) would need a second ranking of the blended values: not provided
+        if (n_obj != 1) { es_set_error("es_rank_transform: elite selection needs a single objective"); return ES_ERR_UNSUPPORTED; }
+        ES_REQUIRE(!elite_idx_out || noise_idx, "es_rank_transform: elite_idx_out needs noise_idx");
+    }
+    if (k_count == 0) return ES_OK;
+    return es_impl_rank_transform(ctx, fpos, fneg, K, n_obj, kind, w0, w1, elite_n, k_begin, k_count, noise_idx,
+                                  weights_out, weights64_out, ranks_out, elite_vals_out, elite_fit_out, elite_idx_out,
+                                  (cudaStream_t)stream);
 }
 
 int es_grad_reconstruct(es_ctx* ctx, const float* table, int64_t table_len, const int64_t* idx, const float* weights,

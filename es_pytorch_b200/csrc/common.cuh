@@ -66,8 +66,8 @@ int es_impl_rollout_f32(es_ctx*, const float*, int64_t, const int64_t*, int, con
 int es_impl_rollout_tc(es_ctx*, const float*, int64_t, const int64_t*, int, const float*, int, float, const int*, int,
                        const float*, const float*, int, float, double*, double*, int, float*, float*, cudaStream_t);
 int es_impl_novelty(es_ctx*, const float*, int, const double*, int, int, double*, int, cudaStream_t);
-int es_impl_centered_rank(es_ctx*, const double*, const double*, int, int, float, float, int, int, float*, int32_t*,
-                          cudaStream_t);
+int es_impl_rank_transform(es_ctx*, const double*, const double*, int, int, int, double, double, int, int, int,
+                           const int64_t*, float*, double*, int32_t*, double*, int32_t*, int64_t*, cudaStream_t);
 int es_impl_grad_reconstruct(es_ctx*, const float*, int64_t, const int64_t*, const float*, int, int, float*,
                              cudaStream_t);
 int es_impl_adam(es_ctx*, float*, float*, float*, const float*, float, float, float, float, float, float, float, float,

@@ -13,7 +13,9 @@
 //   4. rank_scatter_kernel  (key, index) pairs grouped by bucket
 //   5. rank_local_kernel    rank = bucket start + #{(key_j, j) < (key_i, i) inside the bucket}, only for the
 //                           elements of this GPU's shard [k_begin, k_begin+k_count) -- ranks are global
-//   6. rank_finalize_kernel y = float32(rank)/(2K-1) - 0.5, blend, weight = y+ - y-
+//   6. rank_finalize_kernel y = shape(rank) (centered: float32(rank)/(2K-1) - 0.5; also the double-positive, semi-centered
+//                           and max-normalised shapings of rankers.py:61-83), blend, weight = y+ - y- (or the elite
+//                           selection of rankers.py:86-103)
 // The float32 ops are the reference's, one IEEE operation each (no contraction).  Steps 1-4 are replicated on every
 // GPU (O(2K)), step 5 is O(shard * bucket occupancy): the cost no longer grows with the number of GPUs.
 #include "common.cuh"
@@ -162,32 +164,108 @@ __global__ void rank_local_kernel(const unsigned long long* __restrict__ keys, i
     }
 }
 
-__global__ void rank_finalize_kernel(const int* __restrict__ ranks, int K, int n_obj, float w0, float w1, int k_count,
-                                     float* __restrict__ weights_out, int32_t* __restrict__ ranks_out) {
+// ---- rank -> fitness-shaping value (the _rank of each Ranker subclass, src/utils/rankers.py:53-83) -----------------
+struct RkXform {
+    int kind;            // ES_RANK_*
+    int n;               // 2K
+    float denom;         // float32(2K - 1)                        rankers.py:56
+    float semi_c1;       // float32(0.29 * s)                      rankers.py:82 (python float -> float32 operand)
+    float semi_inv_s;    // float32(1 / s)
+    float semi_s;        // float32(s)
+    double w0, w1;       // MultiObjectiveRanker blend             rankers.py:120
+    int elite_n;         // > 0: EliteRanker keeps the elite_n largest values (rankers.py:93-97)
+};
+
+// float32 kinds: every reference operation is one IEEE float32 operation; the result is returned widened (exact)
+__device__ __forceinline__ double rk_shape(const RkXform& xf, int r, double x, double shift, double ymax) {
+    switch (xf.kind) {
+    case ES_RANK_CENTERED:
+        return (double)__fsub_rn(__fdiv_rn((float)r, xf.denom), 0.5f);                       // rankers.py:55-57
+    case ES_RANK_DOUBLE_POSITIVE: {
+        float y = __fsub_rn(__fdiv_rn((float)r, xf.denom), 0.5f);
+        if (y > 0.0f) y = __fmul_rn(y, 2.0f);                                                // rankers.py:64
+        return (double)y;
+    }
+    case ES_RANK_SEMI_CENTERED: {
+        const float t = __fadd_rn((float)r, xf.semi_c1);                                     // y + 0.29*s
+        const float u = __fmul_rn(xf.semi_inv_s, __fmul_rn(t, t));                           // (1/s) * square(.)
+        return (double)__fsub_rn(__fdiv_rn(u, xf.semi_s), 0.5f);                             // / s - 0.5
+    }
+    default: {                                                                                // ES_RANK_MAX_NORMALIZED
+        const double y = __ddiv_rn(__dadd_rn(x, shift), ymax);                                // rankers.py:71-72
+        return __dsub_rn(__dmul_rn(2.0, y), 1.0);                                             // rankers.py:73
+    }
+    }
+}
+
+__device__ __forceinline__ double rk_blend(const RkXform& xf, double y0, double y1) {
+    if (xf.kind == ES_RANK_MAX_NORMALIZED)                                                    // float64 values
+        return __dadd_rn(__dmul_rn(y0, xf.w0), __dmul_rn(y1, xf.w1));
+    return (double)__fadd_rn(__fmul_rn((float)y0, (float)xf.w0), __fmul_rn((float)y1, (float)xf.w1));
+}
+
+__global__ void rank_finalize_kernel(const int* __restrict__ ranks, const double* __restrict__ fpos,
+                                     const double* __restrict__ fneg, const RkStats* __restrict__ stats, int K,
+                                     int n_obj, RkXform xf, int k_begin, int k_count,
+                                     const int64_t* __restrict__ noise_idx, float* __restrict__ weights_out,
+                                     double* __restrict__ weights64_out, int32_t* __restrict__ ranks_out,
+                                     double* __restrict__ elite_vals, int32_t* __restrict__ elite_fit,
+                                     int64_t* __restrict__ elite_idx) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= k_count) return;
     const int n_local = 2 * k_count;
-    const float denom = (float)(2 * K - 1);             // y /= (x.size - 1), rankers.py:56
-    float yp, yn;
-    {
-        const int rp = ranks[k], rn = ranks[k_count + k];
-        yp = __fsub_rn(__fdiv_rn((float)rp, denom), 0.5f);   // rankers.py:55-57
-        yn = __fsub_rn(__fdiv_rn((float)rn, denom), 0.5f);
-        if (ranks_out) { ranks_out[k] = rp; ranks_out[k_count + k] = rn; }
+    double yp = 0.0, yn = 0.0;
+    int rp0 = 0, rn0 = 0;
+    bool reversed = false;
+    for (int c = 0; c < n_obj; ++c) {
+        const int rp = ranks[(size_t)c * n_local + k], rn = ranks[(size_t)c * n_local + k_count + k];
+        if (c == 0) { rp0 = rp; rn0 = rn; }
+        if (ranks_out) { ranks_out[(size_t)c * n_local + k] = rp; ranks_out[(size_t)c * n_local + k_count + k] = rn; }
+        double shift = 0.0, ymax = 1.0, xp = 0.0, xn = 0.0;
+        if (xf.kind == ES_RANK_MAX_NORMALIZED) {
+            const double mn = rk_unkey(stats[c].kmin), mx = rk_unkey(stats[c].kmax);
+            shift = (mn > 0.0) ? -mn : mn;                      // x + (-mn if mn > 0 else mn), rankers.py:71
+            ymax = __dadd_rn(mx, shift);                        // np.max(y): the add is monotone
+            if (c == 0) reversed = ymax < 0.0;                  // dividing by a negative maximum reverses the order
+            xp = fpos[(size_t)(k_begin + k) * n_obj + c];
+            xn = fneg[(size_t)(k_begin + k) * n_obj + c];
+        }
+        const double sp = rk_shape(xf, rp, xp, shift, ymax), sn = rk_shape(xf, rn, xn, shift, ymax);
+        if (n_obj == 1) { yp = sp; yn = sn; }
+        else if (c == 0) { yp = sp; yn = sn; }
+        else { yp = rk_blend(xf, yp, sp); yn = rk_blend(xf, yn, sn); }
     }
-    if (n_obj == 2) {
-        const int rp = ranks[n_local + k], rn = ranks[n_local + k_count + k];
-        const float yp1 = __fsub_rn(__fdiv_rn((float)rp, denom), 0.5f);
-        const float yn1 = __fsub_rn(__fdiv_rn((float)rn, denom), 0.5f);
-        yp = __fadd_rn(__fmul_rn(yp, w0), __fmul_rn(yp1, w1));  // rankers.py:120
-        yn = __fadd_rn(__fmul_rn(yn, w0), __fmul_rn(yn1, w1));
-        if (ranks_out) { ranks_out[n_local + k] = rp; ranks_out[n_local + k_count + k] = rn; }
+    double w;
+    if (xf.elite_n > 0) {
+        // EliteRanker (rankers.py:86-103): the elite_n largest shaped values are kept with their own sign-less weight and
+        // the noise index of their pair; nothing is subtracted.  Slot = distance from the elite threshold (rank order).
+        const int thr = xf.n - xf.elite_n;
+        if (reversed) { rp0 = xf.n - 1 - rp0; rn0 = xf.n - 1 - rn0; }
+        const bool ep = rp0 >= thr, en = rn0 >= thr;
+        if (ep) {
+            if (elite_vals) elite_vals[rp0 - thr] = yp;
+            if (elite_fit) elite_fit[rp0 - thr] = k_begin + k;
+            if (elite_idx) elite_idx[rp0 - thr] = noise_idx[k_begin + k];
+        }
+        if (en) {
+            if (elite_vals) elite_vals[rn0 - thr] = yn;
+            if (elite_fit) elite_fit[rn0 - thr] = K + k_begin + k;
+            if (elite_idx) elite_idx[rn0 - thr] = noise_idx[k_begin + k];
+        }
+        const double a = ep ? yp : 0.0, b = en ? yn : 0.0;
+        w = (xf.kind == ES_RANK_MAX_NORMALIZED) ? __dadd_rn(a, b) : (double)__fadd_rn((float)a, (float)b);
+    } else {
+        w = (xf.kind == ES_RANK_MAX_NORMALIZED) ? __dsub_rn(yp, yn)                 // Ranker._post_rank, rankers.py:44
+                                                : (double)__fsub_rn((float)yp, (float)yn);
     }
-    weights_out[k] = __fsub_rn(yp, yn);                  // rankers.py:44
+    weights_out[k] = (float)w;
+    if (weights64_out) weights64_out[k] = w;
 }
 
-int es_impl_centered_rank(es_ctx* ctx, const double* fpos, const double* fneg, int K, int n_obj, float w0, float w1,
-                          int k_begin, int k_count, float* weights_out, int32_t* ranks_out, cudaStream_t stream) {
+int es_impl_rank_transform(es_ctx* ctx, const double* fpos, const double* fneg, int K, int n_obj, int kind, double w0,
+                           double w1, int elite_n, int k_begin, int k_count, const int64_t* noise_idx,
+                           float* weights_out, double* weights64_out, int32_t* ranks_out, double* elite_vals,
+                           int32_t* elite_fit, int64_t* elite_idx, cudaStream_t stream) {
     const size_t n = 2 * (size_t)K, n_local = 2 * (size_t)k_count;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t key_b = al(n * n_obj * 8), skey_b = key_b, sidx_b = al(n * n_obj * 4);
@@ -228,8 +306,19 @@ int es_impl_centered_rank(es_ctx* ctx, const double* fpos, const double* fneg, i
         rank_local_kernel<<<dim3(lb, n_obj), 128, 0, stream>>>(keys, K, k_begin, k_count, stats, hist, start, skeys, sidx, ranks);
         ES_LAUNCHED(ctx);
     }
-    rank_finalize_kernel<<<es_div_up(k_count, RK_THREADS), RK_THREADS, 0, stream>>>(ranks, K, n_obj, w0, w1, k_count,
-                                                                                   weights_out, ranks_out);
+    RkXform xf;
+    xf.kind = kind;
+    xf.n = (int)n;
+    xf.denom = (float)(n - 1);
+    xf.semi_c1 = (float)(0.29 * (double)n);
+    xf.semi_inv_s = (float)(1.0 / (double)n);
+    xf.semi_s = (float)n;
+    xf.w0 = w0;
+    xf.w1 = w1;
+    xf.elite_n = elite_n;
+    rank_finalize_kernel<<<es_div_up(k_count, RK_THREADS), RK_THREADS, 0, stream>>>(
+        ranks, fpos, fneg, stats, K, n_obj, xf, k_begin, k_count, noise_idx, weights_out, weights64_out, ranks_out,
+        elite_vals, elite_fit, elite_idx);
     ES_LAUNCHED(ctx);
     return ES_OK;
 }

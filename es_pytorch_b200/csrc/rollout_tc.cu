@@ -203,10 +203,15 @@ __device__ __forceinline__ float lds32f(uint32_t saddr) {
 // tanh of two values -> packed bf16x2 (lower half = lo).  tanh.approx.bf16x2 is NOT a packed MUFU op on sm_100
 // (SASS: two MUFU.TANH.BF16 + PRMTs), so the float32 approximation + one pack is both cheaper and more accurate.
 __device__ __forceinline__ uint32_t tanh2_pack(float lo, float hi) {
-    uint32_t y;
     const float a = tanh_fast(lo), b = tanh_fast(hi);
+#ifdef TC_PACK_ALU
+    // round to nearest (ties away from zero) on the ALU pipe: F2FP shares the XU pipe with MUFU.TANH
+    return __byte_perm(__float_as_uint(a) + 0x8000u, __float_as_uint(b) + 0x8000u, 0x7632);
+#else
+    uint32_t y;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(b), "f"(a));
     return y;
+#endif
 }
 // one arrival per warp: every lane orders its own shared writes towards the async proxy first
 __device__ __forceinline__ void warp_arrive_after_smem_writes(uint64_t* bar, int lane) {

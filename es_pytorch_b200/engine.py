@@ -67,6 +67,9 @@ class Engine:
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
+    def zeros(self, shape, dtype):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
     def to_device(self, a, dtype=None) -> torch.Tensor:
         if isinstance(a, torch.Tensor):
             t = a
@@ -249,6 +252,39 @@ class Engine:
         check(self.lib.es_centered_rank(self._ctx, _ptr(fpos), _ptr(fneg), K, n_obj, float(w0), float(w1), int(k_begin),
                                         int(k_count), _ptr(weights), _ptr(ranks), self.stream), 'es_centered_rank')
         return (weights, ranks) if want_ranks else weights
+
+    # ------------------------------------------------------------------ f4 (rankers.py:61-103)
+    def rank_transform(self, fpos, fneg, kind: int = 0, w0: float = 1.0, w1: float = 0.0, elite_n: int = 0,
+                       k_begin: int = 0, k_count: Optional[int] = None, noise_idx=None, want64: bool = False,
+                       want_ranks: bool = False, want_elite: bool = False):
+        """Returns a dict: 'weights' f32[k_count] and, on request, 'weights64', 'ranks', 'elite_vals' / 'elite_fit' /
+        'elite_idx' (compact EliteRanker lists in ascending rank order)."""
+        d = self.device
+        _req(fpos, torch.float64, 'fpos', d); _req(fneg, torch.float64, 'fneg', d)
+        if fpos.dim() == 1:
+            fpos, fneg = fpos.view(-1, 1), fneg.view(-1, 1)
+        K, n_obj = fpos.shape
+        assert fneg.shape == (K, n_obj)
+        if k_count is None:
+            k_count = K - k_begin
+        out = {'weights': self.empty((k_count,), torch.float32)}
+        if want64:
+            out['weights64'] = self.empty((k_count,), torch.float64)
+        if want_ranks:
+            out['ranks'] = self.empty((n_obj, 2, k_count), torch.int32)
+        if want_elite and elite_n > 0:
+            out['elite_vals'] = self.zeros((elite_n,), torch.float64)
+            out['elite_fit'] = self.zeros((elite_n,), torch.int32)
+            if noise_idx is not None:
+                _req(noise_idx, torch.int64, 'noise_idx', d)
+                assert noise_idx.numel() == K
+                out['elite_idx'] = self.zeros((elite_n,), torch.int64)
+        check(self.lib.es_rank_transform(self._ctx, _ptr(fpos), _ptr(fneg), K, n_obj, int(kind), float(w0), float(w1),
+                                         int(elite_n), int(k_begin), int(k_count), _ptr(noise_idx), _ptr(out['weights']),
+                                         _ptr(out.get('weights64')), _ptr(out.get('ranks')), _ptr(out.get('elite_vals')),
+                                         _ptr(out.get('elite_fit')), _ptr(out.get('elite_idx')), self.stream),
+              'es_rank_transform')
+        return out
 
     # ------------------------------------------------------------------ a10
     def grad_reconstruct(self, table, idx, weights, P: int, out: Optional[torch.Tensor] = None):

@@ -41,8 +41,9 @@ class DeviceGeneration:
                  optim: Optimizer, ob_clip: float = 5.0, pos_scale: float = 0.05, coins_per_eval: int = 0,
                  save_obs_chance: float = 0.0, archive: Optional[torch.Tensor] = None, nov_k: int = 10,
                  moo_w: float = 1.0, rollout_mode: int = ES_ROLLOUT_F32, comm: Optional[dist.Comm] = None,
-                 engine: Optional[Engine] = None):
+                 engine: Optional[Engine] = None, ranker=None):
         self.eng = engine or get_engine()
+        self.ranker = ranker                            # a utils.rankers.Ranker; None = Centered / MultiObjective(moo_w)
         e = self.eng
         self.comm = comm or dist.world()
         self.table = table
@@ -166,15 +167,21 @@ class DeviceGeneration:
     def update(self, fpos: torch.Tensor, fneg: torch.Tensor):
         """Ranker.rank + es.approx_grad on the device (rankers.py:46-50, es.py:98-101)."""
         e = self.eng
-        w0, w1 = (1.0, 0.0) if self.n_obj == 1 else (self.moo_w, 1 - self.moo_w)
         with self._timed('rank'):
-            self.weights = e.centered_rank(fpos, fneg, w0, w1, self.k_begin, self.k_local)
+            if self.ranker is not None:
+                # any Ranker of utils.rankers: one weight per pair of this shard, n_fits_ranked as the reference
+                self.weights = self.ranker.rank_device(e, fpos, fneg, self.k_begin, self.k_local)
+                n_ranked = float(self.ranker.n_fits_ranked)
+            else:
+                w0, w1 = (1.0, 0.0) if self.n_obj == 1 else (self.moo_w, 1 - self.moo_w)
+                self.weights = e.centered_rank(fpos, fneg, w0, w1, self.k_begin, self.k_local)
+                n_ranked = float(2 * self.K)
         with self._timed('reconstruct'):
             e.grad_reconstruct(self.table, self.idx, self.weights, self.P, self.gsum)
         with self._timed('allreduce'):
             self.comm.allreduce_sum(self.gsum)
         with self._timed('optimizer'):
-            self.apply_optimizer(self.gsum, float(2 * self.K))
+            self.apply_optimizer(self.gsum, n_ranked)
 
     def apply_optimizer(self, gsum: torch.Tensor, n_ranked: float):
         """grad = gsum/n_ranked; theta += optim.step(l2coeff*theta - grad)  (es.py:100-101)."""

@@ -113,6 +113,30 @@ int es_novelty(es_ctx* ctx, const float* behv, int n, const double* archive, int
 int es_centered_rank(es_ctx* ctx, const double* fpos, const double* fneg, int K, int n_obj, float w0, float w1,
                      int k_begin, int k_count, float* weights_out, int32_t* ranks_out, void* stream);
 
+/* ---- f4: the other fitness shapings of src/utils/rankers.py:61-103 ----------------------------
+ * Same ranking as es_centered_rank, then per fitness (n = 2K, r = rank):
+ *   ES_RANK_CENTERED         y = float32(r)/(n-1) - 0.5                         (rankers.py:53-58)
+ *   ES_RANK_DOUBLE_POSITIVE  centered, then y *= 2 where y > 0                  (rankers.py:61-65)
+ *   ES_RANK_SEMI_CENTERED    y = ((1/n)*square(float32(r) + 0.29*n))/n - 0.5    (rankers.py:78-83), float32
+ *   ES_RANK_MAX_NORMALIZED   float64: y = x + (-mn if mn > 0 else mn); y /= max(y); y = 2*y - 1 (rankers.py:68-75);
+ *                            fitnesses must be finite
+ * n_obj == 2: MultiObjectiveRanker blend y0*w0 + y1*w1 in the kind's dtype (rankers.py:106-120).
+ * elite_n == 0: weight[k] = y[k] - y[K+k] (Ranker._post_rank, rankers.py:42-44).
+ * elite_n  > 0: EliteRanker(inner, pct) with elite_n = max(1, int(2K*pct)) (rankers.py:86-103): only the elite_n
+ *   largest y are kept, nothing is subtracted and each elite keeps the noise index of its pair regardless of its
+ *   sign (as the reference does): weight[k] = [y+ elite]*y+ + [y- elite]*y-;  n_fits_ranked = elite_n.  The compact
+ *   lists the reference returns are written in ascending rank order (np.argpartition's order is unspecified):
+ *   elite_vals_out double [elite_n] = ranked[elite], elite_fit_out int32 [elite_n] = index into concat(pos, neg),
+ *   elite_idx_out int64 [elite_n] = noise_idx[fit % K]; only entries whose pair lies in the shard are written.
+ *   Single objective only (ES_ERR_UNSUPPORTED otherwise).
+ *   weights_out dev float [k_count]; weights64_out dev double [k_count] or NULL = the same weight before the cast to
+ *   float32 (MAX_NORMALIZED is a float64 shaping); noise_idx dev int64 [K] or NULL; ranks_out as es_centered_rank. */
+enum { ES_RANK_CENTERED = 0, ES_RANK_DOUBLE_POSITIVE = 1, ES_RANK_SEMI_CENTERED = 2, ES_RANK_MAX_NORMALIZED = 3 };
+int es_rank_transform(es_ctx* ctx, const double* fpos, const double* fneg, int K, int n_obj, int kind, double w0,
+                      double w1, int elite_n, int k_begin, int k_count, const int64_t* noise_idx, float* weights_out,
+                      double* weights64_out, int32_t* ranks_out, double* elite_vals_out, int32_t* elite_fit_out,
+                      int64_t* elite_idx_out, void* stream);
+
 /* ---- a10: gradient reconstruction ---------------------------------------------------------
  * out[p] = sum_k weights[k] * table[idx[k] + p], p in [0,P): scale_noise/batch_noise,
  * src/utils/utils.py:14-39.  HBM-bound: reads n_idx*P*4 bytes of the table once.

@@ -382,6 +382,66 @@ def moo_ranker(fits_pos: np.ndarray, fits_neg: np.ndarray, w: float):
     return (y[:k] - y[k:]).astype(F32), int(y.size)
 
 
+def double_positive_rank(x: np.ndarray) -> np.ndarray:
+    """DoublePositiveCenteredRanker._rank, rankers.py:61-65: centered ranks, positive half times two (float32)."""
+    y = np.array(centered_rank(x), dtype=F32, copy=True)
+    y[y > 0] = (y[y > 0] * F32(2)).astype(F32)
+    return y
+
+
+def max_normalized(x: np.ndarray) -> np.ndarray:
+    """MaxNormalizedRanker._rank, rankers.py:68-75 (float64; the shift ADDS a non-positive minimum, as written)."""
+    x = np.asarray(x, dtype=np.float64)
+    mn = np.min(x)
+    y = x + (-mn if mn > 0 else mn)
+    y = y / np.max(y)
+    y = 2 * y - 1
+    return np.squeeze(y)
+
+
+def semi_centered_rank(x: np.ndarray) -> np.ndarray:
+    """SemiCenteredRanker._rank, rankers.py:78-83: every python-float operand is rounded to float32 by the array
+    operation (numpy 1.18 value-based casting and numpy 2 weak scalars agree); no squeeze."""
+    y = rank(x.ravel()).reshape(x.shape).astype(F32)
+    s = x.size
+    t = (y + F32(0.29 * s)).astype(F32)
+    u = (F32(1 / s) * np.square(t).astype(F32)).astype(F32)
+    return ((u / F32(s)).astype(F32) - F32(0.5)).astype(F32)
+
+
+SHAPINGS = {'centered': centered_rank, 'double_positive': double_positive_rank, 'max_normalized': max_normalized,
+            'semi_centered': semi_centered_rank}
+
+
+def shaped_ranker(fits_pos: np.ndarray, fits_neg: np.ndarray, shaping: str, w: Optional[float] = None):
+    """Ranker.rank (rankers.py:37-50) for any plain shaping; ``w`` not None = MultiObjectiveRanker(shaping, w)
+    (rankers.py:106-120).  Returns (ranked_fits, n_fits_ranked) with the reference's dtype."""
+    fn_ = SHAPINGS[shaping]
+    fits = np.concatenate((fits_pos, fits_neg))
+    if w is None:
+        y = fn_(fits)
+    else:
+        assert fits.shape[1] == 2
+        r0, r1 = fn_(fits[:, 0]), fn_(fits[:, 1])
+        y = r0 * w + r1 * (1 - w)            # python floats: the arrays keep their dtype (float32 / float64)
+        y = y.astype(r0.dtype)
+    k = len(fits_pos)
+    return y[:k] - y[k:], int(y.size)
+
+
+def elite_ranker(fits_pos: np.ndarray, fits_neg: np.ndarray, noise_inds: np.ndarray, shaping: str,
+                 elite_percent: float):
+    """EliteRanker(shaping, elite_percent).rank, rankers.py:86-103: the n_elite largest shaped values, unsubtracted,
+    with ``noise_inds[fit_index % K]``.  np.argpartition's order is unspecified; returned in ascending (stable) order
+    of the shaped values (note: max_normalized DEcreases with the fitness when max + min < 0, rankers.py:71-72).  Returns (ranked_fits[n_elite], noise_inds[n_elite], fit_index[n_elite], n_elite)."""
+    fits = np.concatenate((fits_pos, fits_neg))
+    ranked = np.asarray(SHAPINGS[shaping](fits)).ravel()
+    n_elite = max(1, int(ranked.size * elite_percent))
+    order = np.argsort(ranked, kind='stable')                      # fit indices by ascending shaped value
+    elite = order[-n_elite:]
+    return ranked[elite], np.asarray(noise_inds)[elite % len(noise_inds)], elite, n_elite
+
+
 # ----------------------------------------------------------------------------
 # gradient reconstruction (src/utils/utils.py:14-39) and update (es.py:98-101)
 # ----------------------------------------------------------------------------
@@ -473,14 +533,22 @@ def approx_grad(flat: np.ndarray, optim, ranked_fits: np.ndarray, noise_inds: np
 
 def generation(table, flat, optim, std, dims, env, rank_seeds, n_per_rank, obmean, obstd, ob_clip, max_steps,
                batch_size, l2coeff, moo_w: Optional[float] = None, archive=None, nov_k=10,
-               coins_per_eval=0, rank_states=None, batched=True):
-    """One whole generation (es.py:38-47 without the reporter / noiseless eval)."""
+               coins_per_eval=0, rank_states=None, batched=True, shaping: str = 'centered',
+               elite_percent: Optional[float] = None):
+    """One whole generation (es.py:38-47 without the reporter / noiseless eval).  ``shaping`` / ``elite_percent`` select
+    the other rankers of rankers.py:61-103 (obj.py:48-50 picks EliteRanker(CenteredRanker(), elite))."""
     pos, neg, inds, steps, obstat = es_test_params(table, flat, std, dims, env, rank_seeds, n_per_rank, obmean, obstd,
                                                 ob_clip, max_steps, coins_per_eval=coins_per_eval, archive=archive,
                                                 nov_k=nov_k, batched=batched, rank_states=rank_states)
-    if archive is None:
+    grad_inds = inds
+    if elite_percent is not None:
+        w, grad_inds, _, n_ranked = elite_ranker(pos, neg, inds, shaping, elite_percent)
+    elif shaping != 'centered':
+        w, n_ranked = shaped_ranker(pos, neg, shaping, None if archive is None else moo_w)
+        w = np.asarray(w).reshape(-1)
+    elif archive is None:
         w, n_ranked = centered_ranker(pos, neg)
     else:
         w, n_ranked = moo_ranker(pos, neg, moo_w)
-    approx_grad(flat, optim, w, inds, n_ranked, table, batch_size, l2coeff)
+    approx_grad(flat, optim, w, grad_inds, n_ranked, table, batch_size, l2coeff)
     return dict(pos=pos, neg=neg, inds=inds, steps=steps, weights=w, n_ranked=n_ranked, obstat=obstat)

@@ -20,6 +20,11 @@ def ref_vectors():
 
 
 @pytest.fixture(scope='session')
+def ranker_vectors():
+    return np.load(os.path.join(GOLDEN, 'ref_rankers.npz'))
+
+
+@pytest.fixture(scope='session')
 def oracle_vectors():
     return np.load(os.path.join(GOLDEN, 'oracle_vectors.npz'))
 

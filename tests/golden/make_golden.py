@@ -69,6 +69,40 @@ def ref_vectors():
     print('ref_vectors.npz', len(out), 'arrays')
 
 
+def ref_ranker_vectors():
+    """The rankers outside the north-star pair (rankers.py:61-103), from the REAL module."""
+    sys.path.insert(0, '/root/reference')
+    from src.utils import rankers as R
+    out = {}
+    rs = np.random.RandomState(4242)
+    plain = {'double_positive': R.DoublePositiveCenteredRanker, 'max_normalized': R.MaxNormalizedRanker,
+             'semi_centered': R.SemiCenteredRanker, 'centered': R.CenteredRanker}
+    for tag, k, off in (('a', 7, 0.0), ('b', 64, 0.0), ('c', 501, 0.0), ('d', 33, 20.0)):
+        pos, neg = rs.randn(k, 1) * 3 + off, rs.randn(k, 1) * 3 + off
+        pos2, neg2 = rs.randn(k, 2) + off, rs.randn(k, 2) + off
+        inds = rs.randint(0, 10 ** 6, k).astype(np.float64)
+        out[f'{tag}_pos'], out[f'{tag}_neg'], out[f'{tag}_pos2'], out[f'{tag}_neg2'] = pos, neg, pos2, neg2
+        out[f'{tag}_inds'] = inds
+        for name, cls in plain.items():
+            if name != 'centered':
+                r = cls()
+                out[f'{tag}_{name}_w'] = r.rank(pos, neg, inds)
+                out[f'{tag}_{name}_n'] = np.array(r.n_fits_ranked)
+                m = R.MultiObjectiveRanker(cls(), 0.3)
+                out[f'{tag}_moo_{name}_w'] = m.rank(pos2, neg2, inds)
+            if name == 'semi_centered':
+                continue        # EliteRanker(SemiCenteredRanker) fails inside the reference (argpartition on a [2K,1] array)
+            for ptag, pct in (('p00', 0.0), ('p10', 0.1), ('p50', 0.5), ('p100', 1.0)):
+                e = R.EliteRanker(cls(), pct)
+                vals = e.rank(pos, neg, inds)
+                order = np.lexsort((e.noise_inds, vals))            # argpartition order is unspecified: store sorted
+                out[f'{tag}_elite_{name}_{ptag}_vals'] = np.asarray(vals)[order]
+                out[f'{tag}_elite_{name}_{ptag}_inds'] = np.asarray(e.noise_inds)[order]
+                out[f'{tag}_elite_{name}_{ptag}_n'] = np.array(e.n_fits_ranked)
+    np.savez_compressed(os.path.join(HERE, 'ref_rankers.npz'), **out)
+    print('ref_rankers.npz', len(out), 'arrays')
+
+
 def small_problem(seed=5, obs_dim=17, act_dim=6, hidden=(64, 64), T=40, table_len=200_003):
     dims = orc.layer_dims(obs_dim, hidden, act_dim)
     P = orc.n_params(dims)
@@ -118,4 +152,5 @@ def oracle_vectors():
 
 if __name__ == '__main__':
     ref_vectors()
+    ref_ranker_vectors()
     oracle_vectors()

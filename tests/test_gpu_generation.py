@@ -57,6 +57,32 @@ def test_device_generation_matches_golden(eng, oracle_vectors):
         assert np.array_equal(a.get_state()[1], b.get_state()[1]) and a.get_state()[2] == b.get_state()[2]
 
 
+@pytest.mark.parametrize('shaping,elite', [('centered', 0.25), ('double_positive', None), ('semi_centered', None),
+                                           ('max_normalized', None), ('max_normalized', 0.5)])
+def test_device_generation_other_rankers(eng, oracle_vectors, shaping, elite):
+    """DeviceGeneration(ranker=...) with the rankers of rankers.py:61-103 (obj.py:50 uses the elite one) against the
+    oracle's generation on the same seeds."""
+    from es_pytorch_b200.nn.optimizers import Adam
+    from es_pytorch_b200.utils import rankers as R
+    v = oracle_vectors
+    dims, P, table, theta, env = _small(eng)
+    cls = {'centered': R.CenteredRanker, 'double_positive': R.DoublePositiveCenteredRanker,
+           'semi_centered': R.SemiCenteredRanker, 'max_normalized': R.MaxNormalizedRanker}[shaping]
+    ranker = cls() if elite is None else R.EliteRanker(cls(), elite)
+    streams = [np.random.RandomState(1000), np.random.RandomState(1001)]
+    gen = _mk_generation(eng, table, theta, env, streams, Adam(P, 0.01), sizes=[17, 64, 64, 6], ranker=ranker)
+    gen.set_obstat(v['obmean'], v['obstd'])
+    flat, opt = theta.copy(), orc.AdamOracle(P, 0.01)
+    ostates = [np.random.RandomState(1000), np.random.RandomState(1001)]
+    for g in range(2):
+        res = orc.generation(table, flat, opt, 0.02, dims, env, [1000, 1001], 6, v['obmean'], v['obstd'], 5.0, env.T,
+                             500, 0.005, rank_states=ostates, shaping=shaping, elite_percent=elite)
+        gen.run(6)
+        assert ranker.n_fits_ranked == res['n_ranked']
+        assert np.array_equal(gen.idx.cpu().numpy(), res['inds'].astype(np.int64))
+        assert np.abs(gen.theta.cpu().numpy() - flat).max() <= 2e-6
+
+
 def test_device_generation_nsra_matches_golden(eng, oracle_vectors):
     from es_pytorch_b200.nn.optimizers import Adam
     v = oracle_vectors

@@ -218,6 +218,147 @@ def test_rank_integer_ties_and_nan(eng):
     assert np.array_equal(w.cpu().numpy(), orc.centered_ranker(pos, neg)[0])
 
 
+# ------------------------------------------------------------------------------------------- f4: rankers.py:61-103
+RANKER_CLASSES = {'centered': 'CenteredRanker', 'double_positive': 'DoublePositiveCenteredRanker',
+                  'max_normalized': 'MaxNormalizedRanker', 'semi_centered': 'SemiCenteredRanker'}
+
+
+def _ranker(name):
+    from es_pytorch_b200.utils import rankers as R
+    return getattr(R, RANKER_CLASSES[name])()
+
+
+@pytest.mark.parametrize('tag', ['a', 'b', 'c', 'd'])
+@pytest.mark.parametrize('name', ['double_positive', 'max_normalized', 'semi_centered'])
+def test_shaped_rankers_golden(eng, ranker_vectors, tag, name):
+    """The public Ranker API against outputs of the real reference module: bit-exact, dtype and shape included."""
+    from es_pytorch_b200.utils import rankers as R
+    v = ranker_vectors
+    r = _ranker(name)
+    w = r.rank(v[f'{tag}_pos'], v[f'{tag}_neg'], v[f'{tag}_inds'])
+    ref = v[f'{tag}_{name}_w']
+    assert w.dtype == ref.dtype and w.shape == ref.shape and r.n_fits_ranked == int(v[f'{tag}_{name}_n'])
+    assert np.array_equal(w, ref)
+    m = R.MultiObjectiveRanker(_ranker(name), 0.3)
+    w2 = m.rank(v[f'{tag}_pos2'], v[f'{tag}_neg2'], v[f'{tag}_inds'])
+    ref2 = v[f'{tag}_moo_{name}_w']
+    assert w2.dtype == ref2.dtype and np.array_equal(w2.reshape(ref2.shape), ref2)
+
+
+@pytest.mark.parametrize('tag', ['a', 'b', 'c', 'd'])
+@pytest.mark.parametrize('name', ['centered', 'double_positive', 'max_normalized'])
+@pytest.mark.parametrize('ptag,pct', [('p00', 0.0), ('p10', 0.1), ('p50', 0.5), ('p100', 1.0)])
+def test_elite_ranker_golden(eng, ranker_vectors, tag, name, ptag, pct):
+    from es_pytorch_b200.utils import rankers as R
+    v = ranker_vectors
+    e = R.EliteRanker(_ranker(name), pct)
+    vals = e.rank(v[f'{tag}_pos'], v[f'{tag}_neg'], v[f'{tag}_inds'])
+    ref_v = v[f'{tag}_elite_{name}_{ptag}_vals']
+    assert e.n_fits_ranked == int(v[f'{tag}_elite_{name}_{ptag}_n']) == len(vals) == len(e.noise_inds)
+    assert vals.dtype == ref_v.dtype
+    order = np.lexsort((e.noise_inds, vals))            # np.argpartition's order is unspecified: compare as sets
+    assert np.array_equal(np.asarray(vals)[order], ref_v)
+    assert np.array_equal(np.asarray(e.noise_inds)[order], v[f'{tag}_elite_{name}_{ptag}_inds'])
+
+
+@pytest.mark.parametrize('name', ['centered', 'double_positive', 'max_normalized', 'semi_centered'])
+@pytest.mark.parametrize('K,n_obj', [(1, 1), (777, 1), (3000, 2), (10000, 1)])
+def test_rank_transform_vs_oracle_and_shards(eng, name, K, n_obj):
+    from es_pytorch_b200 import _lib
+    kind = getattr(_lib, 'ES_RANK_' + name.upper())
+    rs = np.random.RandomState(K + 1)
+    pos, neg = rs.randn(K, n_obj) * 10 + 1, rs.randn(K, n_obj) * 10 + 1
+    if K > 100:
+        pos[5] = pos[17]; neg[3] = pos[5]; pos[40] = 0.0; neg[41] = -0.0     # ties and signed zeros
+    if K == 1 and name == 'max_normalized':
+        pytest.skip('a single pair normalises by max(y) = 0 for some draws')
+    ref, n = orc.shaped_ranker(pos, neg, name, None if n_obj == 1 else 0.37)
+    w0, w1 = (1.0, 0.0) if n_obj == 1 else (0.37, 1 - 0.37)
+    fp, fn = dev(eng, pos), dev(eng, neg)
+    out = eng.rank_transform(fp, fn, kind, w0, w1, want64=True)
+    got = out['weights64'].cpu().numpy()
+    assert np.array_equal(got, np.asarray(ref, dtype=np.float64).reshape(-1))     # float32 shapings widen exactly
+    assert np.array_equal(out['weights'].cpu().numpy(), got.astype(np.float32))
+    if K >= 4:
+        b, cnt = K // 4, K // 2
+        ws = eng.rank_transform(fp, fn, kind, w0, w1, k_begin=b, k_count=cnt, want64=True)['weights64']
+        assert np.array_equal(ws.cpu().numpy(), got[b:b + cnt])
+
+
+@pytest.mark.parametrize('name', ['centered', 'double_positive', 'max_normalized'])
+@pytest.mark.parametrize('K,pct', [(777, 0.05), (10000, 0.1), (10000, 1.0)])
+def test_elite_vs_oracle_pair_weights_and_shards(eng, name, K, pct):
+    """Compact elite lists == oracle (same order: ascending shaped value); the per-pair weights the sharded generation
+    uses are the scatter of that list; shards write disjoint parts of it."""
+    from es_pytorch_b200 import _lib
+    kind = getattr(_lib, 'ES_RANK_' + name.upper())
+    rs = np.random.RandomState(K + 7)
+    pos, neg = rs.randn(K, 1) * 10 + 3, rs.randn(K, 1) * 10 + 3
+    inds = rs.randint(0, 10 ** 8, K).astype(np.int64)
+    vals, sel, fit, n_el = orc.elite_ranker(pos, neg, inds, name, pct)
+    fp, fn, di = dev(eng, pos), dev(eng, neg), dev(eng, inds)
+    out = eng.rank_transform(fp, fn, kind, elite_n=n_el, noise_idx=di, want64=True, want_elite=True)
+    assert np.array_equal(out['elite_fit'].cpu().numpy(), fit)
+    assert np.array_equal(out['elite_idx'].cpu().numpy(), sel)
+    assert np.array_equal(out['elite_vals'].cpu().numpy(), np.asarray(vals, dtype=np.float64))
+    dt = np.float64 if name == 'max_normalized' else np.float32
+    pw = np.zeros(K, dtype=dt)
+    for vv, f in zip(np.asarray(vals, dtype=dt), fit):             # at most two terms per pair: order-free
+        pw[f % K] += vv
+    assert np.array_equal(out['weights64'].cpu().numpy(), pw.astype(np.float64))
+    b, cnt = K // 4, K // 2
+    part = eng.rank_transform(fp, fn, kind, elite_n=n_el, k_begin=b, k_count=cnt, noise_idx=di, want_elite=True)
+    inside = (fit % K >= b) & (fit % K < b + cnt)
+    assert np.array_equal(part['elite_fit'].cpu().numpy()[inside], fit[inside])
+    assert np.all(part['elite_fit'].cpu().numpy()[~inside] == 0)
+    assert np.array_equal(part['weights'].cpu().numpy(), pw[b:b + cnt].astype(np.float32))
+
+
+def test_rank_transform_rejects(eng):
+    from es_pytorch_b200._lib import EsLibraryError
+    from es_pytorch_b200.utils import rankers as R
+    fp = dev(eng, np.zeros((4, 2)))
+    with pytest.raises(EsLibraryError):
+        eng.rank_transform(fp, fp, 0, 0.5, 0.5, elite_n=2)         # elite over two objectives
+    with pytest.raises(EsLibraryError):
+        eng.rank_transform(fp, fp, 7)                              # unknown shaping
+    with pytest.raises(NotImplementedError):
+        R.EliteRanker(R.MultiObjectiveRanker(R.CenteredRanker(), 0.5), 0.1)
+    with pytest.raises(ValueError):
+        R.CenteredRanker().rank(np.zeros((4, 2)), np.zeros((4, 2)), np.arange(4))
+
+
+def test_elite_approx_grad_matches_oracle(eng):
+    """obj.py:50's EliteRanker(CenteredRanker(), elite) through es.approx_grad: theta within 1e-5 of the oracle."""
+    from es_pytorch_b200.core import es
+    from es_pytorch_b200.core.noisetable import NoiseTable
+    from es_pytorch_b200.core.policy import Policy
+    from es_pytorch_b200.nn.nn import FeedForward
+    from es_pytorch_b200.nn.optimizers import Adam
+    from es_pytorch_b200.gym import synthetic_env
+    from es_pytorch_b200.utils import rankers as R
+    import torch.nn as tnn
+    env = synthetic_env.SyntheticEnv(17, 6, 20)
+    net = FeedForward([64, 64], tnn.Tanh(), env, 0.0)
+    P = len(Policy.get_flat(net))
+    table = np.random.RandomState(5).randn(300_000).astype(np.float32)
+    nt = NoiseTable(P, table)
+    policy = Policy(net, 0.02, Adam(P, 0.01))
+    theta0 = policy.flat_params.copy()
+    K = 400
+    rs = np.random.RandomState(9)
+    pos, neg = rs.randn(K, 1), rs.randn(K, 1)
+    inds = rs.randint(0, len(table) - P, K).astype(np.float64)
+    ranker = R.EliteRanker(R.CenteredRanker(), 0.2)
+    ranker.rank(pos, neg, inds)
+    es.approx_grad(policy, ranker, nt, policy.flat_params, 500, 0.005)
+    vals, sel, fit, n_el = orc.elite_ranker(pos, neg, inds, 'centered', 0.2)
+    flat = theta0.copy()
+    orc.approx_grad(flat, orc.AdamOracle(P, 0.01), vals, sel, n_el, table, 500, 0.005)
+    assert ranker.n_fits_ranked == n_el
+    assert np.max(np.abs(policy.flat_params - flat)) <= 1e-5 * max(1.0, np.max(np.abs(flat)))
+
+
 # ------------------------------------------------------------------------------------------- a10
 def test_reconstruct_reference_known_answer(eng):
     """test/utils/utils_test.py:24-40 (integer data: exact in any summation order)."""

@@ -164,3 +164,33 @@ def test_oracle_frozen_vectors(oracle_vectors):
     rews_b, _, _, _ = orc.run_model(env, layers, v['obmean'], v['obstd'], 5.0, env.T, batched=True)
     assert np.allclose(rews_b, rews, rtol=1e-4, atol=1e-5)
     assert np.array_equal(orc.normalise_obs(env.obs_stream[:env.T], v['obmean'], v['obstd'], 5.0), v['obsn'])
+
+
+# ---- the rankers outside the north-star pair (rankers.py:61-103), pinned by the real module ----------------------
+RK = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_rankers.npz'))
+RK_TAGS = ('a', 'b', 'c', 'd')
+
+
+@pytest.mark.parametrize('tag', RK_TAGS)
+@pytest.mark.parametrize('name', ['double_positive', 'max_normalized', 'semi_centered'])
+def test_shaped_rankers_match_reference(tag, name):
+    w, n = orc.shaped_ranker(RK[f'{tag}_pos'], RK[f'{tag}_neg'], name)
+    ref = RK[f'{tag}_{name}_w']
+    assert w.dtype == ref.dtype and w.shape == ref.shape and n == int(RK[f'{tag}_{name}_n'])
+    assert np.array_equal(w, ref)                                   # bit-exact, float32 and float64 shapings alike
+    w2, _ = orc.shaped_ranker(RK[f'{tag}_pos2'], RK[f'{tag}_neg2'], name, w=0.3)
+    ref2 = RK[f'{tag}_moo_{name}_w']
+    assert w2.dtype == ref2.dtype and np.array_equal(w2.reshape(ref2.shape), ref2)
+
+
+@pytest.mark.parametrize('tag', RK_TAGS)
+@pytest.mark.parametrize('name', ['centered', 'double_positive', 'max_normalized'])
+@pytest.mark.parametrize('ptag,pct', [('p00', 0.0), ('p10', 0.1), ('p50', 0.5), ('p100', 1.0)])
+def test_elite_ranker_matches_reference(tag, name, ptag, pct):
+    vals, inds, fit, n = orc.elite_ranker(RK[f'{tag}_pos'], RK[f'{tag}_neg'], RK[f'{tag}_inds'], name, pct)
+    assert n == int(RK[f'{tag}_elite_{name}_{ptag}_n']) == len(vals)
+    order = np.lexsort((inds, vals))                                # the reference's order is unspecified: compare sets
+    ref_v = RK[f'{tag}_elite_{name}_{ptag}_vals']
+    assert vals.dtype == ref_v.dtype
+    assert np.array_equal(vals[order], ref_v)
+    assert np.array_equal(inds[order], RK[f'{tag}_elite_{name}_{ptag}_inds'])
