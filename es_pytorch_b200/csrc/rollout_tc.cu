@@ -92,7 +92,7 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try(bar, parity)) {
-        if (++spins > TC_SPIN_LIMIT) { printf("rollout_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+        if (++spins > TC_SPIN_LIMIT) __trap();   // watchdog (no printf: its call ABI costs registers in every role)
     }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
@@ -195,6 +195,11 @@ __device__ __forceinline__ float2 lds64f(uint32_t saddr) {
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
     return v;
 }
+__device__ __forceinline__ float4 lds128f(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
 __device__ __forceinline__ float lds32f(uint32_t saddr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
@@ -213,11 +218,43 @@ __device__ __forceinline__ uint32_t tanh2_pack(float lo, float hi) {
     return y;
 #endif
 }
+// Transposing butterfly: the warp-wide sums of v[0..7] in 9 shuffles.  Lane L returns the sum of v[tc_sum8_index(L)].
+__device__ __forceinline__ int tc_sum8_index(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
+__device__ __forceinline__ float tc_warp_sum8(const float (&v)[8], int lane) {
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    float a[4], b[2], c;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = (h16 ? v[i + 4] : v[i]) + __shfl_xor_sync(0xffffffffu, h16 ? v[i] : v[i + 4], 16);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) b[i] = (h8 ? a[i + 2] : a[i]) + __shfl_xor_sync(0xffffffffu, h8 ? a[i] : a[i + 2], 8);
+    c = (h4 ? b[1] : b[0]) + __shfl_xor_sync(0xffffffffu, h4 ? b[0] : b[1], 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    return c;
+}
 // one arrival per warp: every lane orders its own shared writes towards the async proxy first
 __device__ __forceinline__ void warp_arrive_after_smem_writes(uint64_t* bar, int lane) {
     fence_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar);
+}
+// read-once table data: do not allocate in L1 (the epilogue warps' U / reward-coefficient lines and the few spilled
+// registers live there; 118 KB of slice per pair would evict them)
+__device__ __forceinline__ float ldg_stream(const float* p) {
+    float v;
+    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+    float4 v;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+// pinned-in-program-order read-only load (the compiler may not hoist it above a preceding fence / barrier arrive)
+__device__ __forceinline__ float ldg_pinned(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -253,15 +290,15 @@ __device__ __forceinline__ void tc_build_l1_rows(uint8_t* b1_base, const float* 
         const int n = 2 * rp;
         const float* __restrict__ wa = w + (size_t)n * obs;
         const float* __restrict__ wb = wa + obs;
-        const float ba = __ldg(bvec + n), bb = __ldg(bvec + n + 1);
+        const float ba = ldg_stream(bvec + n), bb = ldg_stream(bvec + n + 1);
         for (int kc0 = 0; kc0 < nkc; kc0 += KB) {
             float xa0[KB], xa1[KB], xb0[KB], xb1[KB];
 #pragma unroll
             for (int j = 0; j < KB; ++j) {
                 const int k = (kc0 + j) * TC_KC + c0;
                 const int k0 = min(k, obs - 1), k1 = min(k + 1, obs - 1);
-                xa0[j] = __ldg(wa + k0); xa1[j] = __ldg(wa + k1);
-                xb0[j] = __ldg(wb + k0); xb1[j] = __ldg(wb + k1);
+                xa0[j] = ldg_stream(wa + k0); xa1[j] = ldg_stream(wa + k1);
+                xb0[j] = ldg_stream(wb + k0); xb1[j] = ldg_stream(wb + k1);
             }
 #pragma unroll
             for (int j = 0; j < KB; ++j) {
@@ -305,7 +342,14 @@ struct TcParams {
     int dev_noload;               // dev experiment: skip the observation-tile copies (results are garbage)
 };
 
+// a real instruction that consumes x: in-order issue makes the following clock read wait for x's producer (LDTM, LDG)
+#ifdef TC_TRACE_ENABLE      // development build only (es_pytorch_b200.build.build_variant('trace', ['TC_TRACE_ENABLE']))
+#define TC_TOUCH(val_) do { if (p.trace && blockIdx.x == 0) asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p.trace + 2047), "r"(val_) : "memory"); } while (0)
 #define TC_TRACE(role, slot) do { if (p.trace && blockIdx.x == 0 && (slot) < 512) p.trace[(role) * 512 + (slot)] = clock64(); } while (0)
+#else
+#define TC_TOUCH(val_) do { } while (0)
+#define TC_TRACE(role, slot) do { } while (0)
+#endif
 
 struct TcSmemLayout {   // byte offsets from the 1024-aligned dynamic smem base
     uint32_t b1, a_stage, w2p, w2n, w3p, w3n, h, bias, bars, total;
@@ -363,7 +407,12 @@ __device__ __forceinline__ void tc_issue_4k(uint32_t d, uint64_t a_desc, uint64_
     umma_bf16(d, a_desc + 6, b_desc + 6, idesc, 1);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_constant__ TcParams p) {
+#ifdef TC_MAXNREG
+__global__ void __maxnreg__(TC_MAXNREG) rollout_tc_kernel(
+#else
+__global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(
+#endif
+    const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const TcSmemLayout L = tc_layout(p.nkc);
@@ -519,19 +568,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
         const uint32_t tm_d2p = tmem + 128 + eg * 128 + lane_base + h * 32, tm_d2n = tm_d2p + 64;
         const uint32_t tm_d3p = tmem + 384 + eg * 64 + lane_base + h * 16, tm_d3n = tm_d3p + 32;
         const bool has_act = h * 16 < p.act;                  // L3: this warp owns action columns 16h..16h+15
-        const int j1 = 1 % p.act, j2 = 2 % p.act;
-        uint32_t k = 0;                                       // tiles handled by this group so far
+        const int nj = min(16, p.act - h * 16);              // action columns this warp owns (warp-uniform)
+        // (few loop-carried scalars on purpose: the role must fit 72 registers without spilling)
         for (int i = 0; i < my_pairs; ++i) {
-            const int pair = blockIdx.x + i * gridDim.x;
-            const uint32_t bias = smem_u32(bias_all + (i & 1) * 256);
-            const uint32_t b2p = bias + h * 128, b2n = bias + TC_H * 4 + h * 128;
-            const uint32_t b3p = bias + 2 * TC_H * 4 + h * 64, b3n = bias + (2 * TC_H + TC_ACT_PAD) * 4 + h * 64;
-            float fitp = 0.f, fitn = 0.f, pp0 = 0.f, pp1 = 0.f, pp2 = 0.f, pn0 = 0.f, pn1 = 0.f, pn2 = 0.f;
-            bool bias_ready = false;
+            const uint32_t b2p = smem_u32(bias_all + (i & 1) * 256) + h * 128, b2n = b2p + TC_H * 4;
+            const uint32_t b3p = b2p + 2 * TC_H * 4 - h * 64, b3n = b3p + TC_ACT_PAD * 4;
+            // running sums of the pair, ONE register per thread: after every tile the warp reduces its 8 values
+            // {fit+, fit-, pos+[3], pos-[3]} with a transposing butterfly; lane L accumulates value (L>>2)&7 (bit-reversed)
+            float acc = 0.f;
             for (uint32_t g = (uint32_t)i * NMT; g < (uint32_t)(i + 1) * NMT; ++g) {
                 if ((g & 1) != eg) continue;
-                const uint32_t par = k & 1;
-                ++k;
+                const uint32_t par = (g >> 1) & 1;                    // this group has handled g >> 1 tiles before tile g
                 const int m = (int)(g - (uint32_t)i * NMT);
                 const int t = m * TC_MT + row;
                 const float4* __restrict__ up = reinterpret_cast<const float4*>(p.ubase) + ((size_t)(m * 2 + h) * 8) * TC_MT + row;
@@ -539,22 +586,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
                 mbar_wait(&bars[BAR_D1_FULL + eg], par);
                 if (ew == 0 && lane == 0) TC_TRACE(1, 8 * g + 1);
                 tc_fence_after();
-                // ---- epi1: h1+ = tanh(U + V), then h1- = tanh(U - V) (V is re-read from TMEM: cheaper than 32 registers) ----
+                // ---- epi1: h1+ = tanh(U + V) and h1- = tanh(U - V) from one read of U (float32, coalesced float4 loads from L2,
+                //      read once: not allocated in L1) and one read of V (TMEM), 8 columns at a time (small batches keep the
+                //      role below the 72-register budget: a spilled loop variable costs an L2 round trip per tile) ----
 #pragma unroll
-                for (int sgn = 0; sgn < 2; ++sgn) {
-                    const uint32_t hrow = sgn ? hn_row : hp_row;
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    float4 ub[2];
 #pragma unroll
-                    for (int c2 = 0; c2 < 2; ++c2) {
-                        // unperturbed pre-activation (float32; coalesced float4 loads, L1/L2 resident) and the perturbation V
-                        float4 ub[4];
+                    for (int c = 0; c < 2; ++c) ub[c] = ldg_stream4(up + (c4 * 2 + c) * TC_MT);
+                    uint32_t v[8];
+                    tmem_ld8(tm_v + c4 * 8, v);
+                    tmem_ld_wait();
+                    if (c4 == 0) { TC_TOUCH(v[7]); if (ew == 0 && lane == 0) TC_TRACE(2, 8 * g + 0); }
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) ub[c] = __ldg(up + (c2 * 4 + c) * TC_MT);
-                        uint32_t v[16];
-                        tmem_ld16(tm_v + c2 * 16, v);
-                        tmem_ld_wait();
-                        uint32_t w[8];
+                    for (int sgn = 0; sgn < 2; ++sgn) {
+                        uint32_t w[4];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
+                        for (int e = 0; e < 4; ++e) {
                             const float4 u4 = ub[e >> 1];
                             const float u0 = (e & 1) ? u4.z : u4.x, u1 = (e & 1) ? u4.w : u4.y;
                             float z0, z1;
@@ -562,18 +610,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
                             else     add2(z0, z1, __float_as_uint(u0), __float_as_uint(u1), v[2 * e], v[2 * e + 1]);
                             w[e] = tanh2_pack(z0, z1);
                         }
-                        sts128(hrow + (((h * 4 + c2 * 2) ^ sw) << 4), w[0], w[1], w[2], w[3]);
-                        sts128(hrow + (((h * 4 + c2 * 2 + 1) ^ sw) << 4), w[4], w[5], w[6], w[7]);
+                        sts128((sgn ? hn_row : hp_row) + (((h * 4 + c4) ^ sw) << 4), w[0], w[1], w[2], w[3]);
                     }
-                    if (sgn) {                                        // V fully consumed: the buffer may be refilled
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&bars[BAR_D1_FREE + eg]);
+                }
+                if (ew == 0 && lane == 0) TC_TRACE(2, 8 * g + 1);
+                {   // V fully consumed: the buffer may be refilled; both H tiles are complete
+                    tc_fence_before();
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&bars[BAR_D1_FREE + eg]);
+                        mbar_arrive(&bars[BAR_H1P + eg]);
+                        mbar_arrive(&bars[BAR_H1N + eg]);
                     }
-                    warp_arrive_after_smem_writes(&bars[(sgn ? BAR_H1N : BAR_H1P) + eg], lane);
                 }
                 if (ew == 0 && lane == 0) TC_TRACE(1, 8 * g + 2);
-                if (!bias_ready) { mbar_wait(&bars[BAR_W_READY], i & 1); bias_ready = true; }   // biases of this pair are in place
+                if (m < 2) mbar_wait(&bars[BAR_W_READY], i & 1);      // this group's first tile of the pair: biases in place?
                 // ---- epi2 (+ then -): h2 = tanh(D2 + b2), overwrites this warp's part of H ----
 #pragma unroll
                 for (int sgn = 0; sgn < 2; ++sgn) {
@@ -583,26 +635,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
                     const uint32_t b2 = sgn ? b2n : b2p;
                     const uint32_t hrow = sgn ? hn_row : hp_row;
 #pragma unroll
-                    for (int c2 = 0; c2 < 2; ++c2) {
-                        uint32_t d[16];
-                        tmem_ld16((sgn ? tm_d2n : tm_d2p) + c2 * 16, d);
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        uint32_t d[8];
+                        tmem_ld8((sgn ? tm_d2n : tm_d2p) + c4 * 8, d);
+                        const float4 bb0 = lds128f(b2 + c4 * 32), bb1 = lds128f(b2 + c4 * 32 + 16);
                         tmem_ld_wait();
-                        uint32_t w[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float2 bb = lds64f(b2 + (c2 * 16 + 2 * e) * 4);
-                            float z0, z1;
-                            add2(z0, z1, d[2 * e], d[2 * e + 1], __float_as_uint(bb.x), __float_as_uint(bb.y));
-                            w[e] = tanh2_pack(z0, z1);
-                        }
-                        sts128(hrow + (((h * 4 + c2 * 2) ^ sw) << 4), w[0], w[1], w[2], w[3]);
-                        sts128(hrow + (((h * 4 + c2 * 2 + 1) ^ sw) << 4), w[4], w[5], w[6], w[7]);
+                        if (c4 == 0 && sgn == 0) { TC_TOUCH(d[7]); if (ew == 0 && lane == 0) TC_TRACE(2, 8 * g + 2); }
+                        uint32_t w[4];
+                        float z0, z1;
+                        add2(z0, z1, d[0], d[1], __float_as_uint(bb0.x), __float_as_uint(bb0.y)); w[0] = tanh2_pack(z0, z1);
+                        add2(z0, z1, d[2], d[3], __float_as_uint(bb0.z), __float_as_uint(bb0.w)); w[1] = tanh2_pack(z0, z1);
+                        add2(z0, z1, d[4], d[5], __float_as_uint(bb1.x), __float_as_uint(bb1.y)); w[2] = tanh2_pack(z0, z1);
+                        add2(z0, z1, d[6], d[7], __float_as_uint(bb1.z), __float_as_uint(bb1.w)); w[3] = tanh2_pack(z0, z1);
+                        sts128(hrow + (((h * 4 + c4) ^ sw) << 4), w[0], w[1], w[2], w[3]);
                     }
+                    if (ew == 0 && lane == 0 && sgn == 0) TC_TRACE(2, 8 * g + 3);
                     tc_fence_before();
                     warp_arrive_after_smem_writes(&bars[(sgn ? BAR_H2N : BAR_H2P) + eg], lane);
                 }
                 // ---- epi3 (+ then -): a = tanh(D3 + b3); reward and position (action columns 16h..16h+15) ----
-                const float* __restrict__ ccol = p.crt + ((size_t)m * TC_ACT_PAD + h * 16) * TC_MT + row;   // coalesced, L1/L2 resident
+                const float* __restrict__ ccol = p.crt + ((size_t)m * TC_ACT_PAD + h * 16) * TC_MT + row;   // coalesced, L2 resident
+                // reward coefficients of this row (same for both signs): issued right after the H2- arrive, before the wait for
+                // D3 (pinned: hoisted above the fence they would make it wait for the loads)
+                float cc[16];
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) cc[jj] = (jj < nj) ? ldg_pinned(ccol + jj * TC_MT) : 0.f;
+                float tv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int sgn = 0; sgn < 2; ++sgn) {
                     if (ew == 0 && lane == 0 && sgn == 0) TC_TRACE(1, 8 * g + 5);
@@ -610,39 +668,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
                     if (ew == 0 && lane == 0) TC_TRACE(1, 8 * g + 6 + sgn);
                     if (has_act) {
                         tc_fence_after();
-                        uint32_t d[16];
-                        tmem_ld16(sgn ? tm_d3n : tm_d3p, d);
-                        tmem_ld_wait();
                         const uint32_t b3 = sgn ? b3n : b3p;
                         float r = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
+                        // 8 columns per TMEM load, branch-free groups of four (a uniform branch per group only): the padded
+                        // columns have zero weights, zero bias and zero reward coefficient, so they contribute tanh(0) * 0
 #pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) {
-                            const int j = h * 16 + jj;
-                            if (j < p.act) {
-                                const float a = tanh_fast(__uint_as_float(d[jj]) + lds32f(b3 + jj * 4));
-                                r = fmaf(a, __ldg(ccol + jj * TC_MT), r);
-                                if (j == 0) q0 += a;
-                                if (j == j1) q1 += a;
-                                if (j == j2) q2 += a;
+                        for (int hf = 0; hf < 2; ++hf) {
+                            if (hf * 8 < nj) {
+                                uint32_t d[8];
+                                tmem_ld8((sgn ? tm_d3n : tm_d3p) + hf * 8, d);
+                                tmem_ld_wait();
+                                if (hf == 0) { TC_TOUCH(d[7]); if (ew == 0 && lane == 0) TC_TRACE(2, 8 * g + 4 + 2 * sgn); }
+#pragma unroll
+                                for (int g4 = 0; g4 < 2; ++g4) {
+                                    const int gq = hf * 2 + g4;
+                                    if (gq * 4 < nj) {
+                                        const float4 bb = lds128f(b3 + gq * 16);
+                                        const float a0 = tanh_fast(__uint_as_float(d[g4 * 4 + 0]) + bb.x);
+                                        const float a1 = tanh_fast(__uint_as_float(d[g4 * 4 + 1]) + bb.y);
+                                        const float a2 = tanh_fast(__uint_as_float(d[g4 * 4 + 2]) + bb.z);
+                                        const float a3 = tanh_fast(__uint_as_float(d[g4 * 4 + 3]) + bb.w);
+                                        r = fmaf(a0, cc[gq * 4 + 0], r);
+                                        r = fmaf(a1, cc[gq * 4 + 1], r);
+                                        r = fmaf(a2, cc[gq * 4 + 2], r);
+                                        r = fmaf(a3, cc[gq * 4 + 3], r);
+                                        if (gq == 0 && h == 0) {           // position integrator: action components 0, 1 % act, 2 % act
+                                            q0 = a0;
+                                            q1 = (p.act > 1) ? a1 : a0;                  // a[1 % act]
+                                            q2 = (p.act > 2) ? a2 : a0;                  // a[2 % act] (2 % 2 == 2 % 1 == 0)
+                                        }
+                                    }
+                                }
                             }
                         }
                         if (t < p.T) {
-                            if (sgn) { fitn += r; pn0 += q0; pn1 += q1; pn2 += q2; }
-                            else     { fitp += r; pp0 += q0; pp1 += q1; pp2 += q2; }
+                            if (sgn) { tv[1] = r; tv[5] = q0; tv[6] = q1; tv[7] = q2; }
+                            else     { tv[0] = r; tv[2] = q0; tv[3] = q1; tv[4] = q2; }
                         }
+                        if (ew == 0 && lane == 0) TC_TRACE(2, 8 * g + 5 + 2 * sgn);
                         tc_fence_before();
                     }
                 }
+                if (has_act) acc += tc_warp_sum8(tv, lane);
             }
             // ---- flush this warp's partial sums of the pair; the last of the 16 warps adds them in warp order ----
-            float vals[8] = {fitp, fitn, pp0, pp1, pp2, pn0, pn1, pn2};
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) vals[kk] = es_warp_sum(vals[kk]);
+            const int pair = blockIdx.x + i * gridDim.x;
+            if ((lane & 3) == 0) __stcg(p.partial + ((size_t)pair * TC_EPI_WARPS + ew) * 8 + tc_sum8_index(lane), acc);
+            __threadfence();                                        // every writing lane publishes its own store
+            __syncwarp();
             if (lane == 0) {
-                float* slot = p.partial + ((size_t)pair * TC_EPI_WARPS + ew) * 8;
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk) __stcg(slot + kk, vals[kk]);
-                __threadfence();
                 if (atomicAdd(p.tickets + pair, 1u) == TC_EPI_WARPS - 1) {
                     __threadfence();
                     float tot[8];
@@ -690,7 +764,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
 #pragma unroll
                 for (int b = 0; b < WB; ++b) {
                     const int k2 = min(2 * (btid + (b0 + b) * BT), TC_H * TC_H - 2);
-                    e0[b] = __ldg(eps + p.w2 + k2); e1[b] = __ldg(eps + p.w2 + k2 + 1);
+                    e0[b] = ldg_stream(eps + p.w2 + k2); e1[b] = ldg_stream(eps + p.w2 + k2 + 1);
                     t0[b] = __ldg(p.theta + p.w2 + k2); t1[b] = __ldg(p.theta + p.w2 + k2 + 1);
                 }
 #pragma unroll
@@ -712,7 +786,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
                     const int k2 = 2 * (btid + b * BT);
                     const bool live = k2 < p.act * TC_H;
                     const int kq = live ? k2 : 0;
-                    d0[b] = __ldg(eps + p.w3 + kq); d1[b] = __ldg(eps + p.w3 + kq + 1);
+                    d0[b] = ldg_stream(eps + p.w3 + kq); d1[b] = ldg_stream(eps + p.w3 + kq + 1);
                     x0[b] = __ldg(p.theta + p.w3 + kq); x1[b] = __ldg(p.theta + p.w3 + kq + 1);
                 }
 #pragma unroll
@@ -734,13 +808,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(const __grid_
             {
                 float* bias = (float*)(img + I.bias);
                 if (btid < TC_H) {
-                    const float d = __fmul_rn(sg, __ldg(eps + p.b2 + btid)), t = __ldg(p.theta + p.b2 + btid);
+                    const float d = __fmul_rn(sg, ldg_stream(eps + p.b2 + btid)), t = __ldg(p.theta + p.b2 + btid);
                     bias[btid] = __fadd_rn(t, d); bias[TC_H + btid] = __fadd_rn(t, -d);
                 } else if (btid - TC_H < TC_ACT_PAD) {
                     const int j2 = btid - TC_H;
                     float vp = 0.f, vn = 0.f;
                     if (j2 < p.act) {
-                        const float d = __fmul_rn(sg, __ldg(eps + p.b3 + j2)), t = __ldg(p.theta + p.b3 + j2);
+                        const float d = __fmul_rn(sg, ldg_stream(eps + p.b3 + j2)), t = __ldg(p.theta + p.b3 + j2);
                         vp = __fadd_rn(t, d); vn = __fadd_rn(t, -d);
                     }
                     bias[2 * TC_H + j2] = vp; bias[2 * TC_H + TC_ACT_PAD + j2] = vn;

@@ -31,5 +31,9 @@ for g_ in range(24):
     print(f'{g_:3d} | {m} | {e}')
 
 
+print('EPI detail (relative to got D1): epi1 first tmem_ld done, epi1+ done | rel. to got D2+: ld done, epi2+ done | rel. to got D3+: ld done, epi3+ done | rel. to got D3-: ld done, epi3- done')
+for g_ in range(0, 24, 2):
+    x = t[2][8*g_:8*g_+8]; e = epi[8*g_:8*g_+8]
+    print(g_, [int(x[0]-e[1]), int(x[1]-e[1])], [int(x[2]-e[3]), int(x[3]-e[3])], [int(x[4]-e[6]), int(x[5]-e[6])], [int(x[6]-e[7]), int(x[7]-e[7])])
 print('builder warp 0 per image j: [start, slot free, L1 rows done, image ready]')
 for j in range(3): print(j, [int(t[3][4*j+k]-t0) if t[3][4*j+k] else -1 for k in range(4)])
