@@ -64,12 +64,16 @@ def run_reference(args, wl, n_gpus):
     ref = CpuReference(K, wl['obs'], wl['act'], wl['hidden'], wl['T'])
     for _ in range(max(args.warmup, 1)):
         ref.sample(1)
-    t, last = [], None
+    samples = []
     for _ in range(args.steps):
-        last = ref.sample(1)
-        t.append(last['t_generation_s'])
+        samples.append(ref.sample(2))
     ref.close()
-    sec = statistics.mean(t)
+    # the host cores of a GPU box are shared with other tenants: single samples vary by several x.  The median step
+    # is reported (ms_per_step, value); the fastest one is kept alongside as the reference's best case.
+    samples.sort(key=lambda r: r['t_generation_s'])
+    last = samples[len(samples) // 2]
+    sec = last['t_generation_s']
+    best = samples[0]['t_generation_s']
     value = K / sec
     line = dict(metric='perturbations/sec (whole ES generation)', value=value, unit='antithetic pairs/s', n_gpus=n_gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak',
@@ -78,6 +82,7 @@ def run_reference(args, wl, n_gpus):
                 cpu_baseline=dict(value=value, unit='antithetic pairs/s', cores=last['cores'], kind='port',
                                   sample=last['sample'], evaluations_per_sec=2 * value,
                                   breakdown_s=dict(rollouts=last['t_rollouts_s'], rank_reconstruct_adam=last['t_update_s']),
+                                  best_case_value=K / best, steps_s=[round(r['t_generation_s'], 3) for r in samples],
                                   numpy=last['numpy'], torch=last['torch']),
                 e2e=dict(value=value, unit='antithetic pairs/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
@@ -161,6 +166,7 @@ def run_ours(args, wl, n_gpus):
     from es_pytorch_b200.nn.obstat import ObStat
     from es_pytorch_b200.nn.optimizers import Adam
     from es_pytorch_b200.utils.rankers import CenteredRanker
+    from es_pytorch_b200.utils.reporters import Reporter
 
     comm = dist.init_from_env('nccl' if int(os.environ.get('WORLD_SIZE', '1')) > 1 else None)
     assert comm.size == n_gpus, f'--gpus {n_gpus} but WORLD_SIZE={comm.size}; launch with torchrun --nproc-per-node {n_gpus}'
@@ -228,13 +234,18 @@ def run_ours(args, wl, n_gpus):
         fit_fn.stream_env_from_host = False
         ranker = CenteredRanker()
 
+        class _Cfg(dict):
+            __getattr__ = dict.__getitem__
+        # every process carries VIRTUAL_RANKS_PER_GPU reference ranks (one RandomState stream each): es.step's
+        # policies_per_gen / comm.size / 2 is the number of pairs PER STREAM
+        cfg = _Cfg(general=_Cfg(policies_per_gen=2 * n_per_stream * n_gpus, batch_size=500), policy=_Cfg(l2coeff=0.005))
+        quiet = Reporter()
+
         def api_generation():
-            gen_obstat = ObStat(env.observation_space.shape, 0)
-            pos, neg, inds, steps = es.test_params(comm, n_per_stream, policy, nt, gen_obstat, fit_fn, streams[0])
+            # the loop body of the reference's simple_example.py:49-53 / obj.py:77-80
+            tr, gen_obstat = es.step(cfg, comm, policy, nt, env, fit_fn, streams[0], ranker, quiet)
             policy.update_obstat(gen_obstat)
-            ranker.rank(pos, neg, inds)
-            es.approx_grad(policy, ranker, nt, policy.flat_params, 500, 0.005)
-            return pos
+            return tr
 
         for _ in range(args.warmup):
             api_generation()
@@ -260,9 +271,11 @@ def run_ours(args, wl, n_gpus):
         e2e = dict(value=K / sec, unit='antithetic pairs/s', ms_per_step=sec * 1e3,
                    h2d_bytes_per_step=(eng.h2d_bytes - h0) // args.steps,
                    d2h_bytes_per_step=(eng.d2h_bytes - d0) // args.steps,
-                   path='es.test_params(BatchedRollout) -> CenteredRanker.rank -> es.approx_grad, numpy in/out; '
-                        'per step H2D (pinned, async): theta, MT19937 states, obs mean/std; D2H: fitness[2K], indices[K], RNG states, '
-                        'obs statistics, rank weights[K], theta; one stream sync per API call (3 per generation)')
+                   path='es.step(cfg, comm, policy, nt, env, BatchedRollout, rs, CenteredRanker, reporter) + policy.update_obstat '
+                        '= the loop body of the reference scripts (simple_example.py:49-53), including the noiseless evaluation of '
+                        'the new theta; numpy in/out. Per step H2D (pinned, async): theta, MT19937 states, obs mean/std; D2H: '
+                        'fitness[2K], indices[K], RNG states, obs statistics, rank weights[K], theta, noiseless result; one stream '
+                        'synchronisation per generation on one GPU (call-by-call route with 3 when comm.size > 1)')
 
     if rank != 0:
         return
@@ -308,7 +321,7 @@ def run_ours(args, wl, n_gpus):
                                   share_of_step=kern['reconstruct'] / ms_step),
     )
     if not args.no_cpu_baseline and n_gpus == 1:
-        out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
+        out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '3',
                               '--warmup', '1', '--workload', args.workload, '--gpus', '1'] +
                              (['--pairs-per-gpu', str(args.pairs_per_gpu)] if args.pairs_per_gpu else []),
                              capture_output=True, text=True, env={**os.environ, 'RANK': '0', 'WORLD_SIZE': '1'})

@@ -38,6 +38,8 @@ def step(cfg, comm, policy: Policy, nt: NoiseTable, env, fit_fn: Callable, rs: n
     eps_per_proc = int((cfg.general.policies_per_gen / comm.size) / 2)
 
     gen_obstat = ObStat(env.observation_space.shape, 0)
+    if _can_fuse_step(comm, policy, fit_fn, ranker):
+        return _step_fused(cfg, comm, eps_per_proc, policy, nt, gen_obstat, fit_fn, rs, ranker, reporter)
     pos_res, neg_res, inds, steps = test_params(comm, eps_per_proc, policy, nt, gen_obstat, fit_fn, rs)
 
     reporter.print(f'n dupes: {len(inds) - len(set(inds))}')
@@ -47,6 +49,75 @@ def step(cfg, comm, policy: Policy, nt: NoiseTable, env, fit_fn: Callable, rs: n
     noiseless_result = fit_fn(policy.pheno(np.zeros(len(policy))), False)
     reporter.log_gen(ranker.fits, noiseless_result, policy, steps)
 
+    return noiseless_result, gen_obstat
+
+
+def _silent(reporter) -> bool:
+    """True for reporters that discard messages (the O(K) host-side message formatting can be skipped)."""
+    from ..utils.reporters import ReporterSet
+    return type(reporter) is Reporter or (type(reporter) is ReporterSet and not reporter.reporters)
+
+
+def _can_fuse_step(comm, policy: Policy, fit_fn, ranker: Ranker) -> bool:
+    """``step`` can keep the whole generation on the device (one synchronisation) when the evaluation is a
+    ``BatchedRollout`` of a tanh MLP in a single process and the ranker is a float32 shaping without elite selection
+    (the others return host arrays of a different dtype / length: they take the call-by-call route)."""
+    from .._lib import ES_RANK_MAX_NORMALIZED
+    if not getattr(fit_fn, 'is_batched_rollout', False) or comm.size != 1 or not policy._module.is_tanh_mlp():
+        return False
+    try:
+        kind, _, _, elite_n = ranker._spec(fit_fn.n_obj, 2)
+    except Exception:
+        return False
+    return elite_n == 0 and kind != ES_RANK_MAX_NORMALIZED and type(ranker).rank is Ranker.rank
+
+
+def _step_fused(cfg, comm, n: int, policy: Policy, nt: NoiseTable, gen_obstat: ObStat, fit_fn, rs, ranker: Ranker,
+                reporter: Reporter):
+    """es.py:38-51 with every stage queued on the device back to back -- draw, rollouts, rank, reconstruction, optimizer
+    step, noiseless evaluation of the new theta -- and ONE synchronisation before the host-side bookkeeping.  Same
+    results and side effects as the call-by-call route (test_params -> Ranker.rank -> approx_grad -> fit_fn)."""
+    streams = fit_fn.rank_streams if fit_fn.rank_streams is not None else [rs]
+    gen = _device_generation(fit_fn, policy, nt, streams)
+    eng = gen.eng
+    gen.l2coeff, gen.ranker = float(cfg.policy.l2coeff), ranker
+    fpos, fneg = gen.evaluate(n)
+    gen.update(fpos, fneg)
+    gen.l2coeff, gen.ranker = 0.0, None                    # approx_grad passes its own l2coeff on the other route
+    fit0, behv0 = gen.noiseless_eval()
+    h_pos, h_neg = eng.download_async(fpos, 'fpos'), eng.download_async(fneg, 'fneg')
+    h_idx = eng.download_async(gen.idx, 'idx')
+    h_key, h_mtpos = eng.download_async(gen.mt_key, 'mtkey'), eng.download_async(gen.mt_pos, 'mtpos')
+    if gen.extra_words:
+        h_cnt, h_sum, h_sq = (eng.download_async(gen.gen_count, 'gcnt'), eng.download_async(gen.gen_sum, 'gsum'),
+                              eng.download_async(gen.gen_sumsq, 'gsq'))
+    h_w = eng.download_async(gen.weights, ('ranked', id(ranker)))
+    h_theta = eng.download_async(gen.theta, ('theta', id(policy)))
+    h_fit0, h_behv0 = eng.download_async(fit0, 'nlfit'), eng.download_async(behv0, 'nlbehv')
+    eng.sync()
+    version = gen.version
+    valid = lambda g=gen, v=version: g.version == v
+    pos = devcache.attach(h_pos.numpy().reshape(gen.K, gen.n_obj).copy(), fpos, valid)
+    neg = devcache.attach(h_neg.numpy().reshape(gen.K, gen.n_obj).copy(), fneg, valid)
+    inds = devcache.attach(h_idx.numpy().astype(np.float64), gen.idx, valid)
+    gen.store_states(streams, h_key.numpy().copy(), h_mtpos.numpy().copy())
+    if gen.extra_words:
+        gen_obstat.inc(h_sum.numpy().copy(), h_sq.numpy().copy(), float(h_cnt.numpy()[0]))
+    steps = 2 * gen.K * (fit_fn.max_steps - 1)
+    if not _silent(reporter):
+        reporter.print(f'n dupes: {len(inds) - len(set(inds))}')
+    # what Ranker.rank leaves behind (rankers.py:37-50)
+    ranker._pre_rank(pos, neg, inds)
+    w = gen.weights
+    res = h_w.numpy().copy()
+    if not ranker._squeezes() and pos.ndim == 2:
+        res = res.reshape(-1, 1)
+    ranker.ranked_fits = devcache.attach(res, w, lambda r=ranker, t=w: r.ranked_fits_dev is t)
+    # what approx_grad and policy.pheno(zeros) leave behind: flat_params and the module carry the new theta
+    policy.flat_params[...] = h_theta.numpy()
+    policy.set_nn_params(torch.from_numpy(policy.flat_params.copy()))
+    noiseless_result = fit_fn.result_from_device(float(h_fit0.numpy()[0]), h_behv0.numpy()[0].astype(np.float64))
+    reporter.log_gen(ranker.fits, noiseless_result, policy, steps)
     return noiseless_result, gen_obstat
 
 

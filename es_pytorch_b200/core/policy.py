@@ -83,12 +83,13 @@ class Policy:
         """Scatter a flat vector into the module tensors (policy.py:49-59)."""
         flat = params if isinstance(params, torch.Tensor) else torch.from_numpy(np.asarray(params))
         with torch.no_grad():
-            sd, at = {}, 0
-            for name, w in self._module.state_dict().items():
+            at = 0
+            # state_dict order = flat order (policy.py:33-35); copied in place: the effect of the reference's
+            # load_state_dict without rebuilding the dict machinery every evaluation
+            for w in self._module.state_dict().values():
                 n = w.numel()
-                sd[name] = flat[at:at + n].reshape(w.shape).to(w.dtype)
+                w.copy_(flat[at:at + n].reshape(w.shape))
                 at += n
-            self._module.load_state_dict(sd)
         return self._module
 
     def pheno(self, noise: np.ndarray = None) -> torch.nn.Module:

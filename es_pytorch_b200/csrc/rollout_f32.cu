@@ -75,7 +75,7 @@ rollout_f32_kernel(const float* __restrict__ table, const int64_t* __restrict__ 
                    float sigma, const __grid_constant__ RfDesc d, const float* __restrict__ obsn,
                    const float* __restrict__ rew_vec, int T, float pos_scale, double* __restrict__ fit_pos,
                    double* __restrict__ fit_neg, int fit_stride, float* __restrict__ behv_pos,
-                   float* __restrict__ behv_neg) {
+                   float* __restrict__ behv_neg, double* __restrict__ part, unsigned* __restrict__ tickets) {
     extern __shared__ __align__(16) float smem[];
     float* Wsm = smem;                                  // [w_floats]
     float* Xa = Wsm + d.w_floats;                       // [RF_TM][xpitch]
@@ -110,7 +110,12 @@ rollout_f32_kernel(const float* __restrict__ table, const int64_t* __restrict__ 
 
     const int obs_dim = d.in[0];
     const int act_dim = d.out[d.n_layers - 1];
-    for (int t0 = 0; t0 < T; t0 += RF_TM) {
+    // time split (gridDim.y > 1, used when there are fewer policies than SMs): the open-loop episode has no state, so
+    // CTA y evaluates a contiguous range of time tiles; the partial sums are combined in tile order by the last CTA
+    const int n_tiles = (T + RF_TM - 1) / RF_TM;
+    const int tile_lo = (int)((long long)n_tiles * blockIdx.y / gridDim.y);
+    const int tile_hi = (int)((long long)n_tiles * (blockIdx.y + 1) / gridDim.y);
+    for (int t0 = tile_lo * RF_TM; t0 < min(T, tile_hi * RF_TM); t0 += RF_TM) {
         const int rows = min(RF_TM, T - t0);
         // observation tile -> Xa (rows beyond T are zero: computed and ignored)
         // (columns [obs_dim, in4) are re-zeroed every tile: later layers reuse this buffer)
@@ -158,9 +163,31 @@ rollout_f32_kernel(const float* __restrict__ table, const int64_t* __restrict__ 
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        (neg ? fit_neg : fit_pos)[(size_t)pair * fit_stride] = s_fit;
-        float* b = neg ? behv_neg : behv_pos;
-        if (b) { b[pair * 3 + 0] = s_pos[0]; b[pair * 3 + 1] = s_pos[1]; b[pair * 3 + 2] = s_pos[2]; }
+        double f = s_fit;
+        float p0 = s_pos[0], p1 = s_pos[1], p2 = s_pos[2];
+        bool writer = true;
+        if (gridDim.y > 1) {
+            double* mine = part + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * 4;
+            __stcg(mine + 0, f); __stcg(mine + 1, (double)p0); __stcg(mine + 2, (double)p1); __stcg(mine + 3, (double)p2);
+            __threadfence();
+            writer = atomicAdd(tickets + blockIdx.x, 1u) == gridDim.y - 1;
+            if (writer) {
+                __threadfence();
+                tickets[blockIdx.x] = 0;                                 // self-resetting
+                f = 0.0; p0 = p1 = p2 = 0.f;
+                for (unsigned y = 0; y < gridDim.y; ++y) {
+                    const double* q = part + ((size_t)blockIdx.x * gridDim.y + y) * 4;
+                    f += __ldcg(q + 0);
+                    p0 = __fadd_rn(p0, (float)__ldcg(q + 1)); p1 = __fadd_rn(p1, (float)__ldcg(q + 2));
+                    p2 = __fadd_rn(p2, (float)__ldcg(q + 3));
+                }
+            }
+        }
+        if (writer) {
+            (neg ? fit_neg : fit_pos)[(size_t)pair * fit_stride] = f;
+            float* b = neg ? behv_neg : behv_pos;
+            if (b) { b[pair * 3 + 0] = p0; b[pair * 3 + 1] = p1; b[pair * 3 + 2] = p2; }
+        }
     }
 }
 
@@ -196,9 +223,29 @@ int es_impl_rollout_f32(es_ctx* ctx, const float* table, int64_t table_len, cons
         return ES_ERR_UNSUPPORTED;
     }
     ES_REQUIRE(n_pairs <= (1 << 30), "es_rollout_openloop: too many pairs");
+    // fewer policies than SMs (single evaluations of the per-perturbation compatibility path, es.step's noiseless
+    // evaluation): split the episode's time tiles over the idle SMs
+    int n_splits = 1;
+    const int n_tiles = (T + RF_TM - 1) / RF_TM;
+    if (2 * n_pairs < ctx->sm_count) {
+        n_splits = ctx->sm_count / (2 * n_pairs);
+        if (n_splits > n_tiles) n_splits = n_tiles;
+        if (n_splits < 1) n_splits = 1;
+    }
+    double* part = nullptr;
+    unsigned* tickets = nullptr;
+    if (n_splits > 1) {
+        void* scratch = nullptr;
+        int rc = es_ctx_scratch(ctx, (size_t)2 * n_pairs * n_splits * 4 * sizeof(double), &scratch);
+        if (rc) return rc;
+        part = (double*)scratch;
+        rc = es_ctx_counters(ctx, 4096, &tickets);
+        if (rc) return rc;
+    }
     ES_CHECK_CUDA(cudaFuncSetAttribute(rollout_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rollout_f32_kernel<<<2 * n_pairs, RF_THREADS, smem, stream>>>(table, idx, theta, sigma, d, obsn, rew_vec, T, pos_scale,
-                                                                  fit_pos, fit_neg, fit_stride, behv_pos, behv_neg);
+    rollout_f32_kernel<<<dim3(2 * n_pairs, n_splits), RF_THREADS, smem, stream>>>(
+        table, idx, theta, sigma, d, obsn, rew_vec, T, pos_scale, fit_pos, fit_neg, fit_stride, behv_pos, behv_neg, part,
+        tickets);
     ES_LAUNCHED(ctx);
     return ES_OK;
 }

@@ -183,6 +183,19 @@ class DeviceGeneration:
         with self._timed('optimizer'):
             self.apply_optimizer(self.gsum, n_ranked)
 
+    def noiseless_eval(self):
+        """The noiseless evaluation of es.py:48 for the CURRENT theta on the device (sigma = 0, float32 rollout, one
+        policy split over the SMs by time tiles).  Returns (fitness f64[2], behaviour f32[2,3]); row 0 is the result."""
+        e = self.eng
+        if getattr(self, '_nl_bufs', None) is None:
+            self._nl_bufs = (torch.zeros(2, dtype=torch.float64, device=e.device),
+                             torch.zeros(2, 3, dtype=torch.float32, device=e.device),
+                             torch.zeros(1, dtype=torch.int64, device=e.device))
+        fit0, behv0, idx0 = self._nl_bufs
+        e.rollout(self.table, idx0, self.theta, 0.0, self.layer_sizes, self.obsn, self.rew_vec, self.pos_scale,
+                  fit0[0:1], fit0[1:2], 1, behv0[0].view(-1), behv0[1].view(-1), ES_ROLLOUT_F32)
+        return fit0, behv0
+
     def apply_optimizer(self, gsum: torch.Tensor, n_ranked: float):
         """grad = gsum/n_ranked; theta += optim.step(l2coeff*theta - grad)  (es.py:100-101)."""
         self.optim.apply_fused(self.eng, self.theta, gsum, n_ranked, self.l2coeff)
@@ -193,13 +206,50 @@ class DeviceGeneration:
         self.update(fpos, fneg)
 
     # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _mt_view(rs: np.random.RandomState):
+        """(key uint32[624] view, pos ctypes int) straight into the RandomState's MT19937 state block (numpy exposes its
+        address through the documented ``BitGenerator.ctypes`` interface), or None.  Reading / writing 2.5 kB in place costs
+        a fraction of a microsecond; get_state()/set_state() cost ~40 us per stream and per direction."""
+        try:
+            bg = rs._bit_generator
+            if type(bg).__name__ != 'MT19937':
+                return None
+            addr = bg.ctypes.state_address
+            import ctypes
+            key = np.ctypeslib.as_array((ctypes.c_uint32 * ES_MT_N).from_address(addr))
+            pos = ctypes.c_int.from_address(addr + ES_MT_N * 4)
+            probe = rs.get_state()                                   # one-time check that the layout is what we think
+            if not (np.array_equal(key, probe[1]) and pos.value == probe[2]):
+                return None
+            return key, pos
+        except Exception:
+            return None
+
+    def _views(self, rank_states):
+        cache = getattr(self, '_mt_views', None)
+        if cache is None or len(cache[0]) != len(rank_states) or any(a is not b for a, b in zip(cache[0], rank_states)):
+            views = [self._mt_view(rs) for rs in rank_states]
+            cache = (list(rank_states), views if all(v is not None for v in views) else None)
+            self._mt_views = cache
+        return cache[1]
+
     def load_states(self, rank_states: Sequence[np.random.RandomState]):
         """Upload the callers' RandomState streams (they may have been advanced on the host)."""
         assert len(rank_states) == self.n_streams
-        states = [s.get_state() for s in rank_states]
-        self._gauss = [(st[3], st[4]) for st in states]
-        key = np.stack([st[1] for st in states]).astype(np.uint32, copy=False).view(np.int32)
-        pos = np.array([st[2] for st in states], dtype=np.int32)
+        views = self._views(rank_states)
+        if views is not None:
+            key = np.empty((self.n_streams, ES_MT_N), dtype=np.uint32)
+            pos = np.empty(self.n_streams, dtype=np.int32)
+            for r, (k, p) in enumerate(views):
+                key[r] = k
+                pos[r] = p.value
+            key = key.view(np.int32)
+        else:
+            states = [s.get_state() for s in rank_states]
+            self._gauss = [(st[3], st[4]) for st in states]
+            key = np.stack([st[1] for st in states]).astype(np.uint32, copy=False).view(np.int32)
+            pos = np.array([st[2] for st in states], dtype=np.int32)
         self.eng.upload_async(self.mt_key, key, ('mtkey', id(self)))
         self.eng.upload_async(self.mt_pos, pos, ('mtpos', id(self)))
 
@@ -208,6 +258,12 @@ class DeviceGeneration:
         downloaded host copies; otherwise this synchronises)."""
         key = (self.eng.to_host(self.mt_key) if key is None else key).view(np.uint32)
         pos = self.eng.to_host(self.mt_pos) if pos is None else pos
+        views = self._views(rank_states)
+        if views is not None:
+            for r, (k, p) in enumerate(views):                       # the gaussian cache of the stream is left as it is
+                k[:] = key[r]
+                p.value = int(pos[r])
+            return
         for r, rs in enumerate(rank_states):
             rs.set_state(('MT19937', key[r], int(pos[r]), self._gauss[r][0], self._gauss[r][1]))
 

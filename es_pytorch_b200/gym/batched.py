@@ -43,6 +43,16 @@ class BatchedRollout:
     def n_obj(self) -> int:
         return 1 if self.archive is None else 2
 
+    def result_from_device(self, total: float, pos) -> TrainingResult:
+        """The TrainingResult ``__call__`` would build, from an episode total and final position computed on the device."""
+        rews = [float(total)]
+        behv = [float(pos[0]), float(pos[1]), float(pos[2])] * int(self.max_steps)
+        no_obs = np.array([np.zeros(self.env.observation_space.shape)])
+        steps = self.max_steps - 1                              # run_model returns the last loop index (gym_runner.py:50,67)
+        if self.archive is None:
+            return RewardResult(rews, behv, no_obs, steps)
+        return NSRResult(rews, behv[-3:], no_obs, steps, self.archive, self.nov_k)
+
     def __call__(self, model, use_ac_noise=True) -> TrainingResult:
         """Single-policy evaluation with the reference's fit_fn contract (no action noise)."""
         rews, behv, obs, steps = run_model(model, self.env, self.max_steps, None)

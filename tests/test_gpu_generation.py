@@ -188,6 +188,53 @@ def test_api_step_batched_matches_oracle(eng, oracle_vectors):
     assert len(tr.result) == 1 and np.isfinite(tr.result[0]) and ob.count == 0
 
 
+@pytest.mark.parametrize('nsr', [False, True])
+def test_api_step_fused_equals_call_by_call(eng, oracle_vectors, nsr):
+    """es.step's single-synchronisation route leaves exactly what test_params -> rank -> approx_grad -> fit_fn(pheno(0))
+    leave: theta, ranker fields, RandomState streams, generation ObStat and the noiseless TrainingResult."""
+    from es_pytorch_b200 import dist
+    from es_pytorch_b200.core import es
+    from es_pytorch_b200.gym.batched import BatchedRollout
+    from es_pytorch_b200.nn.obstat import ObStat
+    from es_pytorch_b200.utils.rankers import CenteredRanker, MultiObjectiveRanker
+    from es_pytorch_b200.utils.reporters import ReporterSet
+    v = oracle_vectors
+    dims, P, table, theta, spec = _small(eng)
+    cfg = _Cfg(general=_Cfg(policies_per_gen=12, batch_size=500), policy=_Cfg(l2coeff=0.005))
+    comm = dist.world()
+    archive = np.random.RandomState(17).randn(16, 2) if nsr else None
+    out = []
+    for fused in (True, False):
+        env, net, policy, nt = _api_objects(eng, table, theta, spec, (64, 64))
+        net.set_ob_mean_std(v['obmean'], v['obstd'])
+        streams = [np.random.RandomState(1000), np.random.RandomState(1001)]
+        fit_fn = BatchedRollout(env, spec.T, coins_per_eval=1, save_obs_chance=0.5, rank_streams=streams, archive=archive)
+        ranker = MultiObjectiveRanker(CenteredRanker(), 0.5) if nsr else CenteredRanker()
+        assert es._can_fuse_step(comm, policy, fit_fn, ranker)
+        for g in range(2):
+            if fused:
+                tr, ob = es.step(cfg, comm, policy, nt, env, fit_fn, streams[0], ranker, ReporterSet())
+            else:
+                ob = ObStat(env.observation_space.shape, 0)
+                pos, neg, inds, steps = es.test_params(comm, 6, policy, nt, ob, fit_fn, streams[0])
+                ranker.rank(pos, neg, inds)
+                es.approx_grad(policy, ranker, nt, policy.flat_params, 500, 0.005)
+                tr = fit_fn(policy.pheno(np.zeros(len(policy))), False)
+        out.append(dict(theta=policy.flat_params.copy(), w=np.asarray(ranker.ranked_fits).copy(), fits=ranker.fits.copy(),
+                        inds=np.asarray(ranker.noise_inds).copy(), n=ranker.n_fits_ranked, res=list(tr.result),
+                        steps=tr.steps, ob=(ob.sum.copy(), ob.sumsq.copy(), ob.count),
+                        rs=[s.get_state()[1].copy() for s in streams],
+                        module=torch.cat([p.detach().reshape(-1) for p in net.parameters()]).numpy().copy()))
+    a, b = out
+    assert np.array_equal(a['theta'], b['theta']) and np.array_equal(a['module'], b['module'])
+    assert np.array_equal(a['module'], a['theta'])
+    assert np.array_equal(a['w'], b['w']) and a['w'].dtype == b['w'].dtype and a['n'] == b['n']
+    assert np.array_equal(a['fits'], b['fits']) and np.array_equal(a['inds'], b['inds'])
+    assert a['res'] == b['res'] and a['steps'] == b['steps']
+    assert np.array_equal(a['ob'][0], b['ob'][0]) and np.array_equal(a['ob'][1], b['ob'][1]) and a['ob'][2] == b['ob'][2] > 0
+    assert all(np.array_equal(x, y) for x, y in zip(a['rs'], b['rs']))
+
+
 def test_api_opaque_fit_fn_loop_matches_oracle(eng):
     """The per-perturbation compatibility path (an opaque python fit_fn like simple_example.py:37-40)."""
     from es_pytorch_b200 import dist

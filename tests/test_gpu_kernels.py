@@ -152,6 +152,14 @@ def test_rollout_f32_odd_shapes(eng):
     _rollout_case(eng, 5, 1, (8, 8, 8), T=1, n_pairs=2, seed=5)         # single step, single action
 
 
+def test_rollout_f32_time_split(eng):
+    """Fewer policies than SMs: the episode's time tiles are split over the SMs (single evaluations of the compatibility
+    path, es.step's noiseless evaluation); same tolerance as the unsplit kernel."""
+    _rollout_case(eng, 17, 6, (64, 64), T=1000, n_pairs=1, seed=11)
+    _rollout_case(eng, 376, 17, (64, 64), T=333, n_pairs=2, seed=12)
+    _rollout_case(eng, 17, 6, (64, 64), T=40, n_pairs=40, seed=13)       # 80 policies, 2 tiles: 1 split each
+
+
 def test_rollout_sigma_zero_is_symmetric(eng):
     rs = np.random.RandomState(9)
     sizes = [17, 64, 64, 6]
@@ -480,7 +488,10 @@ def _tc_vs_f32(eng, obs, act, T, n_pairs, seed):
 
 
 @pytest.mark.parametrize('obs,act,T,n_pairs', [(376, 17, 1000, 200), (17, 6, 1000, 256), (17, 6, 100, 8), (5, 1, 130, 3),
-                                               (63, 32, 129, 5), (64, 3, 128, 4)])
+                                               (63, 32, 129, 5), (64, 3, 128, 4),
+                                               # several pairs per CTA with an odd tile count (the two epilogue groups swap
+                                               # parity every pair) and with a single tile per pair (one group per pair)
+                                               (17, 6, 300, 333), (17, 6, 100, 400)])
 def test_rollout_tc_matches_f32(eng, obs, act, T, n_pairs):
     """bf16 tensor-core rollout vs the float32 CUDA-core rollout (itself checked against the oracle above).
     Tolerance (bf16 operands, fp32 accumulate, tanh.approx): fitness within 3 % of the population's fitness
