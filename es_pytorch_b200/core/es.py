@@ -60,10 +60,12 @@ def _silent(reporter) -> bool:
 
 def _can_fuse_step(comm, policy: Policy, fit_fn, ranker: Ranker) -> bool:
     """``step`` can keep the whole generation on the device (one synchronisation) when the evaluation is a
-    ``BatchedRollout`` of a tanh MLP in a single process and the ranker is a float32 shaping without elite selection
-    (the others return host arrays of a different dtype / length: they take the call-by-call route)."""
+    ``BatchedRollout`` of a tanh MLP and the ranker is a float32 shaping without elite selection (the others return host
+    arrays of a different dtype / length: they take the call-by-call route)."""
     from .._lib import ES_RANK_MAX_NORMALIZED
-    if not getattr(fit_fn, 'is_batched_rollout', False) or comm.size != 1 or not policy._module.is_tanh_mlp():
+    if not getattr(fit_fn, 'is_batched_rollout', False) or not policy._module.is_tanh_mlp():
+        return False
+    if comm.size != dist.world().size:                       # a communicator this package does not drive
         return False
     try:
         kind, _, _, elite_n = ranker._spec(fit_fn.n_obj, 2)
@@ -86,12 +88,22 @@ def _step_fused(cfg, comm, n: int, policy: Policy, nt: NoiseTable, gen_obstat: O
     gen.l2coeff, gen.ranker = 0.0, None                    # approx_grad passes its own l2coeff on the other route
     fit0, behv0 = gen.noiseless_eval()
     h_pos, h_neg = eng.download_async(fpos, 'fpos'), eng.download_async(fneg, 'fneg')
-    h_idx = eng.download_async(gen.idx, 'idx')
     h_key, h_mtpos = eng.download_async(gen.mt_key, 'mtkey'), eng.download_async(gen.mt_pos, 'mtpos')
     if gen.extra_words:
         h_cnt, h_sum, h_sq = (eng.download_async(gen.gen_count, 'gcnt'), eng.download_async(gen.gen_sum, 'gsum'),
                               eng.download_async(gen.gen_sumsq, 'gsq'))
-    h_w = eng.download_async(gen.weights, ('ranked', id(ranker)))
+    w_all, idx_all = gen.weights, gen.idx
+    if gen.comm.size > 1:
+        # what Ranker.rank / _share_results hand to every rank: all K weights and noise indices (two small allgathers)
+        if getattr(gen, '_step_gather', None) is None or gen._step_gather[0].shape[1] != gen.k_local:
+            gen._step_gather = (eng.empty((gen.comm.size, gen.k_local), torch.float32),
+                                eng.empty((gen.comm.size, gen.k_local), torch.int64))
+        w_all, idx_all = gen._step_gather
+        gen.comm.allgather_into(w_all, gen.weights)
+        gen.comm.allgather_into(idx_all, gen.idx)
+        w_all, idx_all = w_all.view(-1), idx_all.view(-1)
+    h_idx = eng.download_async(idx_all, 'idx')
+    h_w = eng.download_async(w_all, ('ranked', id(ranker)))
     h_theta = eng.download_async(gen.theta, ('theta', id(policy)))
     h_fit0, h_behv0 = eng.download_async(fit0, 'nlfit'), eng.download_async(behv0, 'nlbehv')
     eng.sync()
@@ -99,7 +111,7 @@ def _step_fused(cfg, comm, n: int, policy: Policy, nt: NoiseTable, gen_obstat: O
     valid = lambda g=gen, v=version: g.version == v
     pos = devcache.attach(h_pos.numpy().reshape(gen.K, gen.n_obj).copy(), fpos, valid)
     neg = devcache.attach(h_neg.numpy().reshape(gen.K, gen.n_obj).copy(), fneg, valid)
-    inds = devcache.attach(h_idx.numpy().astype(np.float64), gen.idx, valid)
+    inds = devcache.attach(h_idx.numpy().astype(np.float64), idx_all, valid)
     gen.store_states(streams, h_key.numpy().copy(), h_mtpos.numpy().copy())
     if gen.extra_words:
         gen_obstat.inc(h_sum.numpy().copy(), h_sq.numpy().copy(), float(h_cnt.numpy()[0]))
@@ -108,7 +120,8 @@ def _step_fused(cfg, comm, n: int, policy: Policy, nt: NoiseTable, gen_obstat: O
         reporter.print(f'n dupes: {len(inds) - len(set(inds))}')
     # what Ranker.rank leaves behind (rankers.py:37-50)
     ranker._pre_rank(pos, neg, inds)
-    w = gen.weights
+    w = w_all
+    ranker.ranked_fits_dev = w
     res = h_w.numpy().copy()
     if not ranker._squeezes() and pos.ndim == 2:
         res = res.reshape(-1, 1)

@@ -52,6 +52,78 @@ os.write(1, ('MULTI_OK_%d\\n' % comm.rank).encode())
 '''
 
 
+_STEP_WORKER = '''
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch
+from oracle import es_oracle as orc
+from es_pytorch_b200 import dist
+from es_pytorch_b200.core import es
+from es_pytorch_b200.core.noisetable import NoiseTable
+from es_pytorch_b200.core.policy import Policy
+from es_pytorch_b200.engine import get_engine
+from es_pytorch_b200.gym.batched import BatchedRollout
+from es_pytorch_b200.gym.synthetic_env import SyntheticEnv
+from es_pytorch_b200.nn.nn import FeedForward
+from es_pytorch_b200.nn.optimizers import Adam
+from es_pytorch_b200.utils.rankers import CenteredRanker
+from es_pytorch_b200.utils.reporters import Reporter
+comm = dist.init_from_env('nccl')
+eng = get_engine(int(os.environ['LOCAL_RANK']))
+obs_dim, act_dim, hidden, T, n = 17, 6, (64, 64), 48, 10
+dims = orc.layer_dims(obs_dim, hidden, act_dim); P = orc.n_params(dims)
+rs = np.random.RandomState(0)
+table = rs.randn(P + 200_000).astype(np.float32); theta = (rs.randn(P) * 0.1).astype(np.float32)
+spec = orc.SyntheticEnvSpec(obs_dim, act_dim, T)
+env = SyntheticEnv(obs_dim, act_dim, T)
+net = FeedForward(list(hidden), torch.nn.Tanh(), env, 0.0, 5)
+policy = Policy(net, 0.02, Adam(P, 0.01)); policy.flat_params[...] = theta
+nt = NoiseTable(P, table)
+seeds = [1000 + 2 * r for r in range(comm.size * 2)]            # 2 virtual ranks per GPU
+streams = [np.random.RandomState(s) for s in seeds[2 * comm.rank: 2 * comm.rank + 2]]
+fit_fn = BatchedRollout(env, T, coins_per_eval=1, save_obs_chance=0.2, rank_streams=streams)
+class C(dict): __getattr__ = dict.__getitem__
+cfg = C(general=C(policies_per_gen=2 * n * comm.size, batch_size=500), policy=C(l2coeff=0.005))
+ranker = CenteredRanker()
+assert es._can_fuse_step(comm, policy, fit_fn, ranker)
+flat, opt = theta.copy(), orc.AdamOracle(P, 0.01)
+states = [np.random.RandomState(s) for s in seeds]
+for g in range(2):
+    tr, ob = es.step(cfg, comm, policy, nt, env, fit_fn, streams[0], ranker, Reporter())
+    ref = orc.generation(table, flat, opt, 0.02, dims, spec, seeds, n, np.zeros(obs_dim), np.ones(obs_dim), 5.0, T, 500, 0.005,
+                         coins_per_eval=1, rank_states=states)
+    assert np.array_equal(ranker.noise_inds, ref['inds']), 'all ranks see all indices, rank-major'
+    assert np.array_equal(ranker.ranked_fits, ref['weights']) and ranker.n_fits_ranked == ref['n_ranked'], 'weights'
+    assert np.abs(ranker.fits_pos - ref['pos']).max() < 1e-3
+    assert np.abs(policy.flat_params - flat).max() < 2e-6, 'theta'
+    layers = orc.unflatten(flat, dims)
+    rews, b, _, _ = orc.run_model(spec, layers, np.zeros(obs_dim), np.ones(obs_dim), 5.0, T, batched=True)
+    assert abs(tr.result[0] - orc.reward_result(rews)[0]) <= 1e-5 * max(1.0, np.abs(rews).sum()), 'noiseless result'
+for s, st in zip(streams, states[2 * comm.rank: 2 * comm.rank + 2]):
+    assert np.array_equal(s.get_state()[1], st.get_state()[1]) and s.get_state()[2] == st.get_state()[2]
+os.write(1, ('STEP_OK_%d\\n' % comm.rank).encode())
+'''
+
+
+def _run_two(script):
+    with socket.socket() as sk:
+        sk.bind(('127.0.0.1', 0))
+        port = sk.getsockname()[1]
+    return subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                           '--master-addr', '127.0.0.1', '--master-port', str(port), str(script)],
+                          capture_output=True, text=True, timeout=600)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_two_gpu_es_step_fused(tmp_path):
+    """es.step (single-synchronisation route) on two processes == the oracle's 4-rank generation."""
+    script = tmp_path / 'ws.py'
+    script.write_text(_STEP_WORKER.format(root=ROOT))
+    out = _run_two(script)
+    assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
+    assert 'STEP_OK_0' in out.stdout and 'STEP_OK_1' in out.stdout
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
 def test_two_gpu_generation(tmp_path):
     script = tmp_path / 'w.py'

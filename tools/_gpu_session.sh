@@ -1,2 +1,7 @@
-timeout 900 python -m pytest tests -x -q -m gpu -k "api or generation or stream" 2>&1 | tail -4
-timeout 300 python tools/dev_step_breakdown.py
+timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_generation.py -x -q -m gpu 2>&1 | tail -4
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2_bench_n2.json').read().strip().splitlines()[-1])
+print('N=2', d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'])
+PY
+tail -2 gpurun_out/r2_bench_n2.err
