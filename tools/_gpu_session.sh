@@ -1,7 +1,10 @@
-timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_generation.py -x -q -m gpu 2>&1 | tail -4
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err; python - <<'PY'
+timeout 900 python bench.py > gpurun_out/r1_h_bench.json 2> gpurun_out/r1_h_bench.err
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1_h_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r1_h_launch_run.log 2>&1
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:rollout_tc_kernel -c 1 -o gpurun_out/r1_h_tc -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r1_h_ncu1.log 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:reconstruct_kernel -c 1 -o gpurun_out/r1_h_rec -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r1_h_ncu2.log 2>&1
+python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/r2_bench_n2.json').read().strip().splitlines()[-1])
-print('N=2', d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'])
+d=json.loads(open('gpurun_out/r1_h_bench.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['cpu_baseline'])
 PY
-tail -2 gpurun_out/r2_bench_n2.err
+ls -la gpurun_out/ | tail -8
