@@ -311,7 +311,7 @@ def run_ours(args, wl, n_gpus):
                       note='mode f32 runs on the CUDA cores (FFMA); reported against the tensor peak the '
                            'tcgen05 path is judged by' if mode == _lib.ES_ROLLOUT_F32 else
                            'tcgen05 path; the kernel is bound by the tanh epilogue (2.9 G MUFU.TANH per generation at 4 lanes/clk per '
-                           'SM sub-partition = 0.55 ms floor; ncu: XU 48 %, tensor 23 %) and by the dependent-latency chain of its '
+                           'SM sub-partition = 0.65 ms floor; ncu: XU 48 %, tensor 23 %) and by the dependent-latency chain of its '
                            'per-tile phases, not by the tensor pipe: see profiles/README.md'),
         # the north-star's named HBM-bound kernel
         roofline_reconstruct=dict(kernel='reconstruct_kernel (es_grad_reconstruct)', bound='hbm', achieved=rec_gbs,
