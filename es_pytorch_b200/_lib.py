@@ -26,6 +26,7 @@ SIGNATURES = {
     'es_last_error': (C.c_char_p, []),
     'es_abi_version': (_i32, []),
     'es_launch_count': (_i64, [_vp]),
+    'es_noise_table_changed': (_i32, [_vp]),
     'es_sm_count': (_i32, [_vp]),
     'es_draw_indices': (_i32, [_vp, _vp, _vp, _i32, _i32, _u64, _i32, _vp, _vp, _vp]),
     'es_perturb': (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _i32, _f32, _vp, _vp, _vp]),

@@ -82,7 +82,15 @@ int es_ctx_destroy(es_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->counters) cudaFree(ctx->counters);
+    if (ctx->shadow) cudaFree(ctx->shadow);
     free(ctx);
+    return ES_OK;
+}
+
+int es_noise_table_changed(es_ctx* ctx) {
+    if (!ctx) return ES_ERR_INVALID;
+    ctx->shadow_src = nullptr;          // the shadow (if any) is rebuilt by the next tensor-core rollout
+    ctx->shadow_len = 0;
     return ES_OK;
 }
 

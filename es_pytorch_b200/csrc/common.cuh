@@ -18,6 +18,13 @@ struct es_ctx {
     size_t scratch_bytes;
     unsigned* counters;     // small zero-initialised counter array (last-block detection)
     size_t n_counters;
+    // bf16 shadow of the noise table for the tensor-core rollout (rollout_tc.cu): 8 copies, copy s holds
+    // bf16(table[j + s]) at element j, so that a slice starting at any idx has a 16-byte aligned copy (s = idx % 8)
+    const float* shadow_src;   // table the shadow was built from (identity: pointer + length)
+    int64_t shadow_len;
+    void* shadow;              // [8][shadow_stride] bf16, or NULL (not built / allocation failed)
+    size_t shadow_stride;      // elements per copy (multiple of 8)
+    int shadow_failed;         // allocation failed once: do not retry every call
 };
 
 void es_set_error(const char* fmt, ...);

@@ -166,6 +166,18 @@ __device__ __forceinline__ void sub2(float& o0, float& o1, uint32_t a0, uint32_t
     asm("mov.b64 {%0, %1}, %2;" : "=r"(c0), "=r"(c1) : "l"(c));
     o0 = __uint_as_float(c0); o1 = __uint_as_float(c1);
 }
+// packed fma: o = a * s + c for two lanes (z1 = U + s*V; s = +-sigma with the unscaled shadow operand, +-1 otherwise:
+// fma(v, 1, u) rounds exactly like an add)
+__device__ __forceinline__ void fma2(float& o0, float& o1, uint32_t a0, uint32_t a1, float s, uint32_t c0, uint32_t c1) {
+    unsigned long long a, b, c, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(s), "f"(s));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "r"(c0), "r"(c1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    uint32_t d0, d1;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(d0), "=r"(d1) : "l"(d));
+    o0 = __uint_as_float(d0); o1 = __uint_as_float(d1);
+}
 // warp-uniform leader election: keeps the surrounding control flow (and the descriptors) uniform so the
 // MMA operands stay in uniform registers instead of being re-materialised per instruction
 __device__ __forceinline__ bool elect_one() {
@@ -250,6 +262,11 @@ __device__ __forceinline__ float4 ldg_stream4(const float4* p) {
     asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
+__device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
+    uint4 v;
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 // pinned-in-program-order read-only load (the compiler may not hoist it above a preceding fence / barrier arrive)
 __device__ __forceinline__ float ldg_pinned(const float* p) {
     float v;
@@ -315,12 +332,45 @@ __device__ __forceinline__ void tc_build_l1_rows(uint8_t* b1_base, const float* 
     }
 }
 
+// Layer-1 operand rows from the bf16 shadow: row n of eps1 is 16-byte aligned in shadow copy s = idx % 8 (obs % 8 == 0), so
+// a lane moves one 16-byte unit (8 columns) with one vector load and one vector store into its swizzled place: 47 units
+// per row for obs = 376, against 376 float loads + conversions.  The unit holding column `obs` carries the bias element
+// (unscaled eps_b1[n]; the epilogue multiplies V by sigma) and zeros.  A warp takes 4 rows per iteration.
+__device__ __forceinline__ void tc_build_l1_rows_shadow(uint8_t* b1_base, const __nv_bfloat16* __restrict__ rows,
+                                                        const float* __restrict__ bvec, int obs, int nkc, int worker,
+                                                        int nworkers, int lane) {
+    const int units = obs >> 3;                                  // full 16-byte units of a row
+    const int total = nkc * 8;                                   // units of the padded row (K = nkc * 64)
+    for (int n0 = worker * 4; n0 < TC_H; n0 += nworkers * 4) {
+        for (int u0 = 0; u0 < total; u0 += 32) {
+            const int u = u0 + lane;
+            uint4 v[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int n = n0 + r;
+                v[r] = make_uint4(0, 0, 0, 0);
+                if (u < units) v[r] = ldg_stream_u4(rows + (size_t)n * obs + 8 * u);
+                else if (u == units) v[r].x = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(ldg_stream(bvec + n)));
+            }
+            if (u < total) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int n = n0 + r;
+                    *(uint4*)(b1_base + (size_t)(u >> 3) * TC_B1_CHUNK_BYTES + n * 128 + (((u & 7) ^ (n & 7)) << 4)) = v[r];
+                }
+            }
+        }
+    }
+}
+
 // split of the 32 row pairs of sigma*eps1 between the builder warps (start early) and the epilogue warps (join when
 // they have finished the current pair's tiles and would otherwise idle until the next pair's first L1)
 constexpr int TC_BLD_ROWPAIRS = 16;
 
 struct TcParams {
     const float* table;
+    const __nv_bfloat16* shadow;  // 8 shifted bf16 copies of the table (copy s: element j = bf16(table[j+s])), or NULL
+    size_t shadow_stride;         // elements per copy
     const int64_t* idx;
     const float* theta;
     const __nv_bfloat16* xnt;     // [n_mtiles][nkc][16 KB stage image]
@@ -337,6 +387,7 @@ struct TcParams {
     float* behv_neg;
     int n_pairs, obs, act, T, nkc, n_mtiles, fit_stride;
     float sigma, pos_scale;
+    float v_scale;                // factor of V in z1 = U +- v_scale*V: sigma when the layer-1 operand is the unscaled bf16 shadow, else 1
     int w1, b1, w2, b2, w3, b3;   // flat parameter offsets
     long long* trace;             // optional cycle-stamp trace of CTA 0 (ES_TC_TRACE env), NULL in production
     int dev_noload;               // dev experiment: skip the observation-tile copies (results are garbage)
@@ -569,6 +620,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(
         const uint32_t tm_d3p = tmem + 384 + eg * 64 + lane_base + h * 16, tm_d3n = tm_d3p + 32;
         const bool has_act = h * 16 < p.act;                  // L3: this warp owns action columns 16h..16h+15
         const int nj = min(16, p.act - h * 16);              // action columns this warp owns (warp-uniform)
+        const float vs = p.v_scale;
         // (few loop-carried scalars on purpose: the role must fit 72 registers without spilling)
         for (int i = 0; i < my_pairs; ++i) {
             const uint32_t b2p = smem_u32(bias_all + (i & 1) * 256) + h * 128, b2n = b2p + TC_H * 4;
@@ -606,8 +658,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(
                             const float4 u4 = ub[e >> 1];
                             const float u0 = (e & 1) ? u4.z : u4.x, u1 = (e & 1) ? u4.w : u4.y;
                             float z0, z1;
-                            if (sgn) sub2(z0, z1, __float_as_uint(u0), __float_as_uint(u1), v[2 * e], v[2 * e + 1]);
-                            else     add2(z0, z1, __float_as_uint(u0), __float_as_uint(u1), v[2 * e], v[2 * e + 1]);
+                            fma2(z0, z1, v[2 * e], v[2 * e + 1], sgn ? -vs : vs, __float_as_uint(u0), __float_as_uint(u1));
                             w[e] = tanh2_pack(z0, z1);
                         }
                         sts128((sgn ? hn_row : hp_row) + (((h * 4 + c4) ^ sw) << 4), w[0], w[1], w[2], w[3]);
@@ -755,7 +806,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(
             }
             const float* __restrict__ eps = p.table + p.idx[pair];
             uint8_t* img = my_images + (size_t)(j & 1) * I.total;
-            tc_build_l1_rows(img + I.b1, eps + p.w1, eps + p.b1, sg, p.obs, NKC, 0, TC_H / 2, bw, TC_BLD_WARPS, lane);
+            if (p.shadow) {
+                const int64_t at = p.idx[pair] + p.w1;                    // first element of eps1 in the table
+                const __nv_bfloat16* rows = p.shadow + (size_t)(at & 7) * p.shadow_stride + (at - (at & 7));
+                tc_build_l1_rows_shadow(img + I.b1, rows, eps + p.b1, p.obs, NKC, bw, TC_BLD_WARPS, lane);
+            } else {
+                tc_build_l1_rows(img + I.b1, eps + p.w1, eps + p.b1, sg, p.obs, NKC, 0, TC_H / 2, bw, TC_BLD_WARPS, lane);
+            }
             if (bw == 0 && lane == 0) TC_TRACE(3, 4 * j + 2);
             constexpr int NB2 = (TC_H * TC_H / 2 + BT - 1) / BT;          // column pairs per thread
             constexpr int WB = 8;
@@ -829,9 +886,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(
         for (int j = 0; j < my_pairs; ++j) {
             build_image(j);
             if (j + 1 < my_pairs) {                                      // L2 prefetch of the next slice
-                const char* nxt = (const char*)(p.table + p.idx[blockIdx.x + (j + 1) * gridDim.x]);
+                const int64_t nidx = p.idx[blockIdx.x + (j + 1) * gridDim.x];
+                const char* nxt = (const char*)(p.table + nidx);
                 const int lines = (p.b3 + p.act) * 4 / 128 + 2;
-                for (int l = btid; l < lines; l += BT) prefetch_l2(nxt + (size_t)l * 128);
+                if (p.shadow) {                                          // eps1 from the bf16 shadow, the rest in float32
+                    const int64_t at = nidx + p.w1;
+                    const char* sh = (const char*)(p.shadow + (size_t)(at & 7) * p.shadow_stride + (at - (at & 7)));
+                    const int sh_lines = TC_H * p.obs * 2 / 128 + 1, skip = (p.b1 - 0) * 4 / 128;
+                    for (int l = btid; l < sh_lines; l += BT) prefetch_l2(sh + (size_t)l * 128);
+                    for (int l = skip + btid; l < lines; l += BT) prefetch_l2(nxt + (size_t)l * 128);
+                } else {
+                    for (int l = btid; l < lines; l += BT) prefetch_l2(nxt + (size_t)l * 128);
+                }
             }
         }
     }
@@ -874,6 +940,17 @@ __global__ void __launch_bounds__(TC_H) rollout_tc_ubase_kernel(const float* __r
     *out = acc;
 }
 
+// bf16 shadow of the table: copy s, element j = bf16(table[j + s]) (zero beyond the end)
+__global__ void rollout_tc_shadow_kernel(const float* __restrict__ table, int64_t len, size_t stride, __nv_bfloat16* __restrict__ shadow) {
+    const size_t total = stride / 2;                                     // bf16 pairs per copy
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int s = blockIdx.y;
+        const int64_t j = (int64_t)(2 * i) + s;
+        const float a = (j < len) ? __ldg(table + j) : 0.f, b = (j + 1 < len) ? __ldg(table + j + 1) : 0.f;
+        *(__nv_bfloat162*)(shadow + (size_t)s * stride + 2 * i) = __floats2bfloat162_rn(a, b);
+    }
+}
+
 // reward vectors transposed per tile: crt[(m*32 + j)*128 + row] = rew_vec[128m + row][j] (0 beyond T / act)
 __global__ void rollout_tc_crt_kernel(const float* __restrict__ rew_vec, int T, int act, int n_mtiles, float* __restrict__ crt) {
     const int total = n_mtiles * TC_ACT_PAD * TC_MT;
@@ -908,6 +985,38 @@ int es_impl_rollout_tc(es_ctx* ctx, const float* table, int64_t table_len, const
     p.w1 = 0; p.b1 = p.obs * TC_H; p.w2 = p.b1 + TC_H; p.b2 = p.w2 + TC_H * TC_H; p.w3 = p.b2 + TC_H;
     p.b3 = p.w3 + TC_H * p.act;
     p.trace = nullptr;
+    // bf16 shadow of the table for the layer-1 operand: needs 16-byte aligned rows in every slice (obs and the layer-1
+    // offset multiples of 8); built once per (table pointer, length).  Without it (other shapes, or no memory for the
+    // 8 copies) the builders convert the float32 slice themselves.
+    p.shadow = nullptr;
+    p.shadow_stride = 0;
+    p.v_scale = 1.0f;
+    if (p.obs % 8 == 0 && p.w1 % 8 == 0 && !getenv("ES_TC_NO_SHADOW")) {
+        if (ctx->shadow_src != table || ctx->shadow_len != table_len) {
+            const size_t stride = ((size_t)table_len + 15) & ~(size_t)7;
+            if (ctx->shadow && ctx->shadow_stride != stride) { ES_CHECK_CUDA(cudaFree(ctx->shadow)); ctx->shadow = nullptr; }
+            if (!ctx->shadow && !ctx->shadow_failed) {
+                if (cudaMalloc(&ctx->shadow, 8 * stride * sizeof(__nv_bfloat16)) != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    ctx->shadow = nullptr;
+                    ctx->shadow_failed = 1;
+                }
+            }
+            if (ctx->shadow) {
+                ctx->shadow_stride = stride;
+                rollout_tc_shadow_kernel<<<dim3(ctx->sm_count * 8, 8), 256, 0, stream>>>(table, table_len, stride,
+                                                                                        (__nv_bfloat16*)ctx->shadow);
+                ES_LAUNCHED(ctx);
+                ctx->shadow_src = table;
+                ctx->shadow_len = table_len;
+            }
+        }
+        if (ctx->shadow && ctx->shadow_src == table) {
+            p.shadow = (const __nv_bfloat16*)ctx->shadow;
+            p.shadow_stride = ctx->shadow_stride;
+            p.v_scale = sigma;
+        }
+    }
     p.dev_noload = getenv("ES_TC_NOLOAD") ? 1 : 0;
     if (const char* e = getenv("ES_TC_TRACE")) p.trace = (long long*)strtoull(e, nullptr, 0);   // device pointer, dev tooling only
 

@@ -6,6 +6,7 @@ PyTorch is the container only: tensors provide device memory, streams come from
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Optional, Sequence
 
 import numpy as np
@@ -220,6 +221,13 @@ class Engine:
             _req(behv_pos, torch.float32, 'behv_pos', d); _req(behv_neg, torch.float32, 'behv_neg', d)
             assert behv_pos.numel() == 3 * n and behv_neg.numel() == 3 * n
         ls = (C.c_int * len(layer_sizes))(*[int(x) for x in layer_sizes])
+        if mode == ES_ROLLOUT_TC:
+            # the library keeps a bf16 shadow of the table keyed by (pointer, length); a different tensor object (the
+            # caching allocator reuses addresses) or an in-place torch write (version counter) invalidates it
+            ref, ver = getattr(self, '_tc_table', (None, None))
+            if ref is None or ref() is not table or ver != table._version:
+                check(self.lib.es_noise_table_changed(self._ctx), 'es_noise_table_changed')
+                self._tc_table = (weakref.ref(table), table._version)
         check(self.lib.es_rollout_openloop(self._ctx, _ptr(table), table.numel(), _ptr(idx), n, _ptr(theta),
                                            theta.numel(), float(sigma), ls, len(layer_sizes) - 1, _ptr(obsn),
                                            _ptr(rew_vec), T, float(pos_scale), _ptr(fit_pos), _ptr(fit_neg),

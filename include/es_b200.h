@@ -94,6 +94,11 @@ int es_rollout_openloop(es_ctx* ctx, const float* table, int64_t table_len, cons
                         double* fit_pos, double* fit_neg, int fit_stride, float* behv_pos, float* behv_neg,
                         int mode, void* stream);
 
+/* The tensor-core rollout keeps a bf16 shadow of the noise table (8 shifted copies, 2 bytes x 8 x table_len of HBM, built
+ * on first use) keyed by the table's device pointer and length.  The reference never writes to its table after
+ * NoiseTable.create_shared (src/core/noisetable.py:66-91); a caller that does overwrite it in place must say so.   */
+int es_noise_table_changed(es_ctx* ctx);
+
 /* ---- a13: novelty ---------------------------------------------------------------------
  * mean of the k smallest euclidean distances (float64) between behv[e][0..1] and the
  * archive rows: src/utils/novelty.py:16-18, src/gym/training_result.py:82-97.

@@ -507,6 +507,39 @@ def test_rollout_tc_matches_f32(eng, obs, act, T, n_pairs):
         assert np.corrcoef(r32, rtc)[0, 1] > 0.9995
 
 
+def test_rollout_tc_shadow_tracks_table_contents(eng):
+    """The tensor-core path reads layer 1 from a bf16 shadow of the table (obs % 8 == 0): an in-place rewrite of the table
+    tensor, or a new tensor at a recycled address, must be picked up; obs % 8 != 0 takes the float32-slice path."""
+    from es_pytorch_b200 import _lib
+    rs = np.random.RandomState(5)
+    obs, act, T, n = 24, 6, 100, 40
+    sizes = [obs, 64, 64, act]
+    P = sum(i * o + o for i, o in zip(sizes[:-1], sizes[1:]))
+    L = P + 30_000
+    theta = dev(eng, (rs.randn(P) * 0.1).astype(np.float32))
+    idx = dev(eng, rs.randint(0, L - P, size=n).astype(np.int64))
+    obsn = dev(eng, np.clip(rs.randn(T, obs), -5, 5).astype(np.float32)); rew = dev(eng, rs.randn(T, act).astype(np.float32))
+
+    def run(table, mode):
+        fit = torch.zeros(2, n, dtype=torch.float64, device=eng.device)
+        eng.rollout(table, idx, theta, 0.05, sizes, obsn, rew, 0.05, fit[0], fit[1], mode=mode)
+        return fit.cpu().numpy()
+
+    def close(a, b):
+        return np.abs(a - b).max() <= 0.05 * max(b.std(), 1e-2)
+
+    t1 = dev(eng, rs.randn(L).astype(np.float32))
+    a_tc, a_32 = run(t1, _lib.ES_ROLLOUT_TC), run(t1, _lib.ES_ROLLOUT_F32)
+    assert close(a_tc, a_32)
+    t1.copy_(torch.from_numpy(rs.randn(L).astype(np.float32)))               # in place: same pointer, new contents
+    b_tc, b_32 = run(t1, _lib.ES_ROLLOUT_TC), run(t1, _lib.ES_ROLLOUT_F32)
+    assert close(b_tc, b_32) and not close(b_tc, a_32)
+    del t1
+    t2 = dev(eng, rs.randn(L).astype(np.float32))                             # usually the recycled address of t1
+    c_tc, c_32 = run(t2, _lib.ES_ROLLOUT_TC), run(t2, _lib.ES_ROLLOUT_F32)
+    assert close(c_tc, c_32) and not close(c_tc, b_32)
+
+
 def test_rollout_tc_sigma_zero_symmetric_and_unsupported_shape(eng):
     from es_pytorch_b200 import _lib
     from es_pytorch_b200._lib import EsLibraryError

@@ -1,10 +1,5 @@
-timeout 900 python bench.py > gpurun_out/r1_h_bench.json 2> gpurun_out/r1_h_bench.err
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1_h_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r1_h_launch_run.log 2>&1
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:rollout_tc_kernel -c 1 -o gpurun_out/r1_h_tc -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r1_h_ncu1.log 2>&1
-timeout 900 ncu --set full --clock-control none -k regex:reconstruct_kernel -c 1 -o gpurun_out/r1_h_rec -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r1_h_ncu2.log 2>&1
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r1_h_bench.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['cpu_baseline'])
-PY
-ls -la gpurun_out/ | tail -8
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
+for r in 1 2; do
+  ES_TC_NO_SHADOW=1 timeout 300 python tools/dev_tc_time.py 2>&1 | tail -1 | cut -c1-150
+  timeout 300 python tools/dev_tc_time.py 2>&1 | tail -1 | cut -c1-150
+done
