@@ -335,30 +335,32 @@ __device__ __forceinline__ void tc_build_l1_rows(uint8_t* b1_base, const float* 
 // Layer-1 operand rows from the bf16 shadow: row n of eps1 is 16-byte aligned in shadow copy s = idx % 8 (obs % 8 == 0), so
 // a lane moves one 16-byte unit (8 columns) with one vector load and one vector store into its swizzled place: 47 units
 // per row for obs = 376, against 376 float loads + conversions.  The unit holding column `obs` carries the bias element
-// (unscaled eps_b1[n]; the epilogue multiplies V by sigma) and zeros.  A warp takes 4 rows per iteration.
+// (unscaled eps_b1[n]; the epilogue multiplies V by sigma) and zeros.  8 independent loads in flight per thread.
 __device__ __forceinline__ void tc_build_l1_rows_shadow(uint8_t* b1_base, const __nv_bfloat16* __restrict__ rows,
-                                                        const float* __restrict__ bvec, int obs, int nkc, int worker,
-                                                        int nworkers, int lane) {
+                                                        const float* __restrict__ bvec, int obs, int nkc, int tid,
+                                                        int nthreads) {
     const int units = obs >> 3;                                  // full 16-byte units of a row
     const int total = nkc * 8;                                   // units of the padded row (K = nkc * 64)
-    for (int n0 = worker * 4; n0 < TC_H; n0 += nworkers * 4) {
-        for (int u0 = 0; u0 < total; u0 += 32) {
-            const int u = u0 + lane;
-            uint4 v[4];
+    const int all = TC_H * total;                                // (row, unit) pairs, unit fastest: coalesced 16-byte runs
+    constexpr int NB = 8;                                        // independent 16-byte loads in flight per thread
+    for (int f0 = tid; f0 < all; f0 += nthreads * NB) {
+        uint4 v[NB];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int n = n0 + r;
-                v[r] = make_uint4(0, 0, 0, 0);
-                if (u < units) v[r] = ldg_stream_u4(rows + (size_t)n * obs + 8 * u);
-                else if (u == units) v[r].x = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(ldg_stream(bvec + n)));
+        for (int k = 0; k < NB; ++k) {
+            const int f = f0 + k * nthreads;
+            const int n = f / total, u = f - n * total;
+            v[k] = make_uint4(0, 0, 0, 0);
+            if (f < all) {
+                if (u < units) v[k] = ldg_stream_u4(rows + (size_t)n * obs + 8 * u);
+                else if (u == units) v[k].x = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(ldg_stream(bvec + n)));
             }
-            if (u < total) {
+        }
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int n = n0 + r;
-                    *(uint4*)(b1_base + (size_t)(u >> 3) * TC_B1_CHUNK_BYTES + n * 128 + (((u & 7) ^ (n & 7)) << 4)) = v[r];
-                }
-            }
+        for (int k = 0; k < NB; ++k) {
+            const int f = f0 + k * nthreads;
+            const int n = f / total, u = f - n * total;
+            if (f < all)
+                *(uint4*)(b1_base + (size_t)(u >> 3) * TC_B1_CHUNK_BYTES + n * 128 + (((u & 7) ^ (n & 7)) << 4)) = v[k];
         }
     }
 }
@@ -809,7 +811,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(
             if (p.shadow) {
                 const int64_t at = p.idx[pair] + p.w1;                    // first element of eps1 in the table
                 const __nv_bfloat16* rows = p.shadow + (size_t)(at & 7) * p.shadow_stride + (at - (at & 7));
-                tc_build_l1_rows_shadow(img + I.b1, rows, eps + p.b1, p.obs, NKC, bw, TC_BLD_WARPS, lane);
+                tc_build_l1_rows_shadow(img + I.b1, rows, eps + p.b1, p.obs, NKC, btid, BT);
             } else {
                 tc_build_l1_rows(img + I.b1, eps + p.w1, eps + p.b1, sg, p.obs, NKC, 0, TC_H / 2, bw, TC_BLD_WARPS, lane);
             }
