@@ -925,21 +925,46 @@ __global__ void rollout_tc_prep_kernel(const float* __restrict__ obsn, int T, in
     }
 }
 
-// U[t][n] = b1[n] + sum_k Xn[t][k] * theta1[n][k] in float32, k ascending (rows t >= T are zero): one block per row.
+// U[t][n] = b1[n] + sum_k Xn[t][k] * theta1[n][k] in float32, k ascending (rows t >= T are zero).
+// One block = TC_UB_ROWS time steps x 64 columns; theta1 is read through a transposed shared-memory tile (coalesced global
+// reads, conflict-free column reads), the observation rows are broadcast from shared memory.
 // Output layout (float index): (((m*2 + h)*8 + c)*128 + row)*4 + e  for column n = 32h + 4c + e, t = 128m + row.
-__global__ void __launch_bounds__(TC_H) rollout_tc_ubase_kernel(const float* __restrict__ obsn, const float* __restrict__ theta,
-                                                                 int w1, int b1, int T, int obs, float* __restrict__ ubase) {
-    extern __shared__ float s_x[];
-    const int t = blockIdx.x, n = threadIdx.x;
-    const int m = t / TC_MT, row = t % TC_MT, h = n >> 5, c = (n & 31) >> 2, e = n & 3;
-    float* out = ubase + ((((size_t)(m * 2 + h) * 8 + c) * TC_MT + row) * 4 + e);
-    if (t >= T) { *out = 0.f; return; }
-    for (int k = n; k < obs; k += TC_H) s_x[k] = obsn[(size_t)t * obs + k];
-    __syncthreads();
-    const float* __restrict__ w = theta + w1 + (size_t)n * obs;
-    float acc = __ldg(theta + b1 + n);
-    for (int k = 0; k < obs; ++k) acc = fmaf(s_x[k], __ldg(w + k), acc);
-    *out = acc;
+constexpr int TC_UB_ROWS = 8, TC_UB_KT = 64, TC_UB_RPT = TC_UB_ROWS / 4;   // rows per block / k tile / rows per thread
+__global__ void __launch_bounds__(256) rollout_tc_ubase_kernel(const float* __restrict__ obsn, const float* __restrict__ theta,
+                                                                int w1, int b1, int T, int obs, float* __restrict__ ubase) {
+    __shared__ float s_w[TC_UB_KT][TC_H + 1];                 // [k][n]
+    __shared__ float s_x[TC_UB_ROWS][TC_UB_KT];
+    const int n = threadIdx.x & 63, rg = threadIdx.x >> 6;    // column, row group (TC_UB_RPT rows each)
+    const int t0 = blockIdx.x * TC_UB_ROWS;
+    float acc[TC_UB_RPT];
+#pragma unroll
+    for (int r = 0; r < TC_UB_RPT; ++r) acc[r] = __ldg(theta + b1 + n);
+    for (int k0 = 0; k0 < obs; k0 += TC_UB_KT) {
+        const int kn = min(TC_UB_KT, obs - k0);
+        for (int i = threadIdx.x; i < TC_H * TC_UB_KT; i += 256) {           // theta1[nn][k0 + kk], kk fastest: coalesced
+            const int nn = i / TC_UB_KT, kk = i - nn * TC_UB_KT;
+            s_w[kk][nn] = (kk < kn) ? __ldg(theta + w1 + (size_t)nn * obs + k0 + kk) : 0.f;
+        }
+        for (int i = threadIdx.x; i < TC_UB_ROWS * TC_UB_KT; i += 256) {
+            const int r = i / TC_UB_KT, kk = i - r * TC_UB_KT;
+            const int t = t0 + r;
+            s_x[r][kk] = (kk < kn && t < T) ? obsn[(size_t)t * obs + k0 + kk] : 0.f;
+        }
+        __syncthreads();
+        for (int kk = 0; kk < kn; ++kk) {                                    // k ascending, one fmaf per term as before
+            const float w = s_w[kk][n];
+#pragma unroll
+            for (int r = 0; r < TC_UB_RPT; ++r) acc[r] = fmaf(s_x[rg * TC_UB_RPT + r][kk], w, acc[r]);
+        }
+        __syncthreads();
+    }
+    const int h = n >> 5, c = (n & 31) >> 2, e = n & 3;
+#pragma unroll
+    for (int r = 0; r < TC_UB_RPT; ++r) {
+        const int t = t0 + rg * TC_UB_RPT + r;
+        const int m = t / TC_MT, row = t % TC_MT;
+        ubase[(((size_t)(m * 2 + h) * 8 + c) * TC_MT + row) * 4 + e] = (t < T) ? acc[r] : 0.f;
+    }
 }
 
 // bf16 shadow of the table: copy s, element j = bf16(table[j + s]) (zero beyond the end)
@@ -1054,7 +1079,7 @@ int es_impl_rollout_tc(es_ctx* ctx, const float* table, int64_t table_len, const
         if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
         rollout_tc_prep_kernel<<<blocks, 256, 0, stream>>>(obsn, T, p.obs, p.nkc, p.n_mtiles, (__nv_bfloat16*)scratch);
         ES_LAUNCHED(ctx);
-        rollout_tc_ubase_kernel<<<p.n_mtiles * TC_MT, TC_H, p.obs * sizeof(float), stream>>>(obsn, theta, p.w1, p.b1, T, p.obs, ubase);
+        rollout_tc_ubase_kernel<<<p.n_mtiles * TC_MT / TC_UB_ROWS, 256, 0, stream>>>(obsn, theta, p.w1, p.b1, T, p.obs, ubase);
         ES_LAUNCHED(ctx);
         rollout_tc_crt_kernel<<<es_div_up(p.n_mtiles * TC_ACT_PAD * TC_MT, 256), 256, 0, stream>>>(rew_vec, T, p.act, p.n_mtiles, crt);
         ES_LAUNCHED(ctx);
