@@ -35,7 +35,7 @@ WORKLOADS = {
 }
 VIRTUAL_RANKS_PER_GPU = 8
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (default workload)
-NCU_TRAFFIC = {'rollout': 1.120133e9 + 8.804864e6, 'reconstruct': 1.084531e9 + 4.941824e6}
+NCU_TRAFFIC = {'rollout': 701.363968e6 + 8.559872e6, 'reconstruct': 1.084531e9 + 4.941824e6}
 
 
 def parse():
@@ -305,13 +305,13 @@ def run_ours(args, wl, n_gpus):
         # dominant kernel by time: the fused perturb+rollout
         roofline=dict(kernel='rollout (es_rollout_openloop)', bound='tensor', achieved=roll_tfs, peak=tf_peak,
                       unit='TFLOP/s', frac=roll_tfs / tf_peak, traffic=NCU_TRAFFIC['rollout'] if default_wl else None,
-                      traffic_source='profiles/r1_h_rollout_tc_ncu_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum, 1 launch)',
+                      traffic_source='profiles/r1_i_rollout_tc_ncu_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum, 1 launch)',
                       peak_source=tf_src,
                       algorithmic_flops_per_launch=roll_flop, share_of_step=kern['rollout'] / ms_step,
                       note='mode f32 runs on the CUDA cores (FFMA); reported against the tensor peak the '
                            'tcgen05 path is judged by' if mode == _lib.ES_ROLLOUT_F32 else
                            'tcgen05 path; the kernel is bound by the tanh epilogue (2.9 G MUFU.TANH per generation at 4 lanes/clk per '
-                           'SM sub-partition = 0.65 ms floor; ncu: XU 48 %, tensor 23 %) and by the dependent-latency chain of its '
+                           'SM sub-partition = 0.65 ms floor; ncu: XU 51 %, tensor 25 %) and by the dependent-latency chain of its '
                            'per-tile phases, not by the tensor pipe: see profiles/README.md'),
         # the north-star's named HBM-bound kernel
         roofline_reconstruct=dict(kernel='reconstruct_kernel (es_grad_reconstruct)', bound='hbm', achieved=rec_gbs,
