@@ -9,11 +9,13 @@
 // per 128-step tile of the episode:
 //   z1+- = U +- V.   U = Xn . theta1^T + b1 does not depend on the pair: it is computed ONCE per generation
 //                    in float32 (rollout_tc_ubase_kernel) and read from L2 by the epilogue.
-//                    V (128 x 64, fp32, TMEM) = Xn_tile (128 x K, bf16) . (sigma*eps1)^T is the only per-pair
-//                    L1 MMA; the perturbation term is therefore carried at bf16 *relative* precision and the
-//                    unperturbed pre-activation at full float32 precision.  The sigma*eps_b1 bias rides in a
-//                    constant-1 column of the observation tile.
-//   epi1: h1+- = tanh(U +- V) -> bf16 -> shared (K-major, 128B swizzle) = A operand of L2
+//                    V (128 x 64, fp32, TMEM) = Xn_tile (128 x K, bf16) . eps1^T is the only per-pair L1 MMA
+//                    (eps1 unscaled from the bf16 shadow of the table, z1+- = U +- sigma*V; or sigma*eps1 converted
+//                    by the builders when the shape has no 16-byte aligned rows, z1+- = U +- V); the perturbation
+//                    term is therefore carried at bf16 *relative* precision and the unperturbed pre-activation at
+//                    full float32 precision.  The eps_b1 bias rides in a constant-1 column of the observation tile.
+//   epi1: h1+- = tanh(z1+-) -> bf16 -> shared (K-major, 128B swizzle) = A operand of L2; one read of U and of V
+//         serves both signs, 8 columns at a time (the role must fit 72 registers without spilling)
 //   L2:   D2+- (128 x 64) = h1+- . (theta2 +- sigma*eps2)^T ;  epi2: h2+- = tanh(D2+- + b2+-)
 //   L3:   D3+- (128 x 32) = h2+- . (theta3 +- sigma*eps3)^T ;  epi3: a = tanh(D3 + b3),
 //         r_t = <a_t, c_t>, fitness += r_t, pos += a_t[0..2]
@@ -26,11 +28,13 @@
 //                separate H buffers, TMEM regions and barriers, so one group's waits for its short L2/L3
 //                MMAs are filled by the other group's MUFU/ALU work.  Inside a group the + and - sign
 //                chains are interleaved.  TMEM lane quarter = warp % 4, column half = ((warp-2) % 8) / 4.
-//   warps 18-21  builders: while pair i computes, convert pair i+1's noise slice (float32, arbitrary 4-byte
-//                alignment in the table, which rules out TMA/bulk copies of the slice itself) into a bf16,
-//                pre-swizzled IMAGE of the B operands in an L2-resident scratch (the loads are latency-bound:
-//                ~3k cycles per row pair).  When pair i's last L1 (resp. last L3) has retired, the image is
-//                moved into shared memory with a few cp.async.bulk copies (~2k cycles instead of ~15k).
+//   warps 18-21  builders: while pair i computes, build pair i+1's bf16, pre-swizzled IMAGE of the B operands in an
+//                L2-resident scratch.  The float32 slice has arbitrary 4-byte alignment in the table (no TMA / bulk
+//                copy of the slice itself); eps1 (82 % of it) therefore comes from a bf16 SHADOW of the table kept in
+//                8 copies shifted by 0..7 elements, in one of which every row is 16-byte aligned: one 16-byte load +
+//                one 16-byte store per 8 columns.  theta2/3 +- sigma*eps2/3 and the biases are computed from the
+//                float32 slice.  When pair i's last L1 (resp. last L3) has retired, the image is moved into shared
+//                memory with a few cp.async.bulk copies (~2k cycles instead of ~15k).
 //   warps 22-23  L2/L3 MMA issuers, one per epilogue group (blocking mbarrier waits, no polling).
 //   warp 24      copier: moves a finished operand image into shared memory (2-slot ring with the builders).
 // Per-pair fitness: every epilogue warp writes its partial sums to a scratch slot; the last of the 16 to
