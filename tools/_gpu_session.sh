@@ -1,8 +1,7 @@
-timeout 900 python bench.py > gpurun_out/r1_i_bench.json 2> gpurun_out/r1_i_bench.err
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1_i_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r1_i_launch_run.log 2>&1
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:rollout_tc_kernel -c 1 -o gpurun_out/r1_i_tc -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r1_i_ncu1.log 2>&1
-python - <<'PY'
+timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "rollout_tc or rank_transform or elite or rollout_f32_time" 2>&1 | tail -15 > gpurun_out/r2_memcheck.log; tail -15 gpurun_out/r2_memcheck.log
+timeout 600 python bench.py --workload halfcheetah --no-cpu-baseline > gpurun_out/r2_bench_hc.json 2> gpurun_out/r2_bench_hc.err; python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/r1_i_bench.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['cpu_baseline']['value'], d['cpu_baseline'].get('steps_s'), d['kernel_ms'])
+d=json.loads(open('gpurun_out/r2_bench_hc.json').read().strip().splitlines()[-1])
+print('halfcheetah', round(d['value']), round(d['ms_per_step'],4), round(d['e2e']['value']), d['config']['pairs_total'], {k:round(v,4) for k,v in d['kernel_ms'].items()})
 PY
+tail -2 gpurun_out/r2_bench_hc.err
