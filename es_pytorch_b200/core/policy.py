@@ -76,6 +76,7 @@ class Policy:
     def __getstate__(self):
         d = dict(self.__dict__)
         d['_theta_dev'] = None
+        d.pop('_sd_views', None)
         return d
 
     # -- reference API -----------------------------------------------------------------------------------
@@ -85,8 +86,13 @@ class Policy:
         with torch.no_grad():
             at = 0
             # state_dict order = flat order (policy.py:33-35); copied in place: the effect of the reference's
-            # load_state_dict without rebuilding the dict machinery every evaluation
-            for w in self._module.state_dict().values():
+            # load_state_dict without rebuilding the dict machinery every evaluation.  The tensor list is cached (it
+            # aliases the module's parameters and buffers) and rebuilt if the module was swapped or restructured.
+            ptrs = tuple(p.data_ptr() for p in self._module.parameters())
+            cache = getattr(self, '_sd_views', None)
+            if cache is None or cache[0] is not self._module or cache[2] != ptrs:
+                cache = self._sd_views = (self._module, list(self._module.state_dict().values()), ptrs)
+            for w in cache[1]:
                 n = w.numel()
                 w.copy_(flat[at:at + n].reshape(w.shape))
                 at += n
