@@ -32,6 +32,9 @@ WORKLOADS = {
     'humanoid': dict(obs=376, act=17, hidden=(64, 64), T=1000, pairs=10000, table=250_000_000),
     # BASELINE.json configs[1]: HalfCheetah-shaped synthetic, K=256 (latency-bound; parity-size case)
     'halfcheetah': dict(obs=17, act=6, hidden=(64, 64), T=1000, pairs=256, table=250_000_000),
+    # BASELINE.json configs[4]: NSRA-ES on the Humanoid shape: objective + novelty (k=10 nearest of a 64-entry archive of
+    # final (x, y) positions), dual rank blended with w = 0.5 (MultiObjectiveRanker), K=10000 per GPU here
+    'humanoid-nsra': dict(obs=376, act=17, hidden=(64, 64), T=1000, pairs=10000, table=250_000_000, nsra=True),
 }
 VIRTUAL_RANKS_PER_GPU = 8
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (default workload)
@@ -91,7 +94,7 @@ def run_reference(args, wl, n_gpus):
 def workload_config(args, wl, n_gpus, K):
     return dict(workload=f"{args.workload}-shaped synthetic open-loop env: MLP {wl['obs']}-{'-'.join(map(str, wl['hidden']))}"
                          f"-{wl['act']} tanh, T={wl['T']}, sigma=0.02, l2coeff=0.005, Adam lr=0.01, "
-                         f"noise table {wl['table']} float32",
+                         f"noise table {wl['table']} float32" + (', NSRA: reward + novelty (k=10, archive 64), dual rank w=0.5' if wl.get('nsra') else ''),
                 pairs_total=K, pairs_per_gpu=K // n_gpus, evaluations_total=2 * K,
                 virtual_mpi_ranks_per_gpu=VIRTUAL_RANKS_PER_GPU, save_obs_coins_per_pair=2,
                 parallelism=f'perturbation shards x{n_gpus}, fitness allgather + one grad allreduce',
@@ -165,7 +168,7 @@ def run_ours(args, wl, n_gpus):
     from es_pytorch_b200.nn.nn import FeedForward
     from es_pytorch_b200.nn.obstat import ObStat
     from es_pytorch_b200.nn.optimizers import Adam
-    from es_pytorch_b200.utils.rankers import CenteredRanker
+    from es_pytorch_b200.utils.rankers import CenteredRanker, MultiObjectiveRanker
     from es_pytorch_b200.utils.reporters import Reporter
 
     comm = dist.init_from_env('nccl' if int(os.environ.get('WORLD_SIZE', '1')) > 1 else None)
@@ -191,11 +194,13 @@ def run_ours(args, wl, n_gpus):
     env = SyntheticEnv(wl['obs'], wl['act'], wl['T'])
     seeds = [1000 + rank * VIRTUAL_RANKS_PER_GPU + r for r in range(VIRTUAL_RANKS_PER_GPU)]
     obs_dev, rew_dev = env.device_arrays(eng)
+    archive = np.random.RandomState(17).randn(64, 2) if wl.get('nsra') else None
 
     # ---------------- device-resident generation: `value` ----------------
     gen = DeviceGeneration(table, eng.to_device(theta0.copy()), sizes, obs_dev, rew_dev,
                            [np.random.RandomState(s) for s in seeds], 0.02, 0.005, Adam(P, 0.01), coins_per_eval=1,
-                           save_obs_chance=0.01, rollout_mode=mode, comm=comm, engine=eng)
+                           save_obs_chance=0.01, rollout_mode=mode, comm=comm, engine=eng,
+                           archive=None if archive is None else eng.to_device(archive, torch.float64), nov_k=10, moo_w=0.5)
     for _ in range(args.warmup):
         gen.run(n_per_stream)
     gen.enable_timers(True)
@@ -228,11 +233,11 @@ def run_ours(args, wl, n_gpus):
         nt = NoiseTable(P, table)
         streams = [np.random.RandomState(s) for s in seeds]
         fit_fn = BatchedRollout(env, wl['T'], coins_per_eval=1, save_obs_chance=0.01, rank_streams=streams,
-                                rollout_mode=mode)
+                                rollout_mode=mode, archive=archive, nov_k=10)
         # the synthetic vector env is GPU-resident (its observation / reward streams are env state in HBM, like a
         # simulator running on the device); the per-generation host inputs are theta, the RNG states and the obs statistics
         fit_fn.stream_env_from_host = False
-        ranker = CenteredRanker()
+        ranker = CenteredRanker() if archive is None else MultiObjectiveRanker(CenteredRanker(), 0.5)
 
         class _Cfg(dict):
             __getattr__ = dict.__getitem__

@@ -1,6 +1,6 @@
-timeout 900 python -m pytest tests -x -q -m gpu -k "rollout_tc or generation" 2>&1 | tail -4
-for r in 1 2; do
-for v in "" _head; do
-  if [ -z "$v" ]; then unset ES_B200_LIB; else export ES_B200_LIB=$PWD/es_pytorch_b200/libes_b200$v.so; fi
-  timeout 300 python tools/dev_tc_time.py 2>&1 | tail -1 | cut -c1-150
-done; done
+timeout 600 python bench.py --workload humanoid-nsra --no-cpu-baseline > gpurun_out/r2_bench_nsra.json 2> gpurun_out/r2_bench_nsra.err; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2_bench_nsra.json').read().strip().splitlines()[-1])
+print('nsra', round(d['value']), round(d['ms_per_step'],4), round(d['e2e']['value']), round(d['e2e']['ms_per_step'],4), {k:round(v,4) for k,v in d['kernel_ms'].items()})
+PY
+tail -3 gpurun_out/r2_bench_nsra.err
