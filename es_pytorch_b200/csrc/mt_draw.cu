@@ -77,12 +77,15 @@ __device__ __forceinline__ MtFn mtfn_shfl_up(const MtFn& f, int d) {
     return r;
 }
 
+// ST > 0: number of machine states (extra + 1) known at compile time (the compositions unroll over ST states only)
+template <int ST>
 __global__ void __launch_bounds__(MT_THREADS)
 mt_draw_kernel(uint32_t* __restrict__ mt_key, int32_t* __restrict__ mt_pos, int n_per_stream, uint32_t rng,
                uint32_t mask, int extra, int64_t* __restrict__ idx_out, uint32_t* __restrict__ extra_out) {
     __shared__ uint32_t mt[MT_N];
     __shared__ uint32_t tw[MT_N];
-    __shared__ MtFn s_warp[MT_WARPS];          // inclusive function of each warp
+    __shared__ MtFn s_warp[MT_WARPS];          // inclusive function of each warp, then of everything before it
+    __shared__ MtFn s_block;
     __shared__ int s_stop[MT_WARPS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -90,7 +93,7 @@ mt_draw_kernel(uint32_t* __restrict__ mt_key, int32_t* __restrict__ mt_pos, int 
     uint32_t* key = mt_key + (size_t)stream_id * MT_N;
     int64_t* out = idx_out + (size_t)stream_id * n_per_stream;
     uint32_t* xout = extra_out ? extra_out + (size_t)stream_id * n_per_stream * extra : nullptr;
-    const int S = extra + 1;
+    const int S = ST > 0 ? ST : extra + 1;
 
     for (int i = tid; i < MT_N; i += MT_THREADS) mt[i] = key[i];
     int pos = mt_pos[stream_id];
@@ -166,11 +169,19 @@ mt_draw_kernel(uint32_t* __restrict__ mt_key, int32_t* __restrict__ mt_pos, int 
         }
         if (lane == 31) s_warp[warp] = inc;
         __syncthreads();
-        // ... then the (few) warp totals in order
-        MtFn before = mtfn_identity();                // everything before this warp
-        for (int w = 0; w < warp; ++w) before = mtfn_compose(before, s_warp[w], S);
-        MtFn blk = before;                            // the whole block
-        for (int w = warp; w < MT_WARPS; ++w) blk = mtfn_compose(blk, s_warp[w], S);
+        // ... then the (few) warp totals in order: thread 0 leaves the function of everything before each warp, and of the
+        // whole block
+        if (tid == 0) {
+            MtFn run = mtfn_identity();
+            for (int w = 0; w < MT_WARPS; ++w) {
+                const MtFn tot = s_warp[w];
+                s_warp[w] = run;
+                run = mtfn_compose(run, tot, S);
+            }
+            s_block = run;
+        }
+        __syncthreads();
+        const MtFn before = s_warp[warp], blk = s_block;
         // (3) entry state / offset of this thread = exclusive prefix applied to the block entry state
         MtFn exc = mtfn_shfl_up(inc, 1);
         exc = (lane == 0) ? before : mtfn_compose(before, exc, S);
@@ -248,7 +259,12 @@ int es_impl_draw_indices(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int n_s
         es_set_error("es_draw_indices: upper_bound == 1 with extra_words > 0 is not supported");
         return ES_ERR_UNSUPPORTED;
     }
-    mt_draw_kernel<<<n_streams, MT_THREADS, 0, stream>>>(mt_key, mt_pos, n_per_stream, rng, mask, extra_words, idx_out, extra_out);
+    if (extra_words == 0)
+        mt_draw_kernel<1><<<n_streams, MT_THREADS, 0, stream>>>(mt_key, mt_pos, n_per_stream, rng, mask, extra_words, idx_out, extra_out);
+    else if (extra_words == 4)
+        mt_draw_kernel<5><<<n_streams, MT_THREADS, 0, stream>>>(mt_key, mt_pos, n_per_stream, rng, mask, extra_words, idx_out, extra_out);
+    else
+        mt_draw_kernel<0><<<n_streams, MT_THREADS, 0, stream>>>(mt_key, mt_pos, n_per_stream, rng, mask, extra_words, idx_out, extra_out);
     ES_LAUNCHED(ctx);
     return ES_OK;
 }

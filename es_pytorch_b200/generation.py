@@ -129,9 +129,15 @@ class DeviceGeneration:
         self._bufs_for = n_per_stream
 
     def set_obstat(self, mean: np.ndarray, std: np.ndarray):
-        """Policy.update_obstat -> BaseNet.set_ob_mean_std (policy.py:69-71, nn.py:19-21)."""
-        self.eng.upload_async(self.ob_mean, np.ascontiguousarray(mean, dtype=np.float64).reshape(-1), ('obmean', id(self)))
-        self.eng.upload_async(self.ob_std, np.ascontiguousarray(std, dtype=np.float64).reshape(-1), ('obstd', id(self)))
+        """Policy.update_obstat -> BaseNet.set_ob_mean_std (policy.py:69-71, nn.py:19-21).  Uploaded when they changed."""
+        mean = np.ascontiguousarray(mean, dtype=np.float64).reshape(-1)
+        std = np.ascontiguousarray(std, dtype=np.float64).reshape(-1)
+        last = getattr(self, '_obstat_host', None)
+        if last is not None and np.array_equal(last[0], mean) and np.array_equal(last[1], std):
+            return
+        self._obstat_host = (mean.copy(), std.copy())
+        self.eng.upload_async(self.ob_mean, mean, ('obmean', id(self)))
+        self.eng.upload_async(self.ob_std, std, ('obstd', id(self)))
 
     # ------------------------------------------------------------------------------------------
     def evaluate(self, n_per_stream: int):
