@@ -11,9 +11,9 @@
 //   2. rank_hist_kernel     bucket histogram (RK_BUCKETS linear buckets over [min, max]; -inf first, +inf/NaN last)
 //   3. rank_scan_kernel     exclusive scan of the histogram (one block per objective)
 //   4. rank_scatter_kernel  (key, index) pairs grouped by bucket
-//   5. rank_local_kernel    rank = bucket start + #{(key_j, j) < (key_i, i) inside the bucket}, only for the
-//                           elements of this GPU's shard [k_begin, k_begin+k_count) -- ranks are global
-//   6. rank_finalize_kernel y = shape(rank) (centered: float32(rank)/(2K-1) - 0.5; also the double-positive, semi-centered
+//   5. rank_finalize_kernel rank = bucket start + #{(key_j, j) < (key_i, i) inside the bucket}, only for the
+//                           elements of this GPU's shard [k_begin, k_begin+k_count) -- ranks are global;
+//                           y = shape(rank) (centered: float32(rank)/(2K-1) - 0.5; also the double-positive, semi-centered
 //                           and max-normalised shapings of rankers.py:61-83), blend, weight = y+ - y- (or the elite
 //                           selection of rankers.py:86-103)
 // The float32 ops are the reference's, one IEEE operation each (no contraction).  Steps 1-4 are replicated on every
@@ -35,7 +35,10 @@ __device__ __forceinline__ double rk_unkey(unsigned long long k) {
     return __longlong_as_double((long long)b);
 }
 
-struct RkStats { unsigned long long kmin, kmax; };    // keys of the smallest / largest finite value (per objective)
+// keys of the smallest / largest finite value (per objective); the minimum is stored inverted so that all-zero bytes mean
+// "no finite value yet" for both (one memset initialises the histogram and the statistics)
+struct RkStats { unsigned long long kmin_inv, kmax; };
+__device__ __forceinline__ unsigned long long rk_kmin(const RkStats& st) { return ~st.kmin_inv; }
 
 __device__ __forceinline__ double rk_value(const double* __restrict__ fpos, const double* __restrict__ fneg, int K,
                                            int n_obj, int c, int e) {
@@ -59,7 +62,7 @@ __global__ void rank_keys_kernel(const double* __restrict__ fpos, const double* 
         hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
     if ((threadIdx.x & 31) == 0) {
-        if (lo != 0xFFFFFFFFFFFFFFFFull) atomicMin(&stats[c].kmin, lo);
+        if (lo != 0xFFFFFFFFFFFFFFFFull) atomicMax(&stats[c].kmin_inv, ~lo);
         if (hi != 0ull) atomicMax(&stats[c].kmax, hi);
     }
 }
@@ -75,8 +78,8 @@ __device__ __forceinline__ int rk_bucket(unsigned long long key, double mn, doub
     return 1 + b;
 }
 __device__ __forceinline__ void rk_range(const RkStats& st, double& mn, double& scale) {
-    if (st.kmin > st.kmax) { mn = 0.0; scale = 0.0; return; }          // no finite value
-    mn = rk_unkey(st.kmin);
+    if (rk_kmin(st) > st.kmax) { mn = 0.0; scale = 0.0; return; }      // no finite value
+    mn = rk_unkey(rk_kmin(st));
     const double mx = rk_unkey(st.kmax), span = mx - mn;
     scale = (span > 0.0 && isfinite(span)) ? (double)RK_BUCKETS / span : 0.0;
     if (!isfinite(scale)) scale = 0.0;
@@ -94,8 +97,8 @@ __global__ void rank_hist_kernel(const unsigned long long* __restrict__ keys, in
 // one block per objective: start[b] = sum_{b' < b} hist[b'];  cursor[b] = 0
 __global__ void __launch_bounds__(1024) rank_scan_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ start,
                                                          unsigned* __restrict__ cursor) {
-    __shared__ unsigned s_part[1024];
-    const int c = blockIdx.x, t = threadIdx.x;
+    __shared__ unsigned s_warp[32];
+    const int c = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     constexpr int PER = (RK_NB + 1023) / 1024;
     unsigned loc[PER], sum = 0;
 #pragma unroll
@@ -104,15 +107,26 @@ __global__ void __launch_bounds__(1024) rank_scan_kernel(const unsigned* __restr
         loc[i] = (b < RK_NB) ? hist[(size_t)c * RK_NB + b] : 0u;
         sum += loc[i];
     }
-    s_part[t] = sum;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        const unsigned v = (t >= o) ? s_part[t - o] : 0u;
-        __syncthreads();
-        s_part[t] += v;
-        __syncthreads();
+    // inclusive scan of the per-thread sums: shuffles inside a warp, then the 32 warp totals
+    unsigned inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
     }
-    unsigned run = s_part[t] - sum;                                      // exclusive prefix of this thread's buckets
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned w = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += v;
+        }
+        s_warp[lane] = w;                                                // inclusive totals of warps 0..lane
+    }
+    __syncthreads();
+    unsigned run = inc - sum + (warp > 0 ? s_warp[warp - 1] : 0u);      // exclusive prefix of this thread's buckets
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
         const int b = t * PER + i;
@@ -142,26 +156,28 @@ __device__ __forceinline__ int rk_global_index(int e, int K, int k_begin, int k_
     return (e < k_count) ? (k_begin + e) : (K + k_begin + (e - k_count));
 }
 
-__global__ void rank_local_kernel(const unsigned long long* __restrict__ keys, int K, int k_begin, int k_count,
-                                  const RkStats* __restrict__ stats, const unsigned* __restrict__ hist,
-                                  const unsigned* __restrict__ start, const unsigned long long* __restrict__ skeys,
-                                  const int* __restrict__ sidx, int* __restrict__ ranks /*[n_obj][2*k_count]*/) {
-    const int n = 2 * K, n_local = 2 * k_count, c = blockIdx.y;
+// rank of global element gi of objective c: bucket start + #{(key_j, j) < (key_i, i) inside the bucket}
+struct RkTables {
+    const unsigned long long* keys;      // [n_obj][2K]
+    const RkStats* stats;
+    const unsigned* hist;
+    const unsigned* start;
+    const unsigned long long* skeys;     // keys grouped by bucket
+    const int* sidx;                     // their element indices
+};
+__device__ __forceinline__ int rk_rank_of(const RkTables& tb, int n, int c, int gi) {
     double mn, scale;
-    rk_range(stats[c], mn, scale);
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_local; e += gridDim.x * blockDim.x) {
-        const int gi = rk_global_index(e, K, k_begin, k_count);
-        const unsigned long long k = keys[(size_t)c * n + gi];
-        const int b = rk_bucket(k, mn, scale);
-        const unsigned s0 = start[(size_t)c * RK_NB + b], cnt = hist[(size_t)c * RK_NB + b];
-        int r = (int)s0;
-        for (unsigned j = 0; j < cnt; ++j) {
-            const unsigned long long kj = skeys[(size_t)c * n + s0 + j];
-            const int ij = sidx[(size_t)c * n + s0 + j];
-            r += (kj < k) || (kj == k && ij < gi);
-        }
-        ranks[(size_t)c * n_local + e] = r;
+    rk_range(tb.stats[c], mn, scale);
+    const unsigned long long k = tb.keys[(size_t)c * n + gi];
+    const int b = rk_bucket(k, mn, scale);
+    const unsigned s0 = tb.start[(size_t)c * RK_NB + b], cnt = tb.hist[(size_t)c * RK_NB + b];
+    int r = (int)s0;
+    for (unsigned j = 0; j < cnt; ++j) {
+        const unsigned long long kj = tb.skeys[(size_t)c * n + s0 + j];
+        const int ij = tb.sidx[(size_t)c * n + s0 + j];
+        r += (kj < k) || (kj == k && ij < gi);
     }
+    return r;
 }
 
 // ---- rank -> fitness-shaping value (the _rank of each Ranker subclass, src/utils/rankers.py:53-83) -----------------
@@ -204,7 +220,7 @@ __device__ __forceinline__ double rk_blend(const RkXform& xf, double y0, double 
     return (double)__fadd_rn(__fmul_rn((float)y0, (float)xf.w0), __fmul_rn((float)y1, (float)xf.w1));
 }
 
-__global__ void rank_finalize_kernel(const int* __restrict__ ranks, const double* __restrict__ fpos,
+__global__ void rank_finalize_kernel(const RkTables tb, const double* __restrict__ fpos,
                                      const double* __restrict__ fneg, const RkStats* __restrict__ stats, int K,
                                      int n_obj, RkXform xf, int k_begin, int k_count,
                                      const int64_t* __restrict__ noise_idx, float* __restrict__ weights_out,
@@ -218,12 +234,12 @@ __global__ void rank_finalize_kernel(const int* __restrict__ ranks, const double
     int rp0 = 0, rn0 = 0;
     bool reversed = false;
     for (int c = 0; c < n_obj; ++c) {
-        const int rp = ranks[(size_t)c * n_local + k], rn = ranks[(size_t)c * n_local + k_count + k];
+        const int rp = rk_rank_of(tb, 2 * K, c, k_begin + k), rn = rk_rank_of(tb, 2 * K, c, K + k_begin + k);
         if (c == 0) { rp0 = rp; rn0 = rn; }
         if (ranks_out) { ranks_out[(size_t)c * n_local + k] = rp; ranks_out[(size_t)c * n_local + k_count + k] = rn; }
         double shift = 0.0, ymax = 1.0, xp = 0.0, xn = 0.0;
         if (xf.kind == ES_RANK_MAX_NORMALIZED) {
-            const double mn = rk_unkey(stats[c].kmin), mx = rk_unkey(stats[c].kmax);
+            const double mn = rk_unkey(rk_kmin(stats[c])), mx = rk_unkey(stats[c].kmax);
             shift = (mn > 0.0) ? -mn : mn;                      // x + (-mn if mn > 0 else mn), rankers.py:71
             ymax = __dadd_rn(mx, shift);                        // np.max(y): the add is monotone
             if (c == 0) reversed = ymax < 0.0;                  // dividing by a negative maximum reverses the order
@@ -270,25 +286,20 @@ int es_impl_rank_transform(es_ctx* ctx, const double* fpos, const double* fneg, 
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t key_b = al(n * n_obj * 8), skey_b = key_b, sidx_b = al(n * n_obj * 4);
     const size_t tab_b = al((size_t)RK_NB * n_obj * 4), stat_b = al(sizeof(RkStats) * n_obj);
-    const size_t rank_b = al(n_local * n_obj * 4);
     void* scratch = nullptr;
-    int rc = es_ctx_scratch(ctx, key_b + skey_b + sidx_b + 3 * tab_b + stat_b + rank_b, &scratch);
+    int rc = es_ctx_scratch(ctx, key_b + skey_b + sidx_b + 3 * tab_b + stat_b, &scratch);
     if (rc) return rc;
     char* base = (char*)scratch;
     unsigned long long* keys = (unsigned long long*)base;   base += key_b;
     unsigned long long* skeys = (unsigned long long*)base;  base += skey_b;
     int* sidx = (int*)base;                                 base += sidx_b;
     unsigned* hist = (unsigned*)base;                       base += tab_b;
+    RkStats* stats = (RkStats*)base;                        base += stat_b;      // right behind the histogram: one memset
     unsigned* start = (unsigned*)base;                      base += tab_b;
-    unsigned* cursor = (unsigned*)base;                     base += tab_b;
-    RkStats* stats = (RkStats*)base;                        base += stat_b;
-    int* ranks = (int*)base;
+    unsigned* cursor = (unsigned*)base;
 
-    // kmin = all ones / kmax = 0 ("no finite value yet"), histogram = 0
-    ES_CHECK_CUDA(cudaMemsetAsync(hist, 0, tab_b, stream));
-    ES_CHECK_CUDA(cudaMemsetAsync(stats, 0xFF, stat_b, stream));
-    for (int c = 0; c < n_obj; ++c)
-        ES_CHECK_CUDA(cudaMemsetAsync(&stats[c].kmax, 0, sizeof(unsigned long long), stream));
+    // histogram = 0, statistics = "no finite value yet"
+    ES_CHECK_CUDA(cudaMemsetAsync(hist, 0, tab_b + stat_b, stream));
     int blocks = es_div_up((int64_t)n, RK_THREADS);
     if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
     dim3 grid(blocks, n_obj);
@@ -300,12 +311,6 @@ int es_impl_rank_transform(es_ctx* ctx, const double* fpos, const double* fneg, 
     ES_LAUNCHED(ctx);
     rank_scatter_kernel<<<grid, RK_THREADS, 0, stream>>>(keys, (int)n, stats, start, cursor, skeys, sidx);
     ES_LAUNCHED(ctx);
-    {
-        int lb = es_div_up((int64_t)n_local, 128);
-        if (lb > ctx->sm_count * 16) lb = ctx->sm_count * 16;
-        rank_local_kernel<<<dim3(lb, n_obj), 128, 0, stream>>>(keys, K, k_begin, k_count, stats, hist, start, skeys, sidx, ranks);
-        ES_LAUNCHED(ctx);
-    }
     RkXform xf;
     xf.kind = kind;
     xf.n = (int)n;
@@ -316,8 +321,9 @@ int es_impl_rank_transform(es_ctx* ctx, const double* fpos, const double* fneg, 
     xf.w0 = w0;
     xf.w1 = w1;
     xf.elite_n = elite_n;
-    rank_finalize_kernel<<<es_div_up(k_count, RK_THREADS), RK_THREADS, 0, stream>>>(
-        ranks, fpos, fneg, stats, K, n_obj, xf, k_begin, k_count, noise_idx, weights_out, weights64_out, ranks_out,
+    const RkTables tb = {keys, stats, hist, start, skeys, sidx};
+    rank_finalize_kernel<<<es_div_up(k_count, 128), 128, 0, stream>>>(
+        tb, fpos, fneg, stats, K, n_obj, xf, k_begin, k_count, noise_idx, weights_out, weights64_out, ranks_out,
         elite_vals, elite_fit, elite_idx);
     ES_LAUNCHED(ctx);
     return ES_OK;

@@ -79,9 +79,10 @@ class DeviceGeneration:
         self.ob_std = torch.ones(self.obs_dim, dtype=f64, device=e.device)
         self.obsn = e.empty((self.T, self.obs_dim), f32)
         # generation obs statistics (ObStat(shape, 0), es.py:41): sum, sumsq, [count, n_saved]
-        self.gen_sum = torch.zeros(self.obs_dim, dtype=f64, device=e.device)
-        self.gen_sumsq = torch.zeros(self.obs_dim, dtype=f64, device=e.device)
-        self.gen_count = torch.zeros(2, dtype=f64, device=e.device)
+        self._gen_stats = torch.zeros(2 * self.obs_dim + 2, dtype=f64, device=e.device)   # one buffer: one fill per generation
+        self.gen_sum = self._gen_stats[:self.obs_dim]
+        self.gen_sumsq = self._gen_stats[self.obs_dim:2 * self.obs_dim]
+        self.gen_count = self._gen_stats[2 * self.obs_dim:]
         self._bufs_for = None
         self._host_states = None    # (key, pos) host copies of what store_states last wrote into the callers' streams
         self.version = 0            # bumped by every evaluate(): validity token of the device shadows handed out
@@ -158,7 +159,7 @@ class DeviceGeneration:
         if self.n_obj == 2:
             # second objective column = novelty of the final (x, y) (training_result.py:95-97)
             e.novelty(self.behv.view(-1, 3), self.archive, self.nov_k, self.fit_local.view(-1)[1:], 2)
-        self.gen_sum.zero_(); self.gen_sumsq.zero_(); self.gen_count.zero_()
+        self._gen_stats.zero_()
         if self.extra_words:
             s, q = e.obs_colsum(self.obs_stream[1:self.T + 1])
             e.obstat_accumulate_coins(self.gen_sum, self.gen_sumsq, self.gen_count, s, q, self.T,

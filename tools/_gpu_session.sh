@@ -1,4 +1,4 @@
-timeout 900 python -m pytest tests -x -q -m gpu -k "draw or generation or api" 2>&1 | tail -3
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 timeout 600 python bench.py --no-cpu-baseline --steps 20 > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err
 python - <<'PY'
 import json
