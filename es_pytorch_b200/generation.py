@@ -165,12 +165,12 @@ class DeviceGeneration:
             e.obstat_accumulate_coins(self.gen_sum, self.gen_sumsq, self.gen_count, s, q, self.T,
                                       self.extras.view(-1, 2), self.save_obs_chance)
         if self.comm.size > 1:
-            self.comm.allgather_into(self.fit_all, self.fit_local)
+            with self._timed('allgather'):
+                self.comm.allgather_into(self.fit_all, self.fit_local)
             # [rank][pos|neg][k][obj] -> rank-major [K][obj] per sign (es.py:93-95 ordering)
             self.fpos_all.view(self.comm.size, self.k_local, self.n_obj).copy_(self.fit_all[:, 0])
             self.fneg_all.view(self.comm.size, self.k_local, self.n_obj).copy_(self.fit_all[:, 1])
-            self.comm.allreduce_sum(self.gen_sum); self.comm.allreduce_sum(self.gen_sumsq)
-            self.comm.allreduce_sum(self.gen_count)
+            self.comm.allreduce_sum(self._gen_stats)             # sum, sumsq and counts in one buffer: one collective
             return self.fpos_all, self.fneg_all
         return fp, fn
 

@@ -1,7 +1,6 @@
-timeout 900 python bench.py > gpurun_out/r1_j_bench.json 2> gpurun_out/r1_j_bench.err
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1_j_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r1_j_launch_run.log 2>&1
-python - <<'PY'
+timeout 900 python -m pytest tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -3
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err; python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/r1_j_bench.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['cpu_baseline']['value'], d['cpu_baseline'].get('steps_s'), d['kernel_ms'], d['gpu_launches'], d['clocks'])
+d=json.loads(open('gpurun_out/r2_bench_n2.json').read().strip().splitlines()[-1])
+print('N=2', round(d['value']), round(d['ms_per_step'],4), round(d['e2e']['value']), round(d['e2e']['ms_per_step'],4), {k:round(v,4) for k,v in d['kernel_ms'].items()})
 PY
