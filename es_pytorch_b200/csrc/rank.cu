@@ -150,12 +150,6 @@ __global__ void rank_scatter_kernel(const unsigned long long* __restrict__ keys,
     }
 }
 
-// local element e in [0, 2*k_count): e < k_count -> global index k_begin+e (pos part),
-// else K + k_begin + (e - k_count) (neg part).
-__device__ __forceinline__ int rk_global_index(int e, int K, int k_begin, int k_count) {
-    return (e < k_count) ? (k_begin + e) : (K + k_begin + (e - k_count));
-}
-
 // rank of global element gi of objective c: bucket start + #{(key_j, j) < (key_i, i) inside the bucket}
 struct RkTables {
     const unsigned long long* keys;      // [n_obj][2K]
@@ -282,7 +276,7 @@ int es_impl_rank_transform(es_ctx* ctx, const double* fpos, const double* fneg, 
                            double w1, int elite_n, int k_begin, int k_count, const int64_t* noise_idx,
                            float* weights_out, double* weights64_out, int32_t* ranks_out, double* elite_vals,
                            int32_t* elite_fit, int64_t* elite_idx, cudaStream_t stream) {
-    const size_t n = 2 * (size_t)K, n_local = 2 * (size_t)k_count;
+    const size_t n = 2 * (size_t)K;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t key_b = al(n * n_obj * 8), skey_b = key_b, sidx_b = al(n * n_obj * 4);
     const size_t tab_b = al((size_t)RK_NB * n_obj * 4), stat_b = al(sizeof(RkStats) * n_obj);

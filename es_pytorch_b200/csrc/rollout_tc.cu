@@ -82,17 +82,6 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// non-blocking probe (try_wait may suspend the thread for a system-dependent time when the phase is not complete,
-// which would stall the MMA issuer's polling loop)
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try(bar, parity)) {
@@ -127,25 +116,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -156,15 +126,6 @@ __device__ __forceinline__ void add2(float& o0, float& o1, uint32_t a0, uint32_t
     unsigned long long a, b, c;
     asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
     asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "r"(b0), "r"(b1));
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
-    uint32_t c0, c1;
-    asm("mov.b64 {%0, %1}, %2;" : "=r"(c0), "=r"(c1) : "l"(c));
-    o0 = __uint_as_float(c0); o1 = __uint_as_float(c1);
-}
-__device__ __forceinline__ void sub2(float& o0, float& o1, uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
-    unsigned long long a, b, c;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "r"(b0 ^ 0x80000000u), "r"(b1 ^ 0x80000000u));
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
     uint32_t c0, c1;
     asm("mov.b64 {%0, %1}, %2;" : "=r"(c0), "=r"(c1) : "l"(c));
@@ -196,43 +157,21 @@ __device__ __forceinline__ float tanh_fast(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// two tanh per MUFU op: round the pre-activations to bf16 (the result is stored as bf16 anyway)
-__device__ __forceinline__ uint32_t tanh_bf16x2(float lo, float hi) {
-    uint32_t packed, y;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(packed) : "f"(hi), "f"(lo));      // upper half <- hi, lower half <- lo
-    asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(packed));
-    return y;
-}
 __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ float2 lds64f(uint32_t saddr) {
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
-    return v;
 }
 __device__ __forceinline__ float4 lds128f(uint32_t saddr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
     return v;
 }
-__device__ __forceinline__ float lds32f(uint32_t saddr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
-    return v;
-}
 // tanh of two values -> packed bf16x2 (lower half = lo).  tanh.approx.bf16x2 is NOT a packed MUFU op on sm_100
 // (SASS: two MUFU.TANH.BF16 + PRMTs), so the float32 approximation + one pack is both cheaper and more accurate.
 __device__ __forceinline__ uint32_t tanh2_pack(float lo, float hi) {
     const float a = tanh_fast(lo), b = tanh_fast(hi);
-#ifdef TC_PACK_ALU
-    // round to nearest (ties away from zero) on the ALU pipe: F2FP shares the XU pipe with MUFU.TANH
-    return __byte_perm(__float_as_uint(a) + 0x8000u, __float_as_uint(b) + 0x8000u, 0x7632);
-#else
     uint32_t y;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(b), "f"(a));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(b), "f"(a));      // F2FP: not on the XU pipe, ~1 cycle (measured)
     return y;
-#endif
 }
 // Transposing butterfly: the warp-wide sums of v[0..7] in 9 shuffles.  Lane L returns the sum of v[tc_sum8_index(L)].
 __device__ __forceinline__ int tc_sum8_index(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
@@ -369,9 +308,6 @@ __device__ __forceinline__ void tc_build_l1_rows_shadow(uint8_t* b1_base, const 
     }
 }
 
-// split of the 32 row pairs of sigma*eps1 between the builder warps (start early) and the epilogue warps (join when
-// they have finished the current pair's tiles and would otherwise idle until the next pair's first L1)
-constexpr int TC_BLD_ROWPAIRS = 16;
 
 struct TcParams {
     const float* table;
@@ -464,11 +400,8 @@ __device__ __forceinline__ void tc_issue_4k(uint32_t d, uint64_t a_desc, uint64_
     umma_bf16(d, a_desc + 6, b_desc + 6, idesc, 1);
 }
 
-#ifdef TC_MAXNREG
-__global__ void __maxnreg__(TC_MAXNREG) rollout_tc_kernel(
-#else
+// 25 warps: ptxas and the hardware allocate registers as for 28 -> 72 per thread (a launch with 80 fails)
 __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(
-#endif
     const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
