@@ -18,7 +18,9 @@ Pinning status:
     table content (test/es/noisetable_test.py:19-26);
   * pinned against the real reference modules that import in the build container
     (``src.utils.rankers``, ``src.nn.optimizers``): ``tests/golden/make_golden.py``
-    ran them and committed the vectors;
+    ran them and committed the vectors -- ``ref_vectors.npz`` (CenteredRanker, MultiObjectiveRanker,
+    SGD / Adam / SimpleES steps, legacy RandomState streams) and ``ref_rankers.npz`` (DoublePositiveCentered,
+    SemiCentered, MaxNormalized, EliteRanker and their MultiObjective blends);
   * PARITY UNPINNED by any reference test (this file is the only pin):
     ``Policy.pheno``, ``FeedForward.forward``, ``run_model``, ``test_params`` RNG
     interleaving, ``approx_grad``.
