@@ -70,15 +70,47 @@ __device__ __forceinline__ void rf_dense(const float* __restrict__ Wsm, const fl
     }
 }
 
+// W = theta +- sigma*eps of one policy, rows padded to the layer's pitch (zero padding), biases behind the weights
+__device__ __forceinline__ void rf_stage_weights(float* __restrict__ W, const float* __restrict__ eps,
+                                                 const float* __restrict__ theta, float sigma, bool neg, const RfDesc& d) {
+    for (int l = 0; l < d.n_layers; ++l) {
+        const int in = d.in[l], cnt = d.in[l] * d.out[l];
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const int n = i / in, k = i - n * in;
+            const float dlt = __fmul_rn(sigma, __ldg(eps + d.w_off[l] + i));     // std * noise
+            const float t = __ldg(theta + d.w_off[l] + i);
+            W[d.sw_off[l] + n * d.pitch[l] + k] = __fadd_rn(t, neg ? -dlt : dlt);
+        }
+        for (int i = threadIdx.x; i < d.out[l]; i += blockDim.x) {
+            const float dlt = __fmul_rn(sigma, __ldg(eps + d.b_off[l] + i));
+            W[d.sb_off[l] + i] = __fadd_rn(__ldg(theta + d.b_off[l] + i), neg ? -dlt : dlt);
+        }
+    }
+}
+
+// networks whose padded weights do not fit in shared memory (e.g. the 15-256-256-3 net of configs/simple_conf.json): the
+// perturbed weights of every policy of the launch are staged in a global scratch (L2 resident) by this kernel first
+__global__ void __launch_bounds__(RF_THREADS)
+rollout_f32_stage_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx, const float* __restrict__ theta,
+                         float sigma, const __grid_constant__ RfDesc d, float* __restrict__ wglobal) {
+    float* W = wglobal + (size_t)blockIdx.x * d.w_floats;
+    for (int i = threadIdx.x; i < d.w_floats; i += RF_THREADS) W[i] = 0.f;
+    __syncthreads();
+    rf_stage_weights(W, table + idx[blockIdx.x >> 1], theta, sigma, blockIdx.x & 1, d);
+}
+
+// GW: weights in the global scratch filled by rollout_f32_stage_kernel instead of shared memory
+template <bool GW>
 __global__ void __launch_bounds__(RF_THREADS, 1)
 rollout_f32_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx, const float* __restrict__ theta,
                    float sigma, const __grid_constant__ RfDesc d, const float* __restrict__ obsn,
                    const float* __restrict__ rew_vec, int T, float pos_scale, double* __restrict__ fit_pos,
                    double* __restrict__ fit_neg, int fit_stride, float* __restrict__ behv_pos,
-                   float* __restrict__ behv_neg, double* __restrict__ part, unsigned* __restrict__ tickets) {
+                   float* __restrict__ behv_neg, double* __restrict__ part, unsigned* __restrict__ tickets,
+                   const float* __restrict__ wglobal) {
     extern __shared__ __align__(16) float smem[];
-    float* Wsm = smem;                                  // [w_floats]
-    float* Xa = Wsm + d.w_floats;                       // [RF_TM][xpitch]
+    float* Wsm = GW ? const_cast<float*>(wglobal) + (size_t)blockIdx.x * d.w_floats : smem;    // [w_floats]
+    float* Xa = GW ? smem : smem + d.w_floats;          // [RF_TM][xpitch]
     float* Xb = Xa + RF_TM * d.xpitch;                  // [RF_TM][xpitch]
     float* s_rew = Xb + RF_TM * d.xpitch;               // [RF_TM]
     __shared__ double s_fit;
@@ -89,23 +121,11 @@ rollout_f32_kernel(const float* __restrict__ table, const int64_t* __restrict__ 
     const float* __restrict__ eps = table + idx[pair];
 
     // ---- stage W = theta +- sigma*eps (zero the padding first) ----
-    for (int i = threadIdx.x; i < d.w_floats; i += RF_THREADS) Wsm[i] = 0.f;
+    if (!GW) for (int i = threadIdx.x; i < d.w_floats; i += RF_THREADS) Wsm[i] = 0.f;
     for (int i = threadIdx.x; i < 2 * RF_TM * d.xpitch; i += RF_THREADS) Xa[i] = 0.f;
     if (threadIdx.x == 0) { s_fit = 0.0; s_pos[0] = s_pos[1] = s_pos[2] = 0.f; }
     __syncthreads();
-    for (int l = 0; l < d.n_layers; ++l) {
-        const int in = d.in[l], cnt = d.in[l] * d.out[l];
-        for (int i = threadIdx.x; i < cnt; i += RF_THREADS) {
-            const int n = i / in, k = i - n * in;
-            const float dlt = __fmul_rn(sigma, __ldg(eps + d.w_off[l] + i));     // std * noise
-            const float t = __ldg(theta + d.w_off[l] + i);
-            Wsm[d.sw_off[l] + n * d.pitch[l] + k] = __fadd_rn(t, neg ? -dlt : dlt);
-        }
-        for (int i = threadIdx.x; i < d.out[l]; i += RF_THREADS) {
-            const float dlt = __fmul_rn(sigma, __ldg(eps + d.b_off[l] + i));
-            Wsm[d.sb_off[l] + i] = __fadd_rn(__ldg(theta + d.b_off[l] + i), neg ? -dlt : dlt);
-        }
-    }
+    if (!GW) rf_stage_weights(Wsm, eps, theta, sigma, neg, d);
     __syncthreads();
 
     const int obs_dim = d.in[0];
@@ -217,35 +237,66 @@ int es_impl_rollout_f32(es_ctx* ctx, const float* table, int64_t table_len, cons
     for (int l = 0; l < n_layers; ++l) { d.sb_off[l] = soff; soff += rf_round4(d.out[l]); }
     d.w_floats = rf_round4(soff);
     d.xpitch = xmax;
-    const size_t smem = ((size_t)d.w_floats + 2 * (size_t)RF_TM * d.xpitch + RF_TM) * sizeof(float);
-    if (smem > 227 * 1024) {
-        es_set_error("es_rollout_openloop(F32): network needs %zu bytes of shared memory (> 227 KB)", smem);
+    const size_t act_smem = (2 * (size_t)RF_TM * d.xpitch + RF_TM) * sizeof(float);
+    const size_t smem_w = (size_t)d.w_floats * sizeof(float) + act_smem;
+    const bool gw = smem_w > 227 * 1024;              // weights do not fit beside the activation tiles: global scratch
+    if (act_smem > 227 * 1024) {
+        es_set_error("es_rollout_openloop(F32): layer width needs %zu bytes of shared memory for the activation tiles (> 227 KB)",
+                     act_smem);
         return ES_ERR_UNSUPPORTED;
     }
     ES_REQUIRE(n_pairs <= (1 << 30), "es_rollout_openloop: too many pairs");
-    // fewer policies than SMs (single evaluations of the per-perturbation compatibility path, es.step's noiseless
-    // evaluation): split the episode's time tiles over the idle SMs
-    int n_splits = 1;
     const int n_tiles = (T + RF_TM - 1) / RF_TM;
-    if (2 * n_pairs < ctx->sm_count) {
-        n_splits = ctx->sm_count / (2 * n_pairs);
-        if (n_splits > n_tiles) n_splits = n_tiles;
-        if (n_splits < 1) n_splits = 1;
+    // policies per launch: everything at once with the weights in shared memory; chunks of <= 256 MB of staged weights else
+    int chunk = n_pairs;
+    if (gw) {
+        const size_t per_pair = 2 * (size_t)d.w_floats * sizeof(float);
+        chunk = (int)((256u << 20) / per_pair);
+        if (chunk < 1) chunk = 1;
+        if (chunk > n_pairs) chunk = n_pairs;
     }
-    double* part = nullptr;
-    unsigned* tickets = nullptr;
-    if (n_splits > 1) {
-        void* scratch = nullptr;
-        int rc = es_ctx_scratch(ctx, (size_t)2 * n_pairs * n_splits * 4 * sizeof(double), &scratch);
-        if (rc) return rc;
-        part = (double*)scratch;
-        rc = es_ctx_counters(ctx, 4096, &tickets);
-        if (rc) return rc;
+    for (int p0 = 0; p0 < n_pairs; p0 += chunk) {
+        const int np = (n_pairs - p0 < chunk) ? n_pairs - p0 : chunk;
+        // fewer policies than SMs (single evaluations of the per-perturbation compatibility path, es.step's noiseless
+        // evaluation): split the episode's time tiles over the idle SMs
+        int n_splits = 1;
+        if (2 * np < ctx->sm_count) {
+            n_splits = ctx->sm_count / (2 * np);
+            if (n_splits > n_tiles) n_splits = n_tiles;
+            if (n_splits < 1) n_splits = 1;
+        }
+        const size_t part_bytes = (n_splits > 1) ? ((size_t)2 * np * n_splits * 4 * sizeof(double) + 255) & ~(size_t)255 : 0;
+        const size_t w_bytes = gw ? (size_t)2 * np * d.w_floats * sizeof(float) : 0;
+        double* part = nullptr;
+        unsigned* tickets = nullptr;
+        float* wglobal = nullptr;
+        if (part_bytes + w_bytes) {
+            void* scratch = nullptr;
+            int rc = es_ctx_scratch(ctx, part_bytes + w_bytes, &scratch);
+            if (rc) return rc;
+            part = part_bytes ? (double*)scratch : nullptr;
+            wglobal = gw ? (float*)((char*)scratch + part_bytes) : nullptr;
+            if (n_splits > 1) {
+                rc = es_ctx_counters(ctx, 4096, &tickets);
+                if (rc) return rc;
+            }
+        }
+        double* fp = fit_pos + (size_t)p0 * fit_stride;
+        double* fn = fit_neg + (size_t)p0 * fit_stride;
+        float* bp = behv_pos ? behv_pos + (size_t)p0 * 3 : nullptr;
+        float* bn = behv_neg ? behv_neg + (size_t)p0 * 3 : nullptr;
+        if (gw) {
+            rollout_f32_stage_kernel<<<2 * np, RF_THREADS, 0, stream>>>(table, idx + p0, theta, sigma, d, wglobal);
+            ES_LAUNCHED(ctx);
+            ES_CHECK_CUDA(cudaFuncSetAttribute(rollout_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)act_smem));
+            rollout_f32_kernel<true><<<dim3(2 * np, n_splits), RF_THREADS, act_smem, stream>>>(
+                table, idx + p0, theta, sigma, d, obsn, rew_vec, T, pos_scale, fp, fn, fit_stride, bp, bn, part, tickets, wglobal);
+        } else {
+            ES_CHECK_CUDA(cudaFuncSetAttribute(rollout_f32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+            rollout_f32_kernel<false><<<dim3(2 * np, n_splits), RF_THREADS, smem_w, stream>>>(
+                table, idx + p0, theta, sigma, d, obsn, rew_vec, T, pos_scale, fp, fn, fit_stride, bp, bn, part, tickets, nullptr);
+        }
+        ES_LAUNCHED(ctx);
     }
-    ES_CHECK_CUDA(cudaFuncSetAttribute(rollout_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rollout_f32_kernel<<<dim3(2 * n_pairs, n_splits), RF_THREADS, smem, stream>>>(
-        table, idx, theta, sigma, d, obsn, rew_vec, T, pos_scale, fit_pos, fit_neg, fit_stride, behv_pos, behv_neg, part,
-        tickets);
-    ES_LAUNCHED(ctx);
     return ES_OK;
 }

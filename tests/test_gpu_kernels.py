@@ -152,6 +152,14 @@ def test_rollout_f32_odd_shapes(eng):
     _rollout_case(eng, 5, 1, (8, 8, 8), T=1, n_pairs=2, seed=5)         # single step, single action
 
 
+def test_rollout_f32_large_network_simple_conf_shape(eng):
+    """configs/simple_conf.json's policy (15 -> 256 -> 256 -> 3, P = 70 659): its padded weights (283 KB) do not fit in
+    shared memory, the kernel reads them from a staged global scratch instead.  Same tolerance; also with a time split
+    (1 pair) and with enough pairs to need several launches of staged weights."""
+    _rollout_case(eng, 15, 3, (256, 256), T=40, n_pairs=3, seed=21)
+    _rollout_case(eng, 15, 3, (256, 256), T=100, n_pairs=1, seed=22)
+
+
 def test_rollout_f32_time_split(eng):
     """Fewer policies than SMs: the episode's time tiles are split over the SMs (single evaluations of the compatibility
     path, es.step's noiseless evaluation); same tolerance as the unsplit kernel."""
