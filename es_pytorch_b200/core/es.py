@@ -58,6 +58,26 @@ def _silent(reporter) -> bool:
     return type(reporter) is Reporter or (type(reporter) is ReporterSet and not reporter.reporters)
 
 
+def _queue_common_downloads(eng, gen, fpos, fneg):
+    """Fitness, RNG streams and obs statistics towards pinned host memory with as few copies as possible: the two fitness
+    halves are one buffer on a single GPU, the streams and the statistics are one buffer each."""
+    if gen.comm.size == 1:
+        h_fit = eng.download_async(gen.fit_local, 'fit')             # [pos | neg][K][n_obj]
+        h_pos, h_neg = h_fit[0], h_fit[1]
+    else:
+        h_pos, h_neg = eng.download_async(fpos, 'fpos'), eng.download_async(fneg, 'fneg')
+    h_state = eng.download_async(gen.mt_state, 'mtstate')
+    nk = gen.n_streams * gen.mt_key.shape[1]
+    h_key, h_mtpos = h_state[:nk].view(gen.n_streams, -1), h_state[nk:]
+    h_stats = eng.download_async(gen._gen_stats, 'gstats') if gen.extra_words else None
+    return h_pos, h_neg, h_key, h_mtpos, h_stats
+
+
+def _obstat_from(h_stats, obs_dim):
+    a = h_stats.numpy()
+    return a[:obs_dim].copy(), a[obs_dim:2 * obs_dim].copy(), float(a[2 * obs_dim])
+
+
 def _can_fuse_step(comm, policy: Policy, fit_fn, ranker: Ranker) -> bool:
     """``step`` can keep the whole generation on the device (one synchronisation) when the evaluation is a
     ``BatchedRollout`` of a tanh MLP and the ranker is a float32 shaping without elite selection (the others return host
@@ -87,11 +107,7 @@ def _step_fused(cfg, comm, n: int, policy: Policy, nt: NoiseTable, gen_obstat: O
     gen.update(fpos, fneg)
     gen.l2coeff, gen.ranker = 0.0, None                    # approx_grad passes its own l2coeff on the other route
     fit0, behv0 = gen.noiseless_eval()
-    h_pos, h_neg = eng.download_async(fpos, 'fpos'), eng.download_async(fneg, 'fneg')
-    h_key, h_mtpos = eng.download_async(gen.mt_key, 'mtkey'), eng.download_async(gen.mt_pos, 'mtpos')
-    if gen.extra_words:
-        h_cnt, h_sum, h_sq = (eng.download_async(gen.gen_count, 'gcnt'), eng.download_async(gen.gen_sum, 'gsum'),
-                              eng.download_async(gen.gen_sumsq, 'gsq'))
+    h_pos, h_neg, h_key, h_mtpos, h_stats = _queue_common_downloads(eng, gen, fpos, fneg)
     w_all, idx_all = gen.weights, gen.idx
     if gen.comm.size > 1:
         # what Ranker.rank / _share_results hand to every rank: all K weights and noise indices (two small allgathers)
@@ -113,8 +129,8 @@ def _step_fused(cfg, comm, n: int, policy: Policy, nt: NoiseTable, gen_obstat: O
     neg = devcache.attach(h_neg.numpy().reshape(gen.K, gen.n_obj).copy(), fneg, valid)
     inds = devcache.attach(h_idx.numpy().astype(np.float64), idx_all, valid)
     gen.store_states(streams, h_key.numpy().copy(), h_mtpos.numpy().copy())
-    if gen.extra_words:
-        gen_obstat.inc(h_sum.numpy().copy(), h_sq.numpy().copy(), float(h_cnt.numpy()[0]))
+    if h_stats is not None:
+        gen_obstat.inc(*_obstat_from(h_stats, gen.obs_dim))
     steps = 2 * gen.K * (fit_fn.max_steps - 1)
     if not _silent(reporter):
         reporter.print(f'n dupes: {len(inds) - len(set(inds))}')
@@ -174,12 +190,8 @@ def _test_params_batched(comm, n: int, policy: Policy, nt: NoiseTable, gen_obsta
     # one device->host hop for everything the reference API returns as ndarrays
     eng = gen.eng
     # everything the reference API returns as ndarrays comes back through pinned staging with ONE synchronisation
-    h_pos, h_neg = eng.download_async(fpos, 'fpos'), eng.download_async(fneg, 'fneg')
+    h_pos, h_neg, h_key, h_mtpos, h_stats = _queue_common_downloads(eng, gen, fpos, fneg)
     h_idx = eng.download_async(gen.idx, 'idx')
-    h_key, h_mtpos = eng.download_async(gen.mt_key, 'mtkey'), eng.download_async(gen.mt_pos, 'mtpos')
-    if gen.extra_words:
-        h_cnt, h_sum, h_sq = (eng.download_async(gen.gen_count, 'gcnt'), eng.download_async(gen.gen_sum, 'gsum'),
-                              eng.download_async(gen.gen_sumsq, 'gsq'))
     eng.sync()
     version = gen.version
     valid = lambda g=gen, v=version: g.version == v
@@ -191,8 +203,8 @@ def _test_params_batched(comm, n: int, policy: Policy, nt: NoiseTable, gen_obsta
         inds = np.concatenate(dist.world().allgather_object(idx_local)).astype(np.float64)
     else:
         inds = devcache.attach(idx_local.astype(np.float64), gen.idx, valid)
-    if gen.extra_words:
-        gen_obstat.inc(h_sum.numpy().copy(), h_sq.numpy().copy(), float(h_cnt.numpy()[0]))
+    if h_stats is not None:
+        gen_obstat.inc(*_obstat_from(h_stats, gen.obs_dim))
     steps = 2 * gen.K * (fit_fn.max_steps - 1)          # run_model returns the last loop index (gym_runner.py:50,67)
     return pos, neg, inds, steps
 

@@ -37,6 +37,35 @@ from .engine import Engine, get_engine
 from .nn.optimizers import Optimizer
 
 
+class _NoTimer:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_TIMER = _NoTimer()
+
+
+class _Timed:
+    """Brackets a kernel group with CUDA events on the launching stream."""
+
+    def __init__(self, gen, name):
+        self.gen, self.name = gen, name
+
+    def __enter__(self):
+        self.a = torch.cuda.Event(enable_timing=True)
+        self.b = torch.cuda.Event(enable_timing=True)
+        self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        self.b.record()
+        self.gen.timers.setdefault(self.name, []).append((self.a, self.b))
+        return False
+
+
 class DeviceGeneration:
     def __init__(self, table: torch.Tensor, theta: torch.Tensor, layer_sizes: Sequence[int], obs_stream: torch.Tensor,
                  rew_vec: torch.Tensor, rank_states: Sequence[np.random.RandomState], sigma: float, l2coeff: float,
@@ -70,8 +99,10 @@ class DeviceGeneration:
         self._gauss = [(s.get_state()[3], s.get_state()[4]) for s in rank_states]
         key = np.stack([s.get_state()[1].astype(np.uint32) for s in rank_states]).view(np.int32)
         pos = np.array([s.get_state()[2] for s in rank_states], dtype=np.int32)
-        self.mt_key = e.to_device(key)
-        self.mt_pos = e.to_device(pos)
+        # keys and positions in one buffer (one download brings both back): [R*624 key words | R positions]
+        self.mt_state = e.to_device(np.concatenate((key.reshape(-1), pos)))
+        self.mt_key = self.mt_state[:self.n_streams * ES_MT_N].view(self.n_streams, ES_MT_N)
+        self.mt_pos = self.mt_state[self.n_streams * ES_MT_N:]
 
         f32, f64 = torch.float32, torch.float64
         self.gsum = e.empty((self.P,), f32)
@@ -94,22 +125,7 @@ class DeviceGeneration:
         self.timers = {} if on else None
 
     def _timed(self, name: str):
-        gen = self
-
-        class _T:
-            def __enter__(self_inner):
-                if gen.timers is not None:
-                    self_inner.a = torch.cuda.Event(enable_timing=True)
-                    self_inner.b = torch.cuda.Event(enable_timing=True)
-                    self_inner.a.record()
-                return self_inner
-
-            def __exit__(self_inner, *exc):
-                if gen.timers is not None:
-                    self_inner.b.record()
-                    gen.timers.setdefault(name, []).append((self_inner.a, self_inner.b))
-                return False
-        return _T()
+        return _Timed(self, name) if self.timers is not None else _NO_TIMER
 
     def _ensure_buffers(self, n_per_stream: int):
         if self._bufs_for == n_per_stream:
