@@ -181,10 +181,12 @@ def test_rollout_sigma_zero_is_symmetric(eng):
     assert np.array_equal(f[0], f[1]) and np.all(f[0] == f[0][0])
 
 
-def test_rollout_too_large_fails_loudly(eng):
+def test_rollout_too_wide_fails_loudly(eng):
+    """Weights larger than shared memory are staged in global memory (test_rollout_f32_large_network_...); a layer so wide that
+    the activation tiles themselves do not fit is refused with a message, not computed somewhere else."""
     from es_pytorch_b200._lib import EsLibraryError
-    sizes = [15, 256, 256, 3]                       # configs/simple_conf.json: 283 kB of float32 weights
-    P = orc.n_params(orc.layer_dims(15, (256, 256), 3))
+    sizes = [15, 1024, 3]                           # 2 x 32 x 1024 float32 activation tiles = 262 kB > 227 kB
+    P = orc.n_params(orc.layer_dims(15, (1024,), 3))
     z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=eng.device)
     fit = torch.zeros(2, 1, dtype=torch.float64, device=eng.device)
     with pytest.raises(EsLibraryError, match='shared memory'):
