@@ -233,3 +233,85 @@ def test_two_process_gloo(tmp_path):
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
     assert 'RANK_OK_0' in out.stdout and 'RANK_OK_1' in out.stdout
+
+
+# ---- host-side descriptions of the device calls (no GPU needed) ------------------------------------------------------
+def test_ranker_specs_describe_the_device_call():
+    """Every ranker of src/utils/rankers.py is (shaping kind, blend weights, elite count); the combinations the reference
+    itself cannot run are refused."""
+    from es_pytorch_b200 import _lib
+    from es_pytorch_b200.utils import rankers as R
+    assert R.CenteredRanker()._spec(1, 200) == (_lib.ES_RANK_CENTERED, 1.0, 0.0, 0)
+    assert R.DoublePositiveCenteredRanker()._spec(1, 200)[0] == _lib.ES_RANK_DOUBLE_POSITIVE
+    assert R.SemiCenteredRanker()._spec(1, 200)[0] == _lib.ES_RANK_SEMI_CENTERED and not R.SemiCenteredRanker().squeeze
+    assert R.MaxNormalizedRanker()._spec(1, 200)[0] == _lib.ES_RANK_MAX_NORMALIZED
+    assert R.MultiObjectiveRanker(R.CenteredRanker(), 0.3)._spec(2, 200) == (_lib.ES_RANK_CENTERED, 0.3, 0.7, 0)
+    # rankers.py:94: n_elite = max(1, int(ranked.size * elite_percent))
+    assert R.EliteRanker(R.CenteredRanker(), 0.1)._spec(1, 200)[3] == 20
+    assert R.EliteRanker(R.CenteredRanker(), 0.0)._spec(1, 200)[3] == 1
+    assert R.EliteRanker(R.DoublePositiveCenteredRanker(), 1.0)._spec(1, 200) == (_lib.ES_RANK_DOUBLE_POSITIVE, 1.0, 0.0, 200)
+    with pytest.raises(ValueError):
+        R.CenteredRanker()._spec(2, 200)                      # two objectives need MultiObjectiveRanker
+    with pytest.raises(NotImplementedError):
+        R.EliteRanker(R.MultiObjectiveRanker(R.CenteredRanker(), 0.5), 0.1)
+    with pytest.raises(NotImplementedError):
+        R.MultiObjectiveRanker(R.EliteRanker(R.CenteredRanker(), 0.1), 0.5)
+    with pytest.raises(AssertionError):
+        R.EliteRanker(R.CenteredRanker(), 1.5)                 # rankers.py:89
+
+
+def test_step_takes_the_single_sync_route_only_when_results_are_identical():
+    """es.step keeps a generation on the device for float32 shapings without elite selection evaluated by a BatchedRollout
+    of a tanh MLP; everything else goes call by call (same results, more synchronisations)."""
+    import torch
+    from es_pytorch_b200 import dist
+    from es_pytorch_b200.core import es
+    from es_pytorch_b200.core.policy import Policy
+    from es_pytorch_b200.gym.batched import BatchedRollout
+    from es_pytorch_b200.gym.synthetic_env import SyntheticEnv
+    from es_pytorch_b200.nn.nn import FeedForward
+    from es_pytorch_b200.nn.optimizers import Adam
+    from es_pytorch_b200.utils import rankers as R
+    from es_pytorch_b200.utils.reporters import Reporter, ReporterSet, StdoutReporter
+    env = SyntheticEnv(17, 6, 20)
+    net = FeedForward([64, 64], torch.nn.Tanh(), env, 0.0)
+    policy = Policy(net, 0.02, Adam(len(Policy.get_flat(net)), 0.01))
+    comm = dist.world()
+    batched, batched2 = BatchedRollout(env, 20), BatchedRollout(env, 20, archive=np.zeros((4, 2)))
+    assert es._can_fuse_step(comm, policy, batched, R.CenteredRanker())
+    assert es._can_fuse_step(comm, policy, batched, R.SemiCenteredRanker())
+    assert es._can_fuse_step(comm, policy, batched2, R.MultiObjectiveRanker(R.CenteredRanker(), 0.5))
+    assert not es._can_fuse_step(comm, policy, batched, R.EliteRanker(R.CenteredRanker(), 0.1))     # compact host lists
+    assert not es._can_fuse_step(comm, policy, batched, R.MaxNormalizedRanker())                    # float64 weights
+    assert not es._can_fuse_step(comm, policy, batched2, R.CenteredRanker())                        # needs two objectives
+    assert not es._can_fuse_step(comm, policy, lambda model: None, R.CenteredRanker())              # opaque fit_fn
+    relu = FeedForward([64, 64], torch.nn.ReLU(), env, 0.0)
+    assert not es._can_fuse_step(comm, Policy(relu, 0.02, Adam(len(Policy.get_flat(relu)), 0.01)), batched, R.CenteredRanker())
+
+    class FakeComm:
+        size, rank = 3, 0
+    assert not es._can_fuse_step(FakeComm(), policy, batched, R.CenteredRanker())                   # not this package's world
+    assert es._silent(Reporter()) and es._silent(ReporterSet()) and not es._silent(StdoutReporter(comm))
+
+
+def test_mt19937_streams_are_read_and_written_in_place():
+    """DeviceGeneration reads / writes the callers' RandomState streams through numpy's BitGenerator.ctypes interface:
+    equivalent to get_state()/set_state() on the key and position, the gaussian cache is left alone."""
+    from es_pytorch_b200.generation import DeviceGeneration
+    a, b = np.random.RandomState(123), np.random.RandomState(123)
+    a.randn(3); b.randn(3)                                     # odd count: a cached gaussian is pending in both
+    view = DeviceGeneration._mt_view(a)
+    assert view is not None
+    key, pos = view
+    st = a.get_state()
+    assert np.array_equal(key, st[1]) and pos.value == st[2]
+    # advance b the official way, then write b's stream into a through the view
+    for _ in range(1000):
+        b.randint(0, 250_000_000); b.random()
+    sb = b.get_state()
+    key[:] = sb[1]
+    pos.value = sb[2]
+    assert a.get_state()[3:] == st[3:]                         # has_gauss / cached value untouched
+    assert [a.randint(0, 10 ** 9) for _ in range(50)] == [b.randint(0, 10 ** 9) for _ in range(50)]
+    assert a.randn() == b.randn()                              # both return their cached gaussian first
+    assert DeviceGeneration._mt_view(np.random.default_rng(1)) is None if hasattr(np.random, 'default_rng') else True
