@@ -71,12 +71,13 @@ def run_reference(args, wl, n_gpus):
     for _ in range(args.steps):
         samples.append(ref.sample(2))
     ref.close()
-    # the host cores of a GPU box are shared with other tenants: single samples vary by several x.  The median step
-    # is reported (ms_per_step, value); the fastest one is kept alongside as the reference's best case.
+    # the host cores of a GPU box are shared with other tenants and throttle within seconds: consecutive samples of the same
+    # work vary by several x (e.g. 114 / 293 / 547 s per generation).  The reference is given its BEST case: the fastest
+    # sample is the step that is reported (ms_per_step, value); the median is kept alongside.
     samples.sort(key=lambda r: r['t_generation_s'])
-    last = samples[len(samples) // 2]
+    last = samples[0]
     sec = last['t_generation_s']
-    best = samples[0]['t_generation_s']
+    median_sec = samples[len(samples) // 2]['t_generation_s']
     value = K / sec
     line = dict(metric='perturbations/sec (whole ES generation)', value=value, unit='antithetic pairs/s', n_gpus=n_gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak',
@@ -85,7 +86,8 @@ def run_reference(args, wl, n_gpus):
                 cpu_baseline=dict(value=value, unit='antithetic pairs/s', cores=last['cores'], kind='port',
                                   sample=last['sample'], evaluations_per_sec=2 * value,
                                   breakdown_s=dict(rollouts=last['t_rollouts_s'], rank_reconstruct_adam=last['t_update_s']),
-                                  best_case_value=K / best, steps_s=[round(r['t_generation_s'], 3) for r in samples],
+                                  median_value=K / median_sec, aggregation='fastest of the timed samples (best case for the reference)',
+                                  steps_s=[round(r['t_generation_s'], 3) for r in samples],
                                   numpy=last['numpy'], torch=last['torch']),
                 e2e=dict(value=value, unit='antithetic pairs/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
