@@ -16,7 +16,7 @@
 // activations for a tile of RF_TM time steps ping-pong between two buffers.
 #include "common.cuh"
 
-constexpr int RF_THREADS = 256;
+constexpr int RF_THREADS = 512;   // 16 warps: the dense tasks keep 8 of them busy, the others hide the load / staging latencies
 constexpr int RF_WARPS = RF_THREADS / 32;
 constexpr int RF_TM = 32;   // time steps per tile
 constexpr int RF_RT = 8;    // time steps per thread (register tile)
