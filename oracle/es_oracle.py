@@ -21,9 +21,14 @@ Pinning status:
     ran them and committed the vectors -- ``ref_vectors.npz`` (CenteredRanker, MultiObjectiveRanker,
     SGD / Adam / SimpleES steps, legacy RandomState streams) and ``ref_rankers.npz`` (DoublePositiveCentered,
     SemiCentered, MaxNormalized, EliteRanker and their MultiObjective blends);
-  * PARITY UNPINNED by any reference test (this file is the only pin):
-    ``Policy.pheno``, ``FeedForward.forward``, ``run_model``, ``test_params`` RNG
-    interleaving, ``approx_grad``.
+  * pinned against the REAL reference pipeline executed in the build container (``tests/golden/make_ref_pipeline.py``
+    imports /root/reference's ``src.core.es`` / ``policy`` / ``noisetable`` / ``nn`` / ``gym_runner`` / ``training_result`` /
+    ``obstat`` / ``optimizers`` with inert stand-ins for the absent mpi4py / gym / munch / mlflow and runs two generations;
+    vectors in ``ref_pipeline.npz``): ``Policy.pheno``, ``FeedForward.forward``, ``run_model``, the RNG interleaving of
+    ``test_params``, ``approx_grad``, ``Policy.update_obstat`` -- indices, obs statistics and rank weights reproduce
+    bit-exactly, fitness to a float32 ulp (bit-exact with the same torch CPU threading), theta within 2e-6 (the real Adam computes a float64 step under numpy 2);
+  * still unpinned by anything but this file: the NSRA novelty objective inside ``test_params`` (``NSRResult``; its
+    ``novelty`` function itself is pinned above) and multi-rank layouts beyond ``_share_results``' own test.
 
 Float semantics are those of the reference's pinned stack (numpy 1.18 value-based
 casting): every array op on float32 data stays float32 and python scalars are

@@ -1,0 +1,140 @@
+"""Generates tests/golden/ref_pipeline.npz by running the REAL reference pipeline (/root/reference, build container only):
+
+    src.core.es.test_params -> src.utils.rankers.CenteredRanker.rank -> src.core.es.approx_grad -> Policy.update_obstat
+
+with the real NoiseTable / Policy / FeedForward / gym_runner.run_model / RewardResult / ObStat / Adam on the synthetic open-loop
+env of SURVEY.md section 8d, for two generations.  This pins what no reference test pins: Policy.pheno, FeedForward.forward,
+run_model, the RNG interleaving of test_params, approx_grad, the obs-statistics feedback.
+
+The reference's third-party imports that are absent here (mpi4py, gym, munch, mlflow, mlagents_envs) are replaced by inert stand-ins defined
+below (a 1-rank communicator whose collectives are identities, an empty gym namespace, a dict-with-attributes Munch, no-op
+mlflow functions), and ``np.float`` (removed from numpy >= 1.24, used at src/core/es.py:89) is restored as ``float``.  None
+of this touches the reference's arithmetic.  Nothing from /root/reference is copied: it is imported and executed.
+
+    python tests/golden/make_ref_pipeline.py
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = '/root/reference'
+
+
+def install_stand_ins():
+    np.float = float                                           # src/core/es.py:89
+    mpi4py, MPI = types.ModuleType('mpi4py'), types.ModuleType('mpi4py.MPI')
+
+    class Op:
+        @staticmethod
+        def Create(fn, commute=True):
+            return fn
+
+    class Comm:
+        rank, size = 0, 1
+
+        def Get_rank(self): return 0
+        def Get_size(self): return 1
+        def Alltoall(self, send, recv): recv[...] = send       # one rank: the exchange is the identity
+        def alltoall(self, x): return list(x)
+        def allreduce(self, x, op=None): return x
+        def bcast(self, x, root=0): return x
+        def gather(self, x, root=0): return [x]
+        def scatter(self, x, root=0): return x[0]
+        def Barrier(self): pass
+
+    MPI.Op, MPI.Comm, MPI.COMM_WORLD, MPI.SUM, MPI.Win, MPI.FLOAT, MPI.COMM_TYPE_SHARED = Op, Comm, Comm(), 'sum', object, 4, 0
+    mpi4py.MPI = MPI
+    gym = types.ModuleType('gym')
+    gym.Env = object
+    gym.make = lambda *a, **k: (_ for _ in ()).throw(RuntimeError('no gym here'))
+    gym.utils = types.ModuleType('gym.utils')
+    gym.utils.seeding = types.ModuleType('gym.utils.seeding')
+    gym.utils.seeding._int_list_from_bigint = lambda x: [x]
+    gym.utils.seeding.np_random = lambda seed=None: (np.random.RandomState(seed), seed)
+    gym.spaces = types.ModuleType('gym.spaces')
+    munch = types.ModuleType('munch')
+
+    class Munch(dict):
+        __getattr__ = dict.__getitem__
+        __setattr__ = dict.__setitem__
+
+    munch.Munch, munch.munchify, munch.unmunchify = Munch, (lambda d: d), (lambda d: d)
+    mlflow = types.ModuleType('mlflow')
+    for name in ('log_params', 'log_metrics', 'set_experiment', 'start_run'):
+        setattr(mlflow, name, lambda *a, **k: None)
+    # src/gym/gym_runner.py:8 imports the Unity wrapper, which imports mlagents_envs (absent): empty namespaces
+    ml = {n: types.ModuleType(n) for n in ('mlagents_envs', 'mlagents_envs.base_env', 'mlagents_envs.environment',
+                                           'mlagents_envs.side_channel',
+                                           'mlagents_envs.side_channel.engine_configuration_channel')}
+    ml['mlagents_envs.base_env'].ActionTuple = object
+    ml['mlagents_envs.environment'].UnityEnvironment = object
+    ml['mlagents_envs.side_channel.engine_configuration_channel'].EngineConfigurationChannel = object
+    sys.modules.update(ml)
+    for name, mod in (('mpi4py', mpi4py), ('mpi4py.MPI', MPI), ('gym', gym), ('gym.utils', gym.utils),
+                      ('gym.utils.seeding', gym.utils.seeding), ('gym.spaces', gym.spaces), ('munch', munch), ('mlflow', mlflow)):
+        sys.modules[name] = mod
+    return MPI.COMM_WORLD
+
+
+def main():
+    comm = install_stand_ins()
+    sys.path.insert(0, REF)
+    sys.path.insert(0, ROOT)
+    import torch
+    from src.core import es
+    from src.core.noisetable import NoiseTable
+    from src.core.policy import Policy
+    from src.gym import gym_runner
+    from src.gym.training_result import RewardResult
+    from src.nn.nn import FeedForward
+    from src.nn.obstat import ObStat
+    from src.nn.optimizers import Adam
+    from src.utils.rankers import CenteredRanker
+    from es_pytorch_b200.gym.synthetic_env import SyntheticEnv        # the synthetic env is this repo's, numpy only here
+
+    obs_dim, act_dim, hidden, T, n_pairs = 17, 6, [64, 64], 40, 6
+    env = SyntheticEnv(obs_dim, act_dim, T)
+    torch.manual_seed(0)
+    net = FeedForward(list(hidden), torch.nn.Tanh(), env, 0.0, 5)
+    policy = Policy(net, 0.02, Adam(len(Policy.get_flat(net)), 0.01))
+    P = len(policy)
+    theta0 = (np.random.RandomState(6).randn(P) * 0.1).astype(np.float32)
+    policy.flat_params = theta0.copy()
+    table = np.random.RandomState(5).randn(200_003).astype(np.float32)
+    nt = NoiseTable(P, table)
+    rs = np.random.RandomState(1000)
+    save_obs_chance = 0.3
+
+    def r_fn(model):                                            # simple_example.py:37-40
+        save_obs = rs.random() < save_obs_chance
+        rews, behv, obs, steps = gym_runner.run_model(model, env, T, rs)
+        return RewardResult(rews, behv, obs if save_obs else np.array([np.zeros(env.observation_space.shape)]), steps)
+
+    out = dict(theta0=theta0, table_seed=np.array(5), table_len=np.array(len(table)), cfg=np.array([obs_dim, act_dim, T, n_pairs]),
+               hidden=np.array(hidden), save_obs_chance=np.array(save_obs_chance), seed=np.array(1000))
+    ranker = CenteredRanker()
+    for g in range(2):
+        gen_obstat = ObStat(env.observation_space.shape, 0)
+        pos, neg, inds, steps = es.test_params(comm, n_pairs, policy, nt, gen_obstat, r_fn, rs)
+        out[f'g{g}_obmean'], out[f'g{g}_obstd'] = np.array(net._obmean, dtype=np.float64), np.array(net._obstd, dtype=np.float64)
+        policy.update_obstat(gen_obstat)
+        ranked = ranker.rank(pos, neg, inds)
+        es.approx_grad(policy, ranker, nt, policy.flat_params, 500, 0.005)
+        out[f'g{g}_pos'], out[f'g{g}_neg'], out[f'g{g}_inds'], out[f'g{g}_steps'] = pos, neg, inds, np.array(steps)
+        out[f'g{g}_w'], out[f'g{g}_n_ranked'] = np.asarray(ranked), np.array(ranker.n_fits_ranked)
+        out[f'g{g}_ob_sum'], out[f'g{g}_ob_sumsq'], out[f'g{g}_ob_count'] = gen_obstat.sum, gen_obstat.sumsq, np.array(gen_obstat.count)
+        out[f'g{g}_theta'] = policy.flat_params.copy()
+    out['rs_key'], out['rs_pos'] = rs.get_state()[1], np.array(rs.get_state()[2])
+    # one noiseless evaluation (es.py:48) of the final policy
+    tr = r_fn(policy.pheno(np.zeros(len(policy))))
+    out['noiseless_result'], out['noiseless_behv'] = np.array(tr.result), np.array(tr.behaviour)
+    np.savez_compressed(os.path.join(HERE, 'ref_pipeline.npz'), **out)
+    print('ref_pipeline.npz', len(out), 'arrays; theta dtype', out['g1_theta'].dtype, 'pos dtype', out['g0_pos'].dtype)
+
+
+if __name__ == '__main__':
+    main()

@@ -188,6 +188,41 @@ def test_api_step_batched_matches_oracle(eng, oracle_vectors):
     assert len(tr.result) == 1 and np.isfinite(tr.result[0]) and ob.count == 0
 
 
+def test_api_matches_real_reference_pipeline(eng):
+    """The reference-facing API on the device against vectors produced by the REAL reference code
+    (tests/golden/make_ref_pipeline.py ran src.core.es.test_params -> CenteredRanker.rank -> es.approx_grad ->
+    Policy.update_obstat in the build container): noise indices, steps, obs statistics and rank weights bit-exact, fitness
+    within the float32 rollout's tolerance, theta within 2e-6, the callers' RandomState where the reference left it."""
+    from es_pytorch_b200 import dist
+    from es_pytorch_b200.core import es
+    from es_pytorch_b200.gym.batched import BatchedRollout
+    from es_pytorch_b200.nn.obstat import ObStat
+    from es_pytorch_b200.utils.rankers import CenteredRanker
+    v = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_pipeline.npz'))
+    obs_dim, act_dim, T, n_pairs = [int(x) for x in v['cfg']]
+    table = np.random.RandomState(int(v['table_seed'])).randn(int(v['table_len'])).astype(np.float32)
+    spec = orc.SyntheticEnvSpec(obs_dim, act_dim, T)
+    env, net, policy, nt = _api_objects(eng, table, v['theta0'], spec, tuple(int(h) for h in v['hidden']))
+    rs = np.random.RandomState(int(v['seed']))
+    fit_fn = BatchedRollout(env, T, coins_per_eval=1, save_obs_chance=float(v['save_obs_chance']))
+    ranker, comm = CenteredRanker(), dist.world()
+    for g in range(2):
+        assert np.array_equal(net._obmean, v[f'g{g}_obmean']) and np.array_equal(net._obstd, v[f'g{g}_obstd'])
+        gen_obstat = ObStat(env.observation_space.shape, 0)
+        pos, neg, inds, steps = es.test_params(comm, n_pairs, policy, nt, gen_obstat, fit_fn, rs)
+        assert np.array_equal(inds, v[f'g{g}_inds']) and steps == int(v[f'g{g}_steps'])
+        scale = max(1.0, float(np.abs(v[f'g{g}_pos']).max())) * T ** 0.5
+        assert np.abs(pos - v[f'g{g}_pos']).max() <= 1e-5 * scale and np.abs(neg - v[f'g{g}_neg']).max() <= 1e-5 * scale
+        assert np.array_equal(gen_obstat.sum, v[f'g{g}_ob_sum']) and np.array_equal(gen_obstat.sumsq, v[f'g{g}_ob_sumsq'])
+        assert gen_obstat.count == float(v[f'g{g}_ob_count'])
+        policy.update_obstat(gen_obstat)
+        ranked = ranker.rank(pos, neg, inds)
+        assert np.array_equal(ranked, v[f'g{g}_w']) and ranker.n_fits_ranked == int(v[f'g{g}_n_ranked'])
+        es.approx_grad(policy, ranker, nt, policy.flat_params, 500, 0.005)
+        assert np.abs(policy.flat_params - v[f'g{g}_theta']).max() <= 2e-6
+    assert np.array_equal(rs.get_state()[1], v['rs_key']) and rs.get_state()[2] == int(v['rs_pos'])
+
+
 @pytest.mark.parametrize('nsr', [False, True])
 def test_api_step_fused_equals_call_by_call(eng, oracle_vectors, nsr):
     """es.step's single-synchronisation route leaves exactly what test_params -> rank -> approx_grad -> fit_fn(pheno(0))

@@ -194,3 +194,48 @@ def test_elite_ranker_matches_reference(tag, name, ptag, pct):
     assert vals.dtype == ref_v.dtype
     assert np.array_equal(vals[order], ref_v)
     assert np.array_equal(inds[order], RK[f'{tag}_elite_{name}_{ptag}_inds'])
+
+
+# ---- the REAL reference pipeline, run in the build container by tests/golden/make_ref_pipeline.py --------------------
+def test_oracle_reproduces_the_real_reference_pipeline():
+    """Two generations of src.core.es.test_params -> CenteredRanker.rank -> es.approx_grad -> Policy.update_obstat executed
+    by the reference's own code (real Policy.pheno / FeedForward.forward / gym_runner.run_model / RewardResult / ObStat / Adam).
+    Pins what no reference test pins: the RNG interleaving, pheno, the forward, run_model, approx_grad, the obs feedback."""
+    v = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_pipeline.npz'))
+    obs_dim, act_dim, T, n_pairs = [int(x) for x in v['cfg']]
+    dims = orc.layer_dims(obs_dim, tuple(int(h) for h in v['hidden']), act_dim)
+    P = orc.n_params(dims)
+    table = np.random.RandomState(int(v['table_seed'])).randn(int(v['table_len'])).astype(np.float32)
+    env = orc.SyntheticEnvSpec(obs_dim, act_dim, T)
+    flat = v['theta0'].copy()
+    assert len(flat) == P
+    opt = orc.AdamOracle(P, 0.01)
+    rs = np.random.RandomState(int(v['seed']))
+    stat = orc.ObStatOracle((obs_dim,), 1e-2)                               # Policy.obstat, policy.py:27
+    obmean, obstd = np.zeros(obs_dim), np.ones(obs_dim)
+    for g in range(2):
+        assert np.array_equal(obmean, v[f'g{g}_obmean']) and np.array_equal(obstd, v[f'g{g}_obstd'])
+        pos, neg, inds, steps, gen_stat = orc.es_test_params(table, flat, 0.02, dims, env, [0], n_pairs, obmean, obstd, 5.0, T,
+                                                            coins_per_eval=1, save_obs_chance=float(v['save_obs_chance']),
+                                                            batched=False, rank_states=[rs])
+        assert np.array_equal(inds, v[f'g{g}_inds']) and steps == int(v[f'g{g}_steps'])        # RNG interleaving: exact
+        assert pos.dtype == v[f'g{g}_pos'].dtype and pos.shape == v[f'g{g}_pos'].shape
+        # pheno, forward, run_model: bit-exact when torch's CPU matmul takes the same path as in the generating run; its
+        # blocking depends on the thread count other tests may have set, hence a float32-ulp tolerance
+        scale = max(1.0, float(np.abs(v[f'g{g}_pos']).max()))
+        assert np.abs(pos - v[f'g{g}_pos']).max() <= 1e-6 * scale and np.abs(neg - v[f'g{g}_neg']).max() <= 1e-6 * scale
+        assert np.array_equal(gen_stat.sum, v[f'g{g}_ob_sum']) and np.array_equal(gen_stat.sumsq, v[f'g{g}_ob_sumsq'])
+        assert gen_stat.count == float(v[f'g{g}_ob_count']) > 0
+        stat.inc(gen_stat.sum, gen_stat.sumsq, gen_stat.count)              # Policy.update_obstat, policy.py:69-71
+        obmean, obstd = stat.mean, stat.std
+        w, n_ranked = orc.centered_ranker(pos, neg)
+        assert np.array_equal(w, v[f'g{g}_w']) and n_ranked == int(v[f'g{g}_n_ranked'])
+        orc.approx_grad(flat, opt, w, inds, n_ranked, table, 500, 0.005)
+        # the real Adam computes its step in float64 under numpy 2 (float32 under the reference's numpy 1.18)
+        assert np.abs(flat - v[f'g{g}_theta']).max() <= 2e-6
+    assert np.array_equal(rs.get_state()[1], v['rs_key']) and rs.get_state()[2] == int(v['rs_pos'])
+    rs.random()                                                             # the noiseless evaluation's coin
+    layers = orc.unflatten(orc.pheno_params(flat, 0.02, None), dims)
+    rews, behv, _, _ = orc.run_model(env, layers, obmean, obstd, 5.0, T, batched=False)
+    assert abs(orc.reward_result(rews)[0] - float(v['noiseless_result'][0])) <= 1e-5
+    assert np.allclose(behv[-3:-1], v['noiseless_behv'], rtol=1e-5, atol=1e-6)
