@@ -27,8 +27,9 @@ Pinning status:
     vectors in ``ref_pipeline.npz``): ``Policy.pheno``, ``FeedForward.forward``, ``run_model``, the RNG interleaving of
     ``test_params``, ``approx_grad``, ``Policy.update_obstat`` -- indices, obs statistics and rank weights reproduce
     bit-exactly, fitness to a float32 ulp (bit-exact with the same torch CPU threading), theta within 2e-6 (the real Adam computes a float64 step under numpy 2);
-  * still unpinned by anything but this file: the NSRA novelty objective inside ``test_params`` (``NSRResult``; its
-    ``novelty`` function itself is pinned above) and multi-rank layouts beyond ``_share_results``' own test.
+    The same file holds a real NSRA-style generation (``NSRResult`` + ``MultiObjectiveRanker(CenteredRanker(), 0.5)``) and
+    a real ``EliteRanker(CenteredRanker(), 0.25)`` update (obj.py:50), reproduced the same way;
+  * only pinned by the reference's own test of ``_share_results``: layouts with more than one MPI rank.
 
 Float semantics are those of the reference's pinned stack (numpy 1.18 value-based
 casting): every array op on float32 data stays float32 and python scalars are

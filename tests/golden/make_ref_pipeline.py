@@ -132,6 +132,46 @@ def main():
     # one noiseless evaluation (es.py:48) of the final policy
     tr = r_fn(policy.pheno(np.zeros(len(policy))))
     out['noiseless_result'], out['noiseless_behv'] = np.array(tr.result), np.array(tr.behaviour)
+    # ---- NSRA-style generation: real NSRResult (reward + novelty of the final (x, y)) and MultiObjectiveRanker ----
+    from src.gym.training_result import NSRResult
+    from src.utils.rankers import EliteRanker, MultiObjectiveRanker
+    archive = np.random.RandomState(17).randn(16, 2)
+    policy.flat_params = theta0.copy()
+    policy.optim = Adam(P, 0.01)
+    net.set_ob_mean_std(np.zeros(obs_dim), np.ones(obs_dim))
+    rs2 = np.random.RandomState(2000)
+
+    def nsr_fn(model):                                          # nsra.py's fit_fn shape: one coin, then the rollout
+        save_obs = rs2.random() < save_obs_chance
+        rews, behv, obs, steps = gym_runner.run_model(model, env, T, rs2)
+        return NSRResult(rews, behv, obs if save_obs else np.array([np.zeros(env.observation_space.shape)]), steps, archive, 10)
+
+    gen_obstat = ObStat(env.observation_space.shape, 0)
+    pos, neg, inds, steps = es.test_params(comm, n_pairs, policy, nt, gen_obstat, nsr_fn, rs2)
+    moo = MultiObjectiveRanker(CenteredRanker(), 0.5)
+    ranked = moo.rank(pos, neg, inds)
+    es.approx_grad(policy, moo, nt, policy.flat_params, 500, 0.005)
+    out.update(nsra_archive=archive, nsra_seed=np.array(2000), nsra_pos=pos, nsra_neg=neg, nsra_inds=inds,
+               nsra_w=np.asarray(ranked), nsra_theta=policy.flat_params.copy())
+    # ---- obj.py's EliteRanker(CenteredRanker(), elite) through the real approx_grad ----
+    policy.flat_params = theta0.copy()
+    policy.optim = Adam(P, 0.01)
+    rs3 = np.random.RandomState(3000)
+
+    def r3(model):
+        rs3.random()
+        rews, behv, obs, steps = gym_runner.run_model(model, env, T, rs3)
+        return RewardResult(rews, behv, np.array([np.zeros(env.observation_space.shape)]), steps)
+
+    gen_obstat = ObStat(env.observation_space.shape, 0)
+    pos, neg, inds, steps = es.test_params(comm, n_pairs, policy, nt, gen_obstat, r3, rs3)
+    elite = EliteRanker(CenteredRanker(), 0.25)
+    vals = np.asarray(elite.rank(pos, neg, inds))
+    es.approx_grad(policy, elite, nt, policy.flat_params, 500, 0.005)
+    order = np.lexsort((elite.noise_inds, vals))
+    out.update(elite_seed=np.array(3000), elite_pct=np.array(0.25), elite_pos=pos, elite_neg=neg, elite_inds=inds,
+               elite_vals=vals[order], elite_sel=np.asarray(elite.noise_inds)[order], elite_n=np.array(elite.n_fits_ranked),
+               elite_theta=policy.flat_params.copy())
     np.savez_compressed(os.path.join(HERE, 'ref_pipeline.npz'), **out)
     print('ref_pipeline.npz', len(out), 'arrays; theta dtype', out['g1_theta'].dtype, 'pos dtype', out['g0_pos'].dtype)
 

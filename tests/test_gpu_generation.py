@@ -223,6 +223,45 @@ def test_api_matches_real_reference_pipeline(eng):
     assert np.array_equal(rs.get_state()[1], v['rs_key']) and rs.get_state()[2] == int(v['rs_pos'])
 
 
+def test_api_matches_real_reference_nsra_and_elite(eng):
+    """Same vectors file: the real NSRResult + MultiObjectiveRanker generation and the real EliteRanker update."""
+    from es_pytorch_b200 import dist
+    from es_pytorch_b200.core import es
+    from es_pytorch_b200.gym.batched import BatchedRollout
+    from es_pytorch_b200.nn.obstat import ObStat
+    from es_pytorch_b200.utils.rankers import CenteredRanker, EliteRanker, MultiObjectiveRanker
+    v = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_pipeline.npz'))
+    obs_dim, act_dim, T, n_pairs = [int(x) for x in v['cfg']]
+    table = np.random.RandomState(int(v['table_seed'])).randn(int(v['table_len'])).astype(np.float32)
+    spec = orc.SyntheticEnvSpec(obs_dim, act_dim, T)
+    comm = dist.world()
+    # NSRA
+    env, net, policy, nt = _api_objects(eng, table, v['theta0'], spec, tuple(int(h) for h in v['hidden']))
+    rs = np.random.RandomState(int(v['nsra_seed']))
+    fit_fn = BatchedRollout(env, T, coins_per_eval=1, save_obs_chance=float(v['save_obs_chance']), archive=v['nsra_archive'], nov_k=10)
+    pos, neg, inds, _ = es.test_params(comm, n_pairs, policy, nt, ObStat(env.observation_space.shape, 0), fit_fn, rs)
+    assert np.array_equal(inds, v['nsra_inds']) and pos.shape == (n_pairs, 2)
+    scale = max(1.0, float(np.abs(v['nsra_pos']).max())) * T ** 0.5
+    assert np.abs(pos - v['nsra_pos']).max() <= 1e-5 * scale and np.abs(neg - v['nsra_neg']).max() <= 1e-5 * scale
+    moo = MultiObjectiveRanker(CenteredRanker(), 0.5)
+    assert np.array_equal(moo.rank(pos, neg, inds), v['nsra_w'])
+    es.approx_grad(policy, moo, nt, policy.flat_params, 500, 0.005)
+    assert np.abs(policy.flat_params - v['nsra_theta']).max() <= 2e-6
+    # Elite (obj.py:50)
+    env, net, policy, nt = _api_objects(eng, table, v['theta0'], spec, tuple(int(h) for h in v['hidden']))
+    rs = np.random.RandomState(int(v['elite_seed']))
+    fit_fn = BatchedRollout(env, T, coins_per_eval=1, save_obs_chance=0.0)
+    pos, neg, inds, _ = es.test_params(comm, n_pairs, policy, nt, ObStat(env.observation_space.shape, 0), fit_fn, rs)
+    assert np.array_equal(inds, v['elite_inds'])
+    elite = EliteRanker(CenteredRanker(), float(v['elite_pct']))
+    vals = np.asarray(elite.rank(pos, neg, inds))
+    order = np.lexsort((elite.noise_inds, vals))
+    assert elite.n_fits_ranked == int(v['elite_n']) and np.array_equal(vals[order], v['elite_vals'])
+    assert np.array_equal(np.asarray(elite.noise_inds)[order], v['elite_sel'])
+    es.approx_grad(policy, elite, nt, policy.flat_params, 500, 0.005)
+    assert np.abs(policy.flat_params - v['elite_theta']).max() <= 2e-6
+
+
 @pytest.mark.parametrize('nsr', [False, True])
 def test_api_step_fused_equals_call_by_call(eng, oracle_vectors, nsr):
     """es.step's single-synchronisation route leaves exactly what test_params -> rank -> approx_grad -> fit_fn(pheno(0))

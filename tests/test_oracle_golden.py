@@ -239,3 +239,45 @@ def test_oracle_reproduces_the_real_reference_pipeline():
     rews, behv, _, _ = orc.run_model(env, layers, obmean, obstd, 5.0, T, batched=False)
     assert abs(orc.reward_result(rews)[0] - float(v['noiseless_result'][0])) <= 1e-5
     assert np.allclose(behv[-3:-1], v['noiseless_behv'], rtol=1e-5, atol=1e-6)
+
+
+def _ref_pipeline_setup():
+    v = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_pipeline.npz'))
+    obs_dim, act_dim, T, n_pairs = [int(x) for x in v['cfg']]
+    dims = orc.layer_dims(obs_dim, tuple(int(h) for h in v['hidden']), act_dim)
+    table = np.random.RandomState(int(v['table_seed'])).randn(int(v['table_len'])).astype(np.float32)
+    return v, obs_dim, act_dim, T, n_pairs, dims, table, orc.SyntheticEnvSpec(obs_dim, act_dim, T)
+
+
+def test_oracle_reproduces_the_real_reference_nsra_generation():
+    """Real NSRResult (reward + novelty of the final (x, y) vs an archive, k = 10) through the real test_params, real
+    MultiObjectiveRanker(CenteredRanker(), 0.5) and approx_grad."""
+    v, obs_dim, act_dim, T, n_pairs, dims, table, env = _ref_pipeline_setup()
+    flat, opt = v['theta0'].copy(), orc.AdamOracle(len(v['theta0']), 0.01)
+    rs = np.random.RandomState(int(v['nsra_seed']))
+    pos, neg, inds, _, _ = orc.es_test_params(table, flat, 0.02, dims, env, [0], n_pairs, np.zeros(obs_dim), np.ones(obs_dim), 5.0,
+                                              T, coins_per_eval=1, save_obs_chance=float(v['save_obs_chance']),
+                                              archive=v['nsra_archive'], nov_k=10, batched=False, rank_states=[rs])
+    assert np.array_equal(inds, v['nsra_inds']) and pos.shape == v['nsra_pos'].shape == (n_pairs, 2)
+    assert np.abs(pos - v['nsra_pos']).max() <= 1e-6 * max(1.0, np.abs(v['nsra_pos']).max())
+    assert np.abs(neg - v['nsra_neg']).max() <= 1e-6 * max(1.0, np.abs(v['nsra_neg']).max())
+    w, n_ranked = orc.moo_ranker(pos, neg, 0.5)
+    assert np.array_equal(w, v['nsra_w'])
+    orc.approx_grad(flat, opt, w, inds, n_ranked, table, 500, 0.005)
+    assert np.abs(flat - v['nsra_theta']).max() <= 2e-6
+
+
+def test_oracle_reproduces_the_real_reference_elite_update():
+    """obj.py:50's EliteRanker(CenteredRanker(), elite) through the real approx_grad: the elite keep the noise index of their
+    pair whatever their sign, nothing is subtracted, the sum is divided by the number of elite."""
+    v, obs_dim, act_dim, T, n_pairs, dims, table, env = _ref_pipeline_setup()
+    flat, opt = v['theta0'].copy(), orc.AdamOracle(len(v['theta0']), 0.01)
+    rs = np.random.RandomState(int(v['elite_seed']))
+    pos, neg, inds, _, _ = orc.es_test_params(table, flat, 0.02, dims, env, [0], n_pairs, np.zeros(obs_dim), np.ones(obs_dim), 5.0,
+                                              T, coins_per_eval=1, save_obs_chance=0.0, batched=False, rank_states=[rs])
+    assert np.array_equal(inds, v['elite_inds'])
+    vals, sel, _, n = orc.elite_ranker(pos, neg, inds, 'centered', float(v['elite_pct']))
+    order = np.lexsort((sel, vals))
+    assert n == int(v['elite_n']) and np.array_equal(vals[order], v['elite_vals']) and np.array_equal(sel[order], v['elite_sel'])
+    orc.approx_grad(flat, opt, vals, sel, n, table, 500, 0.005)
+    assert np.abs(flat - v['elite_theta']).max() <= 2e-6
