@@ -221,6 +221,10 @@ def test_api_matches_real_reference_pipeline(eng):
         es.approx_grad(policy, ranker, nt, policy.flat_params, 500, 0.005)
         assert np.abs(policy.flat_params - v[f'g{g}_theta']).max() <= 2e-6
     assert np.array_equal(rs.get_state()[1], v['rs_key']) and rs.get_state()[2] == int(v['rs_pos'])
+    # the noiseless evaluation of the final policy (es.py:48) as the reference's fit_fn returned it
+    tr = fit_fn(policy.pheno(np.zeros(len(policy))), False)
+    assert abs(tr.result[0] - float(v['noiseless_result'][0])) <= 1e-5 * max(1.0, abs(float(v['noiseless_result'][0]))) * T ** 0.5
+    assert np.allclose(tr.behaviour, v['noiseless_behv'], rtol=1e-4, atol=1e-5)
 
 
 def test_api_matches_real_reference_nsra_and_elite(eng):
