@@ -29,7 +29,8 @@ Pinning status:
     bit-exactly, fitness to a float32 ulp (bit-exact with the same torch CPU threading), theta within 2e-6 (the real Adam computes a float64 step under numpy 2);
     The same file holds a real NSRA-style generation (``NSRResult`` + ``MultiObjectiveRanker(CenteredRanker(), 0.5)``) and
     a real ``EliteRanker(CenteredRanker(), 0.25)`` update (obj.py:50), reproduced the same way;
-  * only pinned by the reference's own test of ``_share_results``: layouts with more than one MPI rank.
+    plus the real ``test_params`` on two thread-emulated MPI ranks (rank-major ``_share_results`` rows, per-rank RNG streams,
+    summed steps, ``ObStat.mpi_inc``): what a process carrying two 'virtual ranks' must reproduce.
 
 Float semantics are those of the reference's pinned stack (numpy 1.18 value-based
 casting): every array op on float32 data stays float32 and python scalars are

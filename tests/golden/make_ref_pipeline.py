@@ -172,6 +172,72 @@ def main():
     out.update(elite_seed=np.array(3000), elite_pct=np.array(0.25), elite_pos=pos, elite_neg=neg, elite_inds=inds,
                elite_vals=vals[order], elite_sel=np.asarray(elite.noise_inds)[order], elite_n=np.array(elite.n_fits_ranked),
                elite_theta=policy.flat_params.copy())
+    # ---- two MPI ranks: the real test_params on two threads, each with its own Policy / RandomState, joined by a
+    #      communicator whose Alltoall / allreduce do what MPI's would for size 2 (pins the rank-major layout of
+    #      es._share_results, the per-rank RNG streams and ObStat.mpi_inc) ----
+    import threading
+
+    class TwoRankWorld:
+        def __init__(self):
+            self.barrier = threading.Barrier(2)
+            self.slots = [None, None]
+
+        def exchange(self, rank, value):
+            self.slots[rank] = value
+            self.barrier.wait()
+            both = list(self.slots)
+            self.barrier.wait()
+            return both
+
+    class RankComm:
+        size = 2
+
+        def __init__(self, world, rank):
+            self.world, self.rank = world, rank
+
+        def Get_rank(self): return self.rank
+        def Get_size(self): return 2
+
+        def Alltoall(self, send, recv):                        # block j of recv <- block `rank` of rank j's send
+            both = self.world.exchange(self.rank, np.array(send, copy=True))
+            n = send.shape[0] // 2
+            for j in range(2):
+                recv[j * n:(j + 1) * n] = both[j][self.rank * n:(self.rank + 1) * n]
+
+        def allreduce(self, x, op=None):
+            import copy
+            both = self.world.exchange(self.rank, copy.deepcopy(x))
+            if callable(op):                                   # MPI.Op.Create(sum_obstat): fold in rank order
+                acc = copy.deepcopy(both[0])
+                return op(acc, both[1], None)
+            return both[0] + both[1]
+
+    world = TwoRankWorld()
+    results = [None, None]
+
+    def rank_main(rank):
+        torch.manual_seed(rank)
+        env_r = SyntheticEnv(obs_dim, act_dim, T)
+        net_r = FeedForward(list(hidden), torch.nn.Tanh(), env_r, 0.0, 5)
+        pol_r = Policy(net_r, 0.02, Adam(P, 0.01))
+        pol_r.flat_params = theta0.copy()
+        rs_r = np.random.RandomState(4000 + rank)
+
+        def fn(model):
+            save_obs = rs_r.random() < save_obs_chance
+            rews, behv, obs, steps = gym_runner.run_model(model, env_r, T, rs_r)
+            return RewardResult(rews, behv, obs if save_obs else np.array([np.zeros(env_r.observation_space.shape)]), steps)
+
+        st = ObStat(env_r.observation_space.shape, 0)
+        results[rank] = es.test_params(RankComm(world, rank), 4, pol_r, nt, st, fn, rs_r) + (st,)
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(2)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    (p0, n0, i0, s0, st0), (p1, n1, i1, s1, st1) = results
+    assert np.array_equal(p0, p1) and np.array_equal(i0, i1) and s0 == s1 and np.array_equal(st0.sum, st1.sum)   # every rank sees all
+    out.update(two_seeds=np.array([4000, 4001]), two_n=np.array(4), two_pos=p0, two_neg=n0, two_inds=i0, two_steps=np.array(s0),
+               two_ob_sum=st0.sum, two_ob_sumsq=st0.sumsq, two_ob_count=np.array(st0.count))
     np.savez_compressed(os.path.join(HERE, 'ref_pipeline.npz'), **out)
     print('ref_pipeline.npz', len(out), 'arrays; theta dtype', out['g1_theta'].dtype, 'pos dtype', out['g0_pos'].dtype)
 

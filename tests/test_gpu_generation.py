@@ -266,6 +266,28 @@ def test_api_matches_real_reference_nsra_and_elite(eng):
     assert np.abs(policy.flat_params - v['elite_theta']).max() <= 2e-6
 
 
+def test_api_virtual_ranks_match_real_reference_two_ranks(eng):
+    """One process carrying two RandomState streams ('virtual ranks') == the real reference on two MPI ranks (thread-emulated in
+    make_ref_pipeline.py): rank-major indices and fitness rows, summed steps, merged obs statistics."""
+    from es_pytorch_b200 import dist
+    from es_pytorch_b200.core import es
+    from es_pytorch_b200.gym.batched import BatchedRollout
+    from es_pytorch_b200.nn.obstat import ObStat
+    v = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_pipeline.npz'))
+    obs_dim, act_dim, T, _ = [int(x) for x in v['cfg']]
+    table = np.random.RandomState(int(v['table_seed'])).randn(int(v['table_len'])).astype(np.float32)
+    spec = orc.SyntheticEnvSpec(obs_dim, act_dim, T)
+    env, net, policy, nt = _api_objects(eng, table, v['theta0'], spec, tuple(int(h) for h in v['hidden']))
+    streams = [np.random.RandomState(int(s)) for s in v['two_seeds']]
+    fit_fn = BatchedRollout(env, T, coins_per_eval=1, save_obs_chance=float(v['save_obs_chance']), rank_streams=streams)
+    st = ObStat(env.observation_space.shape, 0)
+    pos, neg, inds, steps = es.test_params(dist.world(), int(v['two_n']), policy, nt, st, fit_fn, streams[0])
+    assert np.array_equal(inds, v['two_inds']) and steps == int(v['two_steps'])
+    scale = max(1.0, float(np.abs(v['two_pos']).max())) * T ** 0.5
+    assert np.abs(pos - v['two_pos']).max() <= 1e-5 * scale and np.abs(neg - v['two_neg']).max() <= 1e-5 * scale
+    assert np.array_equal(st.sum, v['two_ob_sum']) and np.array_equal(st.sumsq, v['two_ob_sumsq']) and st.count == float(v['two_ob_count'])
+
+
 @pytest.mark.parametrize('nsr', [False, True])
 def test_api_step_fused_equals_call_by_call(eng, oracle_vectors, nsr):
     """es.step's single-synchronisation route leaves exactly what test_params -> rank -> approx_grad -> fit_fn(pheno(0))

@@ -281,3 +281,17 @@ def test_oracle_reproduces_the_real_reference_elite_update():
     assert n == int(v['elite_n']) and np.array_equal(vals[order], v['elite_vals']) and np.array_equal(sel[order], v['elite_sel'])
     orc.approx_grad(flat, opt, vals, sel, n, table, 500, 0.005)
     assert np.abs(flat - v['elite_theta']).max() <= 2e-6
+
+
+def test_oracle_reproduces_the_real_reference_two_rank_layout():
+    """The real test_params on two (thread-emulated) MPI ranks, each with its own RandomState: rank-major rows out of
+    es._share_results, summed steps, ObStat.mpi_inc -- what a process carrying two 'virtual ranks' must reproduce."""
+    v, obs_dim, act_dim, T, _, dims, table, env = _ref_pipeline_setup()
+    seeds, n = [int(x) for x in v['two_seeds']], int(v['two_n'])
+    pos, neg, inds, steps, st = orc.es_test_params(table, v['theta0'].copy(), 0.02, dims, env, seeds, n, np.zeros(obs_dim),
+                                                   np.ones(obs_dim), 5.0, T, coins_per_eval=1,
+                                                   save_obs_chance=float(v['save_obs_chance']), batched=False)
+    assert np.array_equal(inds, v['two_inds']) and steps == int(v['two_steps'])
+    assert np.abs(pos - v['two_pos']).max() <= 1e-6 * max(1.0, np.abs(v['two_pos']).max())
+    assert np.abs(neg - v['two_neg']).max() <= 1e-6 * max(1.0, np.abs(v['two_neg']).max())
+    assert np.array_equal(st.sum, v['two_ob_sum']) and np.array_equal(st.sumsq, v['two_ob_sumsq']) and st.count == float(v['two_ob_count'])
