@@ -13,7 +13,7 @@ replaces ``es.test_params`` -> ``Ranker.rank`` -> ``es.approx_grad`` of the refe
     [novelty column]          es_novelty             (novelty.py:16-18)            NSRA only
     [obs statistics]          es_obs_colsum + es_obstat_accumulate_coins           (es.py:73-74)
     allgather fitness         NCCL (only when world size > 1)                       (es.py:84-95)
-    centered rank -> weights  es_centered_rank       (rankers.py:9-58,106-120)
+    rank shaping -> weights   es_centered_rank / es_rank_transform  (rankers.py:9-120)
     sum_k w_k eps_k           es_grad_reconstruct    (utils.py:14-39)
     allreduce partial grad    NCCL (only when world size > 1)
     /2K, l2, Adam/SGD, theta  es_adam_step ...       (es.py:100-101, optimizers.py)
