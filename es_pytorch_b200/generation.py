@@ -24,7 +24,6 @@ shard-local and summed by ONE allreduce; the optimizer step is replicated.
 """
 from __future__ import annotations
 
-import os
 
 from typing import List, Optional, Sequence
 

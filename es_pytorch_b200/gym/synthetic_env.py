@@ -9,7 +9,7 @@ used by the per-perturbation compatibility path of ``gym_runner.run_model``) and
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Tuple
 
 import numpy as np
 
