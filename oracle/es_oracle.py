@@ -28,7 +28,8 @@ Pinning status:
     ``test_params``, ``approx_grad``, ``Policy.update_obstat`` -- indices, obs statistics and rank weights reproduce
     bit-exactly, fitness to a float32 ulp (bit-exact with the same torch CPU threading), theta within 2e-6 (the real Adam computes a float64 step under numpy 2);
     The same file holds a real NSRA-style generation (``NSRResult`` + ``MultiObjectiveRanker(CenteredRanker(), 0.5)``) and
-    a real ``EliteRanker(CenteredRanker(), 0.25)`` update (obj.py:50), reproduced the same way;
+    a real ``EliteRanker(CenteredRanker(), 0.25)`` update (obj.py:50), two momentum-``SGD`` and ``SimpleES`` updates through
+    the real ``approx_grad``, reproduced the same way;
     plus the real ``test_params`` on two thread-emulated MPI ranks (rank-major ``_share_results`` rows, per-rank RNG streams,
     summed steps, ``ObStat.mpi_inc``): what a process carrying two 'virtual ranks' must reproduce.
 

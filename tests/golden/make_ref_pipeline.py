@@ -172,6 +172,24 @@ def main():
     out.update(elite_seed=np.array(3000), elite_pct=np.array(0.25), elite_pos=pos, elite_neg=neg, elite_inds=inds,
                elite_vals=vals[order], elite_sel=np.asarray(elite.noise_inds)[order], elite_n=np.array(elite.n_fits_ranked),
                elite_theta=policy.flat_params.copy())
+    # ---- the other optimizers through the real approx_grad (momentum SGD over two updates, SimpleES) ----
+    from src.nn.optimizers import SGD, SimpleES
+    for tag, make in (('sgd', lambda: SGD(P, 0.01)), ('simple', lambda: SimpleES(P, 0.01))):
+        policy.flat_params = theta0.copy()
+        policy.optim = make()
+        rs4 = np.random.RandomState(5000)
+
+        def r4(model):
+            rs4.random()
+            rews, behv, obs, steps = gym_runner.run_model(model, env, T, rs4)
+            return RewardResult(rews, behv, np.array([np.zeros(env.observation_space.shape)]), steps)
+
+        for g in range(2):
+            pos, neg, inds, steps = es.test_params(comm, n_pairs, policy, nt, ObStat(env.observation_space.shape, 0), r4, rs4)
+            cr = CenteredRanker()
+            cr.rank(pos, neg, inds)
+            es.approx_grad(policy, cr, nt, policy.flat_params, 500, 0.005)
+            out[f'{tag}_g{g}_inds'], out[f'{tag}_g{g}_theta'] = inds, policy.flat_params.copy()
     # ---- two MPI ranks: the real test_params on two threads, each with its own Policy / RandomState, joined by a
     #      communicator whose Alltoall / allreduce do what MPI's would for size 2 (pins the rank-major layout of
     #      es._share_results, the per-rank RNG streams and ObStat.mpi_inc) ----

@@ -266,6 +266,35 @@ def test_api_matches_real_reference_nsra_and_elite(eng):
     assert np.abs(policy.flat_params - v['elite_theta']).max() <= 2e-6
 
 
+@pytest.mark.parametrize('tag', ['sgd', 'simple'])
+def test_api_matches_real_reference_other_optimizers(eng, tag):
+    """Momentum SGD (two consecutive updates) and SimpleES through es.approx_grad against the real reference's vectors."""
+    from es_pytorch_b200 import dist
+    from es_pytorch_b200.core import es
+    from es_pytorch_b200.core.policy import Policy
+    from es_pytorch_b200.gym.batched import BatchedRollout
+    from es_pytorch_b200.nn.obstat import ObStat
+    from es_pytorch_b200.nn.optimizers import SGD, SimpleES
+    from es_pytorch_b200.utils.rankers import CenteredRanker
+    v = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_pipeline.npz'))
+    obs_dim, act_dim, T, n_pairs = [int(x) for x in v['cfg']]
+    table = np.random.RandomState(int(v['table_seed'])).randn(int(v['table_len'])).astype(np.float32)
+    spec = orc.SyntheticEnvSpec(obs_dim, act_dim, T)
+    env, net, policy, nt = _api_objects(eng, table, v['theta0'], spec, tuple(int(h) for h in v['hidden']))
+    P = len(v['theta0'])
+    policy = Policy(net, 0.02, SGD(P, 0.01) if tag == 'sgd' else SimpleES(P, 0.01))
+    policy.flat_params[...] = v['theta0']
+    rs = np.random.RandomState(5000)
+    fit_fn = BatchedRollout(env, T, coins_per_eval=1, save_obs_chance=0.0)
+    for g in range(2):
+        pos, neg, inds, _ = es.test_params(dist.world(), n_pairs, policy, nt, ObStat(env.observation_space.shape, 0), fit_fn, rs)
+        assert np.array_equal(inds, v[f'{tag}_g{g}_inds'])
+        ranker = CenteredRanker()
+        ranker.rank(pos, neg, inds)
+        es.approx_grad(policy, ranker, nt, policy.flat_params, 500, 0.005)
+        assert np.abs(policy.flat_params - v[f'{tag}_g{g}_theta']).max() <= 2e-6
+
+
 def test_api_virtual_ranks_match_real_reference_two_ranks(eng):
     """One process carrying two RandomState streams ('virtual ranks') == the real reference on two MPI ranks (thread-emulated in
     make_ref_pipeline.py): rank-major indices and fitness rows, summed steps, merged obs statistics."""

@@ -295,3 +295,20 @@ def test_oracle_reproduces_the_real_reference_two_rank_layout():
     assert np.abs(pos - v['two_pos']).max() <= 1e-6 * max(1.0, np.abs(v['two_pos']).max())
     assert np.abs(neg - v['two_neg']).max() <= 1e-6 * max(1.0, np.abs(v['two_neg']).max())
     assert np.array_equal(st.sum, v['two_ob_sum']) and np.array_equal(st.sumsq, v['two_ob_sumsq']) and st.count == float(v['two_ob_count'])
+
+
+@pytest.mark.parametrize('tag', ['sgd', 'simple'])
+def test_oracle_reproduces_the_real_reference_other_optimizers(tag):
+    """Momentum SGD (two consecutive updates) and SimpleES through the real es.approx_grad."""
+    v, obs_dim, act_dim, T, n_pairs, dims, table, env = _ref_pipeline_setup()
+    P = len(v['theta0'])
+    flat = v['theta0'].copy()
+    opt = orc.SGDOracle(P, 0.01) if tag == 'sgd' else orc.SimpleESOracle(P, 0.01)
+    rs = np.random.RandomState(5000)
+    for g in range(2):
+        pos, neg, inds, _, _ = orc.es_test_params(table, flat, 0.02, dims, env, [0], n_pairs, np.zeros(obs_dim), np.ones(obs_dim),
+                                                  5.0, T, coins_per_eval=1, batched=False, rank_states=[rs])
+        assert np.array_equal(inds, v[f'{tag}_g{g}_inds'])
+        w, n_ranked = orc.centered_ranker(pos, neg)
+        orc.approx_grad(flat, opt, w, inds, n_ranked, table, 500, 0.005)
+        assert np.abs(flat - v[f'{tag}_g{g}_theta']).max() <= 2e-6
