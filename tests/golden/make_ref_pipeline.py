@@ -190,6 +190,26 @@ def main():
             cr.rank(pos, neg, inds)
             es.approx_grad(policy, cr, nt, policy.flat_params, 500, 0.005)
             out[f'{tag}_g{g}_inds'], out[f'{tag}_g{g}_theta'] = inds, policy.flat_params.copy()
+    # ---- the bench's policy shape (Humanoid-shaped 376-64-64-17), short episode, one generation ----
+    env_h = SyntheticEnv(376, 17, 16)
+    net_h = FeedForward([64, 64], torch.nn.Tanh(), env_h, 0.0, 5)
+    Ph = len(Policy.get_flat(net_h))
+    pol_h = Policy(net_h, 0.02, Adam(Ph, 0.01))
+    theta_h = (np.random.RandomState(8).randn(Ph) * 0.1).astype(np.float32)
+    pol_h.flat_params = theta_h.copy()
+    nt_h = NoiseTable(Ph, table)
+    rs5 = np.random.RandomState(6000)
+
+    def r5(model):
+        rs5.random()
+        rews, behv, obs, steps = gym_runner.run_model(model, env_h, 16, rs5)
+        return RewardResult(rews, behv, np.array([np.zeros(env_h.observation_space.shape)]), steps)
+
+    pos, neg, inds, steps = es.test_params(comm, 3, pol_h, nt_h, ObStat(env_h.observation_space.shape, 0), r5, rs5)
+    cr = CenteredRanker()
+    ranked = cr.rank(pos, neg, inds)
+    es.approx_grad(pol_h, cr, nt_h, pol_h.flat_params, 500, 0.005)
+    out.update(hum_theta0=theta_h, hum_pos=pos, hum_neg=neg, hum_inds=inds, hum_w=np.asarray(ranked), hum_theta=pol_h.flat_params.copy())
     # ---- two MPI ranks: the real test_params on two threads, each with its own Policy / RandomState, joined by a
     #      communicator whose Alltoall / allreduce do what MPI's would for size 2 (pins the rank-major layout of
     #      es._share_results, the per-rank RNG streams and ObStat.mpi_inc) ----

@@ -295,6 +295,37 @@ def test_api_matches_real_reference_other_optimizers(eng, tag):
         assert np.abs(policy.flat_params - v[f'{tag}_g{g}_theta']).max() <= 2e-6
 
 
+@pytest.mark.parametrize('mode', ['f32', 'tc'])
+def test_api_matches_real_reference_humanoid_shape(eng, mode):
+    """The bench's policy shape (376-64-64-17) against the real reference's vectors: float32 rollout to its tolerance; the
+    tensor-core rollout (bf16 table shadow path, obs % 8 == 0) to its own (looser) tolerance, indices exact either way."""
+    from es_pytorch_b200 import _lib, dist
+    from es_pytorch_b200.core import es
+    from es_pytorch_b200.gym.batched import BatchedRollout
+    from es_pytorch_b200.nn.obstat import ObStat
+    from es_pytorch_b200.utils.rankers import CenteredRanker
+    v = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_pipeline.npz'))
+    table = np.random.RandomState(int(v['table_seed'])).randn(int(v['table_len'])).astype(np.float32)
+    spec = orc.SyntheticEnvSpec(376, 17, 16)
+    env, net, policy, nt = _api_objects(eng, table, v['hum_theta0'], spec, (64, 64))
+    rs = np.random.RandomState(6000)
+    fit_fn = BatchedRollout(env, 16, coins_per_eval=1, save_obs_chance=0.0,
+                            rollout_mode=_lib.ES_ROLLOUT_F32 if mode == 'f32' else _lib.ES_ROLLOUT_TC)
+    pos, neg, inds, _ = es.test_params(dist.world(), 3, policy, nt, ObStat(env.observation_space.shape, 0), fit_fn, rs)
+    assert np.array_equal(inds, v['hum_inds'])
+    ref = np.concatenate((v['hum_pos'], v['hum_neg'])).ravel()
+    got = np.concatenate((pos, neg)).ravel()
+    if mode == 'f32':
+        assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()) * 4.0
+        ranker = CenteredRanker()
+        assert np.array_equal(ranker.rank(pos, neg, inds), v['hum_w'])
+        es.approx_grad(policy, ranker, nt, policy.flat_params, 500, 0.005)
+        assert np.abs(policy.flat_params - v['hum_theta']).max() <= 2e-6
+    else:
+        spread = max(ref.std(), 1e-3 * 4.0)
+        assert np.abs(got - ref).max() <= 0.05 * spread + 0.02 * 4.0 * 0.05
+
+
 def test_api_virtual_ranks_match_real_reference_two_ranks(eng):
     """One process carrying two RandomState streams ('virtual ranks') == the real reference on two MPI ranks (thread-emulated in
     make_ref_pipeline.py): rank-major indices and fitness rows, summed steps, merged obs statistics."""

@@ -312,3 +312,23 @@ def test_oracle_reproduces_the_real_reference_other_optimizers(tag):
         w, n_ranked = orc.centered_ranker(pos, neg)
         orc.approx_grad(flat, opt, w, inds, n_ranked, table, 500, 0.005)
         assert np.abs(flat - v[f'{tag}_g{g}_theta']).max() <= 2e-6
+
+
+def test_oracle_reproduces_the_real_reference_humanoid_shape():
+    """The bench's policy shape (376-64-64-17) through the real pipeline (short episode): flat parameter layout of a wide
+    first layer, rank weights, Adam update."""
+    v, _, _, _, _, _, table, _ = _ref_pipeline_setup()
+    dims = orc.layer_dims(376, (64, 64), 17)
+    env = orc.SyntheticEnvSpec(376, 17, 16)
+    flat, opt = v['hum_theta0'].copy(), orc.AdamOracle(len(v['hum_theta0']), 0.01)
+    assert len(flat) == orc.n_params(dims) == 29393
+    rs = np.random.RandomState(6000)
+    pos, neg, inds, _, _ = orc.es_test_params(table, flat, 0.02, dims, env, [0], 3, np.zeros(376), np.ones(376), 5.0, 16,
+                                              coins_per_eval=1, batched=False, rank_states=[rs])
+    assert np.array_equal(inds, v['hum_inds'])
+    assert np.abs(pos - v['hum_pos']).max() <= 1e-6 * max(1.0, np.abs(v['hum_pos']).max())
+    assert np.abs(neg - v['hum_neg']).max() <= 1e-6 * max(1.0, np.abs(v['hum_neg']).max())
+    w, n_ranked = orc.centered_ranker(pos, neg)
+    assert np.array_equal(w, v['hum_w'])
+    orc.approx_grad(flat, opt, w, inds, n_ranked, table, 500, 0.005)
+    assert np.abs(flat - v['hum_theta']).max() <= 2e-6
