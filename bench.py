@@ -9,8 +9,17 @@ A "step" is one generation over synthetic input: draw K noise indices -> theta +
 open-loop MLP rollouts (T steps) -> fitness -> [allgather] -> centered rank -> sum_k w_k eps_k ->
 [allreduce] -> /2K, l2, Adam -> theta'.  ``value`` = antithetic pairs (K) per second with every
 input resident in HBM; ``e2e`` = the same generation driven through the reference-facing API
-(es.test_params / Ranker.rank / es.approx_grad) with host ndarrays in and out.
-Weak scaling: every GPU owns ``--pairs-per-gpu`` pairs (8 virtual MPI-rank streams).
+(es.step) with host ndarrays in and out.
+
+The headline line is WEAK scaling on BASELINE configs[2] (Humanoid-shaped, 10 000 pairs per GPU, 8
+virtual MPI-rank streams per GPU).  The same run also measures, with fewer steps, and reports under
+``also``: the other rollout modes on the same config (``modes``: a parity-grade float32 number is always in
+the line), the fast-vs-float32 parity counters on identical inputs (``parity``), and the two multi-GPU
+configs BASELINE names as STRONG scaling (``strong``: configs[3] K=40 000 total, configs[4] NSRA K=10 000
+total, both sharded over the N GPUs of the run).
+
+Every loop that contains a collective runs a number of iterations that is identical on all ranks by
+construction (``timed_region``): counts are either command-line constants or derived from MAX-all-reduced times.
 """
 from __future__ import annotations
 
@@ -29,19 +38,22 @@ if ROOT not in sys.path:
 WORKLOADS = {
     # BASELINE.json configs[2]: Humanoid-shaped synthetic, K=10000 per GPU, sigma 0.02 (the config the
     # metric's targets -- 60 % HBM on the reconstruction kernel -- are quoted on)
-    'humanoid': dict(obs=376, act=17, hidden=(64, 64), T=1000, pairs=10000, table=250_000_000),
+    'humanoid': dict(obs=376, act=17, hidden=(64, 64), T=1000, pairs=10000, table=250_000_000, strong_total=40000),
     # BASELINE.json configs[1]: HalfCheetah-shaped synthetic, K=256 (latency-bound; parity-size case)
-    'halfcheetah': dict(obs=17, act=6, hidden=(64, 64), T=1000, pairs=256, table=250_000_000),
+    'halfcheetah': dict(obs=17, act=6, hidden=(64, 64), T=1000, pairs=256, table=250_000_000, strong_total=256),
     # BASELINE.json configs[4]: NSRA-ES on the Humanoid shape: objective + novelty (k=10 nearest of a 64-entry archive of
-    # final (x, y) positions), dual rank blended with w = 0.5 (MultiObjectiveRanker), K=10000 per GPU here
-    'humanoid-nsra': dict(obs=376, act=17, hidden=(64, 64), T=1000, pairs=10000, table=250_000_000, nsra=True),
+    # final (x, y) positions), dual rank blended with w = 0.5 (MultiObjectiveRanker)
+    'humanoid-nsra': dict(obs=376, act=17, hidden=(64, 64), T=1000, pairs=10000, table=250_000_000, nsra=True,
+                          strong_total=10000),
 }
 VIRTUAL_RANKS_PER_GPU = 8
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (default workload)
-NCU_TRAFFIC = {'rollout': 701.363968e6 + 8.559872e6, 'reconstruct': 1.084531e9 + 4.941824e6}
+MODE_NAMES = ('f32', 'tc', 'tc3')
+MODE_DTYPE = {'f32': 'f32 (CUDA cores)',
+              'tc': 'f16 mma / f32 accumulate, tanh.approx',
+              'tc3': 'f32-equivalent: f16 hi+lo split operands (3 tcgen05 mma per product), f32 accumulate, accurate tanh'}
 
 
-def parse():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
@@ -49,52 +61,106 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='humanoid', choices=sorted(WORKLOADS))
     ap.add_argument('--pairs-per-gpu', type=int, default=0)
-    ap.add_argument('--mode', default='auto', choices=['auto', 'f32', 'tc'])
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='strong: the workload\'s total pair count (configs[3]: 40000, configs[4]: 10000) is sharded over the GPUs')
+    ap.add_argument('--pairs-total', type=int, default=0, help='total pairs for --scaling strong')
+    ap.add_argument('--mode', default='auto', choices=['auto', 'both'] + list(MODE_NAMES),
+                    help='rollout arithmetic of the headline; auto = the best tensor-core mode that meets the float32 parity '
+                         'bar; both = auto (the other modes are always measured alongside unless --no-also)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    return ap.parse_args()
+    ap.add_argument('--no-also', action='store_true', help='headline only (skip modes / parity / strong-scaling side measurements)')
+    return ap.parse_args(argv)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# collective-safe timed region (used by run_ours; driven on 2 gloo processes by tests/test_host_logic.py)
+# --------------------------------------------------------------------------------------------------------------
+def timed_region(step, steps, warmup, comm, sync, timer, allreduce_max, min_load_s=0.0, on_timed_start=None,
+                 on_timed_end=None):
+    """Run ``warmup`` untimed and ``steps`` timed calls of ``step()`` (which may contain collectives), bracketed by
+    barrier + device sync on both sides, then keep the same load running untimed until ``min_load_s`` seconds of it have
+    been seen (so that a clock sampler polling every ~100 ms observes the load).
+
+    ``timer.start()`` / ``timer.stop() -> seconds`` measure the LOCAL device time; the number of untimed continuation
+    steps is derived from the MAX over ranks of that time (``allreduce_max(float) -> float``), so every rank executes
+    exactly the same number of ``step()`` calls -- a per-rank count would desynchronise the collectives inside ``step``
+    (the round-1 SCALE hang).  Returns (max-over-ranks seconds of the timed steps, extra untimed steps)."""
+    for _ in range(warmup):
+        step()
+    comm.barrier(); sync()
+    if on_timed_start is not None:
+        on_timed_start()
+    timer.start()
+    for _ in range(steps):
+        step()
+    local_s = timer.stop()
+    sync(); comm.barrier()
+    if on_timed_end is not None:
+        on_timed_end()
+    max_s = float(allreduce_max(float(local_s)))
+    extra = 0
+    if max_s < min_load_s:
+        extra = int((min_load_s - max_s) / max(max_s / max(steps, 1), 1e-4)) + 1
+        for _ in range(extra):
+            step()
+        sync(); comm.barrier()
+    return max_s, extra
 
 
 # --------------------------------------------------------------------------------------------------------------
 # the reference's CPU path (oracle/cpu_generation.py), timed on the host cores
 # --------------------------------------------------------------------------------------------------------------
+def total_pairs(args, wl, n_gpus):
+    if args.scaling == 'strong':
+        return args.pairs_total or wl['strong_total']
+    return (args.pairs_per_gpu or wl['pairs']) * n_gpus
+
+
 def run_reference(args, wl, n_gpus):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return                                              # rank 0 alone runs and prints it
     from oracle.cpu_generation import CpuReference
-    K = (args.pairs_per_gpu or wl['pairs']) * n_gpus
-    ref = CpuReference(K, wl['obs'], wl['act'], wl['hidden'], wl['T'])
-    for _ in range(max(args.warmup, 1)):
+    K = total_pairs(args, wl, n_gpus)
+    ref = CpuReference(K, wl['obs'], wl['act'], wl['hidden'], wl['T'], table_len=wl['table'])
+    # Every step is a bounded sample of the K-pair generation: >= 10 s of rollout pairs per worker process (BASELINE.md
+    # section 5 step 4) unless that would push the whole --steps/--warmup run beyond ~4 minutes.
+    calib = ref.sample(1)
+    sec_pair = max(calib['sec_per_pair_per_core'], 1e-3)
+    budget = min(10.0, 240.0 / max(args.steps + max(args.warmup, 1), 1))
+    ppw = max(2, int(round(budget / sec_pair)))
+    for _ in range(max(args.warmup - 1, 0)):
         ref.sample(1)
-    samples = []
-    for _ in range(args.steps):
-        samples.append(ref.sample(2))
+    samples = [ref.sample(ppw) for _ in range(args.steps)]
     ref.close()
     # the host cores of a GPU box are shared with other tenants and throttle within seconds: consecutive samples of the same
-    # work vary by several x (e.g. 114 / 293 / 547 s per generation).  The reference is given its BEST case: the fastest
-    # sample is the step that is reported (ms_per_step, value); the median is kept alongside.
+    # work vary by several x.  `value` is the reference's BEST case (fastest sample); the median is reported beside it.
     samples.sort(key=lambda r: r['t_generation_s'])
-    last = samples[0]
-    sec = last['t_generation_s']
+    best = samples[0]
+    sec = best['t_generation_s']
     median_sec = samples[len(samples) // 2]['t_generation_s']
     value = K / sec
     line = dict(metric='perturbations/sec (whole ES generation)', value=value, unit='antithetic pairs/s', n_gpus=n_gpus,
-                steps=args.steps, warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak',
-                vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
+                steps=args.steps, warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling=args.scaling,
+                vs_baseline=None, dtype='f32', data='synthetic', impl='reference', extrapolated=True,
+                best_value=value, median_value=K / median_sec,
                 config=workload_config(args, wl, n_gpus, K),
-                cpu_baseline=dict(value=value, unit='antithetic pairs/s', cores=last['cores'], kind='port',
-                                  sample=last['sample'], evaluations_per_sec=2 * value,
-                                  breakdown_s=dict(rollouts=last['t_rollouts_s'], rank_reconstruct_adam=last['t_update_s']),
-                                  median_value=K / median_sec, aggregation='fastest of the timed samples (best case for the reference)',
+                cpu_baseline=dict(value=value, unit='antithetic pairs/s', cores=best['cores'], kind='port',
+                                  sample=best['sample'], evaluations_per_sec=2 * value, extrapolated=True,
+                                  pairs_per_worker_per_step=ppw, seconds_of_rollouts_per_worker_per_step=round(ppw * sec_pair, 2),
+                                  breakdown_s=dict(rollouts=best['t_rollouts_s'], rank_reconstruct_adam=best['t_update_s']),
+                                  best_value=value, median_value=K / median_sec,
+                                  aggregation='value = fastest of the timed samples (best case for the reference); median beside it',
                                   steps_s=[round(r['t_generation_s'], 3) for r in samples],
-                                  numpy=last['numpy'], torch=last['torch']),
+                                  table_floats=ref.table_len, numpy=best['numpy'], torch=best['torch']),
                 e2e=dict(value=value, unit='antithetic pairs/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, wl, n_gpus, K):
-    return dict(workload=f"{args.workload}-shaped synthetic open-loop env: MLP {wl['obs']}-{'-'.join(map(str, wl['hidden']))}"
+def workload_config(args, wl, n_gpus, K, name=None):
+    name = name or args.workload
+    return dict(workload=f"{name}-shaped synthetic open-loop env: MLP {wl['obs']}-{'-'.join(map(str, wl['hidden']))}"
                          f"-{wl['act']} tanh, T={wl['T']}, sigma=0.02, l2coeff=0.005, Adam lr=0.01, "
                          f"noise table {wl['table']} float32" + (', NSRA: reward + novelty (k=10, archive 64), dual rank w=0.5' if wl.get('nsra') else ''),
                 pairs_total=K, pairs_per_gpu=K // n_gpus, evaluations_total=2 * K,
@@ -155,6 +221,50 @@ def event_ms(pairs):
     return [a.elapsed_time(b) for a, b in pairs]
 
 
+class _EventTimer:
+    """CUDA events on the launching (current) stream."""
+
+    def __init__(self, torch):
+        self.t0 = torch.cuda.Event(enable_timing=True)
+        self.t1 = torch.cuda.Event(enable_timing=True)
+        self.torch = torch
+
+    def start(self):
+        self.t0.record()
+
+    def stop(self) -> float:
+        self.t1.record()
+        self.torch.cuda.synchronize()
+        return self.t0.elapsed_time(self.t1) * 1e-3
+
+
+def newest_profile_traffic(kernel_regex: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the newest committed ``profiles/*_ncu_raw.csv`` whose
+    kernel name matches (None when no capture matches).  Read at run time so that the number follows the profiles."""
+    import csv
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_ncu_raw.csv')), key=os.path.getmtime):
+        try:
+            with open(path, newline='') as f:
+                rows = list(csv.reader(f))
+            hdr = next(r for r in rows if 'Kernel Name' in r)
+            units = rows[rows.index(hdr) + 1]
+            ki, ri, wi = hdr.index('Kernel Name'), hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+            scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+            vals = []
+            for r in rows[rows.index(hdr) + 2:]:
+                if len(r) > max(ki, ri, wi) and re.search(kernel_regex, r[ki]):
+                    vals.append(float(r[ri].replace(',', '')) * scale.get(units[ri], 1.0) +
+                                float(r[wi].replace(',', '')) * scale.get(units[wi], 1.0))
+            if vals:
+                best = (statistics.mean(vals), os.path.relpath(path, ROOT))
+        except Exception:
+            continue
+    return best
+
+
 def run_ours(args, wl, n_gpus):
     import numpy as np
     import torch
@@ -164,11 +274,10 @@ def run_ours(args, wl, n_gpus):
     from es_pytorch_b200.core.noisetable import NoiseTable
     from es_pytorch_b200.core.policy import Policy
     from es_pytorch_b200.engine import get_engine
-    from es_pytorch_b200.generation import DeviceGeneration
+    from es_pytorch_b200.generation import DeviceGeneration, parity_report
     from es_pytorch_b200.gym.batched import BatchedRollout
     from es_pytorch_b200.gym.synthetic_env import SyntheticEnv
     from es_pytorch_b200.nn.nn import FeedForward
-    from es_pytorch_b200.nn.obstat import ObStat
     from es_pytorch_b200.nn.optimizers import Adam
     from es_pytorch_b200.utils.rankers import CenteredRanker, MultiObjectiveRanker
     from es_pytorch_b200.utils.reporters import Reporter
@@ -179,13 +288,18 @@ def run_ours(args, wl, n_gpus):
     eng = get_engine(local)
     rank = comm.rank
     tc_ok = list(wl['hidden']) == [64, 64] and wl['act'] <= 32 and wl['obs'] <= 1023
-    mode = {'auto': _lib.ES_ROLLOUT_TC if tc_ok else _lib.ES_ROLLOUT_F32, 'f32': _lib.ES_ROLLOUT_F32,
-            'tc': _lib.ES_ROLLOUT_TC}[args.mode]
+    MODE_ID = {'f32': _lib.ES_ROLLOUT_F32, 'tc': _lib.ES_ROLLOUT_TC, 'tc3': _lib.ES_ROLLOUT_TC3}
+    head_mode = args.mode if args.mode in MODE_NAMES else ('tc3' if tc_ok else 'f32')
 
-    k_local = args.pairs_per_gpu or wl['pairs']
-    assert k_local % VIRTUAL_RANKS_PER_GPU == 0
-    n_per_stream = k_local // VIRTUAL_RANKS_PER_GPU
-    K = k_local * n_gpus
+    def allreduce_max(x: float) -> float:
+        t = torch.tensor([x], device=eng.device, dtype=torch.float64)
+        if n_gpus > 1:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item())
+
+    K_head = total_pairs(args, wl, n_gpus)
+    assert K_head % (n_gpus * VIRTUAL_RANKS_PER_GPU) == 0, 'pairs must divide over GPUs x virtual ranks'
+    k_local = K_head // n_gpus
     sizes = [wl['obs'], *wl['hidden'], wl['act']]
     P = sum(i * o + o for i, o in zip(sizes[:-1], sizes[1:]))
 
@@ -196,61 +310,90 @@ def run_ours(args, wl, n_gpus):
     env = SyntheticEnv(wl['obs'], wl['act'], wl['T'])
     seeds = [1000 + rank * VIRTUAL_RANKS_PER_GPU + r for r in range(VIRTUAL_RANKS_PER_GPU)]
     obs_dev, rew_dev = env.device_arrays(eng)
-    archive = np.random.RandomState(17).randn(64, 2) if wl.get('nsra') else None
 
-    # ---------------- device-resident generation: `value` ----------------
-    gen = DeviceGeneration(table, eng.to_device(theta0.copy()), sizes, obs_dev, rew_dev,
-                           [np.random.RandomState(s) for s in seeds], 0.02, 0.005, Adam(P, 0.01), coins_per_eval=1,
-                           save_obs_chance=0.01, rollout_mode=mode, comm=comm, engine=eng,
-                           archive=None if archive is None else eng.to_device(archive, torch.float64), nov_k=10, moo_w=0.5)
-    for _ in range(args.warmup):
-        gen.run(n_per_stream)
-    gen.enable_timers(True)
+    def make_gen(mode_name, nsra):
+        archive = np.random.RandomState(17).randn(64, 2) if nsra else None
+        return DeviceGeneration(table, eng.to_device(theta0.copy()), sizes, obs_dev, rew_dev,
+                                [np.random.RandomState(s) for s in seeds], 0.02, 0.005, Adam(P, 0.01), coins_per_eval=1,
+                                save_obs_chance=0.01, rollout_mode=MODE_ID[mode_name], comm=comm, engine=eng,
+                                archive=None if archive is None else eng.to_device(archive, torch.float64), nov_k=10, moo_w=0.5)
+
+    def measure(gen, pairs_local, steps, warmup, sampler=None):
+        """K-generation timing of ``gen`` at ``pairs_local`` pairs per GPU: max-over-ranks ms per step + per-kernel event
+        means of the timed steps + launches."""
+        nps = pairs_local // VIRTUAL_RANKS_PER_GPU
+        state = {}
+
+        def on_start():
+            gen.enable_timers(True)
+            state['l0'] = eng.launches
+            if sampler is not None and rank == 0:
+                sampler.start()
+
+        def on_end():
+            state['launches'] = eng.launches - state['l0']
+            state['timers'], gen.timers = gen.timers, None          # no event pairs for the untimed continuation
+
+        max_s, extra = timed_region(lambda: gen.run(nps), steps, warmup, comm, torch.cuda.synchronize, _EventTimer(torch),
+                                    allreduce_max, min_load_s=0.6 if sampler is not None else 0.0,
+                                    on_timed_start=on_start, on_timed_end=on_end)
+        kern = {k: statistics.mean(event_ms(v)) for k, v in state['timers'].items()}
+        return dict(ms_step=max_s * 1e3 / steps, kern=kern, launches=state['launches'], extra=extra)
+
+    # ---------------- device-resident generation: `value` (headline config, headline mode) ----------------
+    gen = make_gen(head_mode, bool(wl.get('nsra')))
     sampler = ClockSampler(local)
-    comm.barrier(); torch.cuda.synchronize()
-    if rank == 0:
-        sampler.start()
-    launches0 = eng.launches
-    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(args.steps):
-        gen.run(n_per_stream)
-    t1.record()
-    torch.cuda.synchronize(); comm.barrier()
-    launches = eng.launches - launches0
-    # nvidia-smi answers every ~100 ms and the timed region of a default run is ~20 ms: keep the same load running
-    # (untimed, identical generations) until the sampler has seen ~0.6 s of it, so that the clocks / throttle reasons
-    # reported are the ones under this load rather than a single sample taken at its first instant
-    timed_s = t0.elapsed_time(t1) * 1e-3
-    extra = 0
-    if timed_s < 0.6:
-        extra = int((0.6 - timed_s) / max(timed_s / args.steps, 1e-4)) + 1
-        saved_timers, gen.timers = gen.timers, None          # no event pairs for the untimed continuation
-        for _ in range(extra):
-            gen.run(n_per_stream)
-        torch.cuda.synchronize(); comm.barrier()
-        gen.timers = saved_timers
+    head = measure(gen, k_local, args.steps, args.warmup, sampler)
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
-        clocks['window'] = f'timed region ({args.steps} steps) + {extra} untimed identical generations'
-    # (the per-kernel timers below come from the timed region only)
-    ms_total = torch.tensor([t0.elapsed_time(t1)], device=eng.device, dtype=torch.float64)
-    if n_gpus > 1:
-        td.all_reduce(ms_total, op=td.ReduceOp.MAX)
-    ms_step = float(ms_total.item()) / args.steps
-    kern = {k: statistics.mean(event_ms(v)) for k, v in gen.timers.items()}
-    gen.enable_timers(False)
+        clocks['window'] = f'timed region ({args.steps} steps) + {head["extra"]} untimed identical generations'
+    ms_step, kern, launches = head['ms_step'], head['kern'], head['launches']
+
+    # ---------------- side measurements (fewer steps; every rank runs the same fixed counts) ----------------
+    also = {}
+    if not args.no_also:
+        side_steps, side_warm = max(3, min(args.steps, 5)), 2
+        modes = {}
+        for mname in MODE_NAMES:
+            if mname == head_mode or (mname != 'f32' and not tc_ok):
+                continue
+            gm = make_gen(mname, bool(wl.get('nsra')))
+            r = measure(gm, k_local, side_steps, side_warm)
+            modes[mname] = dict(value=K_head / (r['ms_step'] * 1e-3), ms_per_step=r['ms_step'], rollout_ms=r['kern']['rollout'],
+                                dtype=MODE_DTYPE[mname], steps=side_steps, warmup=side_warm)
+            del gm
+        also['modes'] = modes
+        if tc_ok:
+            # identical inputs (this rank's last drawn indices), rollouts in each mode, rank + reconstruction: how far the
+            # tensor-core arithmetic is from the float32 CUDA-core arithmetic at this config (rank-local, no collectives)
+            also['parity'] = {m: parity_report(gen, MODE_ID[m], MODE_ID['f32']) for m in ('tc3', 'tc')}
+        strong = {}
+        for cname, wname in (('config4_K40000', 'humanoid'), ('config5_nsra_K10000', 'humanoid-nsra')):
+            w2 = WORKLOADS[wname]
+            if (w2['obs'], w2['act'], w2['T'], w2['table']) != (wl['obs'], wl['act'], wl['T'], wl['table']):
+                continue
+            Kt = w2['strong_total']
+            if Kt % (n_gpus * VIRTUAL_RANKS_PER_GPU):
+                continue
+            gs = gen if (wname == args.workload) else make_gen(head_mode, bool(w2.get('nsra')))
+            r = measure(gs, Kt // n_gpus, side_steps, side_warm)
+            strong[cname] = dict(value=Kt / (r['ms_step'] * 1e-3), unit='antithetic pairs/s', ms_per_step=r['ms_step'],
+                                 pairs_total=Kt, pairs_per_gpu=Kt // n_gpus, n_gpus=n_gpus, scaling='strong', mode=head_mode,
+                                 kernel_ms=r['kern'], steps=side_steps, warmup=side_warm)
+        also['strong'] = strong
 
     # ---------------- the reference-facing API with host buffers: `e2e` ----------------
     e2e = None
     if not args.no_e2e:
+        archive = np.random.RandomState(17).randn(64, 2) if wl.get('nsra') else None
+        n_per_stream = k_local // VIRTUAL_RANKS_PER_GPU
         net = FeedForward(list(wl['hidden']), torch.nn.Tanh(), env, 0.0, 5)
         policy = Policy(net, 0.02, Adam(P, 0.01))
         policy.flat_params[...] = theta0
         nt = NoiseTable(P, table)
         streams = [np.random.RandomState(s) for s in seeds]
         fit_fn = BatchedRollout(env, wl['T'], coins_per_eval=1, save_obs_chance=0.01, rank_streams=streams,
-                                rollout_mode=mode, archive=archive, nov_k=10)
+                                rollout_mode=MODE_ID[head_mode], archive=archive, nov_k=10)
         # the synthetic vector env is GPU-resident (its observation / reward streams are env state in HBM, like a
         # simulator running on the device); the per-generation host inputs are theta, the RNG states and the obs statistics
         fit_fn.stream_env_from_host = False
@@ -269,35 +412,29 @@ def run_ours(args, wl, n_gpus):
             policy.update_obstat(gen_obstat)
             return tr
 
-        for _ in range(args.warmup):
-            api_generation()
-        comm.barrier(); torch.cuda.synchronize()
-        h0, d0 = eng.h2d_bytes, eng.d2h_bytes
+        class _WallTimer:
+            def start(self):
+                self.w0 = time.perf_counter()
+
+            def stop(self):
+                torch.cuda.synchronize()
+                return time.perf_counter() - self.w0
+
+        counters = {}
         # (clocks are sampled during the device-resident timed region above; polling nvidia-smi during this
         #  host-synchronous loop perturbs it: every query stalls the API path for tens of ms on these hosts)
-        prof = None
-        if os.environ.get('ES_BENCH_PROFILE'):
-            import cProfile
-            prof = cProfile.Profile(); prof.enable()
-        w0 = time.perf_counter()
-        for _ in range(args.steps):
-            api_generation()
-        torch.cuda.synchronize(); comm.barrier()
-        if prof is not None:
-            import pstats
-            prof.disable(); pstats.Stats(prof, stream=sys.stderr).sort_stats('tottime').print_stats(14)
-        wall = torch.tensor([time.perf_counter() - w0], device=eng.device, dtype=torch.float64)
-        if n_gpus > 1:
-            td.all_reduce(wall, op=td.ReduceOp.MAX)
-        sec = float(wall.item()) / args.steps
-        e2e = dict(value=K / sec, unit='antithetic pairs/s', ms_per_step=sec * 1e3,
-                   h2d_bytes_per_step=(eng.h2d_bytes - h0) // args.steps,
-                   d2h_bytes_per_step=(eng.d2h_bytes - d0) // args.steps,
+        wall_s, _ = timed_region(api_generation, args.steps, args.warmup, comm, torch.cuda.synchronize, _WallTimer(),
+                                 allreduce_max, on_timed_start=lambda: counters.update(h0=eng.h2d_bytes, d0=eng.d2h_bytes),
+                                 on_timed_end=lambda: counters.update(h1=eng.h2d_bytes, d1=eng.d2h_bytes))
+        sec = wall_s / args.steps
+        e2e = dict(value=K_head / sec, unit='antithetic pairs/s', ms_per_step=sec * 1e3,
+                   h2d_bytes_per_step=(counters['h1'] - counters['h0']) // args.steps,
+                   d2h_bytes_per_step=(counters['d1'] - counters['d0']) // args.steps,
                    path='es.step(cfg, comm, policy, nt, env, BatchedRollout, rs, CenteredRanker, reporter) + policy.update_obstat '
                         '= the loop body of the reference scripts (simple_example.py:49-53), including the noiseless evaluation of '
                         'the new theta; numpy in/out. Per step H2D (pinned, async): theta, MT19937 states, obs mean/std; D2H: '
                         'fitness[2K], indices[K], RNG states, obs statistics, rank weights[K], theta, noiseless result; one stream '
-                        'synchronisation per generation on one GPU (call-by-call route with 3 when comm.size > 1)')
+                        'synchronisation per generation')
 
     if rank != 0:
         return
@@ -315,38 +452,42 @@ def run_ours(args, wl, n_gpus):
     mac = sum(i * o for i, o in zip(sizes[:-1], sizes[1:]))
     roll_flop = 2.0 * (2 * k_local) * wl['T'] * mac
     roll_tfs = roll_flop / (kern['rollout'] * 1e-3) / 1e12
-    value = K / (ms_step * 1e-3)
-    default_wl = args.workload == 'humanoid' and not args.pairs_per_gpu and mode == _lib.ES_ROLLOUT_TC
+    value = K_head / (ms_step * 1e-3)
+    default_wl = args.workload == 'humanoid' and not args.pairs_per_gpu and args.scaling == 'weak'
+    roll_regex = {'tc': r'rollout_tc_kernel', 'tc3': r'rollout_tc3_kernel|rollout_tc_kernel<.*2', 'f32': r'rollout_f32_kernel'}[head_mode]
+    roll_traffic = newest_profile_traffic(roll_regex) if default_wl else None
+    rec_traffic = newest_profile_traffic(r'reconstruct_kernel') if default_wl else None
     line = dict(
         metric='perturbations/sec (whole ES generation)', value=value, unit='antithetic pairs/s', n_gpus=n_gpus,
-        steps=args.steps, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling='weak',
-        vs_baseline=None, dtype='f32' if mode == _lib.ES_ROLLOUT_F32 else 'bf16 mma / f32 accumulate',
+        steps=args.steps, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling=args.scaling,
+        vs_baseline=None, dtype=MODE_DTYPE[head_mode], mode=head_mode,
         data='synthetic', impl='ours', evaluations_per_sec=2 * value,
-        config=workload_config(args, wl, n_gpus, K), clocks=clocks, gpu_launches=launches, e2e=e2e,
-        kernel_ms=kern,
+        config=workload_config(args, wl, n_gpus, K_head), clocks=clocks, gpu_launches=launches, e2e=e2e,
+        kernel_ms=kern, also=also,
         # dominant kernel by time: the fused perturb+rollout
         roofline=dict(kernel='rollout (es_rollout_openloop)', bound='tensor', achieved=roll_tfs, peak=tf_peak,
-                      unit='TFLOP/s', frac=roll_tfs / tf_peak, traffic=NCU_TRAFFIC['rollout'] if default_wl else None,
-                      traffic_source='profiles/r1_i_rollout_tc_ncu_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum, 1 launch)',
+                      unit='TFLOP/s', frac=roll_tfs / tf_peak, traffic=roll_traffic[0] if roll_traffic else None,
+                      traffic_source=(roll_traffic[1] + ' (dram__bytes_read.sum + dram__bytes_write.sum per launch)') if roll_traffic else None,
                       peak_source=tf_src,
                       algorithmic_flops_per_launch=roll_flop, share_of_step=kern['rollout'] / ms_step,
-                      note='mode f32 runs on the CUDA cores (FFMA); reported against the tensor peak the '
-                           'tcgen05 path is judged by' if mode == _lib.ES_ROLLOUT_F32 else
-                           'tcgen05 path; the kernel is bound by the tanh epilogue (2.9 G MUFU.TANH per generation at 4 lanes/clk per '
-                           'SM sub-partition = 0.65 ms floor; ncu: XU 51 %, tensor 25 %) and by the dependent-latency chain of its '
-                           'per-tile phases, not by the tensor pipe: see profiles/README.md'),
+                      note={'f32': 'mode f32 runs on the CUDA cores (FFMA); reported against the tensor peak the tcgen05 path is judged by',
+                            'tc': 'tcgen05 path, f16 operands: bound by the tanh epilogue (MUFU) and the per-tile dependent-latency chain, '
+                                  'not by the tensor pipe: see profiles/README.md',
+                            'tc3': 'tcgen05 path at float32-equivalent accuracy: every product is 3 f16 MMAs (hi*hi + hi*lo + lo*hi), so the '
+                                   'tensor pipe ISSUES ~3x the algorithmic FLOPs counted here; achieved/peak is the algorithmic fraction'}[head_mode]),
         # the north-star's named HBM-bound kernel
         roofline_reconstruct=dict(kernel='reconstruct_kernel (es_grad_reconstruct)', bound='hbm', achieved=rec_gbs,
                                   peak=hbm_peak, unit='GB/s', frac=rec_gbs / hbm_peak,
-                                  traffic=NCU_TRAFFIC['reconstruct'] if default_wl else None,
-                                  traffic_source='profiles/r1_h_reconstruct_ncu_raw.csv',
+                                  traffic=rec_traffic[0] if rec_traffic else None,
+                                  traffic_source=rec_traffic[1] if rec_traffic else None,
                                   peak_source=hbm_src, algorithmic_bytes_per_launch=rec_bytes,
                                   share_of_step=kern['reconstruct'] / ms_step),
     )
     if not args.no_cpu_baseline and n_gpus == 1:
         out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '3',
-                              '--warmup', '1', '--workload', args.workload, '--gpus', '1'] +
-                             (['--pairs-per-gpu', str(args.pairs_per_gpu)] if args.pairs_per_gpu else []),
+                              '--warmup', '1', '--workload', args.workload, '--gpus', '1', '--scaling', args.scaling] +
+                             (['--pairs-per-gpu', str(args.pairs_per_gpu)] if args.pairs_per_gpu else []) +
+                             (['--pairs-total', str(args.pairs_total)] if args.pairs_total else []),
                              capture_output=True, text=True, env={**os.environ, 'RANK': '0', 'WORLD_SIZE': '1'})
         try:
             ref = json.loads(out.stdout.strip().splitlines()[-1])

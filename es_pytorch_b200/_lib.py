@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get('ES_B200_LIB') or os.path.join(_HERE, 'libes_b200.so')
 ES_RANK_CENTERED, ES_RANK_DOUBLE_POSITIVE, ES_RANK_SEMI_CENTERED, ES_RANK_MAX_NORMALIZED = 0, 1, 2, 3
 ES_ROLLOUT_F32 = 0
 ES_ROLLOUT_TC = 1
+ES_ROLLOUT_TC3 = 2
 ES_MT_N = 624
 
 _vp, _i32, _i64, _u64, _f32, _f64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_double
@@ -25,6 +26,7 @@ SIGNATURES = {
     'es_ctx_destroy': (_i32, [_vp]),
     'es_last_error': (C.c_char_p, []),
     'es_abi_version': (_i32, []),
+    'es_check_async': (_i32, [_vp]),
     'es_launch_count': (_i64, [_vp]),
     'es_noise_table_changed': (_i32, [_vp]),
     'es_sm_count': (_i32, [_vp]),

@@ -73,6 +73,16 @@ int es_ctx_create(int device, es_ctx** out) {
     if (!c) return ES_ERR_NOMEM;
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    {   // mapped error word for kernel-side argument checks (see es_checked_slice)
+        int* h = nullptr;
+        if (cudaHostAlloc((void**)&h, sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+            *h = 0;
+            int* d = nullptr;
+            if (cudaHostGetDevicePointer((void**)&d, h, 0) == cudaSuccess) { c->err_host = h; c->err_dev = d; }
+            else cudaFreeHost(h);
+        }
+        (void)cudaGetLastError();
+    }
     *out = c;
     return ES_OK;
 }
@@ -83,6 +93,8 @@ int es_ctx_destroy(es_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->shadow) cudaFree(ctx->shadow);
+    if (ctx->shadow_lo) cudaFree(ctx->shadow_lo);
+    if (ctx->err_host) cudaFreeHost((void*)ctx->err_host);
     free(ctx);
     return ES_OK;
 }
@@ -94,12 +106,33 @@ int es_noise_table_changed(es_ctx* ctx) {
     return ES_OK;
 }
 
+static int es_async_error(es_ctx* ctx, const char* where) {
+    if (ctx->err_host && *ctx->err_host) {
+        const int code = *ctx->err_host;
+        *ctx->err_host = 0;
+        if (code == ES_ASYNC_BAD_INDEX)
+            es_set_error("%s: a previous kernel was given a noise index outside the table (index < 0 or index + n_params >= "
+                         "table length; the reference asserts this in NoiseTable.get, src/core/noisetable.py:34): the "
+                         "results of that call are invalid", where);
+        else
+            es_set_error("%s: a previous kernel reported error %d", where, code);
+        return ES_ERR_INVALID;
+    }
+    return ES_OK;
+}
+
+int es_check_async(es_ctx* ctx) {
+    if (!ctx) { es_set_error("es_check_async: ctx is NULL"); return ES_ERR_INVALID; }
+    return es_async_error(ctx, "es_check_async");
+}
+
 int64_t es_launch_count(const es_ctx* ctx) { return ctx ? ctx->launches : -1; }
 int es_sm_count(const es_ctx* ctx) { return ctx ? ctx->sm_count : -1; }
 
 #define ES_ENTER(ctx)                                                        \
     ES_REQUIRE((ctx) != nullptr, "%s: ctx is NULL", __func__);               \
-    ES_CHECK_CUDA(cudaSetDevice((ctx)->device))
+    ES_CHECK_CUDA(cudaSetDevice((ctx)->device));                             \
+    do { int _a = es_async_error((ctx), __func__); if (_a) return _a; } while (0)
 
 int es_draw_indices(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int n_streams, int n_per_stream,
                     uint64_t upper_bound, int extra_words, int64_t* idx_out, uint32_t* extra_out, void* stream) {

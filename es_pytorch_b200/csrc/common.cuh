@@ -25,7 +25,17 @@ struct es_ctx {
     void* shadow;              // [8][shadow_stride] bf16, or NULL (not built / allocation failed)
     size_t shadow_stride;      // elements per copy (multiple of 8)
     int shadow_failed;         // allocation failed once: do not retry every call
+    // float16 hi/lo split shadows for the float32-equivalent tensor-core rollout (rollout_tc2.cu)
+    void* shadow_lo;           // [8][shadow_stride] f16: f16(table[j+s] - float(f16(table[j+s])))
+    int shadow_kind;           // element type `shadow` was built with: 0 none, 1 f16 (hi part)
+    // asynchronous kernel-side argument errors: a mapped, page-locked host word the kernels set when a noise index is
+    // out of range (the reference asserts `len > i + size`, src/core/noisetable.py:34); surfaced by es_check_async and
+    // by the next entry point
+    volatile int* err_host;
+    int* err_dev;
 };
+
+#define ES_ASYNC_BAD_INDEX 1
 
 void es_set_error(const char* fmt, ...);
 
@@ -83,6 +93,17 @@ int es_impl_sgd(es_ctx*, float*, float*, const float*, float, float, float, floa
 int es_impl_simple(es_ctx*, float*, const float*, float, float, float, int, cudaStream_t);
 
 #ifdef __CUDACC__
+// start of the noise slice of one perturbation, checked like NoiseTable.get (src/core/noisetable.py:34:
+// `assert len(self) > i + size`).  An out-of-range index is reported through the ctx's mapped error word and replaced
+// by 0 (a valid address): the launch's results are garbage and the caller is told so by the next entry point /
+// es_check_async.
+__device__ __forceinline__ long long es_checked_slice(long long i, int P, long long table_len, int* err) {
+    if (i < 0 || i + (long long)P >= table_len) {
+        if (err) *(volatile int*)err = ES_ASYNC_BAD_INDEX;
+        return 0;
+    }
+    return i;
+}
 __device__ __forceinline__ float es_warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

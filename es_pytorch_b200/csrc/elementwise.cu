@@ -6,10 +6,10 @@
 
 // ---- a3: theta +- sigma*eps  (src/core/policy.py:61-64) ----------------------------------------
 __global__ void perturb_kernel(const float* __restrict__ theta, const float* __restrict__ table,
-                               const int64_t* __restrict__ idx, int P, float sigma, float* __restrict__ out_pos,
-                               float* __restrict__ out_neg) {
+                               const int64_t* __restrict__ idx, int P, long long table_len, int* __restrict__ err,
+                               float sigma, float* __restrict__ out_pos, float* __restrict__ out_neg) {
     const int k = blockIdx.y;
-    const float* __restrict__ eps = table + idx[k];
+    const float* __restrict__ eps = table + es_checked_slice(idx[k], P, table_len, err);   // noisetable.py:34
     float* op = out_pos + (size_t)k * P;
     float* on = out_neg ? out_neg + (size_t)k * P : nullptr;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
@@ -22,10 +22,9 @@ __global__ void perturb_kernel(const float* __restrict__ theta, const float* __r
 
 int es_impl_perturb(es_ctx* ctx, const float* theta, const float* table, int64_t table_len, const int64_t* idx,
                     int n_idx, int P, float sigma, float* out_pos, float* out_neg, cudaStream_t stream) {
-    (void)table_len;
     ES_REQUIRE(n_idx <= 65535, "es_perturb: at most 65535 slices per call");
     dim3 grid(es_div_up(P, 256) < 64 ? es_div_up(P, 256) : 64, n_idx);
-    perturb_kernel<<<grid, 256, 0, stream>>>(theta, table, idx, P, sigma, out_pos, out_neg);
+    perturb_kernel<<<grid, 256, 0, stream>>>(theta, table, idx, P, (long long)table_len, ctx->err_dev, sigma, out_pos, out_neg);
     ES_LAUNCHED(ctx);
     return ES_OK;
 }

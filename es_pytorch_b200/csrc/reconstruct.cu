@@ -26,8 +26,8 @@ constexpr int RC_MAX_CHUNK = 1024;  // slices staged in shared memory per CTA
 
 __global__ void __launch_bounds__(RC_THREADS, 4)
 reconstruct_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx, const float* __restrict__ w,
-                   int n_idx, int P, int k_per_chunk, int n_chunks, float* __restrict__ partials,
-                   unsigned* __restrict__ tickets, float* __restrict__ out) {
+                   int n_idx, int P, long long table_len, int* __restrict__ err, int k_per_chunk, int n_chunks,
+                   float* __restrict__ partials, unsigned* __restrict__ tickets, float* __restrict__ out) {
     __shared__ long long s_off[RC_MAX_CHUNK];
     __shared__ float s_w[RC_MAX_CHUNK];
     __shared__ bool s_last;
@@ -40,7 +40,7 @@ reconstruct_kernel(const float* __restrict__ table, const int64_t* __restrict__ 
 
     for (int i = threadIdx.x; i < kn_pad; i += RC_THREADS) {
         // padding entries read slice 0 with weight 0 (a valid address, contributes +0)
-        s_off[i] = (i < kn) ? (long long)idx[k0 + i] : 0ll;
+        s_off[i] = (i < kn) ? es_checked_slice((long long)idx[k0 + i], P, table_len, err) : 0ll;   // noisetable.py:34
         s_w[i] = (i < kn) ? w[k0 + i] : 0.0f;
     }
     __syncthreads();
@@ -108,7 +108,6 @@ reconstruct_kernel(const float* __restrict__ table, const int64_t* __restrict__ 
 
 int es_impl_grad_reconstruct(es_ctx* ctx, const float* table, int64_t table_len, const int64_t* idx,
                              const float* weights, int n_idx, int P, float* out, cudaStream_t stream) {
-    (void)table_len;
     const int n_tiles = es_div_up(P, RC_TILE_P);
     // one wave: n_tiles * n_chunks <= sm_count * resident CTAs per SM (launch bound: 4), so no
     // tail wave; never stage more than RC_MAX_CHUNK slices per CTA.
@@ -139,8 +138,8 @@ int es_impl_grad_reconstruct(es_ctx* ctx, const float* table, int64_t table_len,
         if (rc) return rc;
     }
     dim3 grid(n_tiles, n_chunks);
-    reconstruct_kernel<<<grid, RC_THREADS, 0, stream>>>(table, idx, weights, n_idx, P, k_per_chunk, n_chunks, partials,
-                                                        tickets, out);
+    reconstruct_kernel<<<grid, RC_THREADS, 0, stream>>>(table, idx, weights, n_idx, P, (long long)table_len, ctx->err_dev,
+                                                        k_per_chunk, n_chunks, partials, tickets, out);
     ES_LAUNCHED(ctx);
     return ES_OK;
 }

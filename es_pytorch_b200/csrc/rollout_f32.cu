@@ -33,6 +33,8 @@ struct RfDesc {
     int w_floats;                // total shared floats for weights + biases
     int xpitch;                  // activation buffer pitch (floats), multiple of 4
     int P;
+    long long table_len;         // bounds of the noise table (NoiseTable.get's assert, noisetable.py:34)
+    int* err;                    // ctx error word (es_checked_slice)
 };
 
 __device__ __forceinline__ void rf_dense(const float* __restrict__ Wsm, const float* __restrict__ bsm, int in4, int pitch,
@@ -96,7 +98,7 @@ rollout_f32_stage_kernel(const float* __restrict__ table, const int64_t* __restr
     float* W = wglobal + (size_t)blockIdx.x * d.w_floats;
     for (int i = threadIdx.x; i < d.w_floats; i += RF_THREADS) W[i] = 0.f;
     __syncthreads();
-    rf_stage_weights(W, table + idx[blockIdx.x >> 1], theta, sigma, blockIdx.x & 1, d);
+    rf_stage_weights(W, table + es_checked_slice(idx[blockIdx.x >> 1], d.P, d.table_len, d.err), theta, sigma, blockIdx.x & 1, d);
 }
 
 // GW: weights in the global scratch filled by rollout_f32_stage_kernel instead of shared memory
@@ -118,7 +120,7 @@ rollout_f32_kernel(const float* __restrict__ table, const int64_t* __restrict__ 
 
     const int pair = blockIdx.x >> 1;
     const bool neg = blockIdx.x & 1;
-    const float* __restrict__ eps = table + idx[pair];
+    const float* __restrict__ eps = table + es_checked_slice(idx[pair], d.P, d.table_len, d.err);
 
     // ---- stage W = theta +- sigma*eps (zero the padding first) ----
     if (!GW) for (int i = threadIdx.x; i < d.w_floats; i += RF_THREADS) Wsm[i] = 0.f;
@@ -217,11 +219,12 @@ int es_impl_rollout_f32(es_ctx* ctx, const float* table, int64_t table_len, cons
                         const float* theta, int P, float sigma, const int* layer_sizes, int n_layers, const float* obsn,
                         const float* rew_vec, int T, float pos_scale, double* fit_pos, double* fit_neg, int fit_stride,
                         float* behv_pos, float* behv_neg, cudaStream_t stream) {
-    (void)table_len;
     RfDesc d;
     memset(&d, 0, sizeof(d));
     d.n_layers = n_layers;
     d.P = P;
+    d.table_len = table_len;
+    d.err = ctx->err_dev;
     int off = 0, soff = 0, xmax = 0;
     for (int l = 0; l < n_layers; ++l) {
         d.in[l] = layer_sizes[l];

@@ -333,6 +333,9 @@ struct TcParams {
     int w1, b1, w2, b2, w3, b3;   // flat parameter offsets
     long long* trace;             // optional cycle-stamp trace of CTA 0 (ES_TC_TRACE env), NULL in production
     int dev_noload;               // dev experiment: skip the observation-tile copies (results are garbage)
+    long long table_len;          // bounds of the noise table (NoiseTable.get's assert, noisetable.py:34)
+    int P;
+    int* err;                     // ctx error word (es_checked_slice)
 };
 
 // a real instruction that consumes x: in-order issue makes the following clock read wait for x's producer (LDTM, LDG)
@@ -743,10 +746,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(
                 mbar_wait(&bars[BAR_IMG_FREE + (j & 1)], (u & 1) ^ 1);
                 if (bw == 0 && lane == 0) TC_TRACE(3, 4 * j + 1);
             }
-            const float* __restrict__ eps = p.table + p.idx[pair];
+            const long long slice = es_checked_slice(p.idx[pair], p.P, p.table_len, p.err);
+            const float* __restrict__ eps = p.table + slice;
             uint8_t* img = my_images + (size_t)(j & 1) * I.total;
             if (p.shadow) {
-                const int64_t at = p.idx[pair] + p.w1;                    // first element of eps1 in the table
+                const int64_t at = slice + p.w1;                          // first element of eps1 in the table
                 const __nv_bfloat16* rows = p.shadow + (size_t)(at & 7) * p.shadow_stride + (at - (at & 7));
                 tc_build_l1_rows_shadow(img + I.b1, rows, eps + p.b1, p.obs, NKC, btid, BT);
             } else {
@@ -825,7 +829,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(
         for (int j = 0; j < my_pairs; ++j) {
             build_image(j);
             if (j + 1 < my_pairs) {                                      // L2 prefetch of the next slice
-                const int64_t nidx = p.idx[blockIdx.x + (j + 1) * gridDim.x];
+                const int64_t nidx = es_checked_slice(p.idx[blockIdx.x + (j + 1) * gridDim.x], p.P, p.table_len, nullptr);
                 const char* nxt = (const char*)(p.table + nidx);
                 const int lines = (p.b3 + p.act) * 4 / 128 + 2;
                 if (p.shadow) {                                          // eps1 from the bf16 shadow, the rest in float32
@@ -931,7 +935,6 @@ int es_impl_rollout_tc(es_ctx* ctx, const float* table, int64_t table_len, const
                        const float* theta, int P, float sigma, const int* layer_sizes, int n_layers, const float* obsn,
                        const float* rew_vec, int T, float pos_scale, double* fit_pos, double* fit_neg, int fit_stride,
                        float* behv_pos, float* behv_neg, cudaStream_t stream) {
-    (void)table_len; (void)P;
     if (n_layers != 3 || layer_sizes[1] != TC_H || layer_sizes[2] != TC_H || layer_sizes[3] > TC_ACT_PAD ||
         layer_sizes[0] > 1023) {
         es_set_error("es_rollout_openloop(TC): the tensor-core path covers obs(<=1023)-64-64-act(<=32) tanh MLPs; "
@@ -949,6 +952,7 @@ int es_impl_rollout_tc(es_ctx* ctx, const float* table, int64_t table_len, const
     p.w1 = 0; p.b1 = p.obs * TC_H; p.w2 = p.b1 + TC_H; p.b2 = p.w2 + TC_H * TC_H; p.w3 = p.b2 + TC_H;
     p.b3 = p.w3 + TC_H * p.act;
     p.trace = nullptr;
+    p.table_len = table_len; p.P = P; p.err = ctx->err_dev;
     // bf16 shadow of the table for the layer-1 operand: needs 16-byte aligned rows in every slice (obs and the layer-1
     // offset multiples of 8); built once per (table pointer, length).  Without it (other shapes, or no memory for the
     // 8 copies) the builders convert the float32 slice themselves.

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ES_ROLLOUT_F32, ES_ROLLOUT_TC, ES_MT_N, check
+from ._lib import ES_ROLLOUT_F32, ES_ROLLOUT_TC, ES_ROLLOUT_TC3, ES_MT_N, check
 
 _ENGINES = {}
 
@@ -124,7 +124,10 @@ class Engine:
         return st
 
     def sync(self):
+        """Synchronise the current stream, then surface what the kernels flagged asynchronously (a noise index outside
+        the table: the reference's ``assert len(self) > i + size``, noisetable.py:34)."""
         torch.cuda.current_stream(self.device).synchronize()
+        check(self.lib.es_check_async(self._ctx), 'es_check_async')
 
     def to_host(self, t: torch.Tensor) -> np.ndarray:
         """Device tensor -> numpy (synchronises the stream; counts the bytes)."""
@@ -221,7 +224,7 @@ class Engine:
             _req(behv_pos, torch.float32, 'behv_pos', d); _req(behv_neg, torch.float32, 'behv_neg', d)
             assert behv_pos.numel() == 3 * n and behv_neg.numel() == 3 * n
         ls = (C.c_int * len(layer_sizes))(*[int(x) for x in layer_sizes])
-        if mode == ES_ROLLOUT_TC:
+        if mode in (ES_ROLLOUT_TC, ES_ROLLOUT_TC3):
             # the library keeps a bf16 shadow of the table keyed by (pointer, length); a different tensor object (the
             # caching allocator reuses addresses) or an in-place torch write (version counter) invalidates it
             ref, ver = getattr(self, '_tc_table', (None, None))

@@ -306,3 +306,36 @@ class DeviceGeneration:
             rs.set_state(('MT19937', key[r], int(pos[r]), self._gauss[r][0], self._gauss[r][1]))
             out.append(rs)
         return out
+
+
+def parity_report(gen: DeviceGeneration, mode_a: int, mode_b: int = ES_ROLLOUT_F32) -> dict:
+    """How far rollout arithmetic ``mode_a`` is from ``mode_b`` on IDENTICAL inputs: the indices of ``gen``'s last
+    ``evaluate()`` (this process's shard), the current theta and the normalised observation stream.  Both modes roll out
+    the same 2*k_local policies; each fitness vector is ranked (``es_centered_rank``, ranks over the shard) and
+    reconstructed (``es_grad_reconstruct``).  Reported: how many of the 2K integer ranks differ and by how much, the largest
+    change of a rank weight, ||g_a - g_b|| / ||g_b|| of the reconstructed gradient sums, and the fitness error relative to
+    the population's fitness spread.  No collectives; synchronises the stream.  Used by bench.py (``also.parity``) and by
+    tests/test_gpu_generation.py at BASELINE config 3."""
+    e = gen.eng
+    k = gen.k_local
+    f64 = torch.float64
+    res = {}
+    for m in (mode_a, mode_b):
+        f = e.empty((2, k, 1), f64)
+        e.rollout(gen.table, gen.idx, gen.theta, gen.sigma, gen.layer_sizes, gen.obsn, gen.rew_vec, gen.pos_scale,
+                  f[0], f[1], 1, None, None, m)
+        w, r = e.centered_rank(f[0], f[1], 1.0, 0.0, 0, k, want_ranks=True)
+        g = e.grad_reconstruct(gen.table, gen.idx, w, gen.P)
+        res[m] = (f, w, r, g)
+    e.sync()
+    (fa, wa, ra, ga), (fb, wb, rb, gb) = res[mode_a], res[mode_b]
+    dr = (ra.to(torch.int64) - rb.to(torch.int64)).abs()
+    spread = float(fb.std().item())
+    gb64, ga64 = gb.to(f64), ga.to(f64)
+    return dict(pairs=k, ranks_total=int(dr.numel()), ranks_differing=int((dr != 0).sum().item()),
+                max_rank_shift=int(dr.max().item()), max_abs_dw=float((wa - wb).abs().max().item()),
+                grad_rel_err=float(((ga64 - gb64).norm() / gb64.norm()).item()),
+                fitness_max_abs_err=float((fa - fb).abs().max().item()),
+                fitness_rms_err=float((fa - fb).pow(2).mean().sqrt().item()),
+                fitness_spread_std=spread,
+                fitness_rms_err_over_spread=float((fa - fb).pow(2).mean().sqrt().item()) / max(spread, 1e-30))

@@ -39,6 +39,12 @@ int         es_ctx_create(int device, es_ctx** out);
 int         es_ctx_destroy(es_ctx* ctx);
 const char* es_last_error(void);
 int         es_abi_version(void);
+/* Kernel-side argument errors are asynchronous: a kernel that is handed a noise index outside the table (index < 0 or
+ * index + n_params >= table_len -- NoiseTable.get asserts `len(self) > i + size`, src/core/noisetable.py:34) flags it in
+ * a mapped host word, substitutes index 0 and carries on; the results of that launch are invalid.  es_check_async
+ * returns ES_ERR_INVALID (once) if any kernel launched through this ctx and completed so far has flagged an error;
+ * call it after synchronising the stream.  Every entry point performs the same check on entry.                    */
+int         es_check_async(es_ctx* ctx);
 /* kernels launched through this ctx since creation (bench.py's "gpu_launches"). */
 int64_t     es_launch_count(const es_ctx* ctx);
 int         es_sm_count(const es_ctx* ctx);
@@ -85,9 +91,14 @@ int es_normalise_obs(es_ctx* ctx, const float* obs, const double* mean, const do
  *   fit_pos/fit_neg dev double [n_pairs*fit_stride]  (element k*fit_stride)
  *   behv_pos/behv_neg dev float [n_pairs][3] or NULL (final x,y,z)
  *   mode: ES_ROLLOUT_F32 = float32 CUDA-core path (parity reference on device),
- *         ES_ROLLOUT_TC  = tcgen05 tensor-core path                 */
+ *         ES_ROLLOUT_TC  = tcgen05 tensor-core path, float16 operands, tanh.approx (fast; fitness within ~1e-3 of the
+ *                          population spread of the float32 result)
+ *         ES_ROLLOUT_TC3 = tcgen05 tensor-core path at float32-equivalent accuracy: every operand is split into
+ *                          float16 hi + lo parts and every product is three MMAs (hi*hi + hi*lo + lo*hi), float32
+ *                          accumulation in TMEM, accurate tanh, float64 fitness sums                */
 #define ES_ROLLOUT_F32 0
 #define ES_ROLLOUT_TC  1
+#define ES_ROLLOUT_TC3 2
 int es_rollout_openloop(es_ctx* ctx, const float* table, int64_t table_len, const int64_t* idx, int n_pairs,
                         const float* theta, int P, float sigma, const int* layer_sizes, int n_layers,
                         const float* obsn, const float* rew_vec, int T, float pos_scale,
