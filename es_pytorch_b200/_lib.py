@@ -31,6 +31,7 @@ SIGNATURES = {
     'es_noise_table_changed': (_i32, [_vp]),
     'es_sm_count': (_i32, [_vp]),
     'es_draw_indices': (_i32, [_vp, _vp, _vp, _i32, _i32, _u64, _i32, _vp, _vp, _vp]),
+    'es_mt_skip': (_i32, [_vp, _vp, _vp, _i32, _i32, _vp]),
     'es_perturb': (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _i32, _f32, _vp, _vp, _vp]),
     'es_normalise_obs': (_i32, [_vp, _vp, _vp, _vp, _f64, _i32, _i32, _vp, _vp]),
     'es_rollout_openloop': (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _i32, _f32, C.POINTER(_i32), _i32, _vp, _vp, _i32,

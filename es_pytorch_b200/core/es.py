@@ -107,6 +107,7 @@ def _step_fused(cfg, comm, n: int, policy: Policy, nt: NoiseTable, gen_obstat: O
     gen.update(fpos, fneg)
     gen.l2coeff, gen.ranker = 0.0, None                    # approx_grad passes its own l2coeff on the other route
     fit0, behv0 = gen.noiseless_eval()
+    gen.skip_eval_coins(1)                                 # the fit_fn's rs.random() of the noiseless call (es.py:48)
     h_pos, h_neg, h_key, h_mtpos, h_stats = _queue_common_downloads(eng, gen, fpos, fneg)
     w_all, idx_all = gen.weights, gen.idx
     if gen.comm.size > 1:
@@ -154,7 +155,9 @@ def _device_generation(fit_fn, policy: Policy, nt: NoiseTable, streams) -> Devic
     eng = get_engine()
     gen = fit_fn._gen
     theta = policy.theta_dev(eng)
-    if gen is None or gen.theta is not theta or gen.n_streams != len(streams) or gen.table is not nt.device_table(eng):
+    if (gen is None or gen.theta is not theta or gen.n_streams != len(streams) or gen.table is not nt.device_table(eng)
+            or gen.coins_per_eval != int(fit_fn.coins_per_eval) or gen.rollout_mode != fit_fn.rollout_mode
+            or (gen.archive is None) != (fit_fn.archive is None)):
         env = fit_fn.env
         obs_dev, rew_dev = env.device_arrays(eng)
         T = fit_fn.max_steps
@@ -173,10 +176,16 @@ def _device_generation(fit_fn, policy: Policy, nt: NoiseTable, streams) -> Devic
             pinned = bool(getattr(env, 'host_pinned', False))
             eng.upload_async(gen.obs_stream, env.obs_stream[:gen.T + 1], ('obs', id(gen)), src_pinned=pinned)
             eng.upload_async(gen.rew_vec, env.rew_vec[:gen.T], ('rew', id(gen)), src_pinned=pinned)
+    fit_fn._streams_in_use = streams                    # BatchedRollout.__call__ draws the noiseless call's coin from them
     gen.sigma = float(policy.std)                       # scripts decay the noise std between generations
     gen.save_obs_chance = fit_fn.save_obs_chance
-    if fit_fn.archive is not None and (gen.archive is None or gen.archive.shape[0] != len(fit_fn.archive)):
-        gen.archive = eng.to_device(fit_fn.archive, torch.float64)
+    # scripts swap or mutate these between generations (obj.py:81-83 decays lr / ac_std, nsra.py grows the archive): the
+    # cached generation follows the callers' objects instead of keeping its own references
+    gen.optim = policy.optim
+    gen.ob_clip, gen.pos_scale, gen.nov_k = float(policy._module.ob_clip), float(fit_fn.env.pos_scale), int(fit_fn.nov_k)
+    if fit_fn.archive is not None and getattr(gen, '_archive_src', None) is not fit_fn.archive:
+        gen.archive = eng.to_device(fit_fn.archive, torch.float64)      # new array object (or first use): upload again
+        gen._archive_src = fit_fn.archive
     gen.set_obstat(policy._module._obmean, policy._module._obstd)
     return gen
 

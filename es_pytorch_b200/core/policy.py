@@ -23,6 +23,8 @@ def init_normal(m):
 
 
 class Policy:
+    _theta_dev = None          # class-level default: a Policy pickled by the reference has no such attribute
+
     def __init__(self, module: BaseNet, noise_std: float, optim: Optimizer):
         module.apply(init_normal)
         self._module: BaseNet = module
@@ -74,10 +76,18 @@ class Policy:
             pickle.dump(self, f)
 
     def __getstate__(self):
+        # exactly the reference's attribute set (policy.py:23-29): _module, std, flat_params, obstat, optim
         d = dict(self.__dict__)
-        d['_theta_dev'] = None
+        d.pop('_theta_dev', None)
         d.pop('_sd_views', None)
         return d
+
+    def __setstate__(self, d):
+        """Accepts this package's pickles and the reference's (``src.core.policy.Policy`` resolved through the compat
+        shims): device mirrors are rebuilt lazily."""
+        self.__dict__.update(d)
+        self._theta_dev = None
+        self.flat_params = np.ascontiguousarray(self.flat_params, dtype=np.float32)
 
     # -- reference API -----------------------------------------------------------------------------------
     def set_nn_params(self, params) -> torch.nn.Module:

@@ -151,6 +151,14 @@ int es_draw_indices(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int n_stream
                                 extra_out, (cudaStream_t)stream);
 }
 
+int es_mt_skip(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int n_streams, int n_words, void* stream) {
+    ES_ENTER(ctx);
+    ES_REQUIRE(mt_key && mt_pos, "es_mt_skip: NULL pointer");
+    ES_REQUIRE(n_streams >= 0 && n_words >= 0, "es_mt_skip: negative count");
+    if (n_streams == 0 || n_words == 0) return ES_OK;
+    return es_impl_mt_skip(ctx, mt_key, mt_pos, n_streams, n_words, (cudaStream_t)stream);
+}
+
 int es_perturb(es_ctx* ctx, const float* theta, const float* table, int64_t table_len, const int64_t* idx, int n_idx,
                int P, float sigma, float* out_pos, float* out_neg, void* stream) {
     ES_ENTER(ctx);

@@ -71,6 +71,7 @@ static inline int es_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b
 
 // ---- entry points implemented one per .cu file (called from api.cu) -------------------------
 int es_impl_draw_indices(es_ctx*, uint32_t*, int32_t*, int, int, uint64_t, int, int64_t*, uint32_t*, cudaStream_t);
+int es_impl_mt_skip(es_ctx*, uint32_t*, int32_t*, int, int, cudaStream_t);
 int es_impl_perturb(es_ctx*, const float*, const float*, int64_t, const int64_t*, int, int, float, float*, float*,
                     cudaStream_t);
 int es_impl_normalise_obs(es_ctx*, const float*, const double*, const double*, double, int, int, float*, cudaStream_t);

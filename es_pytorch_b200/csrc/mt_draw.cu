@@ -77,6 +77,56 @@ __device__ __forceinline__ MtFn mtfn_shfl_up(const MtFn& f, int d) {
     return r;
 }
 
+
+// next 624-word block of the MT19937 state, by all MT_THREADS threads of the CTA (three dependency-free phases):
+// new[i] = x[i+397] ^ twist(old[i], old[i+1]); x is old for i < 227, new after
+__device__ __forceinline__ void mt_regenerate(uint32_t* mt, int tid) {
+    constexpr int D = MT_N - MT_M;                                   // 227
+    uint32_t y[(D + MT_THREADS - 1) / MT_THREADS];
+    // phase A: i in [0,227)
+    for (int c = 0, i = tid; i < D; i += MT_THREADS, ++c) y[c] = mt[i + MT_M] ^ mt_twist(mt[i], mt[i + 1]);
+    __syncthreads();
+    for (int c = 0, i = tid; i < D; i += MT_THREADS, ++c) mt[i] = y[c];
+    __syncthreads();
+    // phase B: i in [227,454) uses new[i-227], old[i], old[i+1]
+    for (int c = 0, i = D + tid; i < 2 * D; i += MT_THREADS, ++c) y[c] = mt[i - D] ^ mt_twist(mt[i], mt[i + 1]);
+    __syncthreads();
+    for (int c = 0, i = D + tid; i < 2 * D; i += MT_THREADS, ++c) mt[i] = y[c];
+    __syncthreads();
+    // phase C: i in [454,623) uses new[i-227] (phase B), old[i], old[i+1]
+    for (int c = 0, i = 2 * D + tid; i < MT_N - 1; i += MT_THREADS, ++c) y[c] = mt[i - D] ^ mt_twist(mt[i], mt[i + 1]);
+    __syncthreads();
+    for (int c = 0, i = 2 * D + tid; i < MT_N - 1; i += MT_THREADS, ++c) mt[i] = y[c];
+    __syncthreads();
+    if (tid == 0) mt[MT_N - 1] = mt[MT_M - 1] ^ mt_twist(mt[MT_N - 1], mt[0]);
+    __syncthreads();
+}
+
+// Consume `n_words` 32-bit outputs of every stream without using them (the rs.random() coin a fit_fn draws in an
+// evaluation whose other effects are computed elsewhere: the noiseless evaluation of es.py:48 still calls the script's
+// fit_fn, which draws its save_obs coin first, simple_example.py:38 / obj.py:54).
+__global__ void __launch_bounds__(MT_THREADS) mt_skip_kernel(uint32_t* __restrict__ mt_key, int32_t* __restrict__ mt_pos,
+                                                             int n_words) {
+    __shared__ uint32_t mt[MT_N];
+    const int tid = threadIdx.x;
+    uint32_t* key = mt_key + (size_t)blockIdx.x * MT_N;
+    int pos = mt_pos[blockIdx.x];
+    if (pos + n_words <= MT_N) {                       // common case: no regeneration, the key is untouched
+        if (tid == 0) mt_pos[blockIdx.x] = pos + n_words;
+        return;
+    }
+    for (int i = tid; i < MT_N; i += MT_THREADS) mt[i] = key[i];
+    __syncthreads();
+    int left = n_words;
+    while (left > 0) {
+        if (pos >= MT_N) { mt_regenerate(mt, tid); pos = 0; }
+        const int take = min(left, MT_N - pos);
+        pos += take; left -= take;
+    }
+    for (int i = tid; i < MT_N; i += MT_THREADS) key[i] = mt[i];
+    if (tid == 0) mt_pos[blockIdx.x] = pos;
+}
+
 // ST > 0: number of machine states (extra + 1) known at compile time (the compositions unroll over ST states only)
 template <int ST>
 __global__ void __launch_bounds__(MT_THREADS)
@@ -103,26 +153,7 @@ mt_draw_kernel(uint32_t* __restrict__ mt_key, int32_t* __restrict__ mt_pos, int 
     int state = 0;     // machine state at `pos`
     while (produced < n_per_stream || state > 0) {
         if (pos >= MT_N) {
-            // regenerate: new[i] = x[i+397] ^ twist(old[i], old[i+1]); x is old for i < 227, new after
-            constexpr int D = MT_N - MT_M;                                   // 227
-            uint32_t y[(D + MT_THREADS - 1) / MT_THREADS];
-            // phase A: i in [0,227)
-            for (int c = 0, i = tid; i < D; i += MT_THREADS, ++c) y[c] = mt[i + MT_M] ^ mt_twist(mt[i], mt[i + 1]);
-            __syncthreads();
-            for (int c = 0, i = tid; i < D; i += MT_THREADS, ++c) mt[i] = y[c];
-            __syncthreads();
-            // phase B: i in [227,454) uses new[i-227], old[i], old[i+1]
-            for (int c = 0, i = D + tid; i < 2 * D; i += MT_THREADS, ++c) y[c] = mt[i - D] ^ mt_twist(mt[i], mt[i + 1]);
-            __syncthreads();
-            for (int c = 0, i = D + tid; i < 2 * D; i += MT_THREADS, ++c) mt[i] = y[c];
-            __syncthreads();
-            // phase C: i in [454,623) uses new[i-227] (phase B), old[i], old[i+1]
-            for (int c = 0, i = 2 * D + tid; i < MT_N - 1; i += MT_THREADS, ++c) y[c] = mt[i - D] ^ mt_twist(mt[i], mt[i + 1]);
-            __syncthreads();
-            for (int c = 0, i = 2 * D + tid; i < MT_N - 1; i += MT_THREADS, ++c) mt[i] = y[c];
-            __syncthreads();
-            if (tid == 0) mt[MT_N - 1] = mt[MT_M - 1] ^ mt_twist(mt[MT_N - 1], mt[0]);
-            __syncthreads();
+            mt_regenerate(mt, tid);
             pos = 0;
         }
         // temper the available words
@@ -265,6 +296,12 @@ int es_impl_draw_indices(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int n_s
         mt_draw_kernel<5><<<n_streams, MT_THREADS, 0, stream>>>(mt_key, mt_pos, n_per_stream, rng, mask, extra_words, idx_out, extra_out);
     else
         mt_draw_kernel<0><<<n_streams, MT_THREADS, 0, stream>>>(mt_key, mt_pos, n_per_stream, rng, mask, extra_words, idx_out, extra_out);
+    ES_LAUNCHED(ctx);
+    return ES_OK;
+}
+
+int es_impl_mt_skip(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int n_streams, int n_words, cudaStream_t stream) {
+    mt_skip_kernel<<<n_streams, MT_THREADS, 0, stream>>>(mt_key, mt_pos, n_words);
     ES_LAUNCHED(ctx);
     return ES_OK;
 }

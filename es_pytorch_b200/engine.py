@@ -157,6 +157,13 @@ class Engine:
                                        extra_words, _ptr(idx_out), _ptr(extra_out), self.stream), 'es_draw_indices')
         return idx_out, extra_out
 
+    def mt_skip(self, mt_key: torch.Tensor, mt_pos: torch.Tensor, n_words: int):
+        """Advance every stream by ``n_words`` raw 32-bit outputs (a discarded ``rs.random()`` is 2 words)."""
+        d = self.device
+        _req(mt_key, torch.int32, 'mt_key', d); _req(mt_pos, torch.int32, 'mt_pos', d)
+        check(self.lib.es_mt_skip(self._ctx, _ptr(mt_key), _ptr(mt_pos), mt_key.shape[0], int(n_words), self.stream),
+              'es_mt_skip')
+
     # ------------------------------------------------------------------ a3
     def perturb(self, theta, table, idx, sigma: float, want_neg: bool = True):
         d = self.device

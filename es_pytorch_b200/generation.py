@@ -221,6 +221,13 @@ class DeviceGeneration:
                   fit0[0:1], fit0[1:2], 1, behv0[0].view(-1), behv0[1].view(-1), ES_ROLLOUT_F32)
         return fit0, behv0
 
+    def skip_eval_coins(self, n_evals: int = 1):
+        """Every stream discards the save_obs coin(s) of ``n_evals`` evaluations (``coins_per_eval`` doubles = 2 words each):
+        the reference's fit_fn draws ``rs.random()`` in EVERY call, including the noiseless ``fit_fn(policy.pheno(zeros),
+        False)`` of es.py:48 that every rank executes (simple_example.py:38, obj.py:54)."""
+        if self.coins_per_eval:
+            self.eng.mt_skip(self.mt_key, self.mt_pos, 2 * self.coins_per_eval * int(n_evals))
+
     def apply_optimizer(self, gsum: torch.Tensor, n_ranked: float):
         """grad = gsum/n_ranked; theta += optim.step(l2coeff*theta - grad)  (es.py:100-101)."""
         self.optim.apply_fused(self.eng, self.theta, gsum, n_ranked, self.l2coeff)

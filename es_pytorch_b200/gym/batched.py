@@ -37,6 +37,7 @@ class BatchedRollout:
         self.rank_streams = list(rank_streams) if rank_streams is not None else None
         self.rollout_mode = rollout_mode
         self._gen = None            # cached DeviceGeneration (see core.es)
+        self._streams_in_use = None  # the RandomState streams of the last batched evaluation (set by core.es)
         self.stream_env_from_host = False   # True: re-upload the env's obs/reward streams every generation
 
     @property
@@ -54,7 +55,14 @@ class BatchedRollout:
         return NSRResult(rews, behv[-3:], no_obs, steps, self.archive, self.nov_k)
 
     def __call__(self, model, use_ac_noise=True) -> TrainingResult:
-        """Single-policy evaluation with the reference's fit_fn contract (no action noise)."""
+        """Single-policy evaluation with the reference's fit_fn contract (no action noise).  Like the scripts' fit_fn
+        (simple_example.py:38, obj.py:54) it first draws the save_obs coin(s) -- from every stream this process carries:
+        each stream is one reference rank, and every rank runs its own noiseless evaluation (es.py:48)."""
+        streams = self.rank_streams if self.rank_streams is not None else self._streams_in_use
+        if streams is not None:
+            for rs in streams:
+                for _ in range(self.coins_per_eval):
+                    rs.random()
         rews, behv, obs, steps = run_model(model, self.env, self.max_steps, None)
         no_obs = np.array([np.zeros(self.env.observation_space.shape)])
         if self.archive is None:

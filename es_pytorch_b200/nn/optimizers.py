@@ -56,13 +56,28 @@ class Optimizer(ABC):
         pass
 
     # -- pickling (Policy.save pickles the optimizer, policy.py:43-47) --------------------------------
+    # The pickled state is the reference's attribute set: lr, dim, t, hyper-parameters and the moment vectors as float32
+    # ndarrays under their reference names (Adam: m, v; SGD: v -- optimizers.py:39,51-52), so checkpoints written by the
+    # reference load here with their moments, not with zeros.
     def __getstate__(self):
-        d = dict(self.__dict__)
-        d['_dev'] = {k: v.cpu().numpy() for k, v in self._dev.items()}
+        d = {k: v for k, v in self.__dict__.items() if k not in ('_dev', '_host_restore')}
+        pending = self.__dict__.get('_host_restore') or {}
+        for name in self._state_names:
+            if name in self._dev:
+                d[name] = self._dev[name].cpu().numpy()
+            elif name in pending:                                   # restored but not yet used: keep, do not zero
+                d[name] = np.array(pending[name], dtype=np.float32)
+            else:
+                d[name] = np.zeros(self.dim, dtype=np.float32)
         return d
 
     def __setstate__(self, d):
-        host = d.pop('_dev', {})
+        d = dict(d)
+        host = dict(d.pop('_dev', None) or {})                      # round-1 format of this package
+        host.update(d.pop('_host_restore', None) or {})
+        for name in self._state_names:
+            if name in d:                                           # reference format (and this package's current one)
+                host[name] = np.ascontiguousarray(d.pop(name), dtype=np.float32)
         self.__dict__.update(d)
         self._dev = {}
         self._host_restore = host
@@ -87,6 +102,7 @@ class SimpleES(Optimizer):
 
 class SGD(Optimizer):
     kind = 'sgd'
+    _state_names = ('v',)
 
     def __init__(self, dim: int, lr: float, momentum=0.9):
         Optimizer.__init__(self, dim, lr)
@@ -104,6 +120,7 @@ class SGD(Optimizer):
 
 class Adam(Optimizer):
     kind = 'adam'
+    _state_names = ('m', 'v')
 
     def __init__(self, dim: int, lr: float, beta1=0.9, beta2=0.999, epsilon=1e-08):
         Optimizer.__init__(self, dim, lr)

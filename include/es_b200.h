@@ -65,6 +65,11 @@ int es_draw_indices(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int n_stream
                     uint64_t upper_bound, int extra_words, int64_t* idx_out, uint32_t* extra_out,
                     void* stream);
 
+/* Advance every stream by n_words 32-bit outputs without using them: the save_obs coin (rs.random() = 2 words) that the
+ * scripts' fit_fn draws at the start of EVERY evaluation, including the noiseless one of es.step (src/core/es.py:48,
+ * simple_example.py:38, obj.py:54) whose rollout is computed separately.                                              */
+int es_mt_skip(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int n_streams, int n_words, void* stream);
+
 /* ---- a3: materialise theta +- sigma*eps -------------------------------------------
  * Replaces Policy.pheno's arithmetic, src/core/policy.py:61-64 (two separately
  * rounded float32 ops, no FMA).  out_neg may be NULL.  Used by the per-perturbation

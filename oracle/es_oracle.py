@@ -219,14 +219,19 @@ class SyntheticEnvSpec:
 
 
 def run_model(env: SyntheticEnvSpec, layers, obmean, obstd, ob_clip: float, max_steps: int,
-              batched: bool = False):
+              batched: bool = False, ac_std: float = 0.0, rs: Optional[np.random.RandomState] = None):
     """gym_runner.py:33-67 on the synthetic env, ``ac_std == 0`` (no RNG consumed in
     the forward, nn.py:47).  Returns (rews list, behv list (3 per step, padded),
     obs ndarray [steps, obs_dim] of post-step observations, step = last loop index).
 
     ``batched=True`` evaluates all steps in one matrix product (same arithmetic up
     to BLAS summation order) so large parity cases finish in seconds; the per-step
-    loop is the literal restatement."""
+    loop is the literal restatement.
+
+    ``ac_std != 0`` with a stream ``rs``: FeedForward.forward adds ``rs.randn(*a.shape) * ac_std`` to the action at every
+    step (nn.py:47-48; legacy polar-method gaussians from the SAME RandomState that draws the noise indices and the
+    save_obs coins).  ``a += ndarray`` on a float32 tensor yields the float64 sum (numpy's reflected add wraps the
+    result back into a tensor), which the env casts to float32 (``np.asarray(action, dtype=float32)``)."""
     n = min(int(max_steps), env.T)
     xs = normalise_obs(env.obs_stream[:n], obmean, obstd, ob_clip)
     if batched:
@@ -238,6 +243,8 @@ def run_model(env: SyntheticEnvSpec, layers, obmean, obstd, ob_clip: float, max_
     ps = F32(env.pos_scale)
     for t in range(n):
         a = acts[t].astype(F32)
+        if ac_std != 0 and rs is not None:
+            a = (a.astype(np.float64) + rs.randn(env.act_dim) * ac_std).astype(F32)
         acc = F32(0.0)
         for j in range(env.act_dim):           # float32 dot, index order
             acc = F32(acc + F32(a[j] * env.rew_vec[t, j]))
@@ -315,7 +322,7 @@ def es_test_params(table: np.ndarray, flat: np.ndarray, std: float, dims, env: S
                 rank_seeds: Sequence[int], n_per_rank: int, obmean, obstd, ob_clip: float,
                 max_steps: int, coins_per_eval: int = 0, save_obs_chance: float = 0.0,
                 archive: Optional[np.ndarray] = None, nov_k: int = 10, batched: bool = True,
-                rank_states: Optional[List[np.random.RandomState]] = None):
+                rank_states: Optional[List[np.random.RandomState]] = None, ac_std: float = 0.0):
     """es.py:54-81 replayed for R virtual MPI ranks (one legacy RandomState per rank,
     utils.py:63-65).  Per pair: ``nt.sample(rs)`` (one ``randint``), evaluate +noise,
     evaluate -noise (es.py:68-72); each evaluation's fit_fn draws ``coins_per_eval``
@@ -338,7 +345,7 @@ def es_test_params(table: np.ndarray, flat: np.ndarray, std: float, dims, env: S
                 for _c in range(coins_per_eval):
                     save_obs = rs.random() < save_obs_chance
                 layers = unflatten(pheno_params(flat, std, noise if sign > 0 else -noise), dims)
-                rews, behv, obs, step = run_model(env, layers, obmean, obstd, ob_clip, max_steps, batched)
+                rews, behv, obs, step = run_model(env, layers, obmean, obstd, ob_clip, max_steps, batched, ac_std, rs)
                 res.append(reward_result(rews) if archive is None else nsr_result(rews, behv[-3:], archive, nov_k))
                 steps_total += step
                 o = obs if save_obs else np.array([np.zeros((env.obs_dim,))])
@@ -544,12 +551,13 @@ def approx_grad(flat: np.ndarray, optim, ranked_fits: np.ndarray, noise_inds: np
 def generation(table, flat, optim, std, dims, env, rank_seeds, n_per_rank, obmean, obstd, ob_clip, max_steps,
                batch_size, l2coeff, moo_w: Optional[float] = None, archive=None, nov_k=10,
                coins_per_eval=0, rank_states=None, batched=True, shaping: str = 'centered',
-               elite_percent: Optional[float] = None):
+               elite_percent: Optional[float] = None, save_obs_chance: float = 0.0, ac_std: float = 0.0):
     """One whole generation (es.py:38-47 without the reporter / noiseless eval).  ``shaping`` / ``elite_percent`` select
     the other rankers of rankers.py:61-103 (obj.py:48-50 picks EliteRanker(CenteredRanker(), elite))."""
     pos, neg, inds, steps, obstat = es_test_params(table, flat, std, dims, env, rank_seeds, n_per_rank, obmean, obstd,
                                                 ob_clip, max_steps, coins_per_eval=coins_per_eval, archive=archive,
-                                                nov_k=nov_k, batched=batched, rank_states=rank_states)
+                                                nov_k=nov_k, batched=batched, rank_states=rank_states,
+                                                save_obs_chance=save_obs_chance, ac_std=ac_std)
     grad_inds = inds
     if elite_percent is not None:
         w, grad_inds, _, n_ranked = elite_ranker(pos, neg, inds, shaping, elite_percent)
@@ -562,3 +570,24 @@ def generation(table, flat, optim, std, dims, env, rank_seeds, n_per_rank, obmea
         w, n_ranked = moo_ranker(pos, neg, moo_w)
     approx_grad(flat, optim, w, grad_inds, n_ranked, table, batch_size, l2coeff)
     return dict(pos=pos, neg=neg, inds=inds, steps=steps, weights=w, n_ranked=n_ranked, obstat=obstat)
+
+
+def es_step(table, flat, optim, std, dims, env, rank_states, n_per_rank, obmean, obstd, ob_clip, max_steps, batch_size,
+            l2coeff, coins_per_eval=1, save_obs_chance=0.0, batched=True, **kw):
+    """``es.step`` (es.py:38-51): the generation, then the noiseless evaluation ``fit_fn(policy.pheno(zeros), False)`` of the
+    UPDATED parameters that every rank runs for itself.  The scripts' fit_fn draws its save_obs coin(s) in every call
+    (simple_example.py:38, obj.py:54), so each rank's stream advances by ``coins_per_eval`` doubles here too.  Returns the
+    generation's dict plus ``noiseless`` (the result list of rank 0)."""
+    out = generation(table, flat, optim, std, dims, env, [None] * len(rank_states), n_per_rank, obmean, obstd, ob_clip,
+                     max_steps, batch_size, l2coeff, coins_per_eval=coins_per_eval, rank_states=rank_states, batched=batched,
+                     save_obs_chance=save_obs_chance, **kw)
+    noiseless = None
+    for rs in rank_states:
+        for _c in range(coins_per_eval):
+            rs.random()
+        layers = unflatten(pheno_params(flat, std, None), dims)
+        rews, behv, obs, step = run_model(env, layers, obmean, obstd, ob_clip, max_steps, batched)
+        res = reward_result(rews) if kw.get('archive') is None else nsr_result(rews, behv[-3:], kw['archive'], kw.get('nov_k', 10))
+        noiseless = res if noiseless is None else noiseless
+    out['noiseless'] = noiseless
+    return out

@@ -315,3 +315,58 @@ def test_mt19937_streams_are_read_and_written_in_place():
     assert [a.randint(0, 10 ** 9) for _ in range(50)] == [b.randint(0, 10 ** 9) for _ in range(50)]
     assert a.randn() == b.randn()                              # both return their cached gaussian first
     assert DeviceGeneration._mt_view(np.random.default_rng(1)) is None if hasattr(np.random, 'default_rng') else True
+
+
+# ---- bench.py's multi-rank control flow (the round-1 SCALE hang: per-rank iteration counts around collectives) -----------
+_BENCH_LOOP_WORKER = '''
+import os, sys, time
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as td
+import bench
+from es_pytorch_b200 import dist
+comm = dist.init_from_env('gloo')
+assert comm.size == 2
+calls = [0]
+def step():                                   # stands for gen.run(): an allgather and two allreduces per generation
+    calls[0] += 1
+    out = torch.empty(2, 3)
+    comm.allgather_into(out, torch.full((3,), float(comm.rank)))
+    g = torch.ones(4); comm.allreduce_sum(g); comm.allreduce_sum(g)
+class SkewedTimer:                            # rank 1's device clock reads 20x less than rank 0's: a per-rank `extra`
+    def start(self): pass                     # would differ by 20x and desynchronise the collectives inside step()
+    def stop(self): return 0.010 if comm.rank == 0 else 0.0005
+def allreduce_max(x):
+    t = torch.tensor([x], dtype=torch.float64); td.all_reduce(t, op=td.ReduceOp.MAX); return float(t.item())
+marks = []
+max_s, extra = bench.timed_region(step, 5, 2, comm, lambda: None, SkewedTimer(), allreduce_max, min_load_s=0.05,
+                                  on_timed_start=lambda: marks.append(calls[0]), on_timed_end=lambda: marks.append(calls[0]))
+assert max_s == 0.010, max_s                  # MAX over ranks, identical everywhere
+assert extra == int((0.05 - 0.010) / (0.010 / 5)) + 1 == 21, extra
+assert marks == [2, 7] and calls[0] == 2 + 5 + extra
+both = [None, None]
+td.all_gather_object(both, (calls[0], extra, max_s))
+assert both[0] == both[1], both               # every rank ran the same number of generations
+# no continuation needed -> none run
+max_s, extra = bench.timed_region(step, 3, 1, comm, lambda: None, SkewedTimer(), allreduce_max)
+assert extra == 0
+# argument plumbing of the strong-scaling mode
+a = bench.parse(['--gpus', '8', '--scaling', 'strong'])
+assert bench.total_pairs(a, bench.WORKLOADS['humanoid'], 8) == 40000 and bench.total_pairs(a, bench.WORKLOADS['humanoid-nsra'], 8) == 10000
+a = bench.parse(['--gpus', '8'])
+assert bench.total_pairs(a, bench.WORKLOADS['humanoid'], 8) == 80000
+os.write(1, ('LOOP_OK_%d\\n' % comm.rank).encode())
+'''
+
+
+def test_bench_timed_region_is_collective_safe(tmp_path):
+    script = tmp_path / 'w.py'
+    script.write_text(_BENCH_LOOP_WORKER.format(root=ROOT))
+    import socket
+    with socket.socket() as sk:
+        sk.bind(('127.0.0.1', 0))
+        port = sk.getsockname()[1]
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                          '--master-addr', '127.0.0.1', '--master-port', str(port), str(script)],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
+    assert 'LOOP_OK_0' in out.stdout and 'LOOP_OK_1' in out.stdout

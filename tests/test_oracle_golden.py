@@ -332,3 +332,94 @@ def test_oracle_reproduces_the_real_reference_humanoid_shape():
     assert np.array_equal(w, v['hum_w'])
     orc.approx_grad(flat, opt, w, inds, n_ranked, table, 500, 0.005)
     assert np.abs(flat - v['hum_theta']).max() <= 2e-6
+
+
+# ---- the REAL reference es.step / Policy.save / action noise, run by tests/golden/make_ref_step.py ---------------------------
+def _ref_step_setup():
+    v = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_step.npz'))
+    obs_dim, act_dim, T, n_pairs = [int(x) for x in v['cfg']]
+    dims = orc.layer_dims(obs_dim, tuple(int(h) for h in v['hidden']), act_dim)
+    table = np.random.RandomState(int(v['table_seed'])).randn(int(v['table_len'])).astype(np.float32)
+    return v, obs_dim, act_dim, T, n_pairs, dims, table, orc.SyntheticEnvSpec(obs_dim, act_dim, T)
+
+
+def test_oracle_reproduces_the_real_reference_step_including_the_noiseless_coin():
+    """Three generations of the reference's own es.step (es.py:23-51) with an obj.py-style fit_fn: the stream position
+    after every step includes the rs.random() of the noiseless evaluation; the third step starts from the reference's own
+    checkpoint (Adam m, v, t restored by Policy.load)."""
+    v, obs_dim, act_dim, T, n_pairs, dims, table, env = _ref_step_setup()
+    P = orc.n_params(dims)
+    flat, opt = v['theta0'].copy(), orc.AdamOracle(P, 0.01)
+    rs = np.random.RandomState(int(v['seed']))
+    stat = orc.ObStatOracle((obs_dim,), 1e-2)
+    obmean, obstd = np.zeros(obs_dim), np.ones(obs_dim)
+    for g in range(3):
+        if g == 2:                                              # resumed from the reference's pickle
+            assert opt.t == int(v['ckpt_t']) == 2
+            assert np.abs(opt.m - v['ckpt_m']).max() <= 1e-7 and np.abs(opt.v - v['ckpt_v']).max() <= 1e-9
+        out = orc.es_step(table, flat, opt, 0.02, dims, env, [rs], n_pairs, obmean, obstd, 5.0, T, 500, 0.005, coins_per_eval=1,
+                          save_obs_chance=float(v['save_obs_chance']), batched=False)
+        if g < 2:
+            assert np.array_equal(out['inds'], v[f's{g}_inds'])
+            assert np.array_equal(out['obstat'].sum, v[f's{g}_ob_sum']) and out['obstat'].count == float(v[f's{g}_ob_count'])
+        st = rs.get_state()
+        assert np.array_equal(st[1], v[f's{g}_rs_key']) and st[2] == int(v[f's{g}_rs_pos']), f'stream after step {g}'
+        assert np.abs(flat - v[f's{g}_theta']).max() <= 3e-6
+        assert abs(out['noiseless'][0] - float(v[f's{g}_noiseless'][0])) <= 1e-5
+        stat.inc(out['obstat'].sum, out['obstat'].sumsq, out['obstat'].count)
+        obmean, obstd = stat.mean, stat.std
+    assert np.array_equal(stat.sum, v['ckpt_obstat_sum'] + out['obstat'].sum)
+
+
+def test_oracle_reproduces_the_real_reference_action_noise_generation():
+    """ac_std = 0.01 (configs/simple_conf.json:14): FeedForward.forward draws rs.randn(act) at every step of every rollout
+    from the stream that also draws indices and coins (nn.py:47-48).  Indices and the final stream state (key, position
+    AND the cached polar-method gaussian) are exact; fitness to float32 rounding."""
+    v, obs_dim, act_dim, T, n_pairs, dims, table, env = _ref_step_setup()
+    rs = np.random.RandomState(int(v['acn_seed']))
+    flat = v['theta0'].copy()
+    pos, neg, inds, steps, stat = orc.es_test_params(table, flat, 0.02, dims, env, [0], n_pairs, np.zeros(obs_dim), np.ones(obs_dim),
+                                                     5.0, T, coins_per_eval=1, save_obs_chance=float(v['save_obs_chance']),
+                                                     batched=False, rank_states=[rs], ac_std=float(v['acn_std']))
+    assert np.array_equal(inds, v['acn_inds'])
+    st = rs.get_state()
+    assert np.array_equal(st[1], v['acn_rs_key']) and st[2] == int(v['acn_rs_pos'])
+    assert st[3] == int(v['acn_rs_has_gauss']) and st[4] == float(v['acn_rs_gauss'])
+    assert np.abs(pos - v['acn_pos']).max() <= 2e-6 and np.abs(neg - v['acn_neg']).max() <= 2e-6
+    assert np.array_equal(stat.sum, v['acn_ob_sum']) and stat.count == float(v['acn_ob_count'])
+    w, n_ranked = orc.centered_ranker(pos, neg)
+    assert np.array_equal(w, v['acn_w'])
+    orc.approx_grad(flat, orc.AdamOracle(len(flat), 0.01), w, inds, n_ranked, table, 500, 0.005)
+    assert np.abs(flat - v['acn_theta']).max() <= 2e-6
+
+
+def test_reference_checkpoint_unpickles_through_the_shims():
+    """tests/golden/policy-ref was written by the reference's own Policy.save (src.core.policy.Policy, src.nn.nn.FeedForward,
+    src.nn.optimizers.Adam, src.nn.obstat.ObStat).  It must load here with its Adam moments (the reference keeps m / v as
+    plain attributes), and survive a save / load round trip before any optimizer step (no GPU needed for either)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import os, pickle, sys, tempfile
+import numpy as np
+from src.core.policy import Policy
+v = np.load(os.path.join(%r, 'tests', 'golden', 'ref_step.npz'))
+p = Policy.load(os.path.join(%r, 'tests', 'golden', 'policy-ref'))
+import es_pytorch_b200.core.policy as mine, es_pytorch_b200.nn.optimizers as opt
+assert type(p) is mine.Policy and type(p.optim) is opt.Adam and p.optim.t == int(v['ckpt_t']) == 2
+assert p.flat_params.dtype == np.float32 and np.array_equal(p.flat_params, v['s1_theta'])
+assert np.array_equal(p.optim._host_restore['m'], v['ckpt_m']) and np.array_equal(p.optim._host_restore['v'], v['ckpt_v'])
+assert np.array_equal(p.obstat.sum, v['ckpt_obstat_sum']) and p.obstat.count == float(v['ckpt_obstat_count'])
+assert p._theta_dev is None and p._module.is_tanh_mlp() and p._module.layer_sizes() == [17, 64, 64, 6]
+assert np.array_equal(mine.Policy.get_flat(p._module), v['s1_theta'])          # Policy.load scattered flat_params into the module
+d = tempfile.mkdtemp()
+p.save(d, 'again')                                                             # before any step: the moments must survive
+q = mine.Policy.load(os.path.join(d, 'policy-again'))
+assert np.array_equal(q.optim._host_restore['m'], v['ckpt_m']) and np.array_equal(q.optim._host_restore['v'], v['ckpt_v']) and q.optim.t == 2
+state = q.optim.__getstate__()
+assert set(state) >= {'lr', 'dim', 't', 'beta1', 'beta2', 'epsilon', 'm', 'v'} and '_dev' not in state
+print('CKPT_OK')
+''' % (root, root)
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.path.join(root, 'es_pytorch_b200', 'compat'))
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0 and 'CKPT_OK' in out.stdout, (out.stdout + out.stderr)[-3000:]
