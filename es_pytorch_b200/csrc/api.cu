@@ -92,8 +92,7 @@ int es_ctx_destroy(es_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->counters) cudaFree(ctx->counters);
-    if (ctx->shadow) cudaFree(ctx->shadow);
-    if (ctx->shadow_lo) cudaFree(ctx->shadow_lo);
+    es_tc2_free_shadows(ctx);
     if (ctx->err_host) cudaFreeHost((void*)ctx->err_host);
     free(ctx);
     return ES_OK;
@@ -101,8 +100,8 @@ int es_ctx_destroy(es_ctx* ctx) {
 
 int es_noise_table_changed(es_ctx* ctx) {
     if (!ctx) return ES_ERR_INVALID;
-    ctx->shadow_src = nullptr;          // the shadow (if any) is rebuilt by the next tensor-core rollout
-    ctx->shadow_len = 0;
+    ctx->sh16_src = nullptr;            // the shadows (if any) are rebuilt by the next tensor-core rollout
+    ctx->sh16_len = 0;
     return ES_OK;
 }
 
@@ -227,10 +226,10 @@ int es_rollout_openloop(es_ctx* ctx, const float* table, int64_t table_len, cons
         return es_impl_rollout_f32(ctx, table, table_len, idx, n_pairs, theta, P, sigma, layer_sizes, n_layers, obsn,
                                    rew_vec, T, pos_scale, fit_pos, fit_neg, fit_stride, behv_pos, behv_neg,
                                    (cudaStream_t)stream);
-    if (mode == ES_ROLLOUT_TC)
-        return es_impl_rollout_tc(ctx, table, table_len, idx, n_pairs, theta, P, sigma, layer_sizes, n_layers, obsn,
-                                  rew_vec, T, pos_scale, fit_pos, fit_neg, fit_stride, behv_pos, behv_neg,
-                                  (cudaStream_t)stream);
+    if (mode == ES_ROLLOUT_TC || mode == ES_ROLLOUT_TC3)
+        return es_impl_rollout_tc2(ctx, mode == ES_ROLLOUT_TC3, table, table_len, idx, n_pairs, theta, P, sigma, layer_sizes, n_layers,
+                                   obsn, rew_vec, T, pos_scale, fit_pos, fit_neg, fit_stride, behv_pos, behv_neg,
+                                   (cudaStream_t)stream);
     es_set_error("es_rollout_openloop: unknown mode %d", mode);
     return ES_ERR_INVALID;
 }

@@ -18,16 +18,17 @@ struct es_ctx {
     size_t scratch_bytes;
     unsigned* counters;     // small zero-initialised counter array (last-block detection)
     size_t n_counters;
-    // bf16 shadow of the noise table for the tensor-core rollout (rollout_tc.cu): 8 copies, copy s holds
-    // bf16(table[j + s]) at element j, so that a slice starting at any idx has a 16-byte aligned copy (s = idx % 8)
-    const float* shadow_src;   // table the shadow was built from (identity: pointer + length)
-    int64_t shadow_len;
-    void* shadow;              // [8][shadow_stride] bf16, or NULL (not built / allocation failed)
-    size_t shadow_stride;      // elements per copy (multiple of 8)
-    int shadow_failed;         // allocation failed once: do not retry every call
-    // float16 hi/lo split shadows for the float32-equivalent tensor-core rollout (rollout_tc2.cu)
-    void* shadow_lo;           // [8][shadow_stride] f16: f16(table[j+s] - float(f16(table[j+s])))
-    int shadow_kind;           // element type `shadow` was built with: 0 none, 1 f16 (hi part)
+    // float16 shadows for rollout_tc2.cu: hi = f16(table), lo = f16(table - hi) (split rollout only), 8 shifted copies each,
+    // plus the two TMA tensor maps over them (host copy, 64-byte aligned)
+    const float* sh16_src;
+    int64_t sh16_len;
+    void* sh16_hi;
+    void* sh16_lo;
+    void* sh16_maps;
+    int sh16_maps_lo;
+    size_t sh16_stride;
+    int sh16_obs;
+    int sh16_failed;
     // asynchronous kernel-side argument errors: a mapped, page-locked host word the kernels set when a noise index is
     // out of range (the reference asserts `len > i + size`, src/core/noisetable.py:34); surfaced by es_check_async and
     // by the next entry point
@@ -81,8 +82,9 @@ int es_impl_obstat_accumulate_coins(es_ctx*, double*, double*, double*, const fl
                                     const uint32_t*, int, double, cudaStream_t);
 int es_impl_rollout_f32(es_ctx*, const float*, int64_t, const int64_t*, int, const float*, int, float, const int*, int,
                         const float*, const float*, int, float, double*, double*, int, float*, float*, cudaStream_t);
-int es_impl_rollout_tc(es_ctx*, const float*, int64_t, const int64_t*, int, const float*, int, float, const int*, int,
-                       const float*, const float*, int, float, double*, double*, int, float*, float*, cudaStream_t);
+int es_impl_rollout_tc2(es_ctx*, int split, const float*, int64_t, const int64_t*, int, const float*, int, float, const int*,
+                        int, const float*, const float*, int, float, double*, double*, int, float*, float*, cudaStream_t);
+void es_tc2_free_shadows(es_ctx* ctx);
 int es_impl_novelty(es_ctx*, const float*, int, const double*, int, int, double*, int, cudaStream_t);
 int es_impl_rank_transform(es_ctx*, const double*, const double*, int, int, int, double, double, int, int, int,
                            const int64_t*, float*, double*, int32_t*, double*, int32_t*, int64_t*, cudaStream_t);

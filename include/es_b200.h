@@ -110,9 +110,11 @@ int es_rollout_openloop(es_ctx* ctx, const float* table, int64_t table_len, cons
                         double* fit_pos, double* fit_neg, int fit_stride, float* behv_pos, float* behv_neg,
                         int mode, void* stream);
 
-/* The tensor-core rollout keeps a bf16 shadow of the noise table (8 shifted copies, 2 bytes x 8 x table_len of HBM, built
- * on first use) keyed by the table's device pointer and length.  The reference never writes to its table after
- * NoiseTable.create_shared (src/core/noisetable.py:66-91); a caller that does overwrite it in place must say so.   */
+/* The tensor-core rollouts keep float16 shadows of the noise table (8 shifted copies of f16(table), 2 bytes x 8 x table_len
+ * of HBM; ES_ROLLOUT_TC3 a second set for the low-order parts), built on first use and keyed by the table's device pointer,
+ * its length and the policy's obs_dim.  The reference never writes to its table after NoiseTable.create_shared
+ * (src/core/noisetable.py:66-91); a caller that does overwrite it in place must say so.  Table values must be finite and
+ * below 65504 in magnitude (float16 range) for the tensor-core modes.                                               */
 int es_noise_table_changed(es_ctx* ctx);
 
 /* ---- a13: novelty ---------------------------------------------------------------------

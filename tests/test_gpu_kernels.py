@@ -477,50 +477,111 @@ def test_novelty(eng):
         assert out.item() == expect
 
 
-# ------------------------------------------------------------------------------------------- tensor-core rollout
-def _tc_vs_f32(eng, obs, act, T, n_pairs, seed):
+# ------------------------------------------------------------------------------------------- tensor-core rollouts
+def _tc_vs_f32(eng, obs, act, T, n_pairs, seed, mode):
     from es_pytorch_b200 import _lib
     rs = np.random.RandomState(seed)
     sizes = [obs, 64, 64, act]
     P = orc.n_params(orc.layer_dims(obs, (64, 64), act))
     L = P + 1_000_000
     table, theta = dev(eng, rs.randn(L).astype(np.float32)), dev(eng, (rs.randn(P) * 0.1).astype(np.float32))
-    idx = dev(eng, rs.randint(0, L - P, size=n_pairs).astype(np.int64))
-    obsn = dev(eng, np.clip(rs.randn(T, obs), -5, 5).astype(np.float32))
-    rew = dev(eng, rs.randn(T, act).astype(np.float32))
+    idx = dev(eng, rs.randint(0, L - P - 1, size=n_pairs).astype(np.int64))
+    obsn_h, rew_h = np.clip(rs.randn(T, obs), -5, 5).astype(np.float32), rs.randn(T, act).astype(np.float32)
+    obsn, rew = dev(eng, obsn_h), dev(eng, rew_h)
     res = {}
-    for mode in (_lib.ES_ROLLOUT_F32, _lib.ES_ROLLOUT_TC):
+    for md in (_lib.ES_ROLLOUT_F32, mode):
         fit = torch.zeros(2, n_pairs, dtype=torch.float64, device=eng.device)
         behv = torch.zeros(2, n_pairs, 3, dtype=torch.float32, device=eng.device)
-        eng.rollout(table, idx, theta, 0.02, sizes, obsn, rew, 0.05, fit[0], fit[1], 1, behv[0], behv[1], mode)
-        res[mode] = (fit.cpu().numpy(), behv.cpu().numpy())
-    return res[_lib.ES_ROLLOUT_F32], res[_lib.ES_ROLLOUT_TC]
+        eng.rollout(table, idx, theta, 0.02, sizes, obsn, rew, 0.05, fit[0], fit[1], 1, behv[0], behv[1], md)
+        eng.sync()
+        res[md] = (fit.cpu().numpy(), behv.cpu().numpy())
+    return res[_lib.ES_ROLLOUT_F32], res[mode], np.abs(rew_h).sum()
 
 
-@pytest.mark.parametrize('obs,act,T,n_pairs', [(376, 17, 1000, 200), (17, 6, 1000, 256), (17, 6, 100, 8), (5, 1, 130, 3),
-                                               (63, 32, 129, 5), (64, 3, 128, 4),
-                                               # several pairs per CTA with an odd tile count (the two epilogue groups swap
-                                               # parity every pair) and with a single tile per pair (one group per pair)
-                                               (17, 6, 300, 333), (17, 6, 100, 400)])
-def test_rollout_tc_matches_f32(eng, obs, act, T, n_pairs):
-    """bf16 tensor-core rollout vs the float32 CUDA-core rollout (itself checked against the oracle above).
-    Tolerance (bf16 operands, fp32 accumulate, tanh.approx): fitness within 3 % of the population's fitness
-    spread, antithetic differences f+ - f- within 3 % of their spread, ranks essentially unchanged."""
-    (f32, b32), (ftc, btc) = _tc_vs_f32(eng, obs, act, T, n_pairs, seed=obs + T)
+_TC_SHAPES = [(376, 17, 1000, 200), (17, 6, 1000, 256), (17, 6, 100, 8), (5, 1, 130, 3), (63, 32, 129, 5), (64, 3, 128, 4),
+              (24, 9, 257, 150),                      # TMA path (obs % 8 == 0), action columns split 8 + 1 over the two halves
+              # several pairs per CTA with an odd tile count (the two epilogue groups swap parity every pair) and with a
+              # single tile per pair (one group per pair)
+              (17, 6, 300, 333), (17, 6, 100, 400)]
+
+
+@pytest.mark.parametrize('obs,act,T,n_pairs', _TC_SHAPES)
+def test_rollout_tc3_is_float32_equivalent(eng, obs, act, T, n_pairs):
+    """ES_ROLLOUT_TC3 (float16 hi+lo split operands, three tcgen05 MMAs per product, accurate tanh, float64 sums) against
+    the float32 CUDA-core rollout (itself within 1e-5 of the oracle above): same tolerance class as that test -- the
+    fitness differs by less than 1e-5 of the episode's |reward| mass and by a few 1e-6 of the population's fitness spread
+    (measured: 1.4e-6 .. 1.9e-6 rms), where the float16 single-product path is ~1e-3."""
+    from es_pytorch_b200 import _lib
+    (f32, b32), (ftc, btc), mass = _tc_vs_f32(eng, obs, act, T, n_pairs, obs + T, _lib.ES_ROLLOUT_TC3)
+    assert np.abs(ftc - f32).max() <= 1e-5 * max(1.0, mass / 8), (np.abs(ftc - f32).max(), mass)
     spread = max(f32.std(), 1e-3 * np.sqrt(T))
-    assert np.abs(ftc - f32).max() <= 0.05 * spread + 0.02 * np.sqrt(T) * 0.05
+    assert np.sqrt(((ftc - f32) ** 2).mean()) <= 6e-6 * spread + 1e-6
+    assert np.abs(btc - b32).max() <= 2e-6 * 0.05 * T + 1e-6             # final positions: float32 sums of T terms
+    if n_pairs >= 100:                                                   # ranks: only adjacent near-ties may swap
+        r32, rtc = np.argsort(np.argsort(f32.ravel())), np.argsort(np.argsort(ftc.ravel()))
+        assert np.abs(r32 - rtc).max() <= 2 and (r32 != rtc).mean() <= 0.02
+
+
+@pytest.mark.parametrize('obs,act,T,n_pairs', _TC_SHAPES)
+def test_rollout_tc_matches_f32(eng, obs, act, T, n_pairs):
+    """ES_ROLLOUT_TC (float16 operands, one MMA per product, tanh.approx) vs the float32 CUDA-core rollout: fitness within
+    ~1e-3 of the population's fitness spread (measured 0.6e-3 .. 2.3e-3 rms), ranks essentially unchanged."""
+    from es_pytorch_b200 import _lib
+    (f32, b32), (ftc, btc), _ = _tc_vs_f32(eng, obs, act, T, n_pairs, obs + T, _lib.ES_ROLLOUT_TC)
+    spread = max(f32.std(), 1e-3 * np.sqrt(T))
+    assert np.abs(ftc - f32).max() <= 0.02 * spread + 1e-3 * np.sqrt(T) * 0.05
+    assert np.sqrt(((ftc - f32) ** 2).mean()) <= 5e-3 * spread + 2e-4
     d32, dtc = f32[0] - f32[1], ftc[0] - ftc[1]
-    assert np.sqrt(((dtc - d32) ** 2).mean()) <= 0.03 * max(d32.std(), 1e-3 * np.sqrt(T)) + 0.02
-    assert np.abs(btc - b32).max() <= 0.01 * 0.05 * T + 1e-3
+    assert np.sqrt(((dtc - d32) ** 2).mean()) <= 5e-3 * max(d32.std(), 1e-3 * np.sqrt(T)) + 1e-3
+    assert np.abs(btc - b32).max() <= 2e-3 * 0.05 * T + 1e-4
     if n_pairs >= 100:
         r32, rtc = np.argsort(np.argsort(f32.ravel())), np.argsort(np.argsort(ftc.ravel()))
-        assert np.corrcoef(r32, rtc)[0, 1] > 0.9995
+        assert np.corrcoef(r32, rtc)[0, 1] > 0.99999
 
 
-def test_rollout_tc_shadow_tracks_table_contents(eng):
-    """The tensor-core path reads layer 1 from a bf16 shadow of the table (obs % 8 == 0): an in-place rewrite of the table
+def test_rollout_tc3_error_against_float64_truth(eng):
+    """What "float32-equivalent" means, measured: on the Humanoid-shaped policy (T = 1000) the split tensor-core path's
+    fitness error against float64 arithmetic on the same inputs is within 4x of the float32 CUDA-core path's own error
+    (measured 2.4x: 1.8e-6 vs 0.8e-6 of the fitness spread), three orders of magnitude below the single-product path."""
+    from es_pytorch_b200 import _lib
+    rs = np.random.RandomState(376 + 1000)
+    obs, act, T, n = 376, 17, 1000, 24
+    sizes = [obs, 64, 64, act]
+    P = orc.n_params(orc.layer_dims(obs, (64, 64), act))
+    L = P + 1_000_000
+    table_h, theta_h = rs.randn(L).astype(np.float32), (rs.randn(P) * 0.1).astype(np.float32)
+    idx_h = rs.randint(0, L - P - 1, size=n).astype(np.int64)
+    obsn_h, rew_h = np.clip(rs.randn(T, obs), -5, 5).astype(np.float32), rs.randn(T, act).astype(np.float32)
+    truth = np.zeros((2, n))
+    x, c = obsn_h.astype(np.float64), rew_h.astype(np.float64)
+    for k, i in enumerate(idx_h):
+        for s, sign in enumerate((1.0, -1.0)):
+            w = theta_h.astype(np.float64) + sign * np.float64(np.float32(0.02)) * table_h[i:i + P].astype(np.float64)
+            a, at = x, 0
+            for fi, fo in ((obs, 64), (64, 64), (64, act)):
+                W = w[at:at + fi * fo].reshape(fo, fi); at += fi * fo
+                b = w[at:at + fo]; at += fo
+                a = np.tanh(a @ W.T + b)
+            truth[s, k] = (a * c).sum()
+    err = {}
+    for mode in (_lib.ES_ROLLOUT_F32, _lib.ES_ROLLOUT_TC3, _lib.ES_ROLLOUT_TC):
+        fit = torch.zeros(2, n, dtype=torch.float64, device=eng.device)
+        eng.rollout(dev(eng, table_h), dev(eng, idx_h), dev(eng, theta_h), 0.02, sizes, dev(eng, obsn_h), dev(eng, rew_h), 0.05,
+                    fit[0], fit[1], mode=mode)
+        eng.sync()
+        err[mode] = np.sqrt(((fit.cpu().numpy() - truth) ** 2).mean())
+    spread = truth.std()
+    assert err[_lib.ES_ROLLOUT_F32] <= 3e-6 * spread
+    assert err[_lib.ES_ROLLOUT_TC3] <= 4 * err[_lib.ES_ROLLOUT_F32] and err[_lib.ES_ROLLOUT_TC3] <= 6e-6 * spread
+    assert err[_lib.ES_ROLLOUT_TC] >= 50 * err[_lib.ES_ROLLOUT_TC3]
+
+
+@pytest.mark.parametrize('tc_mode', [1, 2])
+def test_rollout_tc_shadow_tracks_table_contents(eng, tc_mode):
+    """The tensor-core paths read layer 1 from float16 shadows of the table (obs % 8 == 0): an in-place rewrite of the table
     tensor, or a new tensor at a recycled address, must be picked up; obs % 8 != 0 takes the float32-slice path."""
     from es_pytorch_b200 import _lib
+    assert (_lib.ES_ROLLOUT_TC, _lib.ES_ROLLOUT_TC3) == (1, 2)
     rs = np.random.RandomState(5)
     obs, act, T, n = 24, 6, 100, 40
     sizes = [obs, 64, 64, act]
@@ -536,21 +597,22 @@ def test_rollout_tc_shadow_tracks_table_contents(eng):
         return fit.cpu().numpy()
 
     def close(a, b):
-        return np.abs(a - b).max() <= 0.05 * max(b.std(), 1e-2)
+        return np.abs(a - b).max() <= 0.02 * max(b.std(), 1e-2)
 
     t1 = dev(eng, rs.randn(L).astype(np.float32))
-    a_tc, a_32 = run(t1, _lib.ES_ROLLOUT_TC), run(t1, _lib.ES_ROLLOUT_F32)
+    a_tc, a_32 = run(t1, tc_mode), run(t1, _lib.ES_ROLLOUT_F32)
     assert close(a_tc, a_32)
     t1.copy_(torch.from_numpy(rs.randn(L).astype(np.float32)))               # in place: same pointer, new contents
-    b_tc, b_32 = run(t1, _lib.ES_ROLLOUT_TC), run(t1, _lib.ES_ROLLOUT_F32)
+    b_tc, b_32 = run(t1, tc_mode), run(t1, _lib.ES_ROLLOUT_F32)
     assert close(b_tc, b_32) and not close(b_tc, a_32)
     del t1
     t2 = dev(eng, rs.randn(L).astype(np.float32))                             # usually the recycled address of t1
-    c_tc, c_32 = run(t2, _lib.ES_ROLLOUT_TC), run(t2, _lib.ES_ROLLOUT_F32)
+    c_tc, c_32 = run(t2, tc_mode), run(t2, _lib.ES_ROLLOUT_F32)
     assert close(c_tc, c_32) and not close(c_tc, b_32)
 
 
-def test_rollout_tc_sigma_zero_symmetric_and_unsupported_shape(eng):
+@pytest.mark.parametrize('tc_mode', [1, 2])
+def test_rollout_tc_sigma_zero_symmetric_and_unsupported_shape(eng, tc_mode):
     from es_pytorch_b200 import _lib
     from es_pytorch_b200._lib import EsLibraryError
     rs = np.random.RandomState(3)
@@ -559,10 +621,10 @@ def test_rollout_tc_sigma_zero_symmetric_and_unsupported_shape(eng):
     idx = dev(eng, rs.randint(0, 5000, size=200).astype(np.int64))
     obsn, rew = dev(eng, rs.randn(256, 17).astype(np.float32)), dev(eng, rs.randn(256, 6).astype(np.float32))
     fit = torch.zeros(2, 200, dtype=torch.float64, device=eng.device)
-    eng.rollout(table, idx, theta, 0.0, [17, 64, 64, 6], obsn, rew, 0.05, fit[0], fit[1], mode=_lib.ES_ROLLOUT_TC)
+    eng.rollout(table, idx, theta, 0.0, [17, 64, 64, 6], obsn, rew, 0.05, fit[0], fit[1], mode=tc_mode)
     f = fit.cpu().numpy()
     assert np.array_equal(f[0], f[1]) and np.all(f[0] == f[0][0])        # sigma = 0: every evaluation identical
     with pytest.raises(EsLibraryError, match='tensor-core path'):
         P2 = orc.n_params(orc.layer_dims(17, (32,), 6))
         eng.rollout(table, idx, dev(eng, np.zeros(P2, dtype=np.float32)), 0.02, [17, 32, 6], obsn, rew, 0.05, fit[0], fit[1],
-                    mode=_lib.ES_ROLLOUT_TC)
+                    mode=tc_mode)
