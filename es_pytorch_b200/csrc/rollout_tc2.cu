@@ -32,12 +32,24 @@
 //     warp moves the image into shared memory with two bulk copies when the previous pair's MMAs have retired.
 //
 // 28 warps (7 warpgroups), setmaxnreg moves registers from the data-movement warpgroups to the 16 epilogue warps:
-//   warp 0 producer (Xn ring) | warp 1 L1 issuer + TMEM owner | warps 2-3 L2/L3 issuers (one per epilogue group)
-//   warps 4-11 epilogue group 0, 12-19 group 1 (alternate tiles; TMEM lane quarter = warp % 4, column half = (warp-4)%8/4)
-//   warps 20-26 builders | warp 27 copier
+//   warp 0 producer (Xn ring) | warp 1 L1 issuer + TMEM owner | warps 2-3 L2/L3 issuers
+//   warps 4-19 epilogue (TMEM lane quarter = warp % 4) | warps 20-26 builders | warp 27 copier
+// Epilogue organisation (what the 512 TMEM columns allow):
+//   SPLIT=0: two groups of 8 warps on alternate tiles (column half = (warp-4)%8/4), 256 columns each; V is free again after
+//            epi1, so the next L1 of a group runs under its own epi2/epi3; issuer warp g serves group g.
+//   SPLIT=1: ONE group of 16 warps on every tile (column quarter = (warp-4)/4), the wide V double-buffered (2 x 128 columns) so
+//            that L1 of tile g+1 runs under the epilogue of tile g; with two groups D2/D3 would have to alias V and every
+//            group sat idle during its own L1 (31 % of the epilogue warps' time in the first version).  Issuer warp s serves
+//            sign s.  In both modes the + sign runs one phase ahead of the - sign (epi1+ | L2+ under epi1- | L2- under epi2+
+//            | L3+ under epi2- | L3- under epi3+ | epi3-), so the short L2/L3 MMAs are hidden behind epilogue work.
 // TMEM (512 columns, 256 per epilogue group):
-//   SPLIT=0: V 0-63 | h+ 64-95 | h- 96-127 | D2+ (D3+) 128-191 | D2- (D3-) 192-255
-//   SPLIT=1: V = D2+ = D3+ 0-63 | D2- (D3-) 64-127 | h+hi 128-159 | h+lo 160-191 | h-hi 192-223 | h-lo 224-255
+//   SPLIT=0 (per group, +256 for group 1): V 0-63 | h+ 64-95 | h- 96-127 | D2+ (D3+) 128-191 | D2- (D3-) 192-255
+//   SPLIT=1: V buffer 0: 0-127, buffer 1: 128-255 (two partial sums each, see below) | h+hi 256-287 | h+lo 288-319 | h-hi 320-351 |
+//            h-lo 352-383 | D2+ (D3+) 384-447 | D2- (D3-) 448-511
+// SPLIT layer 1 issues HALF-as-many, twice-as-wide MMAs: eps1's hi and lo blocks of a K chunk are adjacent in shared memory, so
+// x_hi . [eps_hi ; eps_lo]^T is ONE N = 128 instruction (columns 0-63: x_hi.eps_hi, 64-127: x_hi.eps_lo); x_lo . eps_hi (N = 64) adds
+// into columns 0-63 and the epilogue reads V = cols[n] + cols[64 + n].  (The single L1 issuer warp was the split kernel's
+// limiter at 12 small MMAs per K chunk: ~90 cycles of issue per 35 cycles of tensor work.)
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -258,8 +270,6 @@ struct T2Params {
     const float* ubase;           // float4 [n_mtiles][2 halves][8 chunks][128 rows]
     const float* crt;             // reward vectors transposed per tile: [n_mtiles][32 cols][128 rows]
     uint8_t* images;              // [gridDim.x][2][image bytes]
-    double* partial;              // [n_pairs][16 warps][8]: {fit+, fit-} as doubles, 6 position sums as floats behind them
-    unsigned* tickets;            // [n_pairs] zeroed before launch
     double* fit_pos;
     double* fit_neg;
     float* behv_pos;
@@ -277,22 +287,27 @@ struct T2Params {
 template <bool SPLIT> struct T2Cfg {
     static constexpr int NP = SPLIT ? 2 : 1;              // pieces per operand
     static constexpr int NST = SPLIT ? 4 : 8;             // observation stages in the ring
-    // TMEM column offsets inside a group's 256 columns
-    static constexpr int C_V = 0;
-    static constexpr int C_D2P = SPLIT ? 0 : 128, C_D2N = SPLIT ? 64 : 192;
-    static constexpr int C_HP = SPLIT ? 128 : 64, C_HN = SPLIT ? 192 : 96;     // [+32: lo piece when SPLIT]
+    static constexpr int NG = SPLIT ? 1 : 2;              // epilogue groups
+    static constexpr int GW = T2_EPI_WARPS / NG;          // warps per group (barrier arrival counts)
+    static constexpr int CW = 64 / (GW / 4);              // accumulator columns per epilogue warp (32 / 16)
+    // TMEM columns.  !SPLIT: offsets inside a group's 256 columns.  SPLIT: absolute (one group), V buffer b at 128*b.
+    static constexpr int V_STRIDE = SPLIT ? 128 : 256;    // V of tile g at V_STRIDE * (g & 1)
+    static constexpr int G_STRIDE = SPLIT ? 0 : 256;      // group base of the H / D2 regions
+    static constexpr int C_HP = SPLIT ? 256 : 64, C_HN = SPLIT ? 320 : 96;     // [+32: lo piece when SPLIT]
+    static constexpr int C_D2P = SPLIT ? 384 : 128, C_D2N = SPLIT ? 448 : 192;
 };
 
-struct T2Smem { uint32_t b1, xst, w2, w3, bias, bars, total; };
+struct T2Smem { uint32_t b1, xst, w2, w3, bias, red, bars, total; };
 template <bool SPLIT> __host__ __device__ inline T2Smem t2_layout(int nkc) {
     using C = T2Cfg<SPLIT>;
     T2Smem L;
     uint32_t o = 0;
-    L.b1 = o;   o += (uint32_t)C::NP * nkc * T2_B1_CHUNK;         // [piece][kc][64 rows x 128 B]
+    L.b1 = o;   o += (uint32_t)C::NP * nkc * T2_B1_CHUNK;         // [kc][piece][64 rows x 128 B]
     L.xst = o;  o += (uint32_t)C::NST * T2_STAGE;
     L.w2 = o;   o += 2u * C::NP * T2_B1_CHUNK;                    // [sign][piece][64 rows x 128 B]
     L.w3 = o;   o += 2u * C::NP * T2_W3_BLOCK;                    // [sign][piece][32 rows x 128 B]
     L.bias = o; o += 2 * 1024;                                    // double-buffered by pair parity
+    L.red = o;  o += 2 * T2_EPI_WARPS * 64 + 64;                  // per-pair sums of the epilogue warps [parity][warp][8 doubles] + counters
     L.bars = o; o += 1024;
     L.total = o;
     return L;
@@ -348,11 +363,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
 
     // ---- one-time setup -----------------------------------------------------------------------------------------------
     if (tid == 0) {
+        ((unsigned*)(smem + L.red + 2 * T2_EPI_WARPS * 64))[0] = 0;
+        ((unsigned*)(smem + L.red + 2 * T2_EPI_WARPS * 64))[1] = 0;
         for (int s = 0; s < NST; ++s) { mbar_init(&bars[B2_FULL + s], 1); mbar_init(&bars[B2_EMPTY + s], 1); }
         for (int gq = 0; gq < 2; ++gq) {
-            mbar_init(&bars[B2_D1_FULL + gq], 1); mbar_init(&bars[B2_V_FREE + gq], T2_GRP_WARPS);
-            mbar_init(&bars[B2_H1P + gq], T2_GRP_WARPS); mbar_init(&bars[B2_H1N + gq], T2_GRP_WARPS);
-            mbar_init(&bars[B2_H2P + gq], T2_GRP_WARPS); mbar_init(&bars[B2_H2N + gq], T2_GRP_WARPS);
+            mbar_init(&bars[B2_D1_FULL + gq], 1); mbar_init(&bars[B2_V_FREE + gq], C::GW);
+            mbar_init(&bars[B2_H1P + gq], C::GW); mbar_init(&bars[B2_H1N + gq], C::GW);
+            mbar_init(&bars[B2_H2P + gq], C::GW); mbar_init(&bars[B2_H2N + gq], C::GW);
             mbar_init(&bars[B2_D2P + gq], 1); mbar_init(&bars[B2_D2N + gq], 1);
             mbar_init(&bars[B2_D3P + gq], 1); mbar_init(&bars[B2_D3N + gq], 1);
         }
@@ -387,9 +404,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
             }
         } else if (warp == T2_W_L1) {
             // ===================== L1 MMA issuer (warp-uniform loop; one elected lane issues) =====================
-            const uint32_t id_l1 = umma_idesc_f16(T2_MT, T2_H);
+            const uint32_t id_l1 = umma_idesc_f16(T2_MT, T2_H), id_l1w = umma_idesc_f16(T2_MT, 2 * T2_H);
             const uint64_t a_desc0 = umma_desc_sw128(smem_u32(smem + L.xst)), b_desc0 = umma_desc_sw128(smem_u32(smem + L.b1));
-            const uint64_t b_lo_off = (uint64_t)((NKC * T2_B1_CHUNK) >> 4);        // piece 1 of eps1 behind piece 0
             uint32_t stage = 0, phase = 0, g = 0;
             for (int i = 0; i < my_pairs; ++i) {
                 mbar_wait(&bars[B2_EPS_READY], i & 1);
@@ -397,33 +413,37 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
                     const uint32_t grp = g & 1, use = g >> 1;
                     mbar_wait(&bars[B2_V_FREE + grp], (use & 1) ^ 1);              // the group is done with this V (and what aliases it)
                     tc_fence_after();
-                    const uint32_t d_v = tmem + grp * 256 + C::C_V;
+                    const uint32_t d_v = tmem + grp * C::V_STRIDE;        // V buffer of this tile (grp = g & 1)
                     for (int kc = 0; kc < NKC; ++kc) {
-                        const uint64_t bd = b_desc0 + (uint64_t)kc * (T2_B1_CHUNK >> 4);
-                        mbar_wait(&bars[B2_FULL + stage], phase);
-                        tc_fence_after();
-                        {
-                            const uint64_t ad = a_desc0 + (uint64_t)stage * (T2_STAGE >> 4);
-                            if (elect_one()) {
-                                issue_ss4(d_v, ad, bd, id_l1, kc != 0);                      // x_hi . eps_hi   (x . eps when !SPLIT)
-                                if (SPLIT) issue_ss4(d_v, ad, bd + b_lo_off, id_l1, 1);      // x_hi . eps_lo
-                                umma_commit(&bars[B2_EMPTY + stage]);
-                                if (!SPLIT && kc == NKC - 1) umma_commit(&bars[B2_D1_FULL + grp]);
-                            }
-                            __syncwarp();
-                            if (++stage == NST) { stage = 0; phase ^= 1; }
-                        }
-                        if (SPLIT) {
+                        const uint64_t bd = b_desc0 + (uint64_t)kc * ((NP * T2_B1_CHUNK) >> 4);       // [kc][piece] blocks
+                        if (!SPLIT) {
                             mbar_wait(&bars[B2_FULL + stage], phase);
                             tc_fence_after();
                             const uint64_t ad = a_desc0 + (uint64_t)stage * (T2_STAGE >> 4);
                             if (elect_one()) {
-                                issue_ss4(d_v, ad, bd, id_l1, 1);                            // x_lo . eps_hi
+                                issue_ss4(d_v, ad, bd, id_l1, kc != 0);                      // x . eps
                                 umma_commit(&bars[B2_EMPTY + stage]);
                                 if (kc == NKC - 1) umma_commit(&bars[B2_D1_FULL + grp]);
                             }
                             __syncwarp();
                             if (++stage == NST) { stage = 0; phase ^= 1; }
+                        } else {
+                            // the x_hi and x_lo stages of the chunk are adjacent ring slots (NST even): one issue region for both
+                            const uint32_t st_hi = stage, st_lo = stage + 1;
+                            mbar_wait(&bars[B2_FULL + st_hi], phase);
+                            mbar_wait(&bars[B2_FULL + st_lo], phase);
+                            tc_fence_after();
+                            const uint64_t ah = a_desc0 + (uint64_t)st_hi * (T2_STAGE >> 4), al = a_desc0 + (uint64_t)st_lo * (T2_STAGE >> 4);
+                            if (elect_one()) {
+                                issue_ss4(d_v, ah, bd, id_l1w, kc != 0);                     // x_hi . [eps_hi ; eps_lo]  (N = 128)
+                                umma_commit(&bars[B2_EMPTY + st_hi]);
+                                issue_ss4(d_v, al, bd, id_l1, 1);                            // x_lo . eps_hi           (N = 64, columns 0-63)
+                                umma_commit(&bars[B2_EMPTY + st_lo]);
+                                if (kc == NKC - 1) umma_commit(&bars[B2_D1_FULL + grp]);
+                            }
+                            __syncwarp();
+                            stage += 2;
+                            if (stage == NST) { stage = 0; phase ^= 1; }
                         }
                     }
                 }
@@ -431,89 +451,114 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
                 __syncwarp();
             }
         } else {
-            // ===================== L2 / L3 MMA issuer of one epilogue group =====================
-            const uint32_t eg = warp - T2_W_L23;
+            // ===================== L2 / L3 MMA issuers =====================
+            // !SPLIT: issuer w serves epilogue group w (its alternate tiles, both signs, + first).  SPLIT: issuer w serves sign w of
+            // every tile.  Order per tile and sign: wait H1 -> L2 -> commit D2, wait H2 -> L3 -> commit D3.
+            const uint32_t iw = warp - T2_W_L23;
+            const uint32_t eg = SPLIT ? 0 : iw;
             const uint32_t id_l2 = umma_idesc_f16(T2_MT, T2_H), id_l3 = umma_idesc_f16(T2_MT, T2_ACT_PAD);
             const uint64_t w2d = umma_desc_sw128(smem_u32(smem + L.w2)), w3d = umma_desc_sw128(smem_u32(smem + L.w3));
             constexpr uint64_t W2_BLK = T2_B1_CHUNK >> 4, W3_BLK = T2_W3_BLOCK >> 4;     // [sign][piece] blocks
-            const uint32_t tb = tmem + eg * 256;
+            const uint32_t tb = tmem + eg * C::G_STRIDE;
             uint32_t k = 0;
             for (int i = 0; i < my_pairs; ++i) {
                 mbar_wait(&bars[B2_W_READY], i & 1);
                 tc_fence_after();
                 for (uint32_t g = (uint32_t)i * NMT; g < (uint32_t)(i + 1) * NMT; ++g) {
-                    if ((g & 1) != eg) continue;
+                    if (!SPLIT && (g & 1) != eg) continue;
                     const uint32_t par = k & 1;
                     ++k;
 #pragma unroll 1
-                    for (int layer = 0; layer < 2; ++layer) {
-#pragma unroll 1
-                        for (int sgn = 0; sgn < 2; ++sgn) {
-                            const int hb = layer ? (sgn ? B2_H2N : B2_H2P) : (sgn ? B2_H1N : B2_H1P);
-                            const int db = layer ? (sgn ? B2_D3N : B2_D3P) : (sgn ? B2_D2N : B2_D2P);
-                            mbar_wait(&bars[hb + eg], par);
-                            tc_fence_after();
-                            if (elect_one()) {
-                                const uint32_t a_hi = tb + (sgn ? C::C_HN : C::C_HP), a_lo = a_hi + 32;
-                                const uint32_t d = tb + (sgn ? C::C_D2N : C::C_D2P);          // D3 aliases D2
-                                const uint64_t bh = layer ? w3d + (uint64_t)(sgn * NP) * W3_BLK : w2d + (uint64_t)(sgn * NP) * W2_BLK;
-                                const uint64_t bl = bh + (layer ? W3_BLK : W2_BLK);
-                                const uint32_t id = layer ? id_l3 : id_l2;
-                                issue_ts4(d, a_hi, bh, id, 0);                               // h_hi . w_hi
-                                if (SPLIT) {
-                                    issue_ts4(d, a_hi, bl, id, 1);                           // h_hi . w_lo
-                                    issue_ts4(d, a_lo, bh, id, 1);                           // h_lo . w_hi
-                                }
-                                umma_commit(&bars[db + eg]);
+                    for (int step = 0; step < (SPLIT ? 2 : 4); ++step) {
+                        // !SPLIT: (L2+, L2-, L3+, L3-); SPLIT: (L2 s, L3 s) with s = iw
+                        const int layer = SPLIT ? step : (step >> 1), sgn = SPLIT ? (int)iw : (step & 1);
+                        const int hb = layer ? (sgn ? B2_H2N : B2_H2P) : (sgn ? B2_H1N : B2_H1P);
+                        const int db = layer ? (sgn ? B2_D3N : B2_D3P) : (sgn ? B2_D2N : B2_D2P);
+                        mbar_wait(&bars[hb + eg], par);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t a_hi = tb + (sgn ? C::C_HN : C::C_HP), a_lo = a_hi + 32;
+                            const uint32_t d = tb + (sgn ? C::C_D2N : C::C_D2P);          // D3 aliases D2
+                            const uint64_t bh = layer ? w3d + (uint64_t)(sgn * NP) * W3_BLK : w2d + (uint64_t)(sgn * NP) * W2_BLK;
+                            const uint64_t bl = bh + (layer ? W3_BLK : W2_BLK);
+                            const uint32_t id = layer ? id_l3 : id_l2;
+                            issue_ts4(d, a_hi, bh, id, 0);                               // h_hi . w_hi
+                            if (SPLIT) {
+                                issue_ts4(d, a_hi, bl, id, 1);                           // h_hi . w_lo
+                                issue_ts4(d, a_lo, bh, id, 1);                           // h_lo . w_hi
                             }
-                            __syncwarp();
+                            umma_commit(&bars[db + eg]);
                         }
+                        __syncwarp();
                     }
                 }
-                if (elect_one()) umma_commit(&bars[B2_W_FREE]);                     // this group's L2/L3 of the pair are in flight
+                if (elect_one()) umma_commit(&bars[B2_W_FREE]);                     // this issuer's L2/L3 of the pair are in flight
                 __syncwarp();
             }
         }
     } else if (warp < T2_BLD_WARP0) {
-        // ===================== epilogue warps (two groups on alternate tiles) =====================
+        // ===================== epilogue warps =====================
         reg_inc<T2_REG_EPI>();
+        constexpr int CW = C::CW, NB = CW / 8;                // accumulator columns per warp (32 / 16), batches of 8 columns
         const int ew = warp - T2_EPI_WARP0;                   // 0..15
-        const uint32_t eg = ew >> 3;
-        const int q = warp & 3, h = (ew & 7) >> 2;            // TMEM lane quarter, column half
+        const uint32_t eg = SPLIT ? 0u : (uint32_t)(ew >> 3); // epilogue group
+        const int q = warp & 3;                               // TMEM lane quarter
+        const int cq = SPLIT ? (ew >> 2) : ((ew & 7) >> 2);   // column part of this warp: columns [cq*CW, cq*CW + CW)
         const int row = q * 32 + lane;
-        const uint32_t tb = tmem + eg * 256 + ((uint32_t)(q * 32) << 16);
-        // action columns of this warp (layer 3): [a_lo, a_hi), split so that both halves work when act > 8
-        const int a_split = (p.act <= 24) ? 8 : 16;
-        const int a_lo = h ? a_split : 0, a_hi = h ? p.act : min(p.act, a_split);
-        const int nj = max(0, a_hi - a_lo);                   // <= 16, warp-uniform
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const uint32_t tb = tmem + eg * C::G_STRIDE + lane_off;           // H / D2 regions of the group
+        // action columns of this warp (layer 3): [a_lo, a_hi), at most 16, multiples of 4 (!SPLIT: two parts, SPLIT: four parts)
+        const int a_per = SPLIT ? ((p.act <= 16) ? 4 : 8) : ((p.act <= 24) ? 8 : 16);
+        const int a_lo = cq * a_per;
+        const int a_hi = (cq == (SPLIT ? 3 : 1)) ? p.act : min(p.act, a_lo + a_per);
+        const int nj = max(0, a_hi - a_lo);                   // warp-uniform
         const float sg = p.sigma;
         const bool want_pos = p.behv_pos != nullptr;
+        double* red = (double*)(smem + L.red);                // [pair parity][16 warps][8]: per-pair sums of every epilogue warp
+        unsigned* red_cnt = (unsigned*)(smem + L.red + 2 * T2_EPI_WARPS * 64);
         for (int i = 0; i < my_pairs; ++i) {
-            const uint32_t b2p = smem_u32(bias_all + (i & 1) * 256) + h * 128, b2n = b2p + T2_H * 4;
+            const uint32_t b2p = smem_u32(bias_all + (i & 1) * 256) + cq * CW * 4, b2n = b2p + T2_H * 4;
             const uint32_t b3p = smem_u32(bias_all + (i & 1) * 256) + 2 * T2_H * 4 + a_lo * 4, b3n = b3p + T2_ACT_PAD * 4;
-            double fitp = 0.0, fitn = 0.0;                    // this thread's rows of the pair, float64 (python sum(rews))
+            // this thread's rows of the pair: compensated float32 sums (Kahan; the reference sums python floats, float64)
+            float fps = 0.f, fpc = 0.f, fns = 0.f, fnc = 0.f;
             float pacc = 0.f;                                 // position sums: ONE register (transposing butterfly per tile)
             for (uint32_t g = (uint32_t)i * NMT; g < (uint32_t)(i + 1) * NMT; ++g) {
-                if ((g & 1) != eg) continue;
-                const uint32_t par = (g >> 1) & 1;
+                if (!SPLIT && (g & 1) != eg) continue;
+                const uint32_t vbuf = g & 1, par_v = (g >> 1) & 1;                 // V buffer of the tile and its use count parity
+                const uint32_t par = SPLIT ? (g & 1) : par_v;                      // use count parity of the group's H / D2 / D3 barriers
                 const int m = (int)(g - (uint32_t)i * NMT);
                 const int t = m * T2_MT + row;
-                const float4* __restrict__ up = reinterpret_cast<const float4*>(p.ubase) + ((size_t)(m * 2 + h) * 8) * T2_MT + row;
-                mbar_wait(&bars[B2_D1_FULL + eg], par);
+                const uint32_t tv_ = tmem + vbuf * C::V_STRIDE + lane_off + cq * CW;            // this warp's V columns
+                const float4* __restrict__ up = reinterpret_cast<const float4*>(p.ubase) + ((size_t)m * 16 + cq * (CW / 4)) * T2_MT + row;
+                mbar_wait(&bars[B2_D1_FULL + vbuf], par_v);
                 tc_fence_after();
-                // ---- epi1: h1+- = tanh(U +- sigma V) from one read of U and of V, 8 columns at a time ----
+                // ---- epi1: h1+- = tanh(U +- sigma V), 8 columns at a time; the + sign first (its L2 MMA then runs while the - sign
+                //      is computed); U and V are read again for the - sign (SPLIT: V = the two partial sums of the wide accumulator)
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    float4 ub[2];
+                for (int sgn = 0; sgn < 2; ++sgn) {
+                    const unsigned long long s2 = sgn ? pk(-sg, -sg) : pk(sg, sg);
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) ub[c] = ldg_stream4(up + (c4 * 2 + c) * T2_MT);
-                    uint32_t v[8];
-                    tmem_ld8(tb + C::C_V + h * 32 + c4 * 8, v);
-                    tmem_ld_wait();
+                    for (int c4 = 0; c4 < NB; ++c4) {
+                        float4 ub[2];
 #pragma unroll
-                    for (int sgn = 0; sgn < 2; ++sgn) {
+                        for (int c = 0; c < 2; ++c) ub[c] = ldg_stream4(up + (c4 * 2 + c) * T2_MT);
+                        uint32_t v[8];
+                        tmem_ld8(tv_ + c4 * 8, v);
+                        if (SPLIT) {
+                            uint32_t v2[8];
+                            tmem_ld8(tv_ + 64 + c4 * 8, v2);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float s0, s1;
+                                unpk(add2(pk(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])),
+                                          pk(__uint_as_float(v2[2 * e]), __uint_as_float(v2[2 * e + 1]))), s0, s1);
+                                v[2 * e] = __float_as_uint(s0); v[2 * e + 1] = __float_as_uint(s1);
+                            }
+                        } else {
+                            tmem_ld_wait();
+                        }
                         uint32_t whi[4], wlo[4];
-                        const unsigned long long s2 = sgn ? pk(-sg, -sg) : pk(sg, sg);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const float4 u4 = ub[e >> 1];
@@ -523,18 +568,17 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
                             if (SPLIT) { tanh_acc2(z0, z1, t0, t1); split_h2(t0, t1, whi[e], wlo[e]); }
                             else { whi[e] = pack_h2(tanh_fast(z0), tanh_fast(z1)); }
                         }
-                        const uint32_t hc = tb + (sgn ? C::C_HN : C::C_HP) + h * 16 + c4 * 4;
+                        const uint32_t hc = tb + (sgn ? C::C_HN : C::C_HP) + cq * (CW / 2) + c4 * 4;
                         tmem_st4(hc, whi[0], whi[1], whi[2], whi[3]);
                         if (SPLIT) tmem_st4(hc + 32, wlo[0], wlo[1], wlo[2], wlo[3]);
                     }
-                }
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (!SPLIT) mbar_arrive(&bars[B2_V_FREE + eg]);               // V consumed (SPLIT: D2+/D3+ alias it, freed after epi3+)
-                    mbar_arrive(&bars[B2_H1P + eg]);
-                    mbar_arrive(&bars[B2_H1N + eg]);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (sgn == 0) mbar_arrive(&bars[B2_H1P + eg]);
+                        else { mbar_arrive(&bars[B2_V_FREE + vbuf]); mbar_arrive(&bars[B2_H1N + eg]); }   // V consumed
+                    }
                 }
                 if (m < 2) mbar_wait(&bars[B2_W_READY], i & 1);                    // first tile of the pair: biases in place?
                 // ---- epi2 (+ then -): h2 = tanh(D2 + b2), over h1 ----
@@ -544,9 +588,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
                     tc_fence_after();
                     const uint32_t b2 = sgn ? b2n : b2p;
 #pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) {
+                    for (int c4 = 0; c4 < NB; ++c4) {
                         uint32_t d[8];
-                        tmem_ld8(tb + (sgn ? C::C_D2N : C::C_D2P) + h * 32 + c4 * 8, d);
+                        tmem_ld8(tb + (sgn ? C::C_D2N : C::C_D2P) + cq * CW + c4 * 8, d);
                         const float4 bb0 = lds128f(b2 + c4 * 32), bb1 = lds128f(b2 + c4 * 32 + 16);
                         tmem_ld_wait();
                         const float bs[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
@@ -558,7 +602,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
                             if (SPLIT) { tanh_acc2(z0, z1, t0, t1); split_h2(t0, t1, whi[e], wlo[e]); }
                             else { whi[e] = pack_h2(tanh_fast(z0), tanh_fast(z1)); }
                         }
-                        const uint32_t hc = tb + (sgn ? C::C_HN : C::C_HP) + h * 16 + c4 * 4;
+                        const uint32_t hc = tb + (sgn ? C::C_HN : C::C_HP) + cq * (CW / 2) + c4 * 4;
                         tmem_st4(hc, whi[0], whi[1], whi[2], whi[3]);
                         if (SPLIT) tmem_st4(hc + 32, wlo[0], wlo[1], wlo[2], wlo[3]);
                     }
@@ -601,7 +645,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
                                         r = fmaf(a1, cc[gq * 4 + 1], r);
                                         r = fmaf(a2, cc[gq * 4 + 2], r);
                                         r = fmaf(a3, cc[gq * 4 + 3], r);
-                                        if (gq == 0 && h == 0) {           // position integrator: action components 0, 1 % act, 2 % act
+                                        if (gq == 0 && cq == 0) {          // position integrator: action components 0, 1 % act, 2 % act
                                             q0 = a0;
                                             q1 = (p.act > 1) ? a1 : a0;
                                             q2 = (p.act > 2) ? a2 : a0;
@@ -611,41 +655,39 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
                             }
                         }
                     }
-                    if (SPLIT && sgn == 0) {               // D3+ (which aliases V) has been read: the next L1 of this group may start
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&bars[B2_V_FREE + eg]);
-                    }
                     if (t < p.T) {
-                        if (sgn) { fitn += (double)r; tv[5] = q0; tv[6] = q1; tv[7] = q2; }
-                        else     { fitp += (double)r; tv[2] = q0; tv[3] = q1; tv[4] = q2; }
+                        // Kahan step: (s, c) += r
+                        if (sgn) { const float y = r - fnc, u = fns + y; fnc = (u - fns) - y; fns = u; tv[5] = q0; tv[6] = q1; tv[7] = q2; }
+                        else     { const float y = r - fpc, u = fps + y; fpc = (u - fps) - y; fps = u; tv[2] = q0; tv[3] = q1; tv[4] = q2; }
                     }
                 }
                 tc_fence_before();
-                if (want_pos && h == 0) pacc += warp_sum8(tv, lane);
+                if (want_pos && cq == 0) pacc += warp_sum8(tv, lane);
             }
-            // ---- flush this warp's sums of the pair; the last of the 16 warps adds them in warp order ----
+            // ---- this warp's sums of the pair -> shared memory; the last of the 16 warps adds them in warp order and writes the pair's
+            //      results (no global scratch, no device-wide fence: a CTA-scope release/acquire on a shared counter) ----
             const int pair = blockIdx.x + i * gridDim.x;
-            fitp = warp_sum_d(fitp); fitn = warp_sum_d(fitn);
-            double* mine = p.partial + ((size_t)pair * T2_EPI_WARPS + ew) * 8;
-            if (lane == 0) { __stcg(mine + 0, fitp); __stcg(mine + 1, fitn); }
-            if (want_pos && (lane & 3) == 0) __stcg(reinterpret_cast<float*>(mine + 2) + sum8_index(lane), pacc);
-            __threadfence();
+            const double fitp = warp_sum_d((double)fps - (double)fpc), fitn = warp_sum_d((double)fns - (double)fnc);
+            double* mine = red + ((size_t)(i & 1) * T2_EPI_WARPS + ew) * 8;
+            if (lane == 0) { mine[0] = fitp; mine[1] = fitn; }
+            if (want_pos && (lane & 3) == 0) reinterpret_cast<float*>(mine + 2)[sum8_index(lane)] = pacc;
             __syncwarp();
             if (lane == 0) {
-                if (atomicAdd(p.tickets + pair, 1u) == T2_EPI_WARPS - 1) {
-                    __threadfence();
+                __threadfence_block();
+                // monotonic arrival counter per parity slot (pairs i, i+2, ... share one: no warp can be a whole pair ahead)
+                if (atomicAdd(red_cnt + (i & 1), 1u) == (unsigned)(T2_EPI_WARPS * ((i >> 1) + 1) - 1)) {
+                    __threadfence_block();
                     double fp = 0.0, fn = 0.0;
                     float tot[8];
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) tot[kk] = 0.f;
-                    const double* all = p.partial + (size_t)pair * T2_EPI_WARPS * 8;
+                    const volatile double* all = red + (size_t)(i & 1) * T2_EPI_WARPS * 8;
                     for (int w = 0; w < T2_EPI_WARPS; ++w) {
-                        fp += __ldcg(all + w * 8 + 0); fn += __ldcg(all + w * 8 + 1);
-                        if (want_pos && ((w & 7) >> 2) == 0) {
-                            const float* pf = reinterpret_cast<const float*>(all + w * 8 + 2);
+                        fp += all[w * 8 + 0]; fn += all[w * 8 + 1];
+                        if (want_pos && (SPLIT ? (w >> 2) : ((w & 7) >> 2)) == 0) {
+                            const volatile float* pf = reinterpret_cast<const volatile float*>(all + w * 8 + 2);
 #pragma unroll
-                            for (int kk = 2; kk < 8; ++kk) tot[kk] += __ldcg(pf + kk);
+                            for (int kk = 2; kk < 8; ++kk) tot[kk] += pf[kk];
                         }
                     }
                     p.fit_pos[(size_t)pair * p.fit_stride] = fp;
@@ -681,7 +723,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
 #pragma unroll
                     for (int pc = 0; pc < NP; ++pc)
                         for (int kc = 0; kc < NKC; ++kc)
-                            tma_load_3d(smem + L.b1 + (size_t)(pc * NKC + kc) * T2_B1_CHUNK, pc ? &maps.lo : &maps.hi, 0, unit0 + 8 * kc, 0,
+                            tma_load_3d(smem + L.b1 + (size_t)(kc * NP + pc) * T2_B1_CHUNK, pc ? &maps.lo : &maps.hi, 0, unit0 + 8 * kc, 0,
                                         &bars[B2_EPS_TX]);
                 } else {
                     for (int c = 0; c < NP * NKC; ++c)
@@ -699,9 +741,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
                     const float eb = ldg_stream(p.table + slice + p.b1 + n);
                     __half hi, lo;
                     split_h1(eb, hi, lo);
-                    const uint32_t off = (uint32_t)kcb * T2_B1_CHUNK + n * 128 + ((ub ^ (n & 7)) << 4);
-                    *(uint4*)(smem + L.b1 + off) = make_uint4((uint32_t)__half_as_ushort(SPLIT ? hi : __float2half_rn(eb)), 0, 0, 0);
-                    if (SPLIT) *(uint4*)(smem + L.b1 + (size_t)NKC * T2_B1_CHUNK + off) = make_uint4((uint32_t)__half_as_ushort(lo), 0, 0, 0);
+                    const uint32_t off = (uint32_t)(kcb * NP) * T2_B1_CHUNK + n * 128 + ((ub ^ (n & 7)) << 4);      // [kc][piece] blocks
+                    *(uint4*)(smem + L.b1 + off) = make_uint4((uint32_t)__half_as_ushort(hi), 0, 0, 0);
+                    if (SPLIT) *(uint4*)(smem + L.b1 + T2_B1_CHUNK + off) = make_uint4((uint32_t)__half_as_ushort(lo), 0, 0, 0);
                 }
                 fence_async_smem();
             }
@@ -782,12 +824,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
                     float x0 = 0.f, x1 = 0.f;
                     if (k < p.obs) x0 = ldg_stream(eps + p.w1 + (size_t)n * p.obs + k); else if (k == p.obs) x0 = ldg_stream(eps + p.b1 + n);
                     if (k + 1 < p.obs) x1 = ldg_stream(eps + p.w1 + (size_t)n * p.obs + k + 1); else if (k + 1 == p.obs) x1 = ldg_stream(eps + p.b1 + n);
-                    uint8_t* dst = img + I.b1 + (size_t)(k >> 6) * T2_B1_CHUNK + sw128_off(n, k & 63);
+                    uint8_t* dst = img + I.b1 + (size_t)((k >> 6) * NP) * T2_B1_CHUNK + sw128_off(n, k & 63);     // [kc][piece] blocks
                     if (SPLIT) {
                         __half h0, l0, h1, l1;
                         split_h1(x0, h0, l0); split_h1(x1, h1, l1);
                         *(uint32_t*)dst = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                        *(uint32_t*)(dst + (size_t)NKC * T2_B1_CHUNK) = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                        *(uint32_t*)(dst + T2_B1_CHUNK) = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
                     } else {
                         *(uint32_t*)dst = pack_h2(x0, x1);
                     }
@@ -939,22 +981,17 @@ int t2_launch(es_ctx* ctx, T2Params& p, const T2Maps& maps, const float* obsn, c
     const size_t xnt_bytes = (size_t)p.n_mtiles * p.nkc * NP * T2_STAGE;
     const size_t ub_bytes = (size_t)p.n_mtiles * T2_MT * T2_H * sizeof(float);
     const size_t crt_bytes = (size_t)p.n_mtiles * T2_ACT_PAD * T2_MT * sizeof(float);
-    const size_t part_bytes = (size_t)n_pairs * T2_EPI_WARPS * 8 * sizeof(double);
     const int grid = n_pairs < ctx->sm_count ? n_pairs : ctx->sm_count;
     const size_t img_bytes = (((size_t)grid * 2 * t2_image<SPLIT>(p.nkc, !p.use_tma).total) + 255) & ~(size_t)255;
-    const size_t tick_bytes = ((size_t)n_pairs * sizeof(unsigned) + 255) & ~(size_t)255;
     void* scratch = nullptr;
-    int rc = es_ctx_scratch(ctx, xnt_bytes + ub_bytes + crt_bytes + part_bytes + tick_bytes + img_bytes, &scratch);
+    int rc = es_ctx_scratch(ctx, xnt_bytes + ub_bytes + crt_bytes + img_bytes, &scratch);
     if (rc) return rc;
     char* at = (char*)scratch;
     uint8_t* xnt = (uint8_t*)at; at += xnt_bytes;
     float* ubase = (float*)at; at += ub_bytes;
     float* crt = (float*)at; at += crt_bytes;
-    p.partial = (double*)at; at += part_bytes;
-    p.tickets = (unsigned*)at; at += tick_bytes;
     p.images = (uint8_t*)at;
     p.xnt = xnt; p.ubase = ubase; p.crt = crt;
-    ES_CHECK_CUDA(cudaMemsetAsync(p.tickets, 0, tick_bytes, stream));
     {
         const size_t total = (size_t)p.n_mtiles * p.nkc * T2_MT * T2_KC;
         int blocks = es_div_up((int64_t)total, 256);
