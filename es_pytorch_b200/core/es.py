@@ -67,10 +67,19 @@ def _queue_common_downloads(eng, gen, fpos, fneg):
     else:
         h_pos, h_neg = eng.download_async(fpos, 'fpos'), eng.download_async(fneg, 'fneg')
     h_state = eng.download_async(gen.mt_state, 'mtstate')
-    nk = gen.n_streams * gen.mt_key.shape[1]
-    h_key, h_mtpos = h_state[:nk].view(gen.n_streams, -1), h_state[nk:]
+    R = gen.n_streams
+    nk = R * gen.mt_key.shape[1]
+    h_key, h_mtpos = h_state[:nk].view(R, -1), h_state[nk:nk + R]
+    gen._h_gauss = (h_state[nk + R:nk + 2 * R], h_state[nk + 2 * R:].view(torch.float64))    # valid after the synchronisation
     h_stats = eng.download_async(gen._gen_stats, 'gstats') if gen.extra_words else None
     return h_pos, h_neg, h_key, h_mtpos, h_stats
+
+
+def _host_gauss(gen):
+    """(has_gauss, cached gaussian) host copies of the last _queue_common_downloads, when the generation drew action noise."""
+    if gen.ac_std == 0.0:
+        return None
+    return gen._h_gauss[0].numpy().copy(), gen._h_gauss[1].numpy().copy()
 
 
 def _obstat_from(h_stats, obs_dim):
@@ -129,7 +138,7 @@ def _step_fused(cfg, comm, n: int, policy: Policy, nt: NoiseTable, gen_obstat: O
     pos = devcache.attach(h_pos.numpy().reshape(gen.K, gen.n_obj).copy(), fpos, valid)
     neg = devcache.attach(h_neg.numpy().reshape(gen.K, gen.n_obj).copy(), fneg, valid)
     inds = devcache.attach(h_idx.numpy().astype(np.float64), idx_all, valid)
-    gen.store_states(streams, h_key.numpy().copy(), h_mtpos.numpy().copy())
+    gen.store_states(streams, h_key.numpy().copy(), h_mtpos.numpy().copy(), _host_gauss(gen))
     if h_stats is not None:
         gen_obstat.inc(*_obstat_from(h_stats, gen.obs_dim))
     steps = 2 * gen.K * (fit_fn.max_steps - 1)
@@ -166,7 +175,8 @@ def _device_generation(fit_fn, policy: Policy, nt: NoiseTable, streams) -> Devic
                                rew_dev[:T].contiguous(), streams, policy.std, 0.0, policy.optim,
                                ob_clip=policy._module.ob_clip, pos_scale=env.pos_scale,
                                coins_per_eval=fit_fn.coins_per_eval, save_obs_chance=fit_fn.save_obs_chance,
-                               archive=archive, nov_k=fit_fn.nov_k, rollout_mode=fit_fn.rollout_mode, engine=eng)
+                               archive=archive, nov_k=fit_fn.nov_k, rollout_mode=fit_fn.rollout_mode, engine=eng,
+                               ac_std=float(getattr(policy._module, '_action_std', 0.0) or 0.0))
         fit_fn._gen = gen
     else:
         gen.load_states(streams)
@@ -178,6 +188,11 @@ def _device_generation(fit_fn, policy: Policy, nt: NoiseTable, streams) -> Devic
             eng.upload_async(gen.rew_vec, env.rew_vec[:gen.T], ('rew', id(gen)), src_pinned=pinned)
     fit_fn._streams_in_use = streams                    # BatchedRollout.__call__ draws the noiseless call's coin from them
     gen.sigma = float(policy.std)                       # scripts decay the noise std between generations
+    ac_std = float(getattr(policy._module, '_action_std', 0.0) or 0.0)       # obj.py:81 decays it between generations
+    if ac_std != gen.ac_std:
+        gen.ac_std = ac_std
+        gen._host_states = None                         # the gaussian cache starts / stops travelling: upload afresh
+        gen.load_states(streams)
     gen.save_obs_chance = fit_fn.save_obs_chance
     # scripts swap or mutate these between generations (obj.py:81-83 decays lr / ac_std, nsra.py grows the archive): the
     # cached generation follows the callers' objects instead of keeping its own references
@@ -207,7 +222,7 @@ def _test_params_batched(comm, n: int, policy: Policy, nt: NoiseTable, gen_obsta
     pos = devcache.attach(h_pos.numpy().reshape(gen.K, gen.n_obj).copy(), fpos, valid)
     neg = devcache.attach(h_neg.numpy().reshape(gen.K, gen.n_obj).copy(), fneg, valid)
     idx_local = h_idx.numpy().copy()
-    gen.store_states(streams, h_key.numpy().copy(), h_mtpos.numpy().copy())
+    gen.store_states(streams, h_key.numpy().copy(), h_mtpos.numpy().copy(), _host_gauss(gen))
     if comm.size > 1:
         inds = np.concatenate(dist.world().allgather_object(idx_local)).astype(np.float64)
     else:

@@ -203,10 +203,10 @@ int es_obstat_accumulate_coins(es_ctx* ctx, double* sum, double* sumsq, double* 
                                            n_coins, chance, (cudaStream_t)stream);
 }
 
-int es_rollout_openloop(es_ctx* ctx, const float* table, int64_t table_len, const int64_t* idx, int n_pairs,
-                        const float* theta, int P, float sigma, const int* layer_sizes, int n_layers, const float* obsn,
-                        const float* rew_vec, int T, float pos_scale, double* fit_pos, double* fit_neg, int fit_stride,
-                        float* behv_pos, float* behv_neg, int mode, void* stream) {
+int es_rollout_openloop_noisy(es_ctx* ctx, const float* table, int64_t table_len, const int64_t* idx, int n_pairs,
+                              const float* theta, int P, float sigma, const int* layer_sizes, int n_layers, const float* obsn,
+                              const float* rew_vec, int T, float pos_scale, double* fit_pos, double* fit_neg, int fit_stride,
+                              float* behv_pos, float* behv_neg, const float* act_noise, int mode, void* stream) {
     ES_ENTER(ctx);
     ES_REQUIRE(table && idx && theta && layer_sizes && obsn && rew_vec && fit_pos && fit_neg,
                "es_rollout_openloop: NULL pointer");
@@ -225,13 +225,40 @@ int es_rollout_openloop(es_ctx* ctx, const float* table, int64_t table_len, cons
     if (mode == ES_ROLLOUT_F32)
         return es_impl_rollout_f32(ctx, table, table_len, idx, n_pairs, theta, P, sigma, layer_sizes, n_layers, obsn,
                                    rew_vec, T, pos_scale, fit_pos, fit_neg, fit_stride, behv_pos, behv_neg,
-                                   (cudaStream_t)stream);
+                                   act_noise, (cudaStream_t)stream);
     if (mode == ES_ROLLOUT_TC || mode == ES_ROLLOUT_TC3)
         return es_impl_rollout_tc2(ctx, mode == ES_ROLLOUT_TC3, table, table_len, idx, n_pairs, theta, P, sigma, layer_sizes, n_layers,
                                    obsn, rew_vec, T, pos_scale, fit_pos, fit_neg, fit_stride, behv_pos, behv_neg,
-                                   (cudaStream_t)stream);
+                                   act_noise, (cudaStream_t)stream);
     es_set_error("es_rollout_openloop: unknown mode %d", mode);
     return ES_ERR_INVALID;
+}
+
+int es_rollout_openloop(es_ctx* ctx, const float* table, int64_t table_len, const int64_t* idx, int n_pairs,
+                        const float* theta, int P, float sigma, const int* layer_sizes, int n_layers, const float* obsn,
+                        const float* rew_vec, int T, float pos_scale, double* fit_pos, double* fit_neg, int fit_stride,
+                        float* behv_pos, float* behv_neg, int mode, void* stream) {
+    return es_rollout_openloop_noisy(ctx, table, table_len, idx, n_pairs, theta, P, sigma, layer_sizes, n_layers, obsn, rew_vec, T,
+                                     pos_scale, fit_pos, fit_neg, fit_stride, behv_pos, behv_neg, nullptr, mode, stream);
+}
+
+int es_draw_noisy(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int32_t* has_gauss, double* gauss, int n_streams,
+                  int n_per_stream, uint64_t upper_bound, int coins_per_eval, int normals_per_eval, double scale,
+                  int64_t* idx_out, uint32_t* coin_out, float* noise_out, void* stream) {
+    ES_ENTER(ctx);
+    ES_REQUIRE(mt_key && mt_pos && has_gauss && gauss && idx_out && noise_out, "es_draw_noisy: NULL pointer");
+    ES_REQUIRE(n_streams >= 0 && n_per_stream >= 0 && normals_per_eval >= 0, "es_draw_noisy: negative count");
+    ES_REQUIRE(coins_per_eval >= 0 && coins_per_eval <= 8, "es_draw_noisy: coins_per_eval must be in [0,8]");
+    ES_REQUIRE(coins_per_eval == 0 || coin_out, "es_draw_noisy: coin_out is NULL");
+    // NoiseTable.sample_idx raises ValueError when upper_bound <= 0 (noisetable.py:39)
+    ES_REQUIRE(upper_bound >= 1, "es_draw_noisy: upper_bound must be >= 1 (network too large for noise table)");
+    if (upper_bound - 1 >= 0xFFFFFFFFull) {
+        es_set_error("es_draw_noisy: ranges >= 2^32 use numpy's 64-bit draw path, not implemented");
+        return ES_ERR_UNSUPPORTED;
+    }
+    if (n_streams == 0 || n_per_stream == 0) return ES_OK;
+    return es_impl_draw_noisy(ctx, mt_key, mt_pos, has_gauss, gauss, n_streams, n_per_stream, upper_bound, coins_per_eval,
+                              normals_per_eval, scale, idx_out, coin_out, noise_out, (cudaStream_t)stream);
 }
 
 int es_novelty(es_ctx* ctx, const float* behv, int n, const double* archive, int A, int k, double* out, int out_stride,

@@ -80,10 +80,16 @@ int es_impl_obs_colsum(es_ctx*, const float*, int, int, float*, float*, cudaStre
 int es_impl_obstat_accumulate(es_ctx*, double*, double*, const float*, const float*, int, int, cudaStream_t);
 int es_impl_obstat_accumulate_coins(es_ctx*, double*, double*, double*, const float*, const float*, int, int,
                                     const uint32_t*, int, double, cudaStream_t);
+int es_impl_draw_noisy(es_ctx*, uint32_t*, int32_t*, int32_t*, double*, int, int, uint64_t, int, int, double, int64_t*, uint32_t*,
+                       float*, cudaStream_t);
+// (the trailing const float* of the rollouts: scaled action noise [n_pairs][2][T][act], or NULL)
 int es_impl_rollout_f32(es_ctx*, const float*, int64_t, const int64_t*, int, const float*, int, float, const int*, int,
-                        const float*, const float*, int, float, double*, double*, int, float*, float*, cudaStream_t);
+                        const float*, const float*, int, float, double*, double*, int, float*, float*, const float*, cudaStream_t);
+int es_impl_rollout_f32x(es_ctx*, const float*, int64_t, const int64_t*, int, const float*, int, float, const int*, int,
+                         const float*, const float*, int, float, double*, double*, int, float*, float*, const float*, cudaStream_t);
 int es_impl_rollout_tc2(es_ctx*, int split, const float*, int64_t, const int64_t*, int, const float*, int, float, const int*,
-                        int, const float*, const float*, int, float, double*, double*, int, float*, float*, cudaStream_t);
+                        int, const float*, const float*, int, float, double*, double*, int, float*, float*, const float*,
+                        cudaStream_t);
 void es_tc2_free_shadows(es_ctx* ctx);
 int es_impl_novelty(es_ctx*, const float*, int, const double*, int, int, double*, int, cudaStream_t);
 int es_impl_rank_transform(es_ctx*, const double*, const double*, int, int, int, double, double, int, int, int,

@@ -14,6 +14,7 @@
 // Shared-memory layout: weight rows are padded to a pitch with (pitch/4) odd so that the
 // 128-bit reads of 32 different output rows at the same k hit 32 different bank groups;
 // activations for a tile of RF_TM time steps ping-pong between two buffers.
+#include <stdlib.h>
 #include "common.cuh"
 
 constexpr int RF_THREADS = 512;   // 16 warps: the dense tasks keep 8 of them busy, the others hide the load / staging latencies
@@ -109,7 +110,7 @@ rollout_f32_kernel(const float* __restrict__ table, const int64_t* __restrict__ 
                    const float* __restrict__ rew_vec, int T, float pos_scale, double* __restrict__ fit_pos,
                    double* __restrict__ fit_neg, int fit_stride, float* __restrict__ behv_pos,
                    float* __restrict__ behv_neg, double* __restrict__ part, unsigned* __restrict__ tickets,
-                   const float* __restrict__ wglobal) {
+                   const float* __restrict__ wglobal, const float* __restrict__ act_noise) {
     extern __shared__ __align__(16) float smem[];
     float* Wsm = GW ? const_cast<float*>(wglobal) + (size_t)blockIdx.x * d.w_floats : smem;    // [w_floats]
     float* Xa = GW ? smem : smem + d.w_floats;          // [RF_TM][xpitch]
@@ -161,6 +162,16 @@ rollout_f32_kernel(const float* __restrict__ table, const int64_t* __restrict__ 
             float* tmp = xin; xin = xout; xout = tmp;
         }
         // xin now holds the actions [RF_TM][act_dim]
+        if (act_noise) {
+            // a += rs.randn(act) * ac_std (src/nn/nn.py:47-48): the scaled gaussians of this evaluation, drawn in stream order
+            // by mt_gauss.cu; reward and position see the noisy action (the env receives it, gym_runner.py:53)
+            const float* __restrict__ nz = act_noise + ((size_t)blockIdx.x * T + t0) * act_dim;
+            for (int i = threadIdx.x; i < rows * act_dim; i += RF_THREADS) {
+                const int r = i / act_dim, j = i - r * act_dim;
+                xin[r * d.xpitch + j] = __fadd_rn(xin[r * d.xpitch + j], __ldg(nz + i));
+            }
+            __syncthreads();
+        }
         if (threadIdx.x < rows) {
             const int r = threadIdx.x;
             const float* a = xin + r * d.xpitch;
@@ -218,7 +229,15 @@ static int rf_round4(int x) { return (x + 3) & ~3; }
 int es_impl_rollout_f32(es_ctx* ctx, const float* table, int64_t table_len, const int64_t* idx, int n_pairs,
                         const float* theta, int P, float sigma, const int* layer_sizes, int n_layers, const float* obsn,
                         const float* rew_vec, int T, float pos_scale, double* fit_pos, double* fit_neg, int fit_stride,
-                        float* behv_pos, float* behv_neg, cudaStream_t stream) {
+                        float* behv_pos, float* behv_neg, const float* act_noise, cudaStream_t stream) {
+    // obs-64-64-act networks with enough pairs to fill the GPU: the packed-FMA kernel of rollout_f32x.cu (one CTA per pair);
+    // fewer pairs than half the SMs (single evaluations, es.step's noiseless evaluation) stay here, where the episode's time
+    // tiles are split over the idle SMs.  ES_F32_GENERAL=1 forces this kernel (tests compare the two).
+    if (2 * n_pairs >= ctx->sm_count && !getenv("ES_F32_GENERAL")) {
+        const int rc = es_impl_rollout_f32x(ctx, table, table_len, idx, n_pairs, theta, P, sigma, layer_sizes, n_layers, obsn, rew_vec,
+                                            T, pos_scale, fit_pos, fit_neg, fit_stride, behv_pos, behv_neg, act_noise, stream);
+        if (rc != ES_ERR_UNSUPPORTED) return rc;
+    }
     RfDesc d;
     memset(&d, 0, sizeof(d));
     d.n_layers = n_layers;
@@ -288,16 +307,17 @@ int es_impl_rollout_f32(es_ctx* ctx, const float* table, int64_t table_len, cons
         double* fn = fit_neg + (size_t)p0 * fit_stride;
         float* bp = behv_pos ? behv_pos + (size_t)p0 * 3 : nullptr;
         float* bn = behv_neg ? behv_neg + (size_t)p0 * 3 : nullptr;
+        const float* an = act_noise ? act_noise + (size_t)p0 * 2 * T * layer_sizes[n_layers] : nullptr;
         if (gw) {
             rollout_f32_stage_kernel<<<2 * np, RF_THREADS, 0, stream>>>(table, idx + p0, theta, sigma, d, wglobal);
             ES_LAUNCHED(ctx);
             ES_CHECK_CUDA(cudaFuncSetAttribute(rollout_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)act_smem));
             rollout_f32_kernel<true><<<dim3(2 * np, n_splits), RF_THREADS, act_smem, stream>>>(
-                table, idx + p0, theta, sigma, d, obsn, rew_vec, T, pos_scale, fp, fn, fit_stride, bp, bn, part, tickets, wglobal);
+                table, idx + p0, theta, sigma, d, obsn, rew_vec, T, pos_scale, fp, fn, fit_stride, bp, bn, part, tickets, wglobal, an);
         } else {
             ES_CHECK_CUDA(cudaFuncSetAttribute(rollout_f32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
             rollout_f32_kernel<false><<<dim3(2 * np, n_splits), RF_THREADS, smem_w, stream>>>(
-                table, idx + p0, theta, sigma, d, obsn, rew_vec, T, pos_scale, fp, fn, fit_stride, bp, bn, part, tickets, nullptr);
+                table, idx + p0, theta, sigma, d, obsn, rew_vec, T, pos_scale, fp, fn, fit_stride, bp, bn, part, tickets, nullptr, an);
         }
         ES_LAUNCHED(ctx);
     }

@@ -55,6 +55,11 @@
 #include <stdlib.h>
 #include "common.cuh"
 
+#ifndef T2_NEWTON_MASK
+#define T2_NEWTON_MASK 0x0     // of the four value pairs of an 8-column batch: bit e set -> pair e takes the FMA-pipe reciprocal
+                               // (measured, K = 10 000: mask 0x0 2.445 ms, 0x5 2.462, 0x7 2.476, 0xF 2.594 -- see tanh_acc2)
+#endif
+
 namespace {
 
 constexpr int T2_THREADS = 896;
@@ -172,18 +177,34 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 // tanh of two values to float32 accuracy: tanh|x| = (1 - e) / (1 + e), e = 2^(-2 log2(e) |x|) (no cancellation: e in (0, 1]);
 // max abs error 1.4e-7, mean error ~1e-11 (tools/bench_src/tc_micro.cu).  The elementwise arithmetic is packed.
-__device__ __forceinline__ void tanh_acc2(float x0, float x1, float& t0, float& t1) {
+// NEWTON (a compile-time constant after unrolling) = false: 1 / (1 + e) by rcp.approx (2 MUFU per tanh).  NEWTON = true: the reciprocal on the FMA pipe instead
+// (d = 1 + e in (1, 2]: quadratic minimax start, relative error 1.0e-2, two Newton steps -> 1e-8 before rounding; 7 packed
+// FMA-pipe operations for two values).  ncu shows the split kernel at 62 % XU / 30 % FMA pipe utilisation, but moving
+// reciprocals to the FMA pipe made it SLOWER (2.445 ms -> 2.594 ms with every reciprocal moved): the kernel is bound by issue
+// slots and the per-tile dependency chain, not by the XU pipe.  Kept as a compile-time option (T2_NEWTON_MASK), off.
+__device__ __forceinline__ void tanh_acc2(float x0, float x1, float& t0, float& t1, const bool NEWTON) {
     float y0, y1;
     unpk(mul2(pk(x0, x1), pk(2.885390081777927f, 2.885390081777927f)), y0, y1);
     const float e0 = ex2_approx(-fabsf(y0)), e1 = ex2_approx(-fabsf(y1));
     const unsigned long long e = pk(e0, e1), one = pk(1.0f, 1.0f);
-    float d0, d1;
-    unpk(add2(e, one), d0, d1);
+    const unsigned long long d = add2(e, one);
     const unsigned long long num = fma2(e, pk(-1.0f, -1.0f), one);
     float r0, r1;
-    unpk(mul2(num, pk(rcp_approx(d0), rcp_approx(d1))), r0, r1);
-    t0 = __uint_as_float(__float_as_uint(r0) | (__float_as_uint(x0) & 0x80000000u));
-    t1 = __uint_as_float(__float_as_uint(r1) | (__float_as_uint(x1) & 0x80000000u));
+    if (NEWTON) {
+        // s = -1/d: s0 = -(c0 + c1 d + c2 d^2); s <- s + s (1 + d s) twice, the second step folded into the product with num
+        unsigned long long sN = fma2(fma2(pk(-0.32322488f, -0.32322488f), d, pk(1.45451241f, 1.45451241f)), d, pk(-2.12117935f, -2.12117935f));
+        sN = fma2(sN, fma2(d, sN, one), sN);
+        const unsigned long long q = mul2(num, sN);
+        unpk(fma2(q, fma2(d, sN, one), q), r0, r1);            // = -(1 - e) / (1 + e): only the magnitude is used
+        t0 = __uint_as_float((__float_as_uint(r0) & 0x7FFFFFFFu) | (__float_as_uint(x0) & 0x80000000u));
+        t1 = __uint_as_float((__float_as_uint(r1) & 0x7FFFFFFFu) | (__float_as_uint(x1) & 0x80000000u));
+    } else {
+        float d0, d1;
+        unpk(d, d0, d1);
+        unpk(mul2(num, pk(rcp_approx(d0), rcp_approx(d1))), r0, r1);
+        t0 = __uint_as_float(__float_as_uint(r0) | (__float_as_uint(x0) & 0x80000000u));
+        t1 = __uint_as_float(__float_as_uint(r1) | (__float_as_uint(x1) & 0x80000000u));
+    }
 }
 // two float32 -> packed float16x2 (element 0 in the low half)
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
@@ -269,6 +290,7 @@ struct T2Params {
     const uint8_t* xnt;           // [n_mtiles][nkc][pieces][16 KB stage image]
     const float* ubase;           // float4 [n_mtiles][2 halves][8 chunks][128 rows]
     const float* crt;             // reward vectors transposed per tile: [n_mtiles][32 cols][128 rows]
+    const float* act_noise;       // [n_pairs][2][T][act] scaled action noise (mt_gauss.cu) or NULL
     uint8_t* images;              // [gridDim.x][2][image bytes]
     double* fit_pos;
     double* fit_neg;
@@ -565,7 +587,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
                             const float u0 = (e & 1) ? u4.z : u4.x, u1 = (e & 1) ? u4.w : u4.y;
                             float z0, z1, t0, t1;
                             unpk(fma2(pk(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), s2, pk(u0, u1)), z0, z1);
-                            if (SPLIT) { tanh_acc2(z0, z1, t0, t1); split_h2(t0, t1, whi[e], wlo[e]); }
+                            if (SPLIT) { tanh_acc2(z0, z1, t0, t1, (T2_NEWTON_MASK >> e) & 1); split_h2(t0, t1, whi[e], wlo[e]); }
                             else { whi[e] = pack_h2(tanh_fast(z0), tanh_fast(z1)); }
                         }
                         const uint32_t hc = tb + (sgn ? C::C_HN : C::C_HP) + cq * (CW / 2) + c4 * 4;
@@ -599,7 +621,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
                         for (int e = 0; e < 4; ++e) {
                             float z0, z1, t0, t1;
                             unpk(add2(pk(__uint_as_float(d[2 * e]), __uint_as_float(d[2 * e + 1])), pk(bs[2 * e], bs[2 * e + 1])), z0, z1);
-                            if (SPLIT) { tanh_acc2(z0, z1, t0, t1); split_h2(t0, t1, whi[e], wlo[e]); }
+                            if (SPLIT) { tanh_acc2(z0, z1, t0, t1, (T2_NEWTON_MASK >> e) & 1); split_h2(t0, t1, whi[e], wlo[e]); }
                             else { whi[e] = pack_h2(tanh_fast(z0), tanh_fast(z1)); }
                         }
                         const uint32_t hc = tb + (sgn ? C::C_HN : C::C_HP) + cq * (CW / 2) + c4 * 4;
@@ -616,6 +638,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
                 float cc[16];
 #pragma unroll
                 for (int jj = 0; jj < 16; ++jj) cc[jj] = (jj < nj) ? ldg_pinned(ccol + jj * T2_MT) : 0.f;
+                // this row's action noise of the + evaluation, columns a_lo.. (the - evaluation: T * act further)
+                const float* nzrow = (p.act_noise && t < p.T)
+                    ? p.act_noise + (((size_t)(blockIdx.x + i * gridDim.x) * 2) * p.T + t) * p.act + a_lo : nullptr;
                 float tv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int sgn = 0; sgn < 2; ++sgn) {
@@ -639,8 +664,16 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
                                         const float z0 = __uint_as_float(d[g4 * 4 + 0]) + bb.x, z1 = __uint_as_float(d[g4 * 4 + 1]) + bb.y;
                                         const float z2 = __uint_as_float(d[g4 * 4 + 2]) + bb.z, z3 = __uint_as_float(d[g4 * 4 + 3]) + bb.w;
                                         float a0, a1, a2, a3;
-                                        if (SPLIT) { tanh_acc2(z0, z1, a0, a1); tanh_acc2(z2, z3, a2, a3); }
+                                        if (SPLIT) { tanh_acc2(z0, z1, a0, a1, (T2_NEWTON_MASK >> 0) & 1); tanh_acc2(z2, z3, a2, a3, (T2_NEWTON_MASK >> 1) & 1); }
                                         else { a0 = tanh_fast(z0); a1 = tanh_fast(z1); a2 = tanh_fast(z2); a3 = tanh_fast(z3); }
+                                        if (nzrow) {              // a += rs.randn(act) * ac_std (src/nn/nn.py:47-48), drawn by mt_gauss.cu
+                                            const float* nq = nzrow + (size_t)sgn * p.T * p.act + gq * 4;
+                                            const int left = nj - gq * 4;
+                                            a0 += ldg_stream(nq);
+                                            if (left > 1) a1 += ldg_stream(nq + 1);
+                                            if (left > 2) a2 += ldg_stream(nq + 2);
+                                            if (left > 3) a3 += ldg_stream(nq + 3);
+                                        }
                                         r = fmaf(a0, cc[gq * 4 + 0], r);
                                         r = fmaf(a1, cc[gq * 4 + 1], r);
                                         r = fmaf(a2, cc[gq * 4 + 2], r);
@@ -1023,7 +1056,7 @@ void es_tc2_free_shadows(es_ctx* ctx) {
 int es_impl_rollout_tc2(es_ctx* ctx, int split, const float* table, int64_t table_len, const int64_t* idx, int n_pairs,
                         const float* theta, int P, float sigma, const int* layer_sizes, int n_layers, const float* obsn,
                         const float* rew_vec, int T, float pos_scale, double* fit_pos, double* fit_neg, int fit_stride,
-                        float* behv_pos, float* behv_neg, cudaStream_t stream) {
+                        float* behv_pos, float* behv_neg, const float* act_noise, cudaStream_t stream) {
     if (n_layers != 3 || layer_sizes[1] != T2_H || layer_sizes[2] != T2_H || layer_sizes[3] > T2_ACT_PAD || layer_sizes[0] > 1023) {
         es_set_error("es_rollout_openloop(TC): the tensor-core path covers obs(<=1023)-64-64-act(<=32) tanh MLPs; "
                      "use ES_ROLLOUT_F32 for other shapes");
@@ -1031,7 +1064,7 @@ int es_impl_rollout_tc2(es_ctx* ctx, int split, const float* table, int64_t tabl
     }
     T2Params p;
     memset(&p, 0, sizeof(p));
-    p.table = table; p.idx = idx; p.theta = theta;
+    p.table = table; p.idx = idx; p.theta = theta; p.act_noise = act_noise;
     p.fit_pos = fit_pos; p.fit_neg = fit_neg; p.behv_pos = behv_pos; p.behv_neg = behv_neg;
     p.n_pairs = n_pairs; p.obs = layer_sizes[0]; p.act = layer_sizes[3]; p.T = T; p.fit_stride = fit_stride;
     p.sigma = sigma; p.pos_scale = pos_scale;

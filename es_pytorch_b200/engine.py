@@ -164,6 +164,34 @@ class Engine:
         check(self.lib.es_mt_skip(self._ctx, _ptr(mt_key), _ptr(mt_pos), mt_key.shape[0], int(n_words), self.stream),
               'es_mt_skip')
 
+    def draw_noisy(self, mt_key, mt_pos, has_gauss, gauss, n_per_stream: int, upper_bound: int, coins_per_eval: int,
+                   normals_per_eval: int, scale: float, idx_out=None, coin_out=None, noise_out=None):
+        """All draws of a generation whose policy adds action noise, in the reference's stream order (es_draw_noisy):
+        per pair randint, then per evaluation ``coins_per_eval`` doubles and ``normals_per_eval`` legacy gaussians.
+        has_gauss int32 [R] / gauss float64 [R] are the streams' cached-gaussian state, updated in place.  Returns
+        (idx int64 [R*n], coin words int32 [R*n, 4*coins] or None, noise float32 [R*n, 2, normals_per_eval])."""
+        d = self.device
+        R = mt_key.shape[0]
+        _req(mt_key, torch.int32, 'mt_key', d); _req(mt_pos, torch.int32, 'mt_pos', d)
+        _req(has_gauss, torch.int32, 'has_gauss', d); _req(gauss, torch.float64, 'gauss', d)
+        assert mt_key.shape == (R, ES_MT_N) and mt_pos.numel() == R and has_gauss.numel() == R and gauss.numel() == R
+        n = R * n_per_stream
+        if idx_out is None:
+            idx_out = self.empty((n,), torch.int64)
+        if coins_per_eval and coin_out is None:
+            coin_out = self.empty((n, 4 * coins_per_eval), torch.int32)
+        if noise_out is None:
+            noise_out = self.empty((n, 2, normals_per_eval), torch.float32)
+        _req(idx_out, torch.int64, 'idx_out', d); _req(noise_out, torch.float32, 'noise_out', d)
+        assert idx_out.numel() == n and noise_out.numel() == n * 2 * normals_per_eval
+        if coin_out is not None:
+            _req(coin_out, torch.int32, 'coin_out', d)
+            assert coin_out.numel() == n * 4 * coins_per_eval
+        check(self.lib.es_draw_noisy(self._ctx, _ptr(mt_key), _ptr(mt_pos), _ptr(has_gauss), _ptr(gauss), R, int(n_per_stream),
+                                     int(upper_bound), int(coins_per_eval), int(normals_per_eval), float(scale), _ptr(idx_out),
+                                     _ptr(coin_out), _ptr(noise_out), self.stream), 'es_draw_noisy')
+        return idx_out, coin_out, noise_out
+
     # ------------------------------------------------------------------ a3
     def perturb(self, theta, table, idx, sigma: float, want_neg: bool = True):
         d = self.device
@@ -218,7 +246,9 @@ class Engine:
 
     # ------------------------------------------------------------------ a3+a4+a5
     def rollout(self, table, idx, theta, sigma: float, layer_sizes: Sequence[int], obsn, rew_vec, pos_scale: float,
-                fit_pos, fit_neg, fit_stride: int = 1, behv_pos=None, behv_neg=None, mode: int = ES_ROLLOUT_F32):
+                fit_pos, fit_neg, fit_stride: int = 1, behv_pos=None, behv_neg=None, mode: int = ES_ROLLOUT_F32,
+                act_noise=None):
+        """``act_noise``: float32 [n_pairs, 2, T, act] scaled action noise (``draw_noisy``), added to every action."""
         d = self.device
         _req(table, torch.float32, 'table', d); _req(idx, torch.int64, 'idx', d); _req(theta, torch.float32, 'theta', d)
         _req(obsn, torch.float32, 'obsn', d); _req(rew_vec, torch.float32, 'rew_vec', d)
@@ -230,6 +260,9 @@ class Engine:
         if behv_pos is not None:
             _req(behv_pos, torch.float32, 'behv_pos', d); _req(behv_neg, torch.float32, 'behv_neg', d)
             assert behv_pos.numel() == 3 * n and behv_neg.numel() == 3 * n
+        if act_noise is not None:
+            _req(act_noise, torch.float32, 'act_noise', d)
+            assert act_noise.numel() == n * 2 * T * layer_sizes[-1]
         ls = (C.c_int * len(layer_sizes))(*[int(x) for x in layer_sizes])
         if mode in (ES_ROLLOUT_TC, ES_ROLLOUT_TC3):
             # the library keeps a bf16 shadow of the table keyed by (pointer, length); a different tensor object (the
@@ -238,11 +271,11 @@ class Engine:
             if ref is None or ref() is not table or ver != table._version:
                 check(self.lib.es_noise_table_changed(self._ctx), 'es_noise_table_changed')
                 self._tc_table = (weakref.ref(table), table._version)
-        check(self.lib.es_rollout_openloop(self._ctx, _ptr(table), table.numel(), _ptr(idx), n, _ptr(theta),
-                                           theta.numel(), float(sigma), ls, len(layer_sizes) - 1, _ptr(obsn),
-                                           _ptr(rew_vec), T, float(pos_scale), _ptr(fit_pos), _ptr(fit_neg),
-                                           int(fit_stride), _ptr(behv_pos), _ptr(behv_neg), int(mode), self.stream),
-              'es_rollout_openloop')
+        check(self.lib.es_rollout_openloop_noisy(self._ctx, _ptr(table), table.numel(), _ptr(idx), n, _ptr(theta),
+                                                 theta.numel(), float(sigma), ls, len(layer_sizes) - 1, _ptr(obsn),
+                                                 _ptr(rew_vec), T, float(pos_scale), _ptr(fit_pos), _ptr(fit_neg),
+                                                 int(fit_stride), _ptr(behv_pos), _ptr(behv_neg), _ptr(act_noise), int(mode),
+                                                 self.stream), 'es_rollout_openloop')
 
     # ------------------------------------------------------------------ a13
     def novelty(self, behv, archive, k: int, out, out_stride: int = 1):

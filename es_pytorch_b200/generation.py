@@ -71,7 +71,7 @@ class DeviceGeneration:
                  optim: Optimizer, ob_clip: float = 5.0, pos_scale: float = 0.05, coins_per_eval: int = 0,
                  save_obs_chance: float = 0.0, archive: Optional[torch.Tensor] = None, nov_k: int = 10,
                  moo_w: float = 1.0, rollout_mode: int = ES_ROLLOUT_F32, comm: Optional[dist.Comm] = None,
-                 engine: Optional[Engine] = None, ranker=None):
+                 engine: Optional[Engine] = None, ranker=None, ac_std: float = 0.0):
         self.eng = engine or get_engine()
         self.ranker = ranker                            # a utils.rankers.Ranker; None = Centered / MultiObjective(moo_w)
         e = self.eng
@@ -91,6 +91,9 @@ class DeviceGeneration:
         self.archive, self.nov_k, self.moo_w = archive, int(nov_k), float(moo_w)
         self.n_obj = 1 if archive is None else 2
         self.rollout_mode = rollout_mode
+        # FeedForward._action_std (nn.py:47-48): != 0 -> every step adds rs.randn(act) * ac_std, drawn from the rank streams
+        self.ac_std = float(ac_std or 0.0)
+        self.act_noise = None
         assert self.coins_per_eval in (0, 1), 'fit_fns draw at most one save_obs coin per evaluation'
 
         # per-rank MT19937 streams, resident on the device between generations
@@ -98,10 +101,16 @@ class DeviceGeneration:
         self._gauss = [(s.get_state()[3], s.get_state()[4]) for s in rank_states]
         key = np.stack([s.get_state()[1].astype(np.uint32) for s in rank_states]).view(np.int32)
         pos = np.array([s.get_state()[2] for s in rank_states], dtype=np.int32)
-        # keys and positions in one buffer (one download brings both back): [R*624 key words | R positions]
-        self.mt_state = e.to_device(np.concatenate((key.reshape(-1), pos)))
-        self.mt_key = self.mt_state[:self.n_streams * ES_MT_N].view(self.n_streams, ES_MT_N)
-        self.mt_pos = self.mt_state[self.n_streams * ES_MT_N:]
+        # the whole stream state in one buffer (one download brings everything back):
+        # [R*624 key words | R positions | R has_gauss | R cached gaussians (float64 = 2 words each)]
+        R = self.n_streams
+        has = np.array([g[0] for g in self._gauss], dtype=np.int32)
+        gv = np.array([g[1] for g in self._gauss], dtype=np.float64).view(np.int32)
+        self.mt_state = e.to_device(np.concatenate((key.reshape(-1), pos, has, gv)))
+        self.mt_key = self.mt_state[:R * ES_MT_N].view(R, ES_MT_N)
+        self.mt_pos = self.mt_state[R * ES_MT_N:R * ES_MT_N + R]
+        self.mt_has = self.mt_state[R * ES_MT_N + R:R * ES_MT_N + 2 * R]
+        self.mt_gauss = self.mt_state[R * ES_MT_N + 2 * R:].view(torch.float64)       # byte offset 2504 R: 8-byte aligned
 
         f32, f64 = torch.float32, torch.float64
         self.gsum = e.empty((self.P,), f32)
@@ -163,14 +172,23 @@ class DeviceGeneration:
         self._ensure_buffers(n_per_stream)
         self.version += 1
         with self._timed('draw_indices'):
-            e.draw_indices(self.mt_key, self.mt_pos, n_per_stream, self.table.numel() - self.P, self.extra_words,
-                           self.idx, self.extras)
+            if self.ac_std != 0.0:
+                # indices, coins and the action noise of every rollout, in the reference's stream order (mt_gauss.cu)
+                nrm = self.T * self.act_dim
+                if self.act_noise is None or self.act_noise.shape != (self.k_local, 2, nrm):
+                    self.act_noise = e.empty((self.k_local, 2, nrm), torch.float32)
+                e.draw_noisy(self.mt_key, self.mt_pos, self.mt_has, self.mt_gauss, n_per_stream, self.table.numel() - self.P,
+                             self.coins_per_eval, nrm, self.ac_std, self.idx, self.extras, self.act_noise)
+            else:
+                e.draw_indices(self.mt_key, self.mt_pos, n_per_stream, self.table.numel() - self.P, self.extra_words,
+                               self.idx, self.extras)
         e.normalise_obs(self.obs_stream[:self.T], self.ob_mean, self.ob_std, self.ob_clip, self.obsn)
         fp, fn = self.fit_local[0], self.fit_local[1]
         with self._timed('rollout'):
             e.rollout(self.table, self.idx, self.theta, self.sigma, self.layer_sizes, self.obsn, self.rew_vec,
                       self.pos_scale, fp, fn, self.n_obj, None if self.behv is None else self.behv[0],
-                      None if self.behv is None else self.behv[1], self.rollout_mode)
+                      None if self.behv is None else self.behv[1], self.rollout_mode,
+                      act_noise=self.act_noise if self.ac_std != 0.0 else None)
         if self.n_obj == 2:
             # second objective column = novelty of the final (x, y) (training_result.py:95-97)
             e.novelty(self.behv.view(-1, 3), self.archive, self.nov_k, self.fit_local.view(-1)[1:], 2)
@@ -269,7 +287,7 @@ class DeviceGeneration:
     def load_states(self, rank_states: Sequence[np.random.RandomState]):
         """Upload the callers' RandomState streams if they moved on the host since store_states wrote them."""
         assert len(rank_states) == self.n_streams
-        views = self._views(rank_states)
+        views = None if self.ac_std != 0.0 else self._views(rank_states)     # action noise: the gaussian cache travels too
         if views is not None:
             key = np.empty((self.n_streams, ES_MT_N), dtype=np.uint32)
             pos = np.empty(self.n_streams, dtype=np.int32)
@@ -282,19 +300,34 @@ class DeviceGeneration:
             key = np.stack([st[1] for st in states]).astype(np.uint32, copy=False)
             pos = np.array([st[2] for st in states], dtype=np.int32)
         hs = self._host_states
-        if hs is not None and np.array_equal(hs[1], pos) and np.array_equal(hs[0], key):
+        gs = None
+        if views is None:
+            gs = (np.array([g[0] for g in self._gauss], dtype=np.int32), np.array([g[1] for g in self._gauss], dtype=np.float64))
+        if hs is not None and np.array_equal(hs[1], pos) and np.array_equal(hs[0], key) and \
+                (gs is None or (hs[2] is not None and np.array_equal(hs[2][0], gs[0]) and np.array_equal(hs[2][1], gs[1]))):
             return                                  # the device already holds exactly these streams
         self._host_states = None
         self.eng.upload_async(self.mt_key, key.view(np.int32), ('mtkey', id(self)))
         self.eng.upload_async(self.mt_pos, pos, ('mtpos', id(self)))
+        if gs is not None:
+            self.eng.upload_async(self.mt_has, gs[0], ('mthas', id(self)))
+            self.eng.upload_async(self.mt_gauss, gs[1], ('mtgauss', id(self)))
 
-    def store_states(self, rank_states: Sequence[np.random.RandomState], key=None, pos=None):
+    def store_states(self, rank_states: Sequence[np.random.RandomState], key=None, pos=None, gauss=None):
         """Write the advanced streams back into the callers' RandomState objects (``key``/``pos``: already
-        downloaded host copies; otherwise this synchronises)."""
+        downloaded host copies; otherwise this synchronises).  ``gauss`` = (has_gauss int32 [R], cached float64 [R]) host
+        copies, used (and downloaded when missing) only when the generation drew action noise."""
         key = (self.eng.to_host(self.mt_key) if key is None else key).view(np.uint32)
         pos = self.eng.to_host(self.mt_pos) if pos is None else pos
-        self._host_states = (np.array(key, dtype=np.uint32, copy=True), np.array(pos, dtype=np.int32, copy=True))
-        views = self._views(rank_states)
+        if self.ac_std != 0.0:
+            if gauss is None:
+                gauss = (self.eng.to_host(self.mt_has), self.eng.to_host(self.mt_gauss))
+            self._gauss = [(int(h), float(g)) for h, g in zip(gauss[0], gauss[1])]
+            gauss = (np.array(gauss[0], dtype=np.int32, copy=True), np.array(gauss[1], dtype=np.float64, copy=True))
+        else:
+            gauss = None
+        self._host_states = (np.array(key, dtype=np.uint32, copy=True), np.array(pos, dtype=np.int32, copy=True), gauss)
+        views = None if self.ac_std != 0.0 else self._views(rank_states)
         if views is not None:
             for r, (k, p) in enumerate(views):                       # the gaussian cache of the stream is left as it is
                 k[:] = key[r]
@@ -307,6 +340,8 @@ class DeviceGeneration:
         """Download the MT19937 streams back into numpy RandomState objects (synchronises)."""
         key = self.mt_key.cpu().numpy().view(np.uint32)
         pos = self.mt_pos.cpu().numpy()
+        if self.ac_std != 0.0:
+            self._gauss = [(int(h), float(g)) for h, g in zip(self.mt_has.cpu().numpy(), self.mt_gauss.cpu().numpy())]
         out = []
         for r in range(self.n_streams):
             rs = np.random.RandomState()

@@ -55,15 +55,17 @@ class BatchedRollout:
         return NSRResult(rews, behv[-3:], no_obs, steps, self.archive, self.nov_k)
 
     def __call__(self, model, use_ac_noise=True) -> TrainingResult:
-        """Single-policy evaluation with the reference's fit_fn contract (no action noise).  Like the scripts' fit_fn
-        (simple_example.py:38, obj.py:54) it first draws the save_obs coin(s) -- from every stream this process carries:
-        each stream is one reference rank, and every rank runs its own noiseless evaluation (es.py:48)."""
+        """Single-policy evaluation with the reference's fit_fn contract.  Like the scripts' fit_fn (simple_example.py:38,
+        obj.py:54) it first draws the save_obs coin(s) -- from every stream this process carries: each stream is one
+        reference rank, and every rank runs its own noiseless evaluation (es.py:48).  ``use_ac_noise`` (obj.py:53-55): the
+        rollout draws the policy's action noise from the first stream; es.step's noiseless call passes False."""
         streams = self.rank_streams if self.rank_streams is not None else self._streams_in_use
         if streams is not None:
             for rs in streams:
                 for _ in range(self.coins_per_eval):
                     rs.random()
-        rews, behv, obs, steps = run_model(model, self.env, self.max_steps, None)
+        noise_rs = streams[0] if (use_ac_noise and streams is not None and len(streams)) else None
+        rews, behv, obs, steps = run_model(model, self.env, self.max_steps, noise_rs)
         no_obs = np.array([np.zeros(self.env.observation_space.shape)])
         if self.archive is None:
             return RewardResult(rews, behv, no_obs, steps)

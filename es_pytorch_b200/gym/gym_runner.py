@@ -1,10 +1,11 @@
 """Rollout runner (mirror of src/gym/gym_runner.py:33-67).
 
 ``run_model`` keeps the reference signature.  When the env is the synthetic open-loop env
-and the model is a tanh ``FeedForward`` without action noise, the whole episode is ONE
-launch of the fused rollout kernel (per-policy compatibility path: theta' is the module's
-current weights, sigma = 0); any other env is stepped in the reference's python loop with
-the module's own forward.
+and the model is a tanh ``FeedForward``, the whole episode is ONE launch of the fused rollout
+kernel (per-policy compatibility path: theta' is the module's current weights, sigma = 0;
+action noise, nn.py:47-48, is drawn from ``rs`` for the whole episode at once and added on
+the device); any other env is stepped in the reference's python loop with the module's own
+forward.
 """
 from __future__ import annotations
 
@@ -23,7 +24,7 @@ def pybullet_gym_pos(env):
     return env.robot.robot_body.pose().xyz()
 
 
-def _device_episode(model, env, max_steps: int):
+def _device_episode(model, env, max_steps: int, rs=None):
     from ..engine import get_engine
     from ..core.policy import Policy
     eng = get_engine()
@@ -39,8 +40,16 @@ def _device_episode(model, env, max_steps: int):
     idx = torch.zeros(1, dtype=torch.int64, device=eng.device)
     fit = torch.zeros(2, dtype=torch.float64, device=eng.device)
     behv = torch.zeros(2, 3, dtype=torch.float32, device=eng.device)
+    noise = None
+    ac_std = float(getattr(model, '_action_std', 0) or 0)
+    if rs is not None and ac_std != 0:
+        # nn.py:47-48: T calls of rs.randn(act) * ac_std; one call of rs.randn(T * act) consumes the stream identically
+        # (legacy gaussians are produced one by one, cached second value included).  [pair 0][+ | -][T][act]: both
+        # evaluations of the sigma = 0 "pair" see the same noise, only the first is used.
+        nz = (rs.randn(T * sizes[-1]) * ac_std).astype(np.float32)
+        noise = eng.to_device(np.stack([nz, nz]).reshape(1, 2, -1))
     eng.rollout(table, idx, theta, 0.0, sizes, obsn, rew_dev[:T].contiguous(), env.pos_scale, fit[0:1], fit[1:2], 1,
-                behv[0:1].view(-1), behv[1:2].view(-1))
+                behv[0:1].view(-1), behv[1:2].view(-1), act_noise=noise)
     return float(fit[0].item()), behv[0].cpu().numpy().astype(np.float64), T
 
 
@@ -48,9 +57,9 @@ def run_model(model: torch.nn.Module, env, max_steps: int, rs: np.random.RandomS
               get_pos_fn: Callable = pybullet_gym_pos) -> Tuple[List[float], List[float], np.ndarray, int]:
     """(rewards, positions padded to max_steps triples, post-step observations, last loop index)."""
     fused = (getattr(env, 'is_synthetic_openloop', False) and hasattr(model, 'is_tanh_mlp') and model.is_tanh_mlp()
-             and (rs is None or getattr(model, '_action_std', 0) == 0) and not render)
+             and not render)
     if fused:
-        total, pos, T = _device_episode(model, env, max_steps)
+        total, pos, T = _device_episode(model, env, max_steps, rs)
         # the episode total is exact; it is reported as a one-element reward list so that
         # sum(rews) (training_result.py:28) reproduces it bit for bit
         rews = [total]

@@ -110,6 +110,30 @@ int es_rollout_openloop(es_ctx* ctx, const float* table, int64_t table_len, cons
                         double* fit_pos, double* fit_neg, int fit_stride, float* behv_pos, float* behv_neg,
                         int mode, void* stream);
 
+/* The same with action noise: act_noise dev float [n_pairs][2 (+,-)][T][act_dim] (or NULL = es_rollout_openloop) is added to
+ * the action of every step before the env sees it -- FeedForward.forward's `a += rs.randn(*a.shape) * self._action_std`
+ * (src/nn/nn.py:47-48); reward and position are computed from the noisy action (src/gym/gym_runner.py:52-53).  The array is
+ * what es_draw_noisy wrote for the same pairs.                                                                        */
+int es_rollout_openloop_noisy(es_ctx* ctx, const float* table, int64_t table_len, const int64_t* idx, int n_pairs,
+                              const float* theta, int P, float sigma, const int* layer_sizes, int n_layers,
+                              const float* obsn, const float* rew_vec, int T, float pos_scale,
+                              double* fit_pos, double* fit_neg, int fit_stride, float* behv_pos, float* behv_neg,
+                              const float* act_noise, int mode, void* stream);
+
+/* ---- a2 + a4 with action noise: all draws of a generation in stream order ---------------------------------------------
+ * When FeedForward._action_std != 0 every step of every rollout draws rs.randn(act_dim) from the SAME RandomState that
+ * draws the noise indices and the save_obs coins (src/nn/nn.py:47-48, src/core/es.py:66-72, simple_example.py:37-40).  Per
+ * stream and pair, in the reference's order: randint (as es_draw_indices); then for the + and the - evaluation:
+ * coins_per_eval doubles (2 words each), then normals_per_eval (= steps x act_dim) legacy polar-method gaussians
+ * (numpy legacy_gauss, including the cached second value across calls).  The word stream is reproduced exactly (indices,
+ * coin words, final key / position / has_gauss bit-exact; the cached gaussian to <= 1 ulp of float64, log() being CUDA's).
+ *   has_gauss dev int32 [n_streams], gauss dev double [n_streams]   in/out  (RandomState.get_state()[3], [4])
+ *   coin_out  dev uint32 [n_streams*n_per_stream][4*coins_per_eval]  (+ coins then - coins) or NULL when coins_per_eval == 0
+ *   noise_out dev float [n_streams*n_per_stream][2][normals_per_eval] = float32(gaussian * scale), scale = ac_std          */
+int es_draw_noisy(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int32_t* has_gauss, double* gauss, int n_streams,
+                  int n_per_stream, uint64_t upper_bound, int coins_per_eval, int normals_per_eval, double scale,
+                  int64_t* idx_out, uint32_t* coin_out, float* noise_out, void* stream);
+
 /* The tensor-core rollouts keep float16 shadows of the noise table (8 shifted copies of f16(table), 2 bytes x 8 x table_len
  * of HBM; ES_ROLLOUT_TC3 a second set for the low-order parts), built on first use and keyed by the table's device pointer,
  * its length and the policy's obs_dim.  The reference never writes to its table after NoiseTable.create_shared

@@ -550,3 +550,66 @@ print('STEP_OK')
     env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.path.join(root, 'es_pytorch_b200', 'compat'))
     out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0 and 'STEP_OK' in out.stdout, (out.stdout + out.stderr)[-3000:]
+
+
+@pytest.mark.parametrize('mode', [0, 2])
+def test_api_action_noise_generation_matches_the_real_reference(eng, mode):
+    """ac_std = 0.01 (configs/simple_conf.json:14, obj.json:18, nsra.json:17) through the reference-facing API, against the
+    REAL reference's test_params -> rank -> approx_grad with a noisy FeedForward (tests/golden/ref_step.npz, `acn_*`,
+    generated by make_ref_step.py): FeedForward.forward draws rs.randn(act) at every step from the stream that also draws
+    the indices and the coins (nn.py:47-48).  On the device that is es_draw_noisy + es_rollout_openloop_noisy: indices,
+    obs statistics and the caller's RandomState afterwards (key, position, has_gauss) are exact, the cached gaussian to an
+    ulp, fitness to float32 tolerance, rank weights equal, theta within 3e-6."""
+    from es_pytorch_b200 import dist
+    from es_pytorch_b200.core import es
+    from es_pytorch_b200.gym.batched import BatchedRollout
+    from es_pytorch_b200.nn.obstat import ObStat
+    from es_pytorch_b200.utils.rankers import CenteredRanker
+    v = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_step.npz'))
+    obs_dim, act_dim, T, n_pairs = [int(x) for x in v['cfg']]
+    table = np.random.RandomState(int(v['table_seed'])).randn(int(v['table_len'])).astype(np.float32)
+    spec = orc.SyntheticEnvSpec(obs_dim, act_dim, T)
+    env, net, policy, nt = _api_objects(eng, table, v['theta0'].copy(), spec, tuple(int(h) for h in v['hidden']))
+    net._action_std = float(v['acn_std'])
+    rs = np.random.RandomState(int(v['acn_seed']))
+    fit_fn = BatchedRollout(env, T, coins_per_eval=1, save_obs_chance=float(v['save_obs_chance']), rollout_mode=mode)
+    gen_obstat = ObStat(env.observation_space.shape, 0)
+    pos, neg, inds, steps = es.test_params(dist.world(), n_pairs, policy, nt, gen_obstat, fit_fn, rs)
+    assert np.array_equal(inds, v['acn_inds'])
+    st = rs.get_state()
+    assert np.array_equal(st[1], v['acn_rs_key']) and st[2] == int(v['acn_rs_pos']) and st[3] == int(v['acn_rs_has_gauss'])
+    assert abs(st[4] - float(v['acn_rs_gauss'])) <= 2 * np.spacing(abs(float(v['acn_rs_gauss'])))
+    tol = 2e-5 if mode == 0 else 6e-5
+    assert np.abs(pos - v['acn_pos']).max() <= tol and np.abs(neg - v['acn_neg']).max() <= tol
+    assert np.array_equal(gen_obstat.sum, v['acn_ob_sum']) and gen_obstat.count == float(v['acn_ob_count'])
+    ranker = CenteredRanker()
+    ranker.rank(pos, neg, inds)
+    assert np.array_equal(np.asarray(ranker.ranked_fits).ravel(), v['acn_w'].ravel())
+    es.approx_grad(policy, ranker, nt, policy.flat_params, 500, 0.005)
+    assert np.abs(policy.flat_params - v['acn_theta']).max() <= 3e-6
+
+
+def test_run_model_with_action_noise_stays_on_the_device(eng):
+    """The per-policy route (an opaque fit_fn calling gym_runner.run_model with the rank's stream, simple_example.py:37-40)
+    with ac_std != 0: the episode is still one fused launch -- the T x act gaussians are drawn from the caller's
+    RandomState in one call (same stream consumption as T calls of rs.randn(act)) -- and equals the oracle's step loop."""
+    from es_pytorch_b200.gym.gym_runner import run_model
+    obs_dim, act_dim, T = 17, 6, 60
+    spec = orc.SyntheticEnvSpec(obs_dim, act_dim, T)
+    dims = orc.layer_dims(obs_dim, (64, 64), act_dim)
+    theta = (np.random.RandomState(2).randn(orc.n_params(dims)) * 0.1).astype(np.float32)
+    table = np.zeros(orc.n_params(dims) + 8, dtype=np.float32)
+    env, net, policy, nt = _api_objects(eng, table, theta, spec, (64, 64))
+    net._action_std = 0.01
+    a, b = np.random.RandomState(77), np.random.RandomState(77)
+    a.randn(1)
+    b.randn(1)                                              # both start with a cached gaussian
+    launches = eng.launches
+    rews, behv, obs, step = run_model(policy.pheno(np.zeros(len(policy))), env, T, a)
+    assert eng.launches - launches <= 4, 'one normalise + rollout launches, not a step loop'
+    rr, bb, _, st = orc.run_model(spec, orc.unflatten(theta, dims), np.zeros(obs_dim), np.ones(obs_dim), 5.0, T, batched=False,
+                                  ac_std=0.01, rs=b)
+    assert step == st and abs(sum(rews) - sum(rr)) <= 1e-5 * max(1.0, np.abs(rr).sum())
+    assert np.allclose(behv[-3:], bb[-3:], rtol=1e-4, atol=1e-5)
+    sa, sb = a.get_state(), b.get_state()
+    assert np.array_equal(sa[1], sb[1]) and sa[2:] == sb[2:]

@@ -52,6 +52,95 @@ def test_draw_indices_streams_continue(eng, extra):
     assert pos.cpu().numpy().tolist() == [s.get_state()[2] for s in streams]
 
 
+@pytest.mark.parametrize('N,coins', [(7, 1), (96, 1), (3001, 0), (6000, 1)])
+def test_draw_noisy_matches_numpy_stream(eng, N, coins):
+    """es_draw_noisy against numpy's legacy RandomState in the reference's program order (es.py:66-72 with the fit_fn of
+    simple_example.py:37-40 and nn.py:47-48): per pair randint, then per evaluation the coin and N gaussians.  Indices,
+    coin words and the stream state (key, position, has_gauss) are bit-exact -- over two consecutive generations, from
+    streams that start with and without a cached gaussian, for odd and even N (the cached value crosses evaluations, pairs
+    and generations) --; the gaussians agree to the last bit of float32 (CUDA's log vs glibc's: <= 1 ulp of float64)."""
+    R, n, ub, scale = 3, 5, 250_000_000 - 29393, 0.01
+    streams = [np.random.RandomState(4000 + r) for r in range(R)]
+    streams[1].randn(3)                                    # leaves a cached gaussian
+    streams[2].randint(0, 1000, size=700)                  # mid-block position
+    st = [s.get_state() for s in streams]
+    key = dev(eng, np.stack([x[1].astype(np.uint32) for x in st]).view(np.int32))
+    pos = dev(eng, np.array([x[2] for x in st], dtype=np.int32))
+    has = dev(eng, np.array([x[3] for x in st], dtype=np.int32))
+    gau = dev(eng, np.array([x[4] for x in st], dtype=np.float64))
+    for gen in range(2):
+        idx, coin, noise = eng.draw_noisy(key, pos, has, gau, n, ub, coins, N, scale)
+        eng.sync()
+        ref_idx, ref_coin, ref_noise = [], [], []
+        for s in streams:
+            for _ in range(n):
+                ref_idx.append(int(s.randint(0, ub)))
+                words = []
+                for _sgn in range(2):
+                    words += [int.from_bytes(s.bytes(4), 'little') for _ in range(2 * coins)]
+                    ref_noise.append((s.randn(N) * scale).astype(np.float32))
+                ref_coin.append(words)
+        assert np.array_equal(idx.cpu().numpy(), np.array(ref_idx))
+        if coins:
+            assert np.array_equal(coin.cpu().numpy().view(np.uint32), np.array(ref_coin, dtype=np.uint32))
+        got, want = noise.cpu().numpy().reshape(-1, N), np.stack(ref_noise)
+        assert np.abs(got - want).max() <= np.spacing(np.float32(np.abs(want).max())), np.abs(got - want).max()
+        assert (got == want).mean() > 0.9999
+        ref_st = [s.get_state() for s in streams]
+        assert np.array_equal(key.cpu().numpy().view(np.uint32), np.stack([x[1] for x in ref_st]))
+        assert pos.cpu().numpy().tolist() == [x[2] for x in ref_st]
+        assert has.cpu().numpy().tolist() == [x[3] for x in ref_st]
+        g_dev, g_ref = gau.cpu().numpy(), np.array([x[4] for x in ref_st])
+        assert np.all(np.abs(g_dev - g_ref) <= 2 * np.spacing(np.abs(g_ref))), (g_dev, g_ref)
+
+
+@pytest.mark.parametrize('mode', [0, 1, 2])
+@pytest.mark.parametrize('obs,act,T,n_pairs', [(17, 6, 150, 9), (24, 9, 130, 160)])
+def test_rollout_with_action_noise(eng, mode, obs, act, T, n_pairs):
+    """es_rollout_openloop_noisy: the action of every step gets its noise term before reward and position see it
+    (nn.py:47-48, gym_runner.py:52-53).  The float32 kernels (general: 9 pairs; packed-FMA: 160 pairs) against the oracle's
+    run_model with the same noise values; the tensor-core kernels against the float32 kernel."""
+    rs = np.random.RandomState(obs + T + n_pairs)
+    dims = orc.layer_dims(obs, (64, 64), act)
+    P = orc.n_params(dims)
+    L = P + 300_000
+    table, theta = rs.randn(L).astype(np.float32), (rs.randn(P) * 0.1).astype(np.float32)
+    idx = rs.randint(0, L - P - 1, size=n_pairs).astype(np.int64)
+    env = orc.SyntheticEnvSpec(obs, act, T)
+    noise = (rs.randn(n_pairs, 2, T, act) * 0.05).astype(np.float32)
+    obsn = eng.normalise_obs(dev(eng, env.obs_stream[:T]), dev(eng, np.zeros(obs)), dev(eng, np.ones(obs)), 5.0)
+
+    def run(md, nz):
+        fit = torch.zeros(2, n_pairs, dtype=torch.float64, device=eng.device)
+        behv = torch.zeros(2, n_pairs, 3, dtype=torch.float32, device=eng.device)
+        eng.rollout(dev(eng, table), dev(eng, idx), dev(eng, theta), 0.02, [obs, 64, 64, act], obsn, dev(eng, env.rew_vec),
+                    env.pos_scale, fit[0], fit[1], 1, behv[0], behv[1], md, act_noise=None if nz is None else dev(eng, nz))
+        eng.sync()
+        return fit.cpu().numpy(), behv.cpu().numpy()
+
+    f, b = run(mode, noise)
+    f0, _ = run(mode, None)
+    assert np.abs(f - f0).max() > 1e-3, 'the noise must change the fitness'
+    if mode == 0:
+        class _Replay:                                       # run_model draws rs.randn(act) per step: replay the array
+            def __init__(self, a): self.a, self.i = a.astype(np.float64), 0
+            def randn(self, n): self.i += 1; return self.a[self.i - 1]
+        for k in list(range(min(n_pairs, 4))) + [n_pairs - 1]:
+            eps = orc.table_get(table, int(idx[k]), P)
+            for s, nz in ((0, eps), (1, -eps)):
+                layers = orc.unflatten(orc.pheno_params(theta, 0.02, nz), dims)
+                rews, bb, _, _ = orc.run_model(env, layers, np.zeros(obs), np.ones(obs), 5.0, T, batched=True, ac_std=1.0,
+                                               rs=_Replay(noise[k, s]))
+                assert abs(f[s, k] - orc.reward_result(rews)[0]) <= 1e-5 * max(1.0, np.abs(rews).sum())
+                assert np.allclose(b[s, k], bb[-3:], rtol=1e-4, atol=1e-5)
+    else:
+        f32, b32 = run(0, noise)
+        spread = max(f32.std(), 1e-3 * np.sqrt(T))
+        tol = 6e-6 if mode == 2 else 5e-3
+        assert np.sqrt(((f - f32) ** 2).mean()) <= tol * spread + (1e-6 if mode == 2 else 2e-4)
+        assert np.abs(b - b32).max() <= (2e-6 if mode == 2 else 2e-3) * 0.05 * T + 1e-4
+
+
 def test_draw_indices_errors(eng):
     from es_pytorch_b200._lib import EsLibraryError
     key = dev(eng, np.zeros((1, 624), dtype=np.int32))
@@ -166,6 +255,46 @@ def test_rollout_f32_time_split(eng):
     _rollout_case(eng, 17, 6, (64, 64), T=1000, n_pairs=1, seed=11)
     _rollout_case(eng, 376, 17, (64, 64), T=333, n_pairs=2, seed=12)
     _rollout_case(eng, 17, 6, (64, 64), T=40, n_pairs=40, seed=13)       # 80 policies, 2 tiles: 1 split each
+
+
+def test_rollout_f32x_vs_oracle(eng):
+    """Enough pairs to fill the GPU (2 * n_pairs >= SM count): the packed-FMA kernel of rollout_f32x.cu (one CTA per pair,
+    layer 1 shared by both signs as U +- sigma*V, accumulators paired along k).  Same oracle, same tolerance as the general
+    kernel."""
+    sms = torch.cuda.get_device_properties(eng.device).multi_processor_count
+    n = (sms + 1) // 2
+    _rollout_case(eng, 17, 6, (64, 64), T=150, n_pairs=n + 6, seed=31)       # 2 tiles (128 + 22 rows); obs not a multiple of 4
+    _rollout_case(eng, 376, 17, (64, 64), T=130, n_pairs=n + 2, seed=32)     # the bench's shape
+    _rollout_case(eng, 5, 1, (64, 64), T=3, n_pairs=n + 1, seed=33)          # one action, one partial tile
+    _rollout_case(eng, 63, 32, (64, 64), T=129, n_pairs=2 * sms + 11, seed=34)   # CTAs walk several pairs; act = 32
+
+
+def test_rollout_f32x_matches_general_kernel(eng, monkeypatch):
+    """The two float32 kernels on identical inputs at a size the oracle loop would take minutes for (T = 1000): fitness
+    within 2e-6 of the episode's |reward| mass of each other (both are within 1e-5 of the oracle), positions to float32
+    rounding of a T-term sum."""
+    rs = np.random.RandomState(77)
+    obs, act, T, n = 376, 17, 1000, 300
+    sizes = [obs, 64, 64, act]
+    P = orc.n_params(orc.layer_dims(obs, (64, 64), act))
+    L = P + 400_000
+    table, theta = dev(eng, rs.randn(L).astype(np.float32)), dev(eng, (rs.randn(P) * 0.1).astype(np.float32))
+    idx = dev(eng, rs.randint(0, L - P - 1, size=n).astype(np.int64))
+    rew_h = rs.randn(T, act).astype(np.float32)
+    obsn, rew = dev(eng, np.clip(rs.randn(T, obs), -5, 5).astype(np.float32)), dev(eng, rew_h)
+    out = {}
+    for general in (False, True):
+        if general:
+            monkeypatch.setenv('ES_F32_GENERAL', '1')
+        fit = torch.zeros(2, n, dtype=torch.float64, device=eng.device)
+        behv = torch.zeros(2, n, 3, dtype=torch.float32, device=eng.device)
+        eng.rollout(table, idx, theta, 0.02, sizes, obsn, rew, 0.05, fit[0], fit[1], 1, behv[0], behv[1])
+        eng.sync()
+        out[general] = (fit.cpu().numpy(), behv.cpu().numpy())
+    (fx, bx), (fg, bg) = out[False], out[True]
+    assert not np.array_equal(fx, fg), 'ES_F32_GENERAL did not select the other kernel'
+    assert np.abs(fx - fg).max() <= 2e-6 * np.abs(rew_h).sum()
+    assert np.abs(bx - bg).max() <= 1e-5
 
 
 def test_rollout_sigma_zero_is_symmetric(eng):

@@ -90,8 +90,9 @@ flat, opt = theta.copy(), orc.AdamOracle(P, 0.01)
 states = [np.random.RandomState(s) for s in seeds]
 for g in range(2):
     tr, ob = es.step(cfg, comm, policy, nt, env, fit_fn, streams[0], ranker, Reporter())
-    ref = orc.generation(table, flat, opt, 0.02, dims, spec, seeds, n, np.zeros(obs_dim), np.ones(obs_dim), 5.0, T, 500, 0.005,
-                         coins_per_eval=1, rank_states=states)
+    # es.step = the generation + the noiseless evaluation, whose fit_fn call draws one more coin on EVERY rank (es.py:48)
+    ref = orc.es_step(table, flat, opt, 0.02, dims, spec, states, n, np.zeros(obs_dim), np.ones(obs_dim), 5.0, T, 500, 0.005,
+                      coins_per_eval=1)
     assert np.array_equal(ranker.noise_inds, ref['inds']), 'all ranks see all indices, rank-major'
     assert np.array_equal(ranker.ranked_fits, ref['weights']) and ranker.n_fits_ranked == ref['n_ranked'], 'weights'
     assert np.abs(ranker.fits_pos - ref['pos']).max() < 1e-3
