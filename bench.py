@@ -311,17 +311,17 @@ def run_ours(args, wl, n_gpus):
     seeds = [1000 + rank * VIRTUAL_RANKS_PER_GPU + r for r in range(VIRTUAL_RANKS_PER_GPU)]
     obs_dev, rew_dev = env.device_arrays(eng)
 
-    def make_gen(mode_name, nsra):
+    def make_gen(mode_name, nsra, n_streams=VIRTUAL_RANKS_PER_GPU):
         archive = np.random.RandomState(17).randn(64, 2) if nsra else None
         return DeviceGeneration(table, eng.to_device(theta0.copy()), sizes, obs_dev, rew_dev,
-                                [np.random.RandomState(s) for s in seeds], 0.02, 0.005, Adam(P, 0.01), coins_per_eval=1,
+                                [np.random.RandomState(s) for s in seeds[:n_streams]], 0.02, 0.005, Adam(P, 0.01), coins_per_eval=1,
                                 save_obs_chance=0.01, rollout_mode=MODE_ID[mode_name], comm=comm, engine=eng,
                                 archive=None if archive is None else eng.to_device(archive, torch.float64), nov_k=10, moo_w=0.5)
 
     def measure(gen, pairs_local, steps, warmup, sampler=None):
         """K-generation timing of ``gen`` at ``pairs_local`` pairs per GPU: max-over-ranks ms per step + per-kernel event
         means of the timed steps + launches."""
-        nps = pairs_local // VIRTUAL_RANKS_PER_GPU
+        nps = pairs_local // gen.n_streams
         state = {}
 
         def on_start():
@@ -382,12 +382,15 @@ def run_ours(args, wl, n_gpus):
             if (w2['obs'], w2['act'], w2['T'], w2['table']) != (wl['obs'], wl['act'], wl['T'], wl['table']):
                 continue
             Kt = w2['strong_total']
-            if Kt % (n_gpus * VIRTUAL_RANKS_PER_GPU):
+            if Kt % n_gpus:
                 continue
-            gs = gen if (wname == args.workload) else make_gen(head_mode, bool(w2.get('nsra')))
+            # virtual MPI ranks per GPU: the most (<= 8) that divide the GPU's share (config 5 at 8 GPUs: 1250 pairs = 5 x 250)
+            vr = max(d for d in range(1, VIRTUAL_RANKS_PER_GPU + 1) if (Kt // n_gpus) % d == 0)
+            gs = gen if (wname == args.workload and vr == VIRTUAL_RANKS_PER_GPU) else make_gen(head_mode, bool(w2.get('nsra')), vr)
             r = measure(gs, Kt // n_gpus, side_steps, side_warm)
             strong[cname] = dict(value=Kt / (r['ms_step'] * 1e-3), unit='antithetic pairs/s', ms_per_step=r['ms_step'],
                                  pairs_total=Kt, pairs_per_gpu=Kt // n_gpus, n_gpus=n_gpus, scaling='strong', mode=head_mode,
+                                 virtual_mpi_ranks_per_gpu=vr,
                                  kernel_ms=r['kern'], steps=side_steps, warmup=side_warm)
         also['strong'] = strong
 

@@ -7,19 +7,23 @@
 //   * one CTA = one antithetic PAIR: layer 1 is V = Xn . eps1^T + eps_b1 once for both signs, z1+- = U +- sigma*V with
 //     U = Xn . theta1^T + b1 computed once per generation (float64 accumulation, rounded once).  Layer 1 is 82 % of the
 //     multiply-adds of an evaluation, so the pair costs 0.59 of two separate evaluations;
-//   * register tiles of 4 time steps x 4 units per thread with the accumulators PAIRED ALONG K: acc[i][j] is a float32x2
+//   * register tiles of 8 time steps x 2 units per thread with the accumulators PAIRED ALONG K: acc[i][j] is a float32x2
 //     holding the partial sums over even / odd k, so that both operands of fma.rn.f32x2 come straight out of one 128-bit
-//     shared-memory load each (rows of Xn and rows of eps1 are both contiguous in k): 8 LDS.128 per 32 FFMA2 (64 FMA);
+//     shared-memory load each (rows of Xn and rows of eps1 are both contiguous in k), no transposes, no duplicated operands;
+//   * the shared-memory pipe, not the FMA pipe, is what a CUDA-core GEMM at FFMA2 rate runs out of first: a 128-bit load
+//     costs 4 wavefronts when the lanes read different addresses and 1 when they all read the same one (ncu of the first
+//     version, 4 x 4 tiles with 8 rows x 4 units per warp: 3.3 wavefronts per LDS.128, LSU data pipe 74 %, FMA pipe 48 %).
+//     Here a warp owns 8 time steps x 64 units: the 8 activation rows are read by ALL lanes at the same address (broadcast,
+//     1 wavefront each) and every lane reads its own 2 weight rows (2 x 4 wavefronts): 16 wavefronts per 32 FFMA2 (16 FMA
+//     cycles), where the first version needed 32;
 //   * eps1 is never converted or scaled: cp.async (4-byte granules: a slice has 4-byte alignment only) moves the next pair's
 //     64 x obs block into shared memory while the last tile of the current pair is in its layers 2 / 3;
 //   * the observation tiles are pre-tiled once per generation into the shared-memory image of every (tile, 16-column chunk)
-//     stage (row pitch 20 floats: the 8 rows a warp reads at once fall into 8 different 16-byte bank groups) and thread 0
-//     streams them through a 4-stage ring, two chunks ahead, with one cp.async.bulk each.
+//     stage and thread 0 streams them through a ring of stages, several chunks ahead, with one cp.async.bulk each.
 //
-// Thread mapping (512 threads = 16 warps): rows mg + 32 i, units ng + 16 j (i, j < 4) with
-// mg = 8 (warp & 3) + lane / 4 and ng = 4 (warp / 4) + lane % 4: the 8 rows / 4 units a warp touches in one load are
-// consecutive, and every shared array has a row pitch of 16 bytes mod 128, so all 128-bit loads are conflict-free.
-// Layer 3 (64 -> act): row = tid / 4, units tid % 4 + 4 j.
+// Thread mapping (512 threads = 16 warps): warp w owns time steps 8 w .. 8 w + 7 of the 128-step tile; lane l owns units
+// l and l + 32 in layers 1 / 2 and unit l (< act) in layer 3.  Weight rows have a pitch of 16 bytes mod 128, so the 8 lanes
+// of a quarter warp hit 8 different bank groups.
 #include "common.cuh"
 
 namespace {
@@ -29,15 +33,15 @@ typedef unsigned long long u64;
 constexpr int FX_MT = 128;                          // time steps per tile
 constexpr int FX_H = 64;                            // hidden width
 constexpr int FX_KC = 16;                           // observation columns per stage
-constexpr int FX_NST = 4;                           // stages in the ring
-constexpr int FX_AHEAD = 2;                         // chunks in flight ahead of the one being consumed
-constexpr int FX_XP = FX_KC + 4;                    // stage row pitch (floats)
-constexpr int FX_STAGE_FLOATS = FX_MT * FX_XP;      // 2560 floats = 10 KB
-constexpr int FX_HP = FX_H + 4;                     // row pitch of H / W2 / W3 (floats)
+constexpr int FX_NST = 6;                           // stages in the ring
+constexpr int FX_AHEAD = 4;                         // chunks in flight ahead of the one being consumed
+constexpr int FX_XP = FX_KC;                        // stage row pitch (floats): rows are read by broadcast, no padding
+constexpr int FX_STAGE_FLOATS = FX_MT * FX_XP;      // 2048 floats = 8 KB
+constexpr int FX_HP = FX_H + 4;                     // row pitch of W2 / W3 (floats)
+constexpr int FX_AP = FX_H;                         // row pitch of the activation tile H (read by broadcast)
 constexpr int FX_CWARPS = 16;
 constexpr int FX_CT = FX_CWARPS * 32;
 constexpr int FX_THREADS = FX_CT;                 // (a 17th producer warp would cost the register file of 4 warps: 96 instead of 128 registers)
-constexpr int FX_MAXJ3 = 8;                         // act <= 32
 constexpr uint32_t FX_SPIN_LIMIT = 1u << 28;
 
 struct FxParams {
@@ -45,7 +49,7 @@ struct FxParams {
     const int64_t* idx;
     const float* theta;
     const float* xst;        // [n_tiles][nkc][FX_MT][FX_XP] stage images of the normalised observations
-    const float* uperm;      // [n_tiles][16][FX_CT]: U in thread order (value i*4+j of thread tid)
+    const float* uperm;      // [n_tiles][16][FX_CT]: U in thread order (value i*2+j of thread tid)
     const float* rew;        // [T][act]
     const float* act_noise;  // [n_pairs][2][T][act] scaled action noise (mt_gauss.cu) or NULL
     double* fit_pos;
@@ -69,7 +73,7 @@ __host__ __device__ inline FxSmem fx_layout(int obs, int act) {
     uint32_t o = 0;
     L.e1 = o;   o += (uint32_t)FX_H * L.e1p * 4;
     L.xs = o;   o += (uint32_t)FX_NST * FX_STAGE_FLOATS * 4;
-    L.h = o;    o += (uint32_t)FX_MT * FX_HP * 4;
+    L.h = o;    o += (uint32_t)FX_MT * FX_AP * 4;
     L.w2 = o;   o += 2u * FX_H * FX_HP * 4;
     L.w3 = o;   o += 2u * L.act4 * FX_HP * 4;
     L.bias = o; o += (2u * (FX_H + 32) + FX_H) * 4;   // [sign][b2 (64) | b3 (32)], then eps_b1 (64, unscaled)
@@ -124,26 +128,40 @@ __device__ __forceinline__ double fx_warp_sum_d(double v) {
     return v;
 }
 
-// acc[i][j] += sum_k A[row i][k] * B[row j][k] over NK4 groups of four k; A rows 32 * a_pitch4 apart, B rows 16 * b_pitch4
-// apart (pitches in 16-byte units); the two halves of every accumulator hold the even-k and the odd-k partial sums
+// acc[i][j] += sum_k A[row i][k] * B[row j][k] over NK4 groups of four k.  A: 8 consecutive rows, the same for the whole warp
+// (a_pitch4 apart, pitches in 16-byte units); B: this lane's two rows, 32 * b_pitch4 apart.  The two halves of every
+// accumulator hold the even-k and the odd-k partial sums.
 template <int NK4>
 __device__ __forceinline__ void fx_tile_mma(const ulonglong2* __restrict__ A, int a_pitch4, const ulonglong2* __restrict__ B,
-                                            int b_pitch4, u64 (&acc)[4][4]) {
+                                            int b_pitch4, u64 (&acc)[8][2]) {
 #pragma unroll
     for (int k4 = 0; k4 < NK4; ++k4) {
-        ulonglong2 a[4], b[4];
+        ulonglong2 a[8], b[2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = A[i * 32 * a_pitch4 + k4];
+        for (int j = 0; j < 2; ++j) b[j] = B[j * 32 * b_pitch4 + k4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = B[j * 16 * b_pitch4 + k4];
+        for (int i = 0; i < 8; ++i) a[i] = A[i * a_pitch4 + k4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 2; ++j) {
                 acc[i][j] = fx_fma2(a[i].x, b[j].x, acc[i][j]);
                 acc[i][j] = fx_fma2(a[i].y, b[j].y, acc[i][j]);
             }
     }
+}
+// the warp-wide sums of v[0..7] in 9 shuffles (transposing butterfly): lane L returns the sum over the lanes of v[L / 4]
+__device__ __forceinline__ float fx_warp_sum8(const float (&v)[8], int lane) {
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    float a[4], b[2], c;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = (h16 ? v[i + 4] : v[i]) + __shfl_xor_sync(0xffffffffu, h16 ? v[i] : v[i + 4], 16);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) b[i] = (h8 ? a[i + 2] : a[i]) + __shfl_xor_sync(0xffffffffu, h8 ? a[i] : a[i + 2], 8);
+    c = (h4 ? b[1] : b[0]) + __shfl_xor_sync(0xffffffffu, h4 ? b[0] : b[1], 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    return c;
 }
 
 __global__ void __launch_bounds__(FX_THREADS, 1) rollout_f32x_kernel(const __grid_constant__ FxParams p) {
@@ -178,9 +196,8 @@ __global__ void __launch_bounds__(FX_THREADS, 1) rollout_f32x_kernel(const __gri
     __syncthreads();
 
     // ===================== compute threads =====================
-    const int mg = (warp & 3) * 8 + (lane >> 2), ng = (warp >> 2) * 4 + (lane & 3);
-    const int t3 = tid >> 2, q3 = tid & 3;
-    const int nj3 = act4 >> 2;                                  // layer-3 units of this thread: q3 + 4 j, j < nj3
+    const int r0 = warp * 8;                                    // this warp's rows of the tile: r0 .. r0 + 7
+    const int n3 = min(lane, act4 - 1);                         // layer-3 unit of this lane (lanes >= act idle along)
     const float sg = p.sigma, ps = p.pos_scale;
     const bool want_pos = p.behv_pos != nullptr;
     const int e1p4 = e1p >> 2;
@@ -248,111 +265,100 @@ __global__ void __launch_bounds__(FX_THREADS, 1) rollout_f32x_kernel(const __gri
         const int pair = blockIdx.x + i * gridDim.x;
         fx_cp_async_wait_all();
         fx_bar();                                               // eps1, W2/W3 and the biases of this pair are in place
-        double fs0 = 0.0, fs1 = 0.0;                            // lanes with q3 == 0: reward sums of their row over the tiles
+        double fs0 = 0.0, fs1 = 0.0;                            // lanes 0, 4, .., 28: reward sums of one row of the warp over the tiles
         float pp0 = 0.f, pp1 = 0.f;                             // threads 0..2: position component tid of the + / - evaluation
         for (int m = 0; m < NT; ++m) {
-            // ---- layer 1: V = Xn_tile . eps1^T (both signs) ----
-            float V[4][4];
+            // ---- layer 1: V = Xn_tile . eps1^T + eps_b1 (both signs) ----
+            float V[8][2];
             {
-                u64 acc[4][4];
+                u64 acc[8][2];
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[a][b] = 0ull;
-                const ulonglong2* __restrict__ Bq = reinterpret_cast<const ulonglong2*>(e1) + ng * e1p4;
+                for (int a = 0; a < 8; ++a) { acc[a][0] = 0ull; acc[a][1] = 0ull; }
+                const ulonglong2* __restrict__ Bq = reinterpret_cast<const ulonglong2*>(e1) + lane * e1p4;
                 for (int kc = 0; kc < NKC; ++kc, ++g) {
                     if (tid == 0) produce_to(g + 1 + FX_AHEAD);
                     fx_mbar_wait(&full[stage], phase);
-                    const ulonglong2* __restrict__ Aq = reinterpret_cast<const ulonglong2*>(xs + stage * FX_STAGE_FLOATS) + mg * (FX_XP / 4);
+                    const ulonglong2* __restrict__ Aq = reinterpret_cast<const ulonglong2*>(xs + stage * FX_STAGE_FLOATS) + r0 * (FX_XP / 4);
                     fx_tile_mma<FX_KC / 4>(Aq, FX_XP / 4, Bq + kc * (FX_KC / 4), e1p4, acc);
                     __syncwarp();
                     if (lane == 0) fx_mbar_arrive(&empty[stage]);
                     if (++stage == FX_NST) { stage = 0; phase ^= 1; }
                 }
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+                for (int a = 0; a < 8; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) V[a][b] = fx_hsum(acc[a][b]) + eb1[ng + 16 * b];      // + the bias element of eps
+                    for (int b = 0; b < 2; ++b) V[a][b] = fx_hsum(acc[a][b]) + eb1[lane + 32 * b];      // + the bias element of eps
             }
             const float* __restrict__ up = p.uperm + (size_t)m * 16 * FX_CT + tid;
-            const int t = m * FX_MT + t3;
             const int rows_valid = min(FX_MT, p.T - m * FX_MT);
 #pragma unroll 1
             for (int sgn = 0; sgn < 2; ++sgn) {
                 // ---- epi1: h1 = tanh(U +- sigma V) -> H ----
                 const float s = sgn ? -sg : sg;
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+                for (int a = 0; a < 8; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        H[(mg + 32 * a) * FX_HP + ng + 16 * b] = tanhf(fmaf(s, V[a][b], __ldg(up + (a * 4 + b) * FX_CT)));
+                    for (int b = 0; b < 2; ++b)
+                        H[(r0 + a) * FX_AP + lane + 32 * b] = tanhf(fmaf(s, V[a][b], __ldg(up + (a * 2 + b) * FX_CT)));
                 fx_bar();
                 if (sgn == 0 && m == NT - 1 && i + 1 < my_pairs)      // every warp is past its last read of eps1: fetch the next pair's
                     stage_eps(es_checked_slice(p.idx[pair + gridDim.x], p.P, p.table_len, p.err));
                 // ---- layer 2 ----
-                float D[4][4];
+                float D[8][2];
                 {
-                    u64 acc[4][4];
+                    u64 acc[8][2];
 #pragma unroll
-                    for (int a = 0; a < 4; ++a)
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) acc[a][b] = 0ull;
-                    fx_tile_mma<FX_H / 4>(reinterpret_cast<const ulonglong2*>(H) + mg * (FX_HP / 4), FX_HP / 4,
-                                          reinterpret_cast<const ulonglong2*>(w2s + sgn * FX_H * FX_HP) + ng * (FX_HP / 4), FX_HP / 4, acc);
+                    for (int a = 0; a < 8; ++a) { acc[a][0] = 0ull; acc[a][1] = 0ull; }
+                    fx_tile_mma<FX_H / 4>(reinterpret_cast<const ulonglong2*>(H) + r0 * (FX_AP / 4), FX_AP / 4,
+                                          reinterpret_cast<const ulonglong2*>(w2s + sgn * FX_H * FX_HP) + lane * (FX_HP / 4), FX_HP / 4, acc);
                     const float* b2 = bias + sgn * (FX_H + 32);
 #pragma unroll
-                    for (int a = 0; a < 4; ++a)
+                    for (int a = 0; a < 8; ++a)
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) D[a][b] = tanhf(fx_hsum(acc[a][b]) + b2[ng + 16 * b]);
+                        for (int b = 0; b < 2; ++b) D[a][b] = tanhf(fx_hsum(acc[a][b]) + b2[lane + 32 * b]);
                 }
                 fx_bar();                                           // every thread has read h1
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+                for (int a = 0; a < 8; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) H[(mg + 32 * a) * FX_HP + ng + 16 * b] = D[a][b];
+                    for (int b = 0; b < 2; ++b) H[(r0 + a) * FX_AP + lane + 32 * b] = D[a][b];
                 fx_bar();
-                // ---- layer 3, reward, position ----
+                // ---- layer 3 (lane = action unit), reward, position ----
                 {
-                    u64 acc3[FX_MAXJ3];
+                    u64 acc3[8];
 #pragma unroll
-                    for (int j = 0; j < FX_MAXJ3; ++j) acc3[j] = 0ull;
-                    const ulonglong2* __restrict__ A3 = reinterpret_cast<const ulonglong2*>(H) + t3 * (FX_HP / 4);
-                    const ulonglong2* __restrict__ B3 = reinterpret_cast<const ulonglong2*>(w3s + sgn * act4 * FX_HP) + q3 * (FX_HP / 4);
+                    for (int a = 0; a < 8; ++a) acc3[a] = 0ull;
+                    const ulonglong2* __restrict__ A3 = reinterpret_cast<const ulonglong2*>(H) + r0 * (FX_AP / 4);
+                    const ulonglong2* __restrict__ B3 = reinterpret_cast<const ulonglong2*>(w3s + sgn * act4 * FX_HP) + n3 * (FX_HP / 4);
 #pragma unroll 4
                     for (int k4 = 0; k4 < FX_H / 4; ++k4) {
-                        const ulonglong2 a = A3[k4];
+                        const ulonglong2 b = B3[k4];
 #pragma unroll
-                        for (int j = 0; j < FX_MAXJ3; ++j)
-                            if (j < nj3) {
-                                const ulonglong2 b = B3[j * 4 * (FX_HP / 4) + k4];
-                                acc3[j] = fx_fma2(a.x, b.x, acc3[j]);
-                                acc3[j] = fx_fma2(a.y, b.y, acc3[j]);
-                            }
-                    }
-                    const float* b3 = bias + sgn * (FX_H + 32) + FX_H;
-                    const float* __restrict__ crow = p.rew + (size_t)t * p.act;
-                    const float* __restrict__ nrow = p.act_noise ? p.act_noise + (((size_t)pair * 2 + sgn) * p.T + t) * p.act : nullptr;
-                    float r = 0.f, a0 = 0.f;
-#pragma unroll
-                    for (int j = 0; j < FX_MAXJ3; ++j)
-                        if (j < nj3) {
-                            const int n = q3 + 4 * j;
-                            if (n < p.act) {
-                                float av = tanhf(fx_hsum(acc3[j]) + b3[n]);
-                                if (nrow && t < p.T) av = __fadd_rn(av, __ldg(nrow + n));     // a += randn * ac_std (nn.py:47-48)
-                                const float c = (t < p.T) ? __ldg(crow + n) : 0.f;
-                                r = fmaf(av, c, r);
-                                if (j == 0) a0 = av;
-                            }
+                        for (int a = 0; a < 8; ++a) {
+                            const ulonglong2 x = A3[a * (FX_AP / 4) + k4];
+                            acc3[a] = fx_fma2(x.x, b.x, acc3[a]);
+                            acc3[a] = fx_fma2(x.y, b.y, acc3[a]);
                         }
-                    r += __shfl_xor_sync(0xffffffffu, r, 1);
-                    r += __shfl_xor_sync(0xffffffffu, r, 2);
-                    if (q3 == 0 && t < p.T) { if (sgn) fs1 += (double)r; else fs0 += (double)r; }
-                    if (want_pos) {
-#pragma unroll
-                        for (int jj = 0; jj < 3; ++jj)
-                            if (q3 == jj % p.act) posb[t3 * 4 + jj] = a0;       // action component jj % act (< 3: unit slot j = 0)
                     }
+                    const bool unit = lane < p.act;
+                    const float b3 = bias[sgn * (FX_H + 32) + FX_H + n3];
+                    const int tb = m * FX_MT + r0;                                     // time step of row 0 of this warp
+                    const float* __restrict__ nz = p.act_noise ? p.act_noise + (((size_t)pair * 2 + sgn) * p.T + tb) * p.act + lane : nullptr;
+                    float v[8];
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) {
+                        float av = tanhf(fx_hsum(acc3[a]) + b3);
+                        const bool live = unit && tb + a < p.T;
+                        if (nz && live) av = __fadd_rn(av, __ldg(nz + a * p.act));     // a += randn * ac_std (nn.py:47-48)
+                        v[a] = live ? av * __ldg(p.rew + (size_t)(tb + a) * p.act + lane) : 0.f;
+                        if (want_pos) {
+#pragma unroll
+                            for (int jj = 0; jj < 3; ++jj)
+                                if (lane == jj % p.act) posb[(r0 + a) * 4 + jj] = av;   // action component jj % act
+                        }
+                    }
+                    const float r = fx_warp_sum8(v, lane);             // lanes 4 q .. 4 q + 3: the reward of row q
+                    if ((lane & 3) == 0) { if (sgn) fs1 += (double)r; else fs0 += (double)r; }
                 }
                 fx_bar();                                           // H is free again; the position columns are visible
                 if (want_pos && tid < 3) {
@@ -381,7 +387,7 @@ __global__ void __launch_bounds__(FX_THREADS, 1) rollout_f32x_kernel(const __gri
     }
 }
 
-// observation stream -> stage images [tile][chunk][128 rows][20]: zero beyond T / obs and in the 4 padding columns
+// observation stream -> stage images [tile][chunk][128 rows][16]: zero beyond T / obs
 __global__ void rollout_f32x_prep_kernel(const float* __restrict__ obsn, int T, int obs, int nkc, int n_tiles, float* __restrict__ xst) {
     const size_t total = (size_t)n_tiles * nkc * FX_STAGE_FLOATS;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -395,7 +401,7 @@ __global__ void rollout_f32x_prep_kernel(const float* __restrict__ obsn, int T, 
 }
 
 // U[t][n] = b1[n] + sum_k Xn[t][k] * theta1[n][k], float64 accumulation (k ascending), rounded once; written in the thread
-// order of the rollout kernel: uperm[(m * 16 + i * 4 + j) * 512 + tid] for row mg + 32 i, unit ng + 16 j of tile m
+// order of the rollout kernel: uperm[(m * 16 + i * 2 + j) * 512 + tid] for row 8 (tid / 32) + i, unit tid % 32 + 32 j of tile m
 constexpr int FX_UB_ROWS = 8, FX_UB_KT = 64;
 __global__ void __launch_bounds__(256) rollout_f32x_ubase_kernel(const float* __restrict__ obsn, const float* __restrict__ theta,
                                                                   int w1, int b1, int T, int obs, float* __restrict__ uperm) {
@@ -428,9 +434,9 @@ __global__ void __launch_bounds__(256) rollout_f32x_ubase_kernel(const float* __
     for (int r = 0; r < 2; ++r) {
         const int t = t0 + rg * 2 + r;
         const int m = t / FX_MT, row = t % FX_MT;
-        const int i = row >> 5, mg = row & 31, j = n >> 4, ng = n & 15;
-        const int tid = ((mg >> 3) + 4 * (ng >> 2)) * 32 + (mg & 7) * 4 + (ng & 3);
-        uperm[((size_t)m * 16 + i * 4 + j) * FX_CT + tid] = (t < T) ? (float)acc[r] : 0.f;
+        const int i = row & 7, j = n >> 5;
+        const int tid = (row >> 3) * 32 + (n & 31);
+        uperm[((size_t)m * 16 + i * 2 + j) * FX_CT + tid] = (t < T) ? (float)acc[r] : 0.f;
     }
 }
 

@@ -24,6 +24,17 @@ def pybullet_gym_pos(env):
     return env.robot.robot_body.pose().xyz()
 
 
+def mujoco_pos(env):
+    """Centre of mass of a mujoco model (gym_runner.py:25-30)."""
+    mass = np.reshape(env.model.body_mass, (-1, 1))
+    centre = np.sum(mass * env.data.xipos, 0) / np.sum(mass)
+    return centre[0], centre[1], centre[2]
+
+
+def hbaselines_pos(env):
+    return tuple(env.wrapped_env.get_body_com('torso')[:3])
+
+
 def _device_episode(model, env, max_steps: int, rs=None):
     from ..engine import get_engine
     from ..core.policy import Policy
@@ -72,7 +83,7 @@ def run_model(model: torch.nn.Module, env, max_steps: int, rs: np.random.RandomS
         for step in range(max_steps):
             ob = torch.from_numpy(np.asarray(ob)).float()
             action = model(ob, rs=rs)
-            ob, rew, done, _ = env.step(action.cpu().numpy())
+            ob, rew, done, _ = env.step(action.cpu().numpy() if torch.is_tensor(action) else np.asarray(action))
             rews += [rew]
             obs.append(ob)
             behv.extend(get_pos_fn(env.unwrapped))

@@ -36,6 +36,50 @@ class RewardResult(TrainingResult):
         return [self.reward]
 
 
+class MeanRewardResult(TrainingResult):
+    """Reward per step (training_result.py:67-69; ``steps`` is run_model's last loop index)."""
+
+    def get_result(self) -> List[float]:
+        return [self.reward / self.steps]
+
+
+class DistResult(TrainingResult):
+    """Distance of the final (x, y) from the origin (training_result.py:72-74)."""
+
+    def get_result(self) -> List[float]:
+        return [np.linalg.norm(self.positions[-3:-1])]
+
+
+class XDistResult(DistResult):
+    """Final x (training_result.py:77-79)."""
+
+    def get_result(self) -> List[float]:
+        return [self.positions[-3]]
+
+
+class MultiAgentTrainingResult(TrainingResult):
+    """Record of a multi-agent episode: ``rewards`` / ``obs`` carry one column per agent (training_result.py:33-59).
+    Host-side bookkeeping only: the multi-agent (Unity) runner is outside the synthetic-env hot path."""
+
+    def get_result(self):
+        return self.reward
+
+    @property
+    def ob_sum_sq_cnt(self):
+        per_agent = []
+        for i in range(self.obs.shape[1]):
+            o = self.obs[:, i]
+            per_agent.append((o.sum(axis=0), np.square(o).sum(axis=0), len(o) if np.any(o) else 0))
+        return per_agent
+
+    def trainingresults(self, tr_type):
+        """One single-agent result of class ``tr_type`` per agent."""
+        rews, obs = np.array(self.rewards), np.array(self.obs)
+        return [tr_type(rews[:, i], self.positions, obs[:, i], self.steps) for i in range(rews.shape[1])]
+
+    reward = property(lambda self: np.sum(self.rewards, axis=0).tolist())
+
+
 class NSResult(TrainingResult):
     def __init__(self, rewards, positions, obs, steps, archive: np.ndarray, k: int):
         super().__init__(rewards, positions, obs, steps)

@@ -370,3 +370,34 @@ def test_bench_timed_region_is_collective_safe(tmp_path):
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
     assert 'LOOP_OK_0' in out.stdout and 'LOOP_OK_1' in out.stdout
+
+
+def test_remaining_nets_and_results_keep_the_reference_contracts():
+    """nn.py:53-117 and training_result.py:33-79: the networks that post-process their outputs and the other
+    fitness adaptors.  Against the real reference classes where the checkout is mounted, else against their documented
+    arithmetic."""
+    import torch
+    from es_pytorch_b200.gym.synthetic_env import SyntheticEnv
+    from es_pytorch_b200.gym.training_result import DistResult, MeanRewardResult, MultiAgentTrainingResult, RewardResult, XDistResult
+    from es_pytorch_b200.nn.nn import FeedForward, FFBinned, FFIntegGausAction, FFIntegGausActionMulti
+    env = SyntheticEnv(5, 4, 10)
+    ob = torch.from_numpy(np.random.RandomState(0).randn(5).astype(np.float32))
+    torch.manual_seed(3)
+    a = FFIntegGausAction([8], torch.nn.Tanh(), env, 0.0)
+    raw = a.model(ob).detach().numpy()
+    out = a(ob, rs=np.random.RandomState(5))
+    assert out.shape == (3,) and np.allclose(out, raw[1:] + np.random.RandomState(5).standard_normal(3) * raw[0])
+    assert np.array_equal(a(ob, rs=None), raw[1:]) and not a.is_tanh_mlp()
+    m = FFIntegGausActionMulti([8], torch.nn.Tanh(), env, 0.0)
+    raw = m.model(ob).detach().numpy()
+    assert np.allclose(m(ob, rs=np.random.RandomState(6)), raw[:2] + np.random.RandomState(6).standard_normal(2) * np.abs(raw[2:]))
+    b = FFBinned([8], torch.nn.Tanh(), env, 5)
+    raw = b.model(ob).detach().numpy().reshape(4, 5)
+    assert np.allclose(b(ob, rs=None).numpy(), raw.argmax(1) / 4. * 2. - 1.) and not b.is_tanh_mlp()
+    assert FeedForward([8], torch.nn.Tanh(), env, 0.0).is_tanh_mlp()
+    rews, pos, obs = [1., 2., 3.], [0., 0., 0., 3., 4., 9.], np.ones((3, 5))
+    assert RewardResult(rews, pos, obs, 2).result == [6.] and MeanRewardResult(rews, pos, obs, 2).result == [3.]
+    assert DistResult(rews, pos, obs, 2).result == [5.] and XDistResult(rews, pos, obs, 2).result == [3.]
+    ma = MultiAgentTrainingResult(np.array([[1., 10.], [2., 20.]]), pos, np.ones((2, 2, 5)), 1)
+    assert ma.result == [3., 30.] and len(ma.ob_sum_sq_cnt) == 2 and ma.ob_sum_sq_cnt[1][2] == 2
+    assert [t.result for t in ma.trainingresults(RewardResult)] == [[3.], [30.]]
