@@ -265,6 +265,56 @@ def newest_profile_traffic(kernel_regex: str):
     return best
 
 
+def float64_truth_report(gen, modes, torch):
+    """What 'float32-equivalent' means at this config, measured: the fitness of THIS rank's last drawn pairs in float64
+    arithmetic (torch.float64 matmul + tanh on the device: a measurement reference, not a product path; theta +- sigma*eps
+    formed in float64 from the float32 inputs), and for every rollout mode in ``modes`` (name -> id) the distance of its
+    fitness, integer ranks, rank weights and reconstructed gradient from that truth.  The float32 CUDA-core kernel appears
+    in the same table: it is the yardstick -- no float32 implementation (the reference's torch-CPU forward included) can be
+    closer to another one than both are to the exact result."""
+    import numpy as np
+    e = gen.eng
+    f64 = torch.float64
+    k, P, T = gen.k_local, gen.P, gen.T
+    sizes = gen.layer_sizes
+    theta = gen.theta.to(f64)
+    X = gen.obsn.to(f64)                                        # [T, obs]
+    C = gen.rew_vec.to(f64)                                     # [T, act]
+    ar = torch.arange(P, device=e.device)
+    truth = torch.empty((2, k), dtype=f64, device=e.device)
+    B = 200
+    for b0 in range(0, k, B):
+        idx = gen.idx[b0:b0 + B]
+        eps = gen.table[idx[:, None] + ar[None, :]].to(f64)     # [B, P]
+        for s, sign in enumerate((1.0, -1.0)):
+            W = theta[None, :] + sign * float(np.float32(gen.sigma)) * eps
+            a, at = X[None, :, :], 0
+            for fi, fo in zip(sizes[:-1], sizes[1:]):
+                Wl = W[:, at:at + fi * fo].reshape(-1, fo, fi); at += fi * fo
+                bl = W[:, at:at + fo]; at += fo
+                a = torch.tanh(torch.matmul(a, Wl.transpose(1, 2)) + bl[:, None, :])
+            truth[s, b0:b0 + B] = (a * C[None]).sum(dim=(1, 2))
+    wt, rt = e.centered_rank(truth[0].contiguous(), truth[1].contiguous(), 1.0, 0.0, 0, k, want_ranks=True)
+    gt = e.grad_reconstruct(gen.table, gen.idx, wt, P).to(f64)
+    spread = float(truth.std().item())
+    out = {'pairs': k, 'fitness_spread_std': spread}
+    for name, mode in modes.items():
+        f = e.empty((2, k, 1), f64)
+        e.rollout(gen.table, gen.idx, gen.theta, gen.sigma, sizes, gen.obsn, gen.rew_vec, gen.pos_scale, f[0], f[1], 1, None, None, mode)
+        w, r = e.centered_rank(f[0], f[1], 1.0, 0.0, 0, k, want_ranks=True)
+        g = e.grad_reconstruct(gen.table, gen.idx, w, P).to(f64)
+        e.sync()
+        d = f.view(2, k) - truth
+        dr = (r.to(torch.int64) - rt.to(torch.int64)).abs()
+        out[name + '_vs_f64'] = dict(fitness_rms_err=float(d.pow(2).mean().sqrt().item()),
+                                     fitness_rms_err_over_spread=float(d.pow(2).mean().sqrt().item()) / spread,
+                                     fitness_max_abs_err=float(d.abs().max().item()),
+                                     ranks_differing=int((dr != 0).sum().item()), max_rank_shift=int(dr.max().item()),
+                                     max_abs_dw=float((w - wt).abs().max().item()),
+                                     grad_rel_err=float(((g - gt).norm() / gt.norm()).item()))
+    return out
+
+
 def run_ours(args, wl, n_gpus):
     import numpy as np
     import torch
@@ -376,6 +426,10 @@ def run_ours(args, wl, n_gpus):
                     also['parity'][m + '_vs_f32'] = parity_report(gen, MODE_ID[m], MODE_ID['f32'])
                 except _lib.EsLibraryError as ex:
                     also['parity'][m + '_vs_f32'] = dict(unavailable=str(ex)[:200])
+            try:
+                also['parity']['vs_float64_truth'] = float64_truth_report(gen, {m: MODE_ID[m] for m in MODE_NAMES}, torch)
+            except Exception as ex:                                     # (e.g. out of memory on a shared box)
+                also['parity']['vs_float64_truth'] = dict(unavailable=repr(ex)[:200])
         strong = {}
         for cname, wname in (('config4_K40000', 'humanoid'), ('config5_nsra_K10000', 'humanoid-nsra')):
             w2 = WORKLOADS[wname]
@@ -466,7 +520,8 @@ def run_ours(args, wl, n_gpus):
     roll_tfs = roll_flop / (kern['rollout'] * 1e-3) / 1e12
     value = K_head / (ms_step * 1e-3)
     default_wl = args.workload == 'humanoid' and not args.pairs_per_gpu and args.scaling == 'weak'
-    roll_regex = {'tc': r'rollout_tc_kernel', 'tc3': r'rollout_tc3_kernel|rollout_tc_kernel<.*2', 'f32': r'rollout_f32_kernel'}[head_mode]
+    roll_regex = {'tc': r'rollout_tc2_kernel<(\(bool\))?(0|false)>', 'tc3': r'rollout_tc2_kernel<(\(bool\))?(1|true)>',
+                  'f32': r'rollout_f32x?_kernel'}[head_mode]
     roll_traffic = newest_profile_traffic(roll_regex) if default_wl else None
     rec_traffic = newest_profile_traffic(r'reconstruct_kernel') if default_wl else None
     line = dict(

@@ -52,6 +52,14 @@ def step(cfg, comm, policy: Policy, nt: NoiseTable, env, fit_fn: Callable, rs: n
     return noiseless_result, gen_obstat
 
 
+TRACE = None      # dev: set to a dict to collect perf_counter marks of _step_fused's host phases (tools/dev_step_breakdown.py)
+
+
+def _mark(name, _clock=__import__('time').perf_counter):
+    if TRACE is not None:
+        TRACE.setdefault(name, []).append(_clock())
+
+
 def _silent(reporter) -> bool:
     """True for reporters that discard messages (the O(K) host-side message formatting can be skipped)."""
     from ..utils.reporters import ReporterSet
@@ -109,10 +117,13 @@ def _step_fused(cfg, comm, n: int, policy: Policy, nt: NoiseTable, gen_obstat: O
     step, noiseless evaluation of the new theta -- and ONE synchronisation before the host-side bookkeeping.  Same
     results and side effects as the call-by-call route (test_params -> Ranker.rank -> approx_grad -> fit_fn)."""
     streams = fit_fn.rank_streams if fit_fn.rank_streams is not None else [rs]
+    _mark('t0')
     gen = _device_generation(fit_fn, policy, nt, streams)
+    _mark('t1_prepared')
     eng = gen.eng
     gen.l2coeff, gen.ranker = float(cfg.policy.l2coeff), ranker
     fpos, fneg = gen.evaluate(n)
+    _mark('t2_evaluate_queued')
     gen.update(fpos, fneg)
     gen.l2coeff, gen.ranker = 0.0, None                    # approx_grad passes its own l2coeff on the other route
     fit0, behv0 = gen.noiseless_eval()
@@ -132,7 +143,9 @@ def _step_fused(cfg, comm, n: int, policy: Policy, nt: NoiseTable, gen_obstat: O
     h_w = eng.download_async(w_all, ('ranked', id(ranker)))
     h_theta = eng.download_async(gen.theta, ('theta', id(policy)))
     h_fit0, h_behv0 = eng.download_async(fit0, 'nlfit'), eng.download_async(behv0, 'nlbehv')
+    _mark('t3_all_queued')
     eng.sync()
+    _mark('t4_synced')
     version = gen.version
     valid = lambda g=gen, v=version: g.version == v
     pos = devcache.attach(h_pos.numpy().reshape(gen.K, gen.n_obj).copy(), fpos, valid)
@@ -157,6 +170,7 @@ def _step_fused(cfg, comm, n: int, policy: Policy, nt: NoiseTable, gen_obstat: O
     policy.set_nn_params(torch.from_numpy(policy.flat_params.copy()))
     noiseless_result = fit_fn.result_from_device(float(h_fit0.numpy()[0]), h_behv0.numpy()[0].astype(np.float64))
     reporter.log_gen(ranker.fits, noiseless_result, policy, steps)
+    _mark('t5_done')
     return noiseless_result, gen_obstat
 
 

@@ -10,12 +10,14 @@
 //   * register tiles of 8 time steps x 2 units per thread with the accumulators PAIRED ALONG K: acc[i][j] is a float32x2
 //     holding the partial sums over even / odd k, so that both operands of fma.rn.f32x2 come straight out of one 128-bit
 //     shared-memory load each (rows of Xn and rows of eps1 are both contiguous in k), no transposes, no duplicated operands;
-//   * the shared-memory pipe, not the FMA pipe, is what a CUDA-core GEMM at FFMA2 rate runs out of first: a 128-bit load
-//     costs 4 wavefronts when the lanes read different addresses and 1 when they all read the same one (ncu of the first
-//     version, 4 x 4 tiles with 8 rows x 4 units per warp: 3.3 wavefronts per LDS.128, LSU data pipe 74 %, FMA pipe 48 %).
-//     Here a warp owns 8 time steps x 64 units: the 8 activation rows are read by ALL lanes at the same address (broadcast,
-//     1 wavefront each) and every lane reads its own 2 weight rows (2 x 4 wavefronts): 16 wavefronts per 32 FFMA2 (16 FMA
-//     cycles), where the first version needed 32;
+//   * the shared-memory pipe, not the FMA pipe, is what a CUDA-core GEMM at FFMA2 rate runs out of first.  Measured with ncu
+//     (profiles/r2_m_rollout_f32x_ncu_raw.csv): a 128-bit load costs 4 wavefronts when the lanes of a quarter warp read
+//     different addresses and 2 when the whole warp reads one address.  Here a warp owns 8 time steps x 64 units: the 8
+//     activation rows are read by all lanes at the same address (2 wavefronts each) and every lane reads its own 2 weight
+//     rows (4 each): 24 wavefronts per 32 FFMA2 (= 16 FMA-pipe cycles) -- the same as the first version's 4 x 4 tiles with 8
+//     rows x 4 units per warp (8 loads of ~3.3 wavefronts), and the two run equally fast: LSU data pipe 70 %, FMA pipe 47 %,
+//     24.4 ms per K = 10 000 generation.  With 32 accumulator pairs per thread the balanced tile would be 8 x 4 (16 wavefronts
+//     per 32 FFMA2), which needs 256-thread CTAs (a 128-step tile has only 8 192 outputs) -- not built.
 //   * eps1 is never converted or scaled: cp.async (4-byte granules: a slice has 4-byte alignment only) moves the next pair's
 //     64 x obs block into shared memory while the last tile of the current pair is in its layers 2 / 3;
 //   * the observation tiles are pre-tiled once per generation into the shared-memory image of every (tile, 16-column chunk)

@@ -23,7 +23,7 @@ env = SyntheticEnv(obs, act, T)
 net = FeedForward([64, 64], torch.nn.Tanh(), env, 0.0, 5)
 policy = Policy(net, 0.02, Adam(P, 0.01)); nt = NoiseTable(P, table)
 streams = [np.random.RandomState(1000 + r) for r in range(R)]
-fit_fn = BatchedRollout(env, T, coins_per_eval=1, save_obs_chance=0.01, rank_streams=streams, rollout_mode=_lib.ES_ROLLOUT_TC)
+fit_fn = BatchedRollout(env, T, coins_per_eval=1, save_obs_chance=0.01, rank_streams=streams, rollout_mode=getattr(_lib, os.environ.get('MODE', 'ES_ROLLOUT_TC3')))
 ranker = CenteredRanker(); comm = dist.world()
 class C(dict): __getattr__ = dict.__getitem__
 cfg = C(general=C(policies_per_gen=2 * K // R, batch_size=500), policy=C(l2coeff=0.005))
@@ -46,3 +46,26 @@ for it in range(25):
 for k, v in seg.items(): print(f'{k:28s} {1e3 * np.median(v[5:]):.3f} ms')
 tot = np.median(seg['es.step total'][5:]); pre = np.median(seg['pre: _device_generation'][5:]); sy = np.median(seg['sync'][5:])
 print(f'launch+post (total - pre - sync) = {1e3 * (tot - pre - sy):.3f} ms')
+
+# ---- phase marks inside _step_fused ----
+es.TRACE = {}
+for it in range(30):
+    tr, ob = es.step(cfg, comm, policy, nt, env, fit_fn, streams[0], ranker, rep)
+    policy.update_obstat(ob)
+T = {k: np.array(v[5:]) for k, v in es.TRACE.items()}
+es.TRACE = None
+names = list(T)
+for a, b in zip(names[:-1], names[1:]):
+    print(f'{a:22s} -> {b:22s} {1e3 * np.median(T[b] - T[a]):.3f} ms')
+
+# ---- host profile of the same loop (cProfile): which python frames the non-GPU time is spent in ----
+import cProfile, pstats, io
+pr = cProfile.Profile()
+pr.enable()
+for it in range(40):
+    tr, ob = es.step(cfg, comm, policy, nt, env, fit_fn, streams[0], ranker, rep)
+    policy.update_obstat(ob)
+pr.disable()
+sio = io.StringIO()
+pstats.Stats(pr, stream=sio).sort_stats('tottime').print_stats(28)
+print(sio.getvalue()[:6000])
