@@ -124,21 +124,16 @@ def _step_fused(cfg, comm, n: int, policy: Policy, nt: NoiseTable, gen_obstat: O
     gen.l2coeff, gen.ranker = float(cfg.policy.l2coeff), ranker
     fpos, fneg = gen.evaluate(n)
     _mark('t2_evaluate_queued')
-    gen.update(fpos, fneg)
+    gen.update(fpos, fneg, all_weights=True)
     gen.l2coeff, gen.ranker = 0.0, None                    # approx_grad passes its own l2coeff on the other route
     fit0, behv0 = gen.noiseless_eval()
     gen.skip_eval_coins(1)                                 # the fit_fn's rs.random() of the noiseless call (es.py:48)
     h_pos, h_neg, h_key, h_mtpos, h_stats = _queue_common_downloads(eng, gen, fpos, fneg)
     w_all, idx_all = gen.weights, gen.idx
     if gen.comm.size > 1:
-        # what Ranker.rank / _share_results hand to every rank: all K weights and noise indices (two small allgathers)
-        if getattr(gen, '_step_gather', None) is None or gen._step_gather[0].shape[1] != gen.k_local:
-            gen._step_gather = (eng.empty((gen.comm.size, gen.k_local), torch.float32),
-                                eng.empty((gen.comm.size, gen.k_local), torch.int64))
-        w_all, idx_all = gen._step_gather
-        gen.comm.allgather_into(w_all, gen.weights)
-        gen.comm.allgather_into(idx_all, gen.idx)
-        w_all, idx_all = w_all.view(-1), idx_all.view(-1)
+        # what Ranker.rank / _share_results hand to every rank: all K weights and noise indices.  Both are already here: the
+        # indices travelled with the fitness rows (one allgather, as in es.py:89-95) and every process finalised all K weights
+        w_all, idx_all = gen.weights_all, gen.idx_all
     h_idx = eng.download_async(idx_all, 'idx')
     h_w = eng.download_async(w_all, ('ranked', id(ranker)))
     h_theta = eng.download_async(gen.theta, ('theta', id(policy)))
@@ -229,18 +224,18 @@ def _test_params_batched(comm, n: int, policy: Policy, nt: NoiseTable, gen_obsta
     eng = gen.eng
     # everything the reference API returns as ndarrays comes back through pinned staging with ONE synchronisation
     h_pos, h_neg, h_key, h_mtpos, h_stats = _queue_common_downloads(eng, gen, fpos, fneg)
-    h_idx = eng.download_async(gen.idx, 'idx')
+    # the noise indices of ALL ranks: they travelled with the fitness rows (one allgather, like es.py:89-95's rows)
+    idx_dev = gen.idx_all if gen.comm.size > 1 else gen.idx
+    h_idx = eng.download_async(idx_dev, 'idx')
     eng.sync()
     version = gen.version
     valid = lambda g=gen, v=version: g.version == v
     pos = devcache.attach(h_pos.numpy().reshape(gen.K, gen.n_obj).copy(), fpos, valid)
     neg = devcache.attach(h_neg.numpy().reshape(gen.K, gen.n_obj).copy(), fneg, valid)
-    idx_local = h_idx.numpy().copy()
     gen.store_states(streams, h_key.numpy().copy(), h_mtpos.numpy().copy(), _host_gauss(gen))
-    if comm.size > 1:
-        inds = np.concatenate(dist.world().allgather_object(idx_local)).astype(np.float64)
-    else:
-        inds = devcache.attach(idx_local.astype(np.float64), gen.idx, valid)
+    inds = h_idx.numpy().astype(np.float64)
+    if gen.comm.size == 1:
+        inds = devcache.attach(inds, gen.idx, valid)
     if h_stats is not None:
         gen_obstat.inc(*_obstat_from(h_stats, gen.obs_dim))
     steps = 2 * gen.K * (fit_fn.max_steps - 1)          # run_model returns the last loop index (gym_runner.py:50,67)

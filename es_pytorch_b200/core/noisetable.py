@@ -73,8 +73,11 @@ class NoiseTable:
         ``gym_seeding=True`` routes the seed through ``gym.utils.seeding.np_random`` like
         noisetable.py:61-64 (needs a gym that provides it; the two disagree in gym 0.17)."""
         if gym_seeding:
-            import gym
-            rs, _ = gym.utils.seeding.np_random(seed)
+            from gym.utils import seeding
+            try:
+                rs, _ = seeding.np_random(seed, hashed=True)          # the shim's restatement of gym 0.17.1's seed hashing
+            except TypeError:
+                rs, _ = seeding.np_random(seed)                       # a real gym installation
         else:
             rs = np.random.RandomState(seed)
         return rs.randn(size).astype(np.float32)

@@ -117,11 +117,9 @@ class DeviceGeneration:
         self.ob_mean = torch.zeros(self.obs_dim, dtype=f64, device=e.device)
         self.ob_std = torch.ones(self.obs_dim, dtype=f64, device=e.device)
         self.obsn = e.empty((self.T, self.obs_dim), f32)
-        # generation obs statistics (ObStat(shape, 0), es.py:41): sum, sumsq, [count, n_saved]
-        self._gen_stats = torch.zeros(2 * self.obs_dim + 2, dtype=f64, device=e.device)   # one buffer: one fill per generation
-        self.gen_sum = self._gen_stats[:self.obs_dim]
-        self.gen_sumsq = self._gen_stats[self.obs_dim:2 * self.obs_dim]
-        self.gen_count = self._gen_stats[2 * self.obs_dim:]
+        # generation obs statistics (ObStat(shape, 0), es.py:41): sum, sumsq, [count, n_saved] -- a view into the
+        # buffer this process shares with the others (see _ensure_buffers)
+        self._gen_stats = self.gen_sum = self.gen_sumsq = self.gen_count = None
         self._bufs_for = None
         self._host_states = None    # (key, pos) host copies of what store_states last wrote into the callers' streams
         self.version = 0            # bumped by every evaluate(): validity token of the device shadows handed out
@@ -145,10 +143,24 @@ class DeviceGeneration:
         self.idx = e.empty((self.k_local,), i64)
         self.extra_words = 4 * self.coins_per_eval       # 2 evaluations x coins x 2 words per double
         self.extras = e.empty((self.k_local, self.extra_words), torch.int32) if self.extra_words else None
-        self.fit_local = e.empty((2, self.k_local, self.n_obj), f64)          # [pos|neg][k][obj]
-        self.fit_all = e.empty((self.comm.size, 2, self.k_local, self.n_obj), f64) if self.comm.size > 1 else None
-        self.fpos_all = e.empty((self.K, self.n_obj), f64) if self.comm.size > 1 else None
-        self.fneg_all = e.empty((self.K, self.n_obj), f64) if self.comm.size > 1 else None
+        # What a process shares per generation is ONE float64 buffer -- the reference's _share_results rows (fitness of both
+        # signs and the noise index as float64, es.py:89-91) plus the generation's obs statistics (ObStat.mpi_inc, es.py:77)
+        # -- so that one allgather serves the ranks, the indices and the statistics:
+        #   [fitness [pos|neg][k][obj] | idx [k] | obs sum, sumsq, count, n_saved]
+        nf, ns = 2 * self.k_local * self.n_obj, 2 * self.obs_dim + 2
+        self.share_local = torch.zeros(nf + self.k_local + ns, dtype=f64, device=e.device)
+        self.fit_local = self.share_local[:nf].view(2, self.k_local, self.n_obj)
+        self.idx_f64 = self.share_local[nf:nf + self.k_local]
+        self._gen_stats = self.share_local[nf + self.k_local:]
+        self.gen_sum = self._gen_stats[:self.obs_dim]
+        self.gen_sumsq = self._gen_stats[self.obs_dim:2 * self.obs_dim]
+        self.gen_count = self._gen_stats[2 * self.obs_dim:]
+        G = self.comm.size
+        self.share_all = e.empty((G, nf + self.k_local + ns), f64) if G > 1 else None
+        self.fit_all = self.share_all[:, :nf].view(G, 2, self.k_local, self.n_obj) if G > 1 else None
+        self.fpos_all = e.empty((self.K, self.n_obj), f64) if G > 1 else None
+        self.fneg_all = e.empty((self.K, self.n_obj), f64) if G > 1 else None
+        self.idx_all = e.empty((self.K,), i64) if G > 1 else None             # every process's indices, rank-major
         self.behv = e.empty((2, self.k_local, 3), f32) if self.n_obj == 2 else None
         self.weights = None
         self._bufs_for = n_per_stream
@@ -198,27 +210,36 @@ class DeviceGeneration:
             e.obstat_accumulate_coins(self.gen_sum, self.gen_sumsq, self.gen_count, s, q, self.T,
                                       self.extras.view(-1, 2), self.save_obs_chance)
         if self.comm.size > 1:
+            nf = 2 * self.k_local * self.n_obj
+            self.idx_f64.copy_(self.idx)                         # exact: indices < 2^53 (the reference shares them as float64 too)
             with self._timed('allgather'):
-                self.comm.allgather_into(self.fit_all, self.fit_local)
+                self.comm.allgather_into(self.share_all, self.share_local)
             # [rank][pos|neg][k][obj] -> rank-major [K][obj] per sign (es.py:93-95 ordering)
             self.fpos_all.view(self.comm.size, self.k_local, self.n_obj).copy_(self.fit_all[:, 0])
             self.fneg_all.view(self.comm.size, self.k_local, self.n_obj).copy_(self.fit_all[:, 1])
-            self.comm.allreduce_sum(self._gen_stats)             # sum, sumsq and counts in one buffer: one collective
+            self.idx_all.view(self.comm.size, self.k_local).copy_(self.share_all[:, nf:nf + self.k_local])
+            # obs statistics of all processes (rank order: the same float64 sum everywhere), in place of the local ones
+            self._gen_stats.copy_(self.share_all[:, nf + self.k_local:].sum(dim=0))
             return self.fpos_all, self.fneg_all
         return fp, fn
 
-    def update(self, fpos: torch.Tensor, fneg: torch.Tensor):
-        """Ranker.rank + es.approx_grad on the device (rankers.py:46-50, es.py:98-101)."""
+    def update(self, fpos: torch.Tensor, fneg: torch.Tensor, all_weights: bool = False):
+        """Ranker.rank + es.approx_grad on the device (rankers.py:46-50, es.py:98-101).  ``all_weights``: finalise the weights
+        of all K pairs on every process (``self.weights_all``; what Ranker.rank hands to a script) instead of only this
+        shard's -- a few microseconds more than the shard, and no collective."""
         e = self.eng
+        kb, kc = (0, self.K) if (all_weights and self.comm.size > 1) else (self.k_begin, self.k_local)
         with self._timed('rank'):
             if self.ranker is not None:
-                # any Ranker of utils.rankers: one weight per pair of this shard, n_fits_ranked as the reference
-                self.weights = self.ranker.rank_device(e, fpos, fneg, self.k_begin, self.k_local)
+                # any Ranker of utils.rankers: one weight per pair, n_fits_ranked as the reference
+                w = self.ranker.rank_device(e, fpos, fneg, kb, kc)
                 n_ranked = float(self.ranker.n_fits_ranked)
             else:
                 w0, w1 = (1.0, 0.0) if self.n_obj == 1 else (self.moo_w, 1 - self.moo_w)
-                self.weights = e.centered_rank(fpos, fneg, w0, w1, self.k_begin, self.k_local)
+                w = e.centered_rank(fpos, fneg, w0, w1, kb, kc)
                 n_ranked = float(2 * self.K)
+            self.weights_all = w if kc == self.K else None
+            self.weights = w[self.k_begin:self.k_begin + self.k_local] if (kc == self.K and self.comm.size > 1) else w
         with self._timed('reconstruct'):
             e.grad_reconstruct(self.table, self.idx, self.weights, self.P, self.gsum)
         with self._timed('allreduce'):

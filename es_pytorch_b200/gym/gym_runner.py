@@ -94,3 +94,11 @@ def run_model(model: torch.nn.Module, env, max_steps: int, rs: np.random.RandomS
                 break
     behv += behv[-3:] * (max_steps - int(len(behv) / 3))
     return rews, behv, np.array(obs), step
+
+
+def multi_agent_gym_runner(policies, env, max_steps: int, rs: np.random.RandomState = None, save_obs: bool = False,
+                           render: bool = False):
+    """gym_runner.py:70-110 drives a Unity ML-Agents environment (src/gym/unity.py); that simulator and its wrapper are
+    outside this package's scope."""
+    raise NotImplementedError('multi_agent_gym_runner needs the Unity ML-Agents wrapper (src.gym.unity), which is not part of '
+                              'es_pytorch_b200: the device path covers single-agent rollouts on the synthetic env')

@@ -141,13 +141,13 @@ def test_policy_flat_layout_and_pickle(tmp_path):
 
 
 def test_reference_scripts_import_against_the_shims():
-    """simple_example.py / obj.py / nsra.py resolve every import against es_pytorch_b200/compat
+    """simple_example.py / obj.py / nsra.py / multi_agent.py resolve every import against es_pytorch_b200/compat
     (only where the reference checkout is mounted: the build container)."""
     if not os.path.isdir('/root/reference'):
         pytest.skip('reference checkout not present on this box')
     code = textwrap.dedent('''
         import importlib.util, sys
-        for s in ('simple_example', 'obj', 'nsra'):
+        for s in ('simple_example', 'obj', 'nsra', 'multi_agent'):
             spec = importlib.util.spec_from_file_location('ref_' + s, '/root/reference/%s.py' % s)
             m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
         import src.core.es, es_pytorch_b200.core.es
@@ -401,3 +401,42 @@ def test_remaining_nets_and_results_keep_the_reference_contracts():
     ma = MultiAgentTrainingResult(np.array([[1., 10.], [2., 20.]]), pos, np.ones((2, 2, 5)), 1)
     assert ma.result == [3., 30.] and len(ma.ob_sum_sq_cnt) == 2 and ma.ob_sum_sq_cnt[1][2] == 2
     assert [t.result for t in ma.trainingresults(RewardResult)] == [[3.], [30.]]
+
+
+def test_run_state_checkpoint_round_trip(tmp_path):
+    """the policy pickle plus what the reference omits -- the ranks' RandomState streams (position AND cached
+    gaussian), the table seed, the generation counter.  A resumed run draws exactly what the original would have drawn."""
+    import torch
+    from es_pytorch_b200.core.policy import Policy
+    from es_pytorch_b200.gym.synthetic_env import SyntheticEnv
+    from es_pytorch_b200.nn.nn import FeedForward
+    from es_pytorch_b200.nn.optimizers import Adam
+    from es_pytorch_b200.utils.checkpoint import load_run_state, save_run_state
+    env = SyntheticEnv(5, 2, 10)
+    policy = Policy(FeedForward([8], torch.nn.Tanh(), env, 0.01, 5), 0.02, Adam(74, 0.01))
+    streams = [np.random.RandomState(50 + r) for r in range(3)]
+    streams[1].randn(3)                                     # cached gaussian
+    streams[2].randint(0, 1000, size=700)
+    path = save_run_state(str(tmp_path), 'g7', policy, streams, table_seed=123, generation=7, extra={'best': 1.5})
+    want = [(s.randint(0, 10 ** 6), s.random(), s.randn(3).tolist()) for s in streams]
+    st = load_run_state(path)
+    assert st['table_seed'] == 123 and st['generation'] == 7 and st['extra'] == {'best': 1.5}
+    assert [(s.randint(0, 10 ** 6), s.random(), s.randn(3).tolist()) for s in st['streams']] == want
+    assert np.array_equal(st['policy'].flat_params, policy.flat_params) and st['policy'].std == 0.02
+    assert st['policy']._module._action_std == 0.01
+
+
+def test_gym_017_seed_hash_restatement_is_self_consistent():
+    """gym 0.17.1 hashes the table seed before seeding the RandomState (noisetable.py:63); the shim's restatement
+    (unpinned: the package is not available offline) must at least be deterministic, differ from the direct seeding and
+    round-trip its big-int helpers."""
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + COMPAT)
+    code = ('from gym.utils import seeding as s; import numpy as np\n'
+            'a = s.np_random(123, hashed=True)[0].randn(3); b = s.np_random(123, hashed=True)[0].randn(3)\n'
+            'c = s.np_random(123)[0].randn(3)\n'
+            'assert np.array_equal(a, b) and not np.array_equal(a, c)\n'
+            'h = s.hash_seed(123); assert 0 <= h < 2 ** 64 and s._int_list_from_bigint(h) == [h % 2 ** 32, h >> 32]\n'
+            'assert s._bigint_from_bytes(bytes([1, 0, 0, 0, 2, 0, 0, 0])) == 1 + 2 * 2 ** 32\n'
+            'print("OK")')
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env)
+    assert out.returncode == 0 and 'OK' in out.stdout, out.stderr[-2000:]
