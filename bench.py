@@ -550,6 +550,21 @@ def run_ours(args, wl, n_gpus):
                                   peak_source=hbm_src, algorithmic_bytes_per_launch=rec_bytes,
                                   share_of_step=kern['reconstruct'] / ms_step),
     )
+    # the same roofline arithmetic for every rollout mode measured in this run (headline + also.modes): algorithmic TFLOP/s
+    # against the measured dense f16/bf16 peak, and what the tensor pipe actually ISSUES (layer 1 once per pair; x3 for the
+    # split-operand mode; the float32 mode runs on the CUDA cores: its issued work is FFMA, against the same yardstick)
+    issued_factor = {'tc': 1.0, 'tc3': 3.0, 'f32': 1.0}
+    l1, l23 = sizes[0] * sizes[1], sum(i * o for i, o in zip(sizes[1:-1], sizes[2:]))
+    issued_flop = 2.0 * k_local * wl['T'] * (l1 + 2 * l23)
+    by_mode = {head_mode: kern['rollout']}
+    for mname, mres in (also.get('modes') or {}).items():
+        if 'rollout_ms' in mres:
+            by_mode[mname] = mres['rollout_ms']
+    line['roofline_by_mode'] = {
+        m: dict(rollout_ms=ms, algorithmic_tflops=roll_flop / (ms * 1e-3) / 1e12, frac=roll_flop / (ms * 1e-3) / 1e12 / tf_peak,
+                issued_tflops=issued_factor[m] * issued_flop / (ms * 1e-3) / 1e12,
+                issued_frac=issued_factor[m] * issued_flop / (ms * 1e-3) / 1e12 / tf_peak, dtype=MODE_DTYPE[m])
+        for m, ms in by_mode.items()}
     if not args.no_cpu_baseline and n_gpus == 1:
         out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '3',
                               '--warmup', '1', '--workload', args.workload, '--gpus', '1', '--scaling', args.scaling] +
