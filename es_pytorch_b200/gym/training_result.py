@@ -31,30 +31,19 @@ class TrainingResult(ABC):
     behaviour = property(lambda self: self.positions[-3:-1])
 
 
-class RewardResult(TrainingResult):
-    def get_result(self) -> List[float]:
-        return [self.reward]
+def _adaptor(name: str, base, fn, doc: str):
+    """A TrainingResult subclass whose ``get_result`` is ``fn`` (module-level classes: picklable under their own names)."""
+    return type(name, (base,), {'get_result': fn, '__doc__': doc, '__module__': __name__})
 
 
-class MeanRewardResult(TrainingResult):
-    """Reward per step (training_result.py:67-69; ``steps`` is run_model's last loop index)."""
-
-    def get_result(self) -> List[float]:
-        return [self.reward / self.steps]
-
-
-class DistResult(TrainingResult):
-    """Distance of the final (x, y) from the origin (training_result.py:72-74)."""
-
-    def get_result(self) -> List[float]:
-        return [np.linalg.norm(self.positions[-3:-1])]
-
-
-class XDistResult(DistResult):
-    """Final x (training_result.py:77-79)."""
-
-    def get_result(self) -> List[float]:
-        return [self.positions[-3]]
+# single-objective adaptors: (training_result.py:62-79)
+RewardResult = _adaptor('RewardResult', TrainingResult, lambda self: [self.reward],
+                        'Fitness = the total reward of the episode (python sum of the per-step rewards).')
+MeanRewardResult = _adaptor('MeanRewardResult', TrainingResult, lambda self: [self.reward / self.steps],
+                            'Reward per step; ``steps`` is the last loop index run_model returns.')
+DistResult = _adaptor('DistResult', TrainingResult, lambda self: [np.linalg.norm(self.positions[-3:-1])],
+                      'Distance of the final (x, y) from the origin.')
+XDistResult = _adaptor('XDistResult', DistResult, lambda self: [self.positions[-3]], 'Final x.')
 
 
 class MultiAgentTrainingResult(TrainingResult):

@@ -88,18 +88,21 @@ class DefaultMpiReporter(MpiReporter):
         self.print('\n\n----------------------------------------')
         self.log({'gen': self.gen})
 
+    def _summary(self, fits, noiseless_tr, steps) -> Dict[str, float]:
+        """One flat record per generation (the metric names are what the reference's logs / mlflow runs use)."""
+        cols = np.asarray(fits, dtype=np.float64).reshape(len(fits), -1)
+        rec = {}
+        for i in range(cols.shape[1]):
+            rec[f'avg-{i}'] = float(np.round(cols[:, i].mean(), 2))
+            rec[f'max-{i}'] = float(np.round(cols[:, i].max(), 2))
+        rec['dist'], rec['rew'] = calc_dist_rew(noiseless_tr)
+        rec['steps'], rec['cum steps'], rec['n fits ranked'] = steps, self.cum_steps, len(fits)
+        return rec
+
     def _log_gen(self, fits, noiseless_tr, policy, steps):
-        for i, col in enumerate(np.asarray(fits).reshape(len(fits), -1).T):
-            self.log({f'avg-{i}': np.mean(col).round(2).item()})
-            self.log({f'max-{i}': np.max(col).round(2).item()})
         self.cum_steps += steps
-        dist_, rew = calc_dist_rew(noiseless_tr)
-        self.log({'dist': dist_})
-        self.log({'rew': rew})
-        self.print('')
-        self.log({'steps': steps})
-        self.log({'cum steps': self.cum_steps})
-        self.log({'n fits ranked': len(fits)})
+        for key, value in self._summary(fits, noiseless_tr, steps).items():
+            self.log({key: value})
 
     def _end_gen(self):
         self.log({'time': round(time.time() - self.gen_start_time, 2)})
@@ -121,12 +124,11 @@ class DefaultMpiReporterSet(DefaultMpiReporter):
     def _log_gen(self, fits, noiseless_tr, policy, steps):
         super()._log_gen(fits, noiseless_tr, policy, steps)
         dist_, rew = calc_dist_rew(noiseless_tr)
-        improved = rew > self.best_rew or dist_ > self.best_dist
-        self.best_rew, self.best_dist = max(rew, self.best_rew), max(dist_, self.best_dist)
-        if improved:
+        if rew > self.best_rew or dist_ > self.best_dist:             # a new best in either measure: keep the policy
             policy.save(self.policy_folder, str(self.gen))
             self.print(f'saving policy with rew:{rew:0.2f} and dist:{dist_:0.2f}')
-        np.save(os.path.join(self.fit_folder, f'{self.gen}.np'), fits)
+        self.best_rew, self.best_dist = max(rew, self.best_rew), max(dist_, self.best_dist)
+        np.save(os.path.join(self.fit_folder, f'{self.gen}.np'), fits)   # every generation's fitness matrix
 
     def _log(self, d):
         for r in self.reporters:

@@ -440,3 +440,35 @@ def test_gym_017_seed_hash_restatement_is_self_consistent():
             'print("OK")')
     out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env)
     assert out.returncode == 0 and 'OK' in out.stdout, out.stderr[-2000:]
+
+
+def test_reporter_set_saves_fits_and_best_policy(tmp_path, monkeypatch):
+    """DefaultMpiReporterSet (obj.py:24-28): per-generation np.save of the fitness matrix (reporters.py:188) and a policy
+    checkpoint whenever the noiseless reward or distance improves; only rank 0 writes."""
+    from es_pytorch_b200.gym.training_result import RewardResult
+    from es_pytorch_b200.utils.reporters import DefaultMpiReporterSet, Reporter
+    monkeypatch.chdir(tmp_path)
+
+    class Comm:
+        rank, size = 0, 1
+
+    class Rec(Reporter):
+        def __init__(self): self.logged, self.lines = {}, []
+        def log(self, d): self.logged.update(d)
+        def print(self, s): self.lines.append(s)
+
+    class Pol:
+        saved = []
+        def save(self, folder, suffix): Pol.saved.append((folder, suffix))
+
+    rec = Rec()
+    rep = DefaultMpiReporterSet(Comm(), 'run', rec, None)
+    fits = np.array([[1.0], [3.0], [2.0], [6.0]])
+    for g, total in enumerate((5.0, 4.0, 9.0)):
+        rep.start_gen()
+        rep.log_gen(fits + g, RewardResult([total], [0., 0., 0., 3., 4., 0.] , np.zeros((1, 2)), 7), Pol(), 10)
+        rep.end_gen()
+        assert np.array_equal(np.load(os.path.join('saved', 'run', 'fits', f'{g}.np.npy')), fits + g)
+    assert [s for _, s in Pol.saved] == ['0', '2']                    # generation 1 improved neither reward nor distance
+    assert rec.logged['avg-0'] == 5.0 and rec.logged['max-0'] == 8.0 and rec.logged['cum steps'] == 30 and rec.logged['dist'] == 5.0
+    assert rec.logged['n fits ranked'] == 4 and 'time' in rec.logged and rec.logged['gen'] == 2
