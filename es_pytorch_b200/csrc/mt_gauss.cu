@@ -10,11 +10,20 @@
 // (4 words) x1, x2 = 2 u - 1 until r2 = x1^2 + x2^2 is in (0, 1); f = sqrt(-2 log(r2) / r2); returns f*x2 and caches f*x1 for
 // the next call.  The number of words a rollout consumes therefore depends on the words themselves, and the indices of all
 // later pairs depend on it: the stream has to be walked in order.  Attempts inside one rollout are independent of each other,
-// which is the parallelism used here: the CTA of a stream tests MG_THREADS attempts at once, ranks the accepted ones with a
-// ballot scan and lets every accepting thread write its two gaussians at their place in the rollout's noise array.
+// which is the parallelism used here: the CTA of a stream (736 threads) tests 1 472 attempts per step, ranks the accepted ones
+// with a ballot scan and records their four words in order; mt_gauss_finish_kernel turns the records into gaussians on the
+// whole GPU (float64 log / sqrt off the sequential path).
 //
 // One CTA per stream.  The state lives in a ring of MG_RING 624-word blocks in shared memory (raw words for the recurrence and
-// for the state handed back, tempered words for the consumers), regenerated ahead of the cursor.
+// for the state handed back, tempered words for the attempt windows), regenerated ahead of the cursor by the whole CTA with two
+// barriers per block (see `ensure`).  What the time goes to, measured with cycle counters (MG_PROFILE) and ncu on the way from
+// 109 ms to 72 ms per K = 10 000, T*act = 17 000 generation with 8 streams: the regeneration (69 blocks per rollout) is the
+// limiter and it is instruction-issue bound (issue slots 61 %): the textbook three dependent 227-word phases cost ~1 100 cycles
+// per block with 4 or 10 warps; ONE pass that recomputes up to three twists per word is as slow (~100 instructions per word);
+// sharing the 623 twists through shared memory, warp-aligned ranges, branch-free word expressions and hoisted index arithmetic
+// bring a block to ~450 cycles.  Splitting the CTA into producer and consumer warps did not help (the producer alone sets the
+// pace), neither did moving the float64 math out (it was not the limiter).  A polynomial jump-ahead that spreads one stream's
+// regeneration over many SMs is the known way beyond this; not built.
 //
 // Output noise[((stream * n_pairs + pair) * 2 + sign) * N + t * act + j] = float32(gauss * scale): the float64 product rounded
 // once; the rollout kernels add it to the float32 action (the reference forms the float64 sum and the env rounds it to
@@ -27,9 +36,14 @@
 namespace {
 
 constexpr int MG_N = 624, MG_M = 397, MG_D = MG_N - MG_M;      // 227
-constexpr int MG_THREADS = 512, MG_WARPS = MG_THREADS / 32;
-constexpr int MG_RING = 8;                                     // blocks in the ring (4992 words)
-constexpr int MG_WIN = 4 * MG_THREADS;                         // words tested per step
+constexpr int MG_THREADS = 736, MG_WARPS = MG_THREADS / 32;    // 23 warps: see the word <-> thread map of the regeneration
+static_assert(MG_WARPS <= 32, "one shuffle scan over the warp totals");
+constexpr int MG_RING = 20;                                    // blocks in the ring (raw + tempered + one block of twists: 102 KB of shared memory)
+constexpr int MG_RW = MG_RING * MG_N, MG_RQ = MG_RW / 4;       // ring words; the tempered ring is stored as 4 quarter rings (see mg_tw_slot)
+static_assert(MG_RW % 4 == 0, "quarter rings");
+constexpr int MG_APT = 2;                                      // attempts per thread and step (consecutive attempts)
+constexpr int MG_WIN = 4 * MG_APT * MG_THREADS;                // words tested per step (5888 = 9.4 blocks)
+static_assert((MG_RING - 2) * MG_N >= MG_WIN + MG_N, "the ring holds the cursor's block and a whole window ahead of it");
 
 __device__ __forceinline__ uint32_t mg_twist(uint32_t u, uint32_t v) {
     const uint32_t y = (u & 0x80000000u) | (v & 0x7FFFFFFFu);
@@ -42,66 +56,106 @@ __device__ __forceinline__ uint32_t mg_temper(uint32_t y) {
     y ^= y >> 18;
     return y;
 }
+// Where ring word k (0 <= k < MG_RW) of the TEMPERED stream lives: word k sits in quarter ring k % 4 at k / 4, so that the four
+// words of consecutive attempts (k = s + 4a + q) are consecutive in shared memory for a fixed q: the attempt windows read
+// without bank conflicts (stride-4 or stride-8 word reads were 4- / 8-way conflicts and half of a window step's time)
+__device__ __forceinline__ int mg_tw_slot(int k) { return (k & 3) * MG_RQ + (k >> 2); }
 // legacy_double: (a >> 5, b >> 6) -> [0, 1) with 53 bits
 __device__ __forceinline__ double mg_double(uint32_t a, uint32_t b) {
     return __dmul_rn(__dadd_rn(__dmul_rn((double)(a >> 5), 67108864.0), (double)(b >> 6)), 1.0 / 9007199254740992.0);
 }
-
-struct MgStream {
-    uint32_t* raw;      // [MG_RING][624]
-    uint32_t* tw;       // [MG_RING][624]
-    int gen_b;          // newest generated block (block 0 = the incoming state)
+struct MgShared {
+    int wtot[2][MG_WARPS];
+    int end;
 };
 
-// next block of the recurrence into ring slot (gen_b + 1) % MG_RING (separate source and destination: 3 phases, 3 barriers)
-__device__ __forceinline__ void mg_regenerate(MgStream& s, int tid) {
-    const uint32_t* __restrict__ src = s.raw + (s.gen_b % MG_RING) * MG_N;
-    uint32_t* __restrict__ dst = s.raw + ((s.gen_b + 1) % MG_RING) * MG_N;
-    uint32_t* __restrict__ twd = s.tw + ((s.gen_b + 1) % MG_RING) * MG_N;
-    if (tid < MG_D) { const uint32_t y = src[tid + MG_M] ^ mg_twist(src[tid], src[tid + 1]); dst[tid] = y; twd[tid] = mg_temper(y); }
-    __syncthreads();
-    if (tid < MG_D) { const int i = MG_D + tid; const uint32_t y = dst[i - MG_D] ^ mg_twist(src[i], src[i + 1]); dst[i] = y; twd[i] = mg_temper(y); }
-    __syncthreads();
-    if (tid < MG_N - 2 * MG_D) {
-        const int i = 2 * MG_D + tid;
-        const uint32_t nxt = (i == MG_N - 1) ? dst[0] : src[i + 1];
-        const uint32_t y = dst[i - MG_D] ^ mg_twist(src[i], nxt);
-        dst[i] = y; twd[i] = mg_temper(y);
-    }
-    __syncthreads();
-    ++s.gen_b;
-}
-// make words [.., upto) available (upto is uniform over the CTA)
-__device__ __forceinline__ void mg_ensure(MgStream& s, long long upto, int tid) {
-    while ((long long)(s.gen_b + 1) * MG_N < upto) mg_regenerate(s, tid);
-}
-__device__ __forceinline__ uint32_t mg_word(const MgStream& s, long long at) {
-    return s.tw[(int)(at % (MG_RING * MG_N))];
-}
+// is a gaussian cached at the start of evaluation e of a stream?  Every evaluation draws N values; an accepted attempt makes
+// two, so the cache state only depends on the parity of N and of e (c0 = the stream's incoming has_gauss)
+__device__ __forceinline__ int mg_cached(int c0, int N, int e) { return (N & 1) ? (c0 ^ (e & 1)) : c0; }
 
-__global__ void __launch_bounds__(MG_THREADS)
+__global__ void __launch_bounds__(MG_THREADS, 1)
 mt_gauss_kernel(uint32_t* __restrict__ mt_key, int32_t* __restrict__ mt_pos, int32_t* __restrict__ has_gauss_io,
-                double* __restrict__ gauss_io, int n_pairs, uint32_t rng, uint32_t mask, int coins, int N, double scale,
-                int64_t* __restrict__ idx_out, uint32_t* __restrict__ extra_out, float* __restrict__ noise_out) {
-    __shared__ uint32_t s_raw[MG_RING * MG_N];
-    __shared__ uint32_t s_tw[MG_RING * MG_N];
-    __shared__ int s_wtot[2][MG_WARPS];
-    __shared__ int s_end;
-    __shared__ int s_has;
-    __shared__ double s_spare;
+                const double* __restrict__ gauss_io, int n_pairs, uint32_t rng, uint32_t mask, int coins, int N,
+                int64_t* __restrict__ idx_out, uint32_t* __restrict__ extra_out, uint4* __restrict__ acc4, int a_max,
+                int32_t* __restrict__ c0_out, double* __restrict__ gauss0_out) {
+    extern __shared__ uint32_t mg_smem[];
+    uint32_t* s_raw = mg_smem;                                 // [MG_RING][624] raw state words (the recurrence, the state handed back)
+    uint32_t* s_tw = mg_smem + MG_RING * MG_N;                 // [MG_RING][624] tempered words (what the consumers read)
+    uint32_t* s_T = mg_smem + 2 * MG_RING * MG_N;              // [624] twists of the block being regenerated
+    __shared__ MgShared sh;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int sid = blockIdx.x;
-    MgStream st{s_raw, s_tw, 0};
     for (int i = tid; i < MG_N; i += MG_THREADS) {
         const uint32_t y = mt_key[(size_t)sid * MG_N + i];
-        s_raw[i] = y; s_tw[i] = mg_temper(y);
+        s_raw[i] = y; s_tw[mg_tw_slot(i)] = mg_temper(y);
     }
-    if (tid == 0) { s_has = has_gauss_io[sid]; s_spare = gauss_io[sid]; }
+    const long long cur0 = mt_pos[sid];
+    const int c0 = has_gauss_io[sid] ? 1 : 0;
+    if (tid == 0) { c0_out[sid] = c0; gauss0_out[sid] = gauss_io[sid]; }     // what the finishing kernel needs of the incoming cache
     __syncthreads();
-    long long cur = mt_pos[sid];                                   // absolute word position (block 0 = the incoming state)
-    int has = s_has;
-    double spare = s_spare;
+
+    // the cursor as (block, offset in the block, offset in the ring): 32-bit bookkeeping, no 64-bit divisions per step
+    int gen_b = 0;                                             // newest generated block (block 0 = the incoming state)
+#ifdef MG_PROFILE
+    long long pr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_start = clock64();
+#endif
+    int cblk = (int)(cur0 / MG_N), coff = (int)(cur0 % MG_N), cring = (int)(cur0 % (MG_RING * MG_N));
+    auto advance = [&](int n) {
+        coff += n;
+        while (coff >= MG_N) { coff -= MG_N; ++cblk; }
+        cring += n;
+        if (cring >= MG_RING * MG_N) cring -= MG_RING * MG_N;
+    };
+    // Next block of the recurrence into ring slot (b + 1) % MG_RING by the whole CTA.  The recurrence
+    // N[i] = N[i-227] ^ tw(O[i], O[i+1]) is XOR-linear in its first term, so with the 623 twists T[k] = tw(O[k], O[k+1]) of the
+    // OLD block (one per thread, exchanged through shared memory) every new word is a few XORs of old words and twists -- two
+    // barriers per block instead of the three dependent 227-word phases of the textbook form:
+    //   i <  227:  N[i] = O[i+397] ^ T[i]
+    //   i <  454:  N[i] = O[i+170] ^ T[i-227] ^ T[i]
+    //   i <  623:  N[i] = O[i-57]  ^ T[i-454] ^ T[i-227] ^ T[i]
+    //   N[623] = N[396] ^ tw(O[623], N[0])
+    // (recomputing the twists instead of sharing them -- one barrier, ~100 instructions per word -- measured slower.)
+    // word of this thread in the regeneration: every warp stays inside one of the three ranges and all three ranges run the SAME
+    // code (an unused twist index points at s_T[623], which holds 0); the odd word out (N[623], the longest expression) has a
+    // warp of its own: threads 0-226 | 256-482 | 512-680 | 704.  Everything that does not depend on the block is computed once.
+    const int my_i = (tid < 256) ? (tid < MG_D ? tid : -1) : (tid < 512) ? (tid - 256 < MG_D ? tid - 256 + MG_D : -1)
+                   : (tid < 704) ? (tid - 512 < MG_N - 1 - 2 * MG_D ? tid - 512 + 2 * MG_D : -1) : (tid == 704 ? MG_N - 1 : -1);
+    const bool plain = my_i >= 0 && my_i < MG_N - 1;
+    const int r_o = !plain ? 0 : (my_i < MG_D ? my_i + MG_M : my_i < 2 * MG_D ? my_i + MG_M - MG_D : my_i + MG_M - 2 * MG_D);
+    const int r_a = plain ? my_i : MG_N - 1;
+    const int r_b = (plain && my_i >= MG_D) ? my_i - MG_D : MG_N - 1;
+    const int r_c = (plain && my_i >= 2 * MG_D) ? my_i - 2 * MG_D : MG_N - 1;
+    const int r_tw = my_i >= 0 ? (my_i & 3) * MG_RQ + (my_i >> 2) : 0;       // mg_tw_slot(nslot * 624 + i) = r_tw + nslot * 156
+    if (tid == 0) s_T[MG_N - 1] = 0;
+    auto ensure = [&](int n) {                                 // the next n words are in the ring (n uniform over the CTA)
+        const int blocks = cblk + (coff + n + MG_N - 1) / MG_N;               // blocks [0, blocks) are needed
+        while (gen_b + 1 < blocks) {
+            const uint32_t* __restrict__ O = s_raw + (gen_b % MG_RING) * MG_N;
+            const int nslot = (gen_b + 1) % MG_RING;
+            uint32_t* __restrict__ dst = s_raw + nslot * MG_N;
+            if (tid < MG_N - 1) s_T[tid] = mg_twist(O[tid], O[tid + 1]);
+            __syncthreads();
+            if (plain) {
+                const uint32_t y = O[r_o] ^ s_T[r_a] ^ s_T[r_b] ^ s_T[r_c];
+                dst[my_i] = y; s_tw[r_tw + nslot * (MG_N / 4)] = mg_temper(y);
+            } else if (my_i == MG_N - 1) {
+                const uint32_t n0 = O[MG_M] ^ s_T[0];
+                const uint32_t n396 = O[396 + MG_M - MG_D] ^ s_T[396 - MG_D] ^ s_T[396];
+                const uint32_t y = n396 ^ mg_twist(O[MG_N - 1], n0);
+                dst[my_i] = y; s_tw[r_tw + nslot * (MG_N / 4)] = mg_temper(y);
+            }
+            __syncthreads();
+            ++gen_b;
+        }
+    };
+    auto word = [&](int ahead) -> uint32_t {                   // the word `ahead` positions after the cursor
+        int a = cring + ahead;
+        if (a >= MG_RW) a -= MG_RW;
+        return s_tw[mg_tw_slot(a)];
+    };
+    const int warp = tid >> 5;
     int64_t* idx_o = idx_out + (size_t)sid * n_pairs;
     uint32_t* ext_o = extra_out ? extra_out + (size_t)sid * n_pairs * 4 * coins : nullptr;
     unsigned step = 0;
@@ -110,84 +164,138 @@ mt_gauss_kernel(uint32_t* __restrict__ mt_key, int32_t* __restrict__ mt_pos, int
         // ---- rs.randint: masked rejection, every thread walks the same few words ----
         uint32_t w;
         do {
-            mg_ensure(st, cur + 1, tid);
-            w = mg_word(st, cur) & mask;
-            ++cur;
+            ensure(1);
+            w = word(0) & mask;
+            advance(1);
         } while (w > rng);
         if (tid == 0) idx_o[pair] = (int64_t)w;
         for (int sgn = 0; sgn < 2; ++sgn) {
             // ---- the fit_fn's save_obs coin(s) ----
-            mg_ensure(st, cur + 2 * coins, tid);
-            if (ext_o && tid < 2 * coins) ext_o[(size_t)pair * 4 * coins + sgn * 2 * coins + tid] = mg_word(st, cur + tid);
-            cur += 2 * coins;
-            // ---- T x randn(act): N gaussians ----
-            float* out = noise_out + ((size_t)((size_t)sid * n_pairs + pair) * 2 + sgn) * N;
-            int o = 0;
-            if (has && N > 0) {                                    // the cached second gaussian of an earlier attempt
-                if (tid == 0) { out[0] = (float)(spare * scale); s_has = 0; }
-                o = 1; has = 0; spare = 0.0;
-            }
-            while (o < N) {
-                const int need = (N - o + 1) >> 1;                 // accepted attempts still to find
-                mg_ensure(st, cur + MG_WIN, tid);
-                int at = (int)(cur % (MG_RING * MG_N)) + 4 * tid;  // ring offsets of this thread's four words
-                uint32_t wd[4];
+            ensure(2 * coins);
+            if (ext_o && tid < 2 * coins) ext_o[(size_t)pair * 4 * coins + sgn * 2 * coins + tid] = word(tid);
+            advance(2 * coins);
+            // ---- T x randn(act): N gaussians = the cached one (if any) + accepted attempts, two values each.  Only the accept /
+            //      reject arithmetic steers the stream: the accepted attempts' words are recorded in order and turned into
+            //      gaussians by mt_gauss_finish_kernel on the whole GPU ----
+            const int e = pair * 2 + sgn;
+            uint4* rec = acc4 + ((size_t)sid * 2 * n_pairs + e) * a_max;
+            int need = (N - mg_cached(c0, N, e) + 1) >> 1;            // accepted attempts still to find
+            int found = 0;
+            while (need > 0) {
+                // only as many words as the remaining attempts can use at the usual acceptance rate are regenerated up front
+                ensure(MG_WIN);
+                // this thread's MG_APT consecutive attempts (4 words each).  x = 2 u - 1 with u = (a >> 5, b >> 6) / 2^53: the
+                // 53-bit integer converts exactly, and one fused multiply-add rounds the exact value of 2 u - 1 once -- the
+                // reference's (2.0 * u) - 1.0 rounds the same exact value once (2 u is exact)
+                uint32_t wd[MG_APT][4];
+                bool acc[MG_APT];
+                unsigned bal[MG_APT];
+                const int ph = cring & 3;                      // the cursor's phase: word q of every attempt sits in quarter ring (ph + q) & 3
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    int a = at + q;
-                    if (a >= MG_RING * MG_N) a -= MG_RING * MG_N;
-                    wd[q] = s_tw[a];
+                for (int j = 0; j < MG_APT; ++j) {
+                    const int b4 = (cring >> 2) + MG_APT * tid + j;            // (ring offset of the attempt's first word) / 4, before wrapping
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        int k4 = b4 + ((ph + q) >> 2);
+                        if (k4 >= MG_RQ) k4 -= MG_RQ;
+                        wd[j][q] = s_tw[((ph + q) & 3) * MG_RQ + k4];
+                    }
+                    // u = (a >> 5, b >> 6) as a 53-bit integer, exactly, in float64; x = 2 u / 2^53 - 1: one fused multiply-add rounds
+                    // the exact value once, like the reference's (2.0 * u) - 1.0 (2 u is exact)
+                    const double v1 = fma((double)(wd[j][0] >> 5), 67108864.0, (double)(wd[j][1] >> 6));
+                    const double v2 = fma((double)(wd[j][2] >> 5), 67108864.0, (double)(wd[j][3] >> 6));
+                    const double x1 = fma(v1, 1.0 / 4503599627370496.0, -1.0), x2 = fma(v2, 1.0 / 4503599627370496.0, -1.0);
+                    const double r2 = __dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2));
+                    acc[j] = r2 < 1.0 && r2 != 0.0;
+                    bal[j] = __ballot_sync(0xffffffffu, acc[j]);
                 }
-                const double x1 = __dadd_rn(__dmul_rn(2.0, mg_double(wd[0], wd[1])), -1.0);
-                const double x2 = __dadd_rn(__dmul_rn(2.0, mg_double(wd[2], wd[3])), -1.0);
-                const double r2 = __dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2));
-                const bool acc = r2 < 1.0 && r2 != 0.0;
-                const unsigned bal = __ballot_sync(0xffffffffu, acc);
                 const unsigned buf = step & 1;
                 ++step;
-                if (lane == 0) s_wtot[buf][warp] = __popc(bal);
-                __syncthreads();
-                int before = 0, total = 0;
+                int wsum = 0, below = 0;                       // accepted in this warp; accepted by lower lanes
 #pragma unroll
-                for (int q = 0; q < MG_WARPS; ++q) {
-                    const int c = s_wtot[buf][q];
-                    before += (q < warp) ? c : 0;
-                    total += c;
+                for (int j = 0; j < MG_APT; ++j) { wsum += __popc(bal[j]); below += __popc(bal[j] & ((1u << lane) - 1u)); }
+                if (lane == 0) sh.wtot[buf][warp] = wsum;
+                __syncthreads();
+                int scan = (lane < MG_WARPS) ? sh.wtot[buf][lane] : 0;      // inclusive scan of the warp totals
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, scan, d);
+                    if (lane >= d) scan += up;
                 }
-                const int rank = before + __popc(bal & ((1u << lane) - 1u));
-                if (acc && rank < need) {
-                    const double f = sqrt(__ddiv_rn(__dmul_rn(-2.0, log(r2)), r2));
-                    const int p = o + 2 * rank;
-                    out[p] = (float)(__dmul_rn(__dmul_rn(f, x2), scale));
-                    const double g2 = __dmul_rn(f, x1);
-                    if (p + 1 < N) out[p + 1] = (float)(__dmul_rn(g2, scale));
-                    else { s_spare = g2; s_has = 1; }              // the last attempt's second value stays cached
-                    if (rank == need - 1) s_end = tid + 1;
+                const int total = __shfl_sync(0xffffffffu, scan, MG_WARPS - 1);
+                const int before = warp ? __shfl_sync(0xffffffffu, scan, warp - 1) : 0;
+                int rank = before + below;                     // rank of this thread's first attempt among the accepted ones
+#pragma unroll
+                for (int j = 0; j < MG_APT; ++j) {
+                    if (acc[j] && rank < need) {
+                        rec[found + rank] = make_uint4(wd[j][0], wd[j][1], wd[j][2], wd[j][3]);
+                        if (rank == need - 1) sh.end = MG_APT * tid + j + 1;
+                    }
+                    rank += acc[j] ? 1 : 0;
                 }
                 if (total >= need) {
-                    __syncthreads();                               // s_end (and s_has / s_spare) are written
-                    cur += 4 * s_end;
-                    o = N;
+                    __syncthreads();                           // sh.end is written
+                    advance(4 * sh.end);
+                    need = 0;
+                    __syncthreads();                           // ... and read by everyone before the next rollout can write it
                 } else {
-                    cur += MG_WIN;
-                    o += 2 * total;
+                    advance(MG_WIN);
+                    need -= total;
+                    found += total;
                 }
             }
-            // the cache after this rollout (s_has: cleared by the consumer above, set by the thread that produced an (N+1)-th value)
-            __syncthreads();
-            has = s_has; spare = s_spare;
-            __syncthreads();
         }
     }
-    // ---- hand the state back: the block the cursor is in, and its position ----
-    const int b_last = (int)(cur / MG_N) - ((cur % MG_N == 0 && cur > 0) ? 1 : 0);      // position 624 = block exhausted
-    mg_ensure(st, (long long)(b_last + 1) * MG_N, tid);
-    const uint32_t* fin = s_raw + (b_last % MG_RING) * MG_N;
-    for (int i = tid; i < MG_N; i += MG_THREADS) mt_key[(size_t)sid * MG_N + i] = fin[i];
+#ifdef MG_PROFILE
+    if (sid == 0 && (tid == 0 || tid == 300 || tid == 623))
+        printf("tid %d: %lld blocks: twist %lld, bar1 %lld, xor+temper %lld, bar2 %lld cycles per block; total kernel %lld cycles, %u steps\n", tid, pr[4],
+               pr[0] / max(pr[4], 1LL), pr[1] / max(pr[4], 1LL), pr[2] / max(pr[4], 1LL), pr[3] / max(pr[4], 1LL), clock64() - t_start, step);
+#endif
+    // ---- hand the state back: the block the cursor is in (position 624 = block exhausted), and its position ----
+    const bool at_end = coff == 0 && (cblk > 0);
+    const int b_last = at_end ? cblk - 1 : cblk;
+    ensure(0);                                                 // (block b_last is in the ring: the cursor has been there)
+    const uint32_t* last = s_raw + (b_last % MG_RING) * MG_N;
+    for (int i = tid; i < MG_N; i += MG_THREADS) mt_key[(size_t)sid * MG_N + i] = last[i];
     if (tid == 0) {
-        mt_pos[sid] = (int32_t)(cur - (long long)b_last * MG_N);
-        has_gauss_io[sid] = has;
-        gauss_io[sid] = has ? spare : 0.0;
+        mt_pos[sid] = at_end ? MG_N : coff;
+        has_gauss_io[sid] = mg_cached(c0, N, 2 * n_pairs);     // (the cached VALUE is written by the finishing kernel)
+    }
+}
+
+// The recorded attempts -> gaussians, on the whole GPU: attempt r of evaluation e gives values c_e + 2r (f*x2) and c_e + 2r + 1
+// (f*x1) of the evaluation's N; a value N (the second of the last attempt) is the cache: the first value of the stream's next
+// evaluation, or the cached gaussian the stream hands back.
+__global__ void __launch_bounds__(256)
+mt_gauss_finish_kernel(const uint4* __restrict__ acc4, int a_max, const int32_t* __restrict__ c0_in, const double* __restrict__ gauss0,
+                       int n_streams, int n_pairs, int N, double scale, float* __restrict__ noise_out, double* __restrict__ gauss_io) {
+    const long long per_eval = a_max;
+    const long long total = (long long)n_streams * 2 * n_pairs * per_eval;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i % per_eval);
+        const long long ge = i / per_eval;                     // evaluation, stream-major
+        const int e = (int)(ge % (2 * n_pairs)), sid = (int)(ge / (2 * n_pairs));
+        const int c0 = c0_in[sid];
+        const int ce = mg_cached(c0, N, e);
+        const int need = (N - ce + 1) >> 1;
+        float* out = noise_out + (size_t)ge * N;
+        if (r == 0) {
+            if (e == 0 && ce && N > 0) out[0] = (float)__dmul_rn(gauss0[sid], scale);     // the stream's incoming cached gaussian
+            if (e == 2 * n_pairs - 1 && !mg_cached(c0, N, 2 * n_pairs)) gauss_io[sid] = 0.0;   // nothing cached afterwards
+            if (N == 0 && e == 0 && c0) gauss_io[sid] = gauss0[sid];                       // no draws at all: the cache is untouched
+        }
+        if (r >= need) continue;
+        const uint4 w = acc4[i];
+        const double x1 = __dadd_rn(__dmul_rn(2.0, mg_double(w.x, w.y)), -1.0);
+        const double x2 = __dadd_rn(__dmul_rn(2.0, mg_double(w.z, w.w)), -1.0);
+        const double r2 = __dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2));
+        const double f = sqrt(__ddiv_rn(__dmul_rn(-2.0, log(r2)), r2));
+        const int p = ce + 2 * r;
+        out[p] = (float)__dmul_rn(__dmul_rn(f, x2), scale);
+        const double g2 = __dmul_rn(f, x1);
+        if (p + 1 < N) out[p + 1] = (float)__dmul_rn(g2, scale);
+        else if (e + 1 < 2 * n_pairs) out[N] = (float)__dmul_rn(g2, scale);              // = value 0 of the stream's next evaluation
+        else gauss_io[sid] = g2;                                                          // the cache the stream hands back
     }
 }
 
@@ -203,8 +311,27 @@ int es_impl_draw_noisy(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int32_t* 
         es_set_error("es_draw_noisy: upper_bound == 1 is not supported");
         return ES_ERR_UNSUPPORTED;
     }
-    mt_gauss_kernel<<<n_streams, MG_THREADS, 0, stream>>>(mt_key, mt_pos, has_gauss, gauss, n_per_stream, rng, mask, coins,
-                                                          normals_per_eval, scale, idx_out, extra_out, noise_out);
+    // scratch: the accepted attempts' words [stream][evaluation][a_max] (16 bytes per two gaussians), the incoming cache per stream
+    const int a_max = (normals_per_eval + 1) / 2 > 0 ? (normals_per_eval + 1) / 2 : 1;
+    const size_t n_eval = (size_t)n_streams * 2 * n_per_stream;
+    const size_t acc_bytes = (n_eval * a_max * sizeof(uint4) + 255) & ~(size_t)255;
+    const size_t c0_bytes = ((size_t)n_streams * sizeof(int32_t) + 255) & ~(size_t)255;
+    void* scratch = nullptr;
+    int rc = es_ctx_scratch(ctx, acc_bytes + c0_bytes + (size_t)n_streams * sizeof(double), &scratch);
+    if (rc) return rc;
+    uint4* acc4 = (uint4*)scratch;
+    int32_t* c0 = (int32_t*)((char*)scratch + acc_bytes);
+    double* gauss0 = (double*)((char*)scratch + acc_bytes + c0_bytes);
+    const size_t smem = (size_t)(2 * MG_RING + 1) * MG_N * sizeof(uint32_t);
+    ES_CHECK_CUDA(cudaFuncSetAttribute(mt_gauss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mt_gauss_kernel<<<n_streams, MG_THREADS, smem, stream>>>(mt_key, mt_pos, has_gauss, gauss, n_per_stream, rng, mask, coins,
+                                                             normals_per_eval, idx_out, extra_out, acc4, a_max, c0, gauss0);
+    ES_LAUNCHED(ctx);
+    const long long total = (long long)n_eval * a_max;
+    int blocks = es_div_up(total, 256);
+    if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+    mt_gauss_finish_kernel<<<blocks, 256, 0, stream>>>(acc4, a_max, c0, gauss0, n_streams, n_per_stream, normals_per_eval, scale,
+                                                       noise_out, gauss);
     ES_LAUNCHED(ctx);
     return ES_OK;
 }
