@@ -16,8 +16,11 @@
 //     activation rows are read by all lanes at the same address (2 wavefronts each) and every lane reads its own 2 weight
 //     rows (4 each): 24 wavefronts per 32 FFMA2 (= 16 FMA-pipe cycles) -- the same as the first version's 4 x 4 tiles with 8
 //     rows x 4 units per warp (8 loads of ~3.3 wavefronts), and the two run equally fast: LSU data pipe 70 %, FMA pipe 47 %,
-//     24.4 ms per K = 10 000 generation.  With 32 accumulator pairs per thread the balanced tile would be 8 x 4 (16 wavefronts
-//     per 32 FFMA2), which needs 256-thread CTAs (a 128-step tile has only 8 192 outputs) -- not built.
+//     24.4 ms per K = 10 000 generation.  tools/bench_src/lds_bench.cu measures the load costs directly: 2.4 cycles for a
+//     128-bit load with 1, 2 or 4 distinct addresses per warp, 4.0 with 8 or more.  By that model 8 x 4 tiles for layer 1 (two
+//     teams of 8 warps splitting the K chunks, half-warp-broadcast rows, partial sums merged through shared memory) should cut
+//     layer 1's LSU time by a third; built and measured: 25.6 ms, no gain (64 accumulator registers leave the compiler no room
+//     to prefetch the next operands) -- reverted.
 //   * eps1 is never converted or scaled: cp.async (4-byte granules: a slice has 4-byte alignment only) moves the next pair's
 //     64 x obs block into shared memory while the last tile of the current pair is in its layers 2 / 3;
 //   * the observation tiles are pre-tiled once per generation into the shared-memory image of every (tile, 16-column chunk)
