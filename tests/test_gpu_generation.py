@@ -613,3 +613,54 @@ def test_run_model_with_action_noise_stays_on_the_device(eng):
     assert np.allclose(behv[-3:], bb[-3:], rtol=1e-4, atol=1e-5)
     sa, sb = a.get_state(), b.get_state()
     assert np.array_equal(sa[1], sb[1]) and sa[2:] == sb[2:]
+
+
+@pytest.mark.parametrize('n_streams', [1, 3])
+def test_api_step_fused_with_action_noise_matches_the_oracle(eng, n_streams):
+    """es.step on the single-synchronisation route with a BatchedRollout and ac_std = 0.01, two generations with the ac_std /
+    sigma decays of obj.py:81-82 in between: per generation the device draws indices, coins and T x act gaussians per
+    rollout in stream order (es_draw_noisy), the noiseless evaluation draws its coin but no noise (fit_fn(model, False),
+    es.py:48).  Against the oracle's es_step: indices and the callers' RandomState objects (key, position, has_gauss)
+    exact, cached gaussian to 2 ulp, fitness and theta to float32 tolerance."""
+    from es_pytorch_b200 import dist
+    from es_pytorch_b200.core import es
+    from es_pytorch_b200.gym.batched import BatchedRollout
+    from es_pytorch_b200.utils.rankers import CenteredRanker
+    from es_pytorch_b200.utils.reporters import Reporter
+    obs_dim, act_dim, hidden, T, n = 17, 5, (64, 64), 37, 4          # T * act odd: the gaussian cache crosses rollouts
+    spec = orc.SyntheticEnvSpec(obs_dim, act_dim, T)
+    dims = orc.layer_dims(obs_dim, hidden, act_dim)
+    P = orc.n_params(dims)
+    rs0 = np.random.RandomState(5)
+    table, theta = rs0.randn(P + 150_000).astype(np.float32), (rs0.randn(P) * 0.1).astype(np.float32)
+    env, net, policy, nt = _api_objects(eng, table, theta.copy(), spec, hidden)
+    net._action_std = 0.01
+    seeds = [910 + 3 * r for r in range(n_streams)]
+    streams = [np.random.RandomState(s) for s in seeds]
+    ref_streams = [np.random.RandomState(s) for s in seeds]
+    streams[0].randn(1); ref_streams[0].randn(1)                      # the first stream starts with a cached gaussian
+    fit_fn = BatchedRollout(env, T, coins_per_eval=1, save_obs_chance=0.25, rank_streams=streams)
+    cfg = _Cfg(general=_Cfg(policies_per_gen=2 * n, batch_size=500), policy=_Cfg(l2coeff=0.005))
+    ranker = CenteredRanker()
+    assert es._can_fuse_step(dist.world(), policy, fit_fn, ranker)
+    flat, opt = theta.copy(), orc.AdamOracle(P, 0.01)
+    stat = orc.ObStatOracle((obs_dim,), 1e-2)
+    obmean, obstd, std, ac_std = np.zeros(obs_dim), np.ones(obs_dim), 0.02, 0.01
+    for g in range(2):
+        tr, gen_obstat = es.step(cfg, dist.world(), policy, nt, env, fit_fn, streams[0], ranker, Reporter())
+        policy.update_obstat(gen_obstat)
+        ref = orc.es_step(table, flat, opt, std, dims, spec, ref_streams, n, obmean, obstd, 5.0, T, 500, 0.005, coins_per_eval=1,
+                          save_obs_chance=0.25, batched=False, ac_std=ac_std)
+        stat.inc(ref['obstat'].sum, ref['obstat'].sumsq, ref['obstat'].count)
+        obmean, obstd = stat.mean, stat.std
+        assert np.array_equal(np.asarray(ranker.noise_inds), ref['inds'])
+        assert np.abs(ranker.fits_pos - ref['pos']).max() <= 1e-4 and np.abs(ranker.fits_neg - ref['neg']).max() <= 1e-4
+        assert np.array_equal(gen_obstat.sum, ref['obstat'].sum) and gen_obstat.count == ref['obstat'].count
+        assert np.abs(policy.flat_params - flat).max() <= 3e-6
+        assert abs(tr.result[0] - ref['noiseless'][0]) <= 1e-4
+        for a, b in zip(streams, ref_streams):
+            sa, sb = a.get_state(), b.get_state()
+            assert np.array_equal(sa[1], sb[1]) and sa[2] == sb[2] and sa[3] == sb[3], f'stream state after generation {g}'
+            assert abs(sa[4] - sb[4]) <= 2 * np.spacing(abs(sb[4]))
+        ac_std *= 0.5; net._action_std = ac_std                       # obj.py:81
+        std *= 0.9; policy.std = std                                  # obj.py:82
