@@ -206,7 +206,13 @@ class DeviceGeneration:
             e.novelty(self.behv.view(-1, 3), self.archive, self.nov_k, self.fit_local.view(-1)[1:], 2)
         self._gen_stats.zero_()
         if self.extra_words:
-            s, q = e.obs_colsum(self.obs_stream[1:self.T + 1])
+            # column sums of the post-step observations of a rollout: the open-loop stream is the same for every rollout and
+            # every generation, so they are computed once per content of the stream (torch's version counter sees every write)
+            ver = self.obs_stream._version
+            if getattr(self, '_colsum_for', None) != ver:
+                self._colsum = e.obs_colsum(self.obs_stream[1:self.T + 1])
+                self._colsum_for = ver
+            s, q = self._colsum
             e.obstat_accumulate_coins(self.gen_sum, self.gen_sumsq, self.gen_count, s, q, self.T,
                                       self.extras.view(-1, 2), self.save_obs_chance)
         if self.comm.size > 1:
