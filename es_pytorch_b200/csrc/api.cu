@@ -113,6 +113,10 @@ static int es_async_error(es_ctx* ctx, const char* where) {
             es_set_error("%s: a previous kernel was given a noise index outside the table (index < 0 or index + n_params >= "
                          "table length; the reference asserts this in NoiseTable.get, src/core/noisetable.py:34): the "
                          "results of that call are invalid", where);
+        else if (code == ES_ASYNC_RNG_OVERFLOW)
+            es_set_error("%s: es_draw_noisy consumed more MT19937 words than its jump-ahead pass had generated (a > 12 sigma "
+                         "event of the polar method's acceptance count, or a bug): the draws of that call are invalid; set "
+                         "ES_MT_JUMP=0 to use the sequential kernel", where);
         else
             es_set_error("%s: a previous kernel reported error %d", where, code);
         return ES_ERR_INVALID;

@@ -37,6 +37,7 @@ struct es_ctx {
 };
 
 #define ES_ASYNC_BAD_INDEX 1
+#define ES_ASYNC_RNG_OVERFLOW 2      // es_draw_noisy (jump-ahead path): the stream consumed more words than were generated ahead
 
 void es_set_error(const char* fmt, ...);
 

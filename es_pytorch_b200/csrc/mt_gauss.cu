@@ -31,7 +31,10 @@
 // relative on a term that is ~1e-2 of the action).
 // log() here is CUDA's (<= 1 ulp), the reference's is glibc's: a gaussian can differ in its last float64 bit, which the
 // float32 noise array does not see; the accept/reject arithmetic (the only part that steers the stream) is exact.
+#include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
+#include "mt19937.cuh"
 
 namespace {
 
@@ -45,17 +48,8 @@ constexpr int MG_APT = 2;                                      // attempts per t
 constexpr int MG_WIN = 4 * MG_APT * MG_THREADS;                // words tested per step (5888 = 9.4 blocks)
 static_assert((MG_RING - 2) * MG_N >= MG_WIN + MG_N, "the ring holds the cursor's block and a whole window ahead of it");
 
-__device__ __forceinline__ uint32_t mg_twist(uint32_t u, uint32_t v) {
-    const uint32_t y = (u & 0x80000000u) | (v & 0x7FFFFFFFu);
-    return (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
-}
-__device__ __forceinline__ uint32_t mg_temper(uint32_t y) {
-    y ^= y >> 11;
-    y ^= (y << 7) & 0x9D2C5680u;
-    y ^= (y << 15) & 0xEFC60000u;
-    y ^= y >> 18;
-    return y;
-}
+__device__ __forceinline__ uint32_t mg_twist(uint32_t u, uint32_t v) { return mt19937_twist(u, v); }
+__device__ __forceinline__ uint32_t mg_temper(uint32_t y) { return mt19937_temper(y); }
 // Where ring word k (0 <= k < MG_RW) of the TEMPERED stream lives: word k sits in quarter ring k % 4 at k / 4, so that the four
 // words of consecutive attempts (k = s + 4a + q) are consecutive in shared memory for a fixed q: the attempt windows read
 // without bank conflicts (stride-4 or stride-8 word reads were 4- / 8-way conflicts and half of a window step's time)
@@ -299,6 +293,203 @@ mt_gauss_finish_kernel(const uint4* __restrict__ acc4, int a_max, const int32_t*
     }
 }
 
+// =====================================================================================================================
+// Jump-ahead: ONE stream regenerated by many CTAs.
+//
+// The state transition of MT19937 is linear over GF(2); with g_r(x) = x^(624 * 2^r) mod phi(x) (phi = its characteristic
+// polynomial, tools/mt_jump/make_jump_polys.py) every word of the raw sequence obeys x[n + 624 * 2^r] = XOR_{i : g_r,i = 1}
+// x[n + i].  So the state 2^r blocks ahead is, word by word, an XOR of ~10 000 words out of the next 20 560: independent per
+// word, no recurrence to follow.  mt_fill_kernel gives every CTA one segment of 2^lb blocks of one stream: it jumps from the
+// stream's current state to its segment's first block (one jump per set bit of the block index), regenerates the segment and
+// writes the TEMPERED words to global memory; mt_gauss_gw_kernel then walks the stream exactly like mt_gauss_kernel, but reads
+// the words instead of regenerating them -- what is left on the sequential path is the accept / reject bookkeeping.
+// =====================================================================================================================
+constexpr int MJ_NPOLY = 18;
+constexpr int MJ_WIN_BLOCKS = 33;                              // the state block + 32 more: 20 592 words >= 19 937 + 624
+__device__ const uint32_t mj_polys[MJ_NPOLY][MT_NW] = {
+#include "mt_jump_polys.inc"
+};
+
+__global__ void __launch_bounds__(MG_THREADS, 1)
+mt_fill_kernel(const uint32_t* __restrict__ mt_key, int n_seg, int lb_log2, uint32_t* __restrict__ words, size_t stride_words) {
+    extern __shared__ uint32_t mj_smem[];
+    uint32_t* xs = mj_smem;                                    // [33][624] raw words: the jump window; blocks 0 / 1: ping-pong of the fill
+    uint32_t* s_T = mj_smem + MJ_WIN_BLOCKS * MT_NW;           // [624] twists
+    uint32_t* s_g = s_T + MT_NW;                               // [624] the polynomial of the current jump
+    const int tid = threadIdx.x;
+    const int sid = blockIdx.x / n_seg, k = blockIdx.x % n_seg;
+    Mt19937Regen rg;
+    rg.init(tid);
+    uint32_t* __restrict__ out = words + (size_t)sid * stride_words;
+    for (int i = tid; i < MT_NW; i += MG_THREADS) {
+        const uint32_t y = mt_key[(size_t)sid * MT_NW + i];
+        xs[i] = y;
+        if (k == 0) out[i] = mt19937_temper(y);               // block 0 = the incoming state: its unread words belong to the stream
+    }
+    if (tid == 0) s_T[MT_NW - 1] = 0;
+    __syncthreads();
+    auto regen = [&](const uint32_t* __restrict__ O, uint32_t* __restrict__ dst, uint32_t* __restrict__ tw_out) {
+        if (tid < MT_NW - 1) s_T[tid] = mt19937_twist(O[tid], O[tid + 1]);
+        __syncthreads();
+        if (rg.my_i >= 0) {
+            const uint32_t y = rg.word(O, s_T);
+            dst[rg.my_i] = y;
+            if (tw_out) tw_out[rg.my_i] = mt19937_temper(y);
+        }
+        __syncthreads();
+    };
+    // ---- jump to block k << lb_log2: one jump per set bit ----
+    const unsigned target = (unsigned)k << lb_log2;
+    for (int r = MJ_NPOLY - 1; r >= 0; --r) {
+        if (!((target >> r) & 1u)) continue;
+        for (int b = 1; b < MJ_WIN_BLOCKS; ++b) regen(xs + (b - 1) * MT_NW, xs + b * MT_NW, nullptr);
+        for (int i = tid; i < MT_NW; i += MG_THREADS) s_g[i] = mj_polys[r][i];
+        __syncthreads();
+        uint32_t acc = 0;
+        if (tid < MT_NW) {
+            for (int w = 0; w < MT_NW; ++w) {
+                uint32_t gw = s_g[w];
+                const uint32_t* __restrict__ xw = xs + tid + 32 * w;
+                while (gw) {
+                    const int bit = __ffs(gw) - 1;
+                    acc ^= xw[bit];
+                    gw &= gw - 1;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < MT_NW) xs[tid] = acc;                        // (word 0: only its top bit is state, and that bit is right)
+        __syncthreads();
+    }
+    // ---- regenerate the segment: blocks target + 1 .. target + 2^lb ----
+    const int Lb = 1 << lb_log2;
+    int cur = 0;
+    for (int b = 0; b < Lb; ++b) {
+        regen(xs + cur * MT_NW, xs + (cur ^ 1) * MT_NW, out + ((size_t)1 + target + b) * MT_NW);
+        cur ^= 1;
+    }
+}
+
+// mt_gauss_kernel over words in global memory (mt_fill_kernel's output): the same walk, no regeneration.
+__global__ void __launch_bounds__(MG_THREADS, 1)
+mt_gauss_gw_kernel(uint32_t* __restrict__ mt_key, int32_t* __restrict__ mt_pos, int32_t* __restrict__ has_gauss_io,
+                   const double* __restrict__ gauss_io, int n_pairs, uint32_t rng, uint32_t mask, int coins, int N,
+                   int64_t* __restrict__ idx_out, uint32_t* __restrict__ extra_out, uint4* __restrict__ acc4, int a_max,
+                   int32_t* __restrict__ c0_out, double* __restrict__ gauss0_out, const uint32_t* __restrict__ words,
+                   size_t stride_words, int* __restrict__ err) {
+    __shared__ MgShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sid = blockIdx.x;
+    const uint32_t* __restrict__ gw = words + (size_t)sid * stride_words;
+    const size_t limit = stride_words - 8;                     // the walk may read up to here
+    size_t cpos = (size_t)mt_pos[sid];                         // absolute word position (block 0 = the incoming state)
+    const int c0 = has_gauss_io[sid] ? 1 : 0;
+    if (tid == 0) { c0_out[sid] = c0; gauss0_out[sid] = gauss_io[sid]; }
+    int64_t* idx_o = idx_out + (size_t)sid * n_pairs;
+    uint32_t* ext_o = extra_out ? extra_out + (size_t)sid * n_pairs * 4 * coins : nullptr;
+    unsigned step = 0;
+    bool overflow = false;
+
+    for (int pair = 0; pair < n_pairs && !overflow; ++pair) {
+        uint32_t w;
+        do {
+            if (cpos + 1 > limit) { overflow = true; break; }
+            w = __ldg(gw + cpos) & mask;
+            ++cpos;
+        } while (w > rng);
+        if (overflow) break;
+        if (tid == 0) idx_o[pair] = (int64_t)w;
+        for (int sgn = 0; sgn < 2 && !overflow; ++sgn) {
+            if (cpos + 2 * coins > limit) { overflow = true; break; }
+            if (ext_o && tid < 2 * coins) ext_o[(size_t)pair * 4 * coins + sgn * 2 * coins + tid] = __ldg(gw + cpos + tid);
+            cpos += 2 * coins;
+            const int e = pair * 2 + sgn;
+            uint4* rec = acc4 + ((size_t)sid * 2 * n_pairs + e) * a_max;
+            int need = (N - mg_cached(c0, N, e) + 1) >> 1;
+            int found = 0;
+            bool have_next = false;
+            uint32_t nx[MG_APT][4];
+            while (need > 0) {
+                if (cpos + MG_WIN > limit) { overflow = true; break; }
+                uint32_t wd[MG_APT][4];
+                bool acc[MG_APT];
+                unsigned bal[MG_APT];
+                const uint32_t* __restrict__ mine = gw + cpos + 4 * MG_APT * tid;
+#pragma unroll
+                for (int j = 0; j < MG_APT; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) wd[j][q] = have_next ? nx[j][q] : __ldg(mine + 4 * j + q);
+                // the next window's words, assuming this one is used up (true for all but the last window of a rollout): in
+                // flight while this window is processed
+                const bool can_next = cpos + 2 * (size_t)MG_WIN <= limit;
+                if (can_next) {
+#pragma unroll
+                    for (int j = 0; j < MG_APT; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) nx[j][q] = __ldg(mine + MG_WIN + 4 * j + q);
+                }
+#pragma unroll
+                for (int j = 0; j < MG_APT; ++j) {
+                    const double v1 = fma((double)(wd[j][0] >> 5), 67108864.0, (double)(wd[j][1] >> 6));
+                    const double v2 = fma((double)(wd[j][2] >> 5), 67108864.0, (double)(wd[j][3] >> 6));
+                    const double x1 = fma(v1, 1.0 / 4503599627370496.0, -1.0), x2 = fma(v2, 1.0 / 4503599627370496.0, -1.0);
+                    const double r2 = __dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2));
+                    acc[j] = r2 < 1.0 && r2 != 0.0;
+                    bal[j] = __ballot_sync(0xffffffffu, acc[j]);
+                }
+                const unsigned buf = step & 1;
+                ++step;
+                int wsum = 0, below = 0;
+#pragma unroll
+                for (int j = 0; j < MG_APT; ++j) { wsum += __popc(bal[j]); below += __popc(bal[j] & ((1u << lane) - 1u)); }
+                if (lane == 0) sh.wtot[buf][warp] = wsum;
+                __syncthreads();
+                int scan = (lane < MG_WARPS) ? sh.wtot[buf][lane] : 0;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, scan, d);
+                    if (lane >= d) scan += up;
+                }
+                const int total = __shfl_sync(0xffffffffu, scan, MG_WARPS - 1);
+                const int before = warp ? __shfl_sync(0xffffffffu, scan, warp - 1) : 0;
+                int rank = before + below;
+#pragma unroll
+                for (int j = 0; j < MG_APT; ++j) {
+                    if (acc[j] && rank < need) {
+                        rec[found + rank] = make_uint4(wd[j][0], wd[j][1], wd[j][2], wd[j][3]);
+                        if (rank == need - 1) sh.end = MG_APT * tid + j + 1;
+                    }
+                    rank += acc[j] ? 1 : 0;
+                }
+                if (total >= need) {
+                    __syncthreads();
+                    cpos += 4 * (size_t)sh.end;
+                    need = 0;
+                    __syncthreads();
+                } else {
+                    cpos += MG_WIN;
+                    need -= total;
+                    found += total;
+                    have_next = can_next;
+                }
+            }
+        }
+    }
+    if (overflow) {                                            // more words than the fill provided: nothing is handed back
+        if (tid == 0 && err) *(volatile int*)err = ES_ASYNC_RNG_OVERFLOW;
+        return;
+    }
+    // ---- hand the state back: the raw words behind the tempered words of the cursor's block ----
+    const size_t blk = cpos / MT_NW, off = cpos % MT_NW;
+    const bool at_end = off == 0 && blk > 0;
+    const size_t b_last = at_end ? blk - 1 : blk;
+    for (int i = tid; i < MT_NW; i += MG_THREADS) mt_key[(size_t)sid * MT_NW + i] = mt19937_untemper(__ldg(gw + b_last * MT_NW + i));
+    if (tid == 0) {
+        mt_pos[sid] = at_end ? MT_NW : (int32_t)off;
+        has_gauss_io[sid] = mg_cached(c0, N, 2 * n_pairs);
+    }
+}
+
 }  // namespace
 
 int es_impl_draw_noisy(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int32_t* has_gauss, double* gauss, int n_streams,
@@ -311,27 +502,69 @@ int es_impl_draw_noisy(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int32_t* 
         es_set_error("es_draw_noisy: upper_bound == 1 is not supported");
         return ES_ERR_UNSUPPORTED;
     }
-    // scratch: the accepted attempts' words [stream][evaluation][a_max] (16 bytes per two gaussians), the incoming cache per stream
-    const int a_max = (normals_per_eval + 1) / 2 > 0 ? (normals_per_eval + 1) / 2 : 1;
+    const int N = normals_per_eval;
+    // ---- how many words can a stream consume?  Per rollout ceil(N / 2) accepted attempts at acceptance pi / 4 (a negative
+    //      binomial count), 4 words each; per pair one index draw (~1.08 words with rejections, bounded generously) and the
+    //      coins.  The jump-ahead pass generates the mean + 12 sigma of the total (+ slack); the walk flags an overflow. ----
+    const double p_acc = 0.78539816339744830962, n_acc = (N + 1) / 2;
+    const double att_mean = n_acc / p_acc, att_sd = sqrt(n_acc * (1.0 - p_acc)) / p_acc;
+    const double evals = 2.0 * n_per_stream;
+    const double words_max = 624.0 + n_per_stream * (8.0 + 4.0 * coins) + 4.0 * (evals * att_mean + 12.0 * sqrt(evals) * att_sd + 64.0) +
+                             2.0 * MG_WIN + 16.0 * MT_NW;
+    const long long blocks_needed = (long long)(words_max / MT_NW) + 1;
+    // jump-ahead when a stream is long enough to be worth splitting (ES_MT_JUMP=0 / 1 overrides; ES_MT_JUMP_LB: log2 of the
+    // segment length in blocks, for tests)
+    const char* ej = getenv("ES_MT_JUMP");
+    const bool jump = ej ? atoi(ej) != 0 : blocks_needed >= 2048;
+    int lb_log2 = 3;
+    if (jump) {
+        const char* el = getenv("ES_MT_JUMP_LB");
+        if (el) lb_log2 = atoi(el);
+        else
+            while (lb_log2 < MJ_NPOLY - 1 && (long long)n_streams * ((blocks_needed + (1LL << lb_log2) - 1) >> lb_log2) > 4LL * ctx->sm_count) ++lb_log2;
+        if (lb_log2 < 0) lb_log2 = 0;
+        if (lb_log2 > MJ_NPOLY - 1) lb_log2 = MJ_NPOLY - 1;
+    }
+    const long long n_seg = jump ? (blocks_needed + (1LL << lb_log2) - 1) >> lb_log2 : 0;
+    if (jump && ((n_seg << lb_log2) >> MJ_NPOLY) != 0) {       // the block index of a segment start must fit the available jumps
+        es_set_error("es_draw_noisy: %lld blocks per stream exceed the jump-ahead range (2^%d blocks)", n_seg << lb_log2, MJ_NPOLY);
+        return ES_ERR_UNSUPPORTED;
+    }
+    const size_t stride_words = jump ? (size_t)(1 + (n_seg << lb_log2)) * MT_NW : 0;
+    // scratch: [the streams' words (jump-ahead only)] the accepted attempts' words [stream][evaluation][a_max] (16 bytes per two
+    // gaussians), the incoming cache per stream
+    const int a_max = (N + 1) / 2 > 0 ? (N + 1) / 2 : 1;
     const size_t n_eval = (size_t)n_streams * 2 * n_per_stream;
+    const size_t words_bytes = ((size_t)n_streams * stride_words * sizeof(uint32_t) + 255) & ~(size_t)255;
     const size_t acc_bytes = (n_eval * a_max * sizeof(uint4) + 255) & ~(size_t)255;
     const size_t c0_bytes = ((size_t)n_streams * sizeof(int32_t) + 255) & ~(size_t)255;
     void* scratch = nullptr;
-    int rc = es_ctx_scratch(ctx, acc_bytes + c0_bytes + (size_t)n_streams * sizeof(double), &scratch);
+    int rc = es_ctx_scratch(ctx, words_bytes + acc_bytes + c0_bytes + (size_t)n_streams * sizeof(double), &scratch);
     if (rc) return rc;
-    uint4* acc4 = (uint4*)scratch;
-    int32_t* c0 = (int32_t*)((char*)scratch + acc_bytes);
-    double* gauss0 = (double*)((char*)scratch + acc_bytes + c0_bytes);
-    const size_t smem = (size_t)(2 * MG_RING + 1) * MG_N * sizeof(uint32_t);
-    ES_CHECK_CUDA(cudaFuncSetAttribute(mt_gauss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mt_gauss_kernel<<<n_streams, MG_THREADS, smem, stream>>>(mt_key, mt_pos, has_gauss, gauss, n_per_stream, rng, mask, coins,
-                                                             normals_per_eval, idx_out, extra_out, acc4, a_max, c0, gauss0);
-    ES_LAUNCHED(ctx);
+    uint32_t* words = (uint32_t*)scratch;
+    uint4* acc4 = (uint4*)((char*)scratch + words_bytes);
+    int32_t* c0 = (int32_t*)((char*)scratch + words_bytes + acc_bytes);
+    double* gauss0 = (double*)((char*)scratch + words_bytes + acc_bytes + c0_bytes);
+    if (jump) {
+        const size_t smem = (size_t)(MJ_WIN_BLOCKS + 2) * MT_NW * sizeof(uint32_t);
+        ES_CHECK_CUDA(cudaFuncSetAttribute(mt_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mt_fill_kernel<<<(unsigned)(n_streams * n_seg), MG_THREADS, smem, stream>>>(mt_key, (int)n_seg, lb_log2, words, stride_words);
+        ES_LAUNCHED(ctx);
+        mt_gauss_gw_kernel<<<n_streams, MG_THREADS, 0, stream>>>(mt_key, mt_pos, has_gauss, gauss, n_per_stream, rng, mask, coins, N,
+                                                               idx_out, extra_out, acc4, a_max, c0, gauss0, words, stride_words,
+                                                               ctx->err_dev);
+        ES_LAUNCHED(ctx);
+    } else {
+        const size_t smem = (size_t)(2 * MG_RING + 1) * MG_N * sizeof(uint32_t);
+        ES_CHECK_CUDA(cudaFuncSetAttribute(mt_gauss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mt_gauss_kernel<<<n_streams, MG_THREADS, smem, stream>>>(mt_key, mt_pos, has_gauss, gauss, n_per_stream, rng, mask, coins, N,
+                                                                 idx_out, extra_out, acc4, a_max, c0, gauss0);
+        ES_LAUNCHED(ctx);
+    }
     const long long total = (long long)n_eval * a_max;
     int blocks = es_div_up(total, 256);
     if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
-    mt_gauss_finish_kernel<<<blocks, 256, 0, stream>>>(acc4, a_max, c0, gauss0, n_streams, n_per_stream, normals_per_eval, scale,
-                                                       noise_out, gauss);
+    mt_gauss_finish_kernel<<<blocks, 256, 0, stream>>>(acc4, a_max, c0, gauss0, n_streams, n_per_stream, N, scale, noise_out, gauss);
     ES_LAUNCHED(ctx);
     return ES_OK;
 }
