@@ -306,6 +306,28 @@ mt_gauss_finish_kernel(const uint4* __restrict__ acc4, int a_max, const int32_t*
 // =====================================================================================================================
 constexpr int MJ_NPOLY = 18;
 constexpr int MJ_WIN_BLOCKS = 33;                              // the state block + 32 more: 20 592 words >= 19 937 + 624
+// Layout of a stream's tempered words in global memory: chunks of MJ_C = 4 * MG_THREADS words (one 16-byte cp.async per thread
+// moves a chunk into the walker's shared-memory ring); inside a chunk word k sits at (k % 4) * MJ_C / 4 + k / 4, so that the
+// q-th words of consecutive attempts are consecutive: the attempt windows read shared memory without bank conflicts.
+constexpr int MJ_C = 4 * MG_THREADS, MJ_CQ = MJ_C / 4;
+#ifndef MJ_NCH_T
+#define MJ_NCH_T 16
+#endif
+constexpr int MJ_NCH = MJ_NCH_T;                               // chunks in the walker's ring (11.5 KB each); a power of two
+#ifndef MJ_LOOK_T
+#define MJ_LOOK_T 12
+#endif
+constexpr int MJ_LOOK = MJ_LOOK_T;                             // chunks requested beyond the one a read needs (HBM latency / step time)
+#ifndef MJ_APT_T
+#define MJ_APT_T 2
+#endif
+constexpr int MJ_APT = MJ_APT_T;                               // attempts per thread and step of the walker
+constexpr int MJ_WIN = 4 * MJ_APT * MG_THREADS;                // words per step (MJ_APT chunks)
+static_assert(MJ_APT + 1 + MJ_LOOK <= MJ_NCH, "a window (MJ_APT chunks, unaligned: + 1) and the read-ahead fit the ring");
+__device__ __forceinline__ uint32_t mj_pos(uint32_t w) {       // position of stream word w in the chunked layout
+    const uint32_t c = w / MJ_C, k = w - c * MJ_C;
+    return c * MJ_C + (k & 3u) * MJ_CQ + (k >> 2);
+}
 __device__ const uint32_t mj_polys[MJ_NPOLY][MT_NW] = {
 #include "mt_jump_polys.inc"
 };
@@ -324,17 +346,18 @@ mt_fill_kernel(const uint32_t* __restrict__ mt_key, int n_seg, int lb_log2, uint
     for (int i = tid; i < MT_NW; i += MG_THREADS) {
         const uint32_t y = mt_key[(size_t)sid * MT_NW + i];
         xs[i] = y;
-        if (k == 0) out[i] = mt19937_temper(y);               // block 0 = the incoming state: its unread words belong to the stream
+        if (k == 0) out[mj_pos((uint32_t)i)] = mt19937_temper(y);   // block 0 = the incoming state: its unread words belong to the stream
     }
     if (tid == 0) s_T[MT_NW - 1] = 0;
     __syncthreads();
-    auto regen = [&](const uint32_t* __restrict__ O, uint32_t* __restrict__ dst, uint32_t* __restrict__ tw_out) {
+    // (blk >= 0: the block's index in the stream: its tempered words go to global memory)
+    auto regen = [&](const uint32_t* __restrict__ O, uint32_t* __restrict__ dst, long long blk) {
         if (tid < MT_NW - 1) s_T[tid] = mt19937_twist(O[tid], O[tid + 1]);
         __syncthreads();
         if (rg.my_i >= 0) {
             const uint32_t y = rg.word(O, s_T);
             dst[rg.my_i] = y;
-            if (tw_out) tw_out[rg.my_i] = mt19937_temper(y);
+            if (blk >= 0) out[mj_pos((uint32_t)(blk * MT_NW + rg.my_i))] = mt19937_temper(y);
         }
         __syncthreads();
     };
@@ -342,7 +365,7 @@ mt_fill_kernel(const uint32_t* __restrict__ mt_key, int n_seg, int lb_log2, uint
     const unsigned target = (unsigned)k << lb_log2;
     for (int r = MJ_NPOLY - 1; r >= 0; --r) {
         if (!((target >> r) & 1u)) continue;
-        for (int b = 1; b < MJ_WIN_BLOCKS; ++b) regen(xs + (b - 1) * MT_NW, xs + b * MT_NW, nullptr);
+        for (int b = 1; b < MJ_WIN_BLOCKS; ++b) regen(xs + (b - 1) * MT_NW, xs + b * MT_NW, -1);
         for (int i = tid; i < MT_NW; i += MG_THREADS) s_g[i] = mj_polys[r][i];
         __syncthreads();
         uint32_t acc = 0;
@@ -365,26 +388,68 @@ mt_fill_kernel(const uint32_t* __restrict__ mt_key, int n_seg, int lb_log2, uint
     const int Lb = 1 << lb_log2;
     int cur = 0;
     for (int b = 0; b < Lb; ++b) {
-        regen(xs + cur * MT_NW, xs + (cur ^ 1) * MT_NW, out + ((size_t)1 + target + b) * MT_NW);
+        regen(xs + cur * MT_NW, xs + (cur ^ 1) * MT_NW, (long long)1 + target + b);
         cur ^= 1;
     }
 }
 
-// mt_gauss_kernel over words in global memory (mt_fill_kernel's output): the same walk, no regeneration.
+// mt_gauss_kernel over words in global memory (mt_fill_kernel's output): the same walk, no regeneration.  The words stream
+// through a ring of MJ_NCH chunks in shared memory, MJ_LOOK chunks ahead of the reads (one 16-byte cp.async per thread and chunk).
 __global__ void __launch_bounds__(MG_THREADS, 1)
 mt_gauss_gw_kernel(uint32_t* __restrict__ mt_key, int32_t* __restrict__ mt_pos, int32_t* __restrict__ has_gauss_io,
                    const double* __restrict__ gauss_io, int n_pairs, uint32_t rng, uint32_t mask, int coins, int N,
                    int64_t* __restrict__ idx_out, uint32_t* __restrict__ extra_out, uint4* __restrict__ acc4, int a_max,
                    int32_t* __restrict__ c0_out, double* __restrict__ gauss0_out, const uint32_t* __restrict__ words,
-                   size_t stride_words, int* __restrict__ err) {
+                   size_t stride_words, uint32_t limit, int* __restrict__ err) {
+    extern __shared__ __align__(16) uint32_t gw_ring[];        // [MJ_NCH][MJ_C]
     __shared__ MgShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sid = blockIdx.x;
     const uint32_t* __restrict__ gw = words + (size_t)sid * stride_words;
-    const size_t limit = stride_words - 8;                     // the walk may read up to here
-    size_t cpos = (size_t)mt_pos[sid];                         // absolute word position (block 0 = the incoming state)
+    const uint32_t cpos0 = (uint32_t)mt_pos[sid];
+    // the cursor: absolute word position (block 0 = the incoming state) as (chunk, offset in the chunk)
+    uint32_t cpos = cpos0;
+    int cch = (int)(cpos0 / MJ_C), cko = (int)(cpos0 % MJ_C);
+    int issued = cch;                                          // chunks [cch0, issued) have been requested
+    int landed = cch - 1;                                      // chunks <= landed are in shared memory and visible to every thread
     const int c0 = has_gauss_io[sid] ? 1 : 0;
     if (tid == 0) { c0_out[sid] = c0; gauss0_out[sid] = gauss_io[sid]; }
+    auto advance = [&](int n) {
+        cpos += (uint32_t)n;
+        cko += n;
+        while (cko >= MJ_C) { cko -= MJ_C; ++cch; }
+    };
+    const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(gw_ring) + 16u * (uint32_t)tid;     // (hoisted: the conversion reads a special register)
+    auto ensure = [&](int n) {                                 // the next n words are in the ring (n >= 1, uniform over the CTA)
+        int last = cch, rest = cko + n - 1;
+        while (rest >= MJ_C) { rest -= MJ_C; ++last; }
+        int want = last + 1 + MJ_LOOK;
+        if (want > cch + MJ_NCH) want = cch + MJ_NCH;          // never over a chunk that is still being read
+        while (issued < want) {
+            const uint32_t* src = gw + (size_t)issued * MJ_C + 4 * tid;
+            const uint32_t dst = ring_u32 + (uint32_t)((issued & (MJ_NCH - 1)) * (MJ_C * 4));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            ++issued;
+        }
+        if (last > landed) {
+            const int pending_ok = issued - 1 - last;          // the most recent groups that may still be in flight
+            switch (pending_ok < 12 ? pending_ok : 12) {
+#define MJ_WAIT_CASE(N) case N: asm volatile("cp.async.wait_group " #N ";" ::: "memory"); break;
+                MJ_WAIT_CASE(12) MJ_WAIT_CASE(11) MJ_WAIT_CASE(10) MJ_WAIT_CASE(9) MJ_WAIT_CASE(8) MJ_WAIT_CASE(7) MJ_WAIT_CASE(6)
+                MJ_WAIT_CASE(5) MJ_WAIT_CASE(4) MJ_WAIT_CASE(3) MJ_WAIT_CASE(2) MJ_WAIT_CASE(1)
+#undef MJ_WAIT_CASE
+                default: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+            }
+            __syncthreads();
+            landed = last;
+        }
+    };
+    auto ring_word = [&](int ko) -> uint32_t {                 // the word at offset ko (>= 0) from the start of the cursor's chunk
+        int c = cch;
+        while (ko >= MJ_C) { ko -= MJ_C; ++c; }
+        return gw_ring[(c % MJ_NCH) * MJ_C + (ko & 3) * MJ_CQ + (ko >> 2)];
+    };
     int64_t* idx_o = idx_out + (size_t)sid * n_pairs;
     uint32_t* ext_o = extra_out ? extra_out + (size_t)sid * n_pairs * 4 * coins : nullptr;
     unsigned step = 0;
@@ -394,42 +459,48 @@ mt_gauss_gw_kernel(uint32_t* __restrict__ mt_key, int32_t* __restrict__ mt_pos, 
         uint32_t w;
         do {
             if (cpos + 1 > limit) { overflow = true; break; }
-            w = __ldg(gw + cpos) & mask;
-            ++cpos;
+            ensure(1);
+            w = ring_word(cko) & mask;
+            advance(1);
         } while (w > rng);
         if (overflow) break;
         if (tid == 0) idx_o[pair] = (int64_t)w;
         for (int sgn = 0; sgn < 2 && !overflow; ++sgn) {
             if (cpos + 2 * coins > limit) { overflow = true; break; }
-            if (ext_o && tid < 2 * coins) ext_o[(size_t)pair * 4 * coins + sgn * 2 * coins + tid] = __ldg(gw + cpos + tid);
-            cpos += 2 * coins;
+            if (coins) {
+                ensure(2 * coins);
+                if (ext_o && tid < 2 * coins) ext_o[(size_t)pair * 4 * coins + sgn * 2 * coins + tid] = ring_word(cko + tid);
+                advance(2 * coins);
+            }
             const int e = pair * 2 + sgn;
             uint4* rec = acc4 + ((size_t)sid * 2 * n_pairs + e) * a_max;
             int need = (N - mg_cached(c0, N, e) + 1) >> 1;
             int found = 0;
-            bool have_next = false;
-            uint32_t nx[MG_APT][4];
             while (need > 0) {
-                if (cpos + MG_WIN > limit) { overflow = true; break; }
-                uint32_t wd[MG_APT][4];
-                bool acc[MG_APT];
-                unsigned bal[MG_APT];
-                const uint32_t* __restrict__ mine = gw + cpos + 4 * MG_APT * tid;
+                if (cpos + MJ_WIN > limit) { overflow = true; break; }
+                ensure(MJ_WIN);
+                uint32_t wd[MJ_APT][4];
+                bool acc[MJ_APT];
+                unsigned bal[MJ_APT];
+                // Addresses with as little integer work as possible (the first version spent 420 instructions per thread and
+                // window, three quarters of them index arithmetic).  All attempts of a window share the cursor's phase ph: word
+                // q of an attempt sits in quarter (ph + q) % 4 of its chunk, at the attempt's quarter index -- or, for the
+                // words that wrap around the quarter count (ph + q >= 4), at the next quarter index.
+                const int ph = cko & 3;
+                int qoff[4];
 #pragma unroll
-                for (int j = 0; j < MG_APT; ++j)
+                for (int q = 0; q < 4; ++q) qoff[q] = ((ph + q) & 3) * MJ_CQ;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) wd[j][q] = have_next ? nx[j][q] : __ldg(mine + 4 * j + q);
-                // the next window's words, assuming this one is used up (true for all but the last window of a rollout): in
-                // flight while this window is processed
-                const bool can_next = cpos + 2 * (size_t)MG_WIN <= limit;
-                if (can_next) {
+                for (int j = 0; j < MJ_APT; ++j) {
+                    int qa = (cko >> 2) + MJ_APT * tid + j, c = cch;           // quarter index of the attempt's first word, its chunk
 #pragma unroll
-                    for (int j = 0; j < MG_APT; ++j)
+                    for (int u = 0; u < MJ_APT; ++u)
+                        if (qa >= MJ_CQ) { qa -= MJ_CQ; ++c; }
+                    int qb = qa + 1, cb = c;                                   // ... of the words behind the wrap
+                    if (qb >= MJ_CQ) { qb = 0; ++cb; }
+                    const int base0 = (c & (MJ_NCH - 1)) * MJ_C + qa, base1 = (cb & (MJ_NCH - 1)) * MJ_C + qb;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) nx[j][q] = __ldg(mine + MG_WIN + 4 * j + q);
-                }
-#pragma unroll
-                for (int j = 0; j < MG_APT; ++j) {
+                    for (int q = 0; q < 4; ++q) wd[j][q] = gw_ring[qoff[q] + ((ph + q) >= 4 ? base1 : base0)];
                     const double v1 = fma((double)(wd[j][0] >> 5), 67108864.0, (double)(wd[j][1] >> 6));
                     const double v2 = fma((double)(wd[j][2] >> 5), 67108864.0, (double)(wd[j][3] >> 6));
                     const double x1 = fma(v1, 1.0 / 4503599627370496.0, -1.0), x2 = fma(v2, 1.0 / 4503599627370496.0, -1.0);
@@ -441,7 +512,7 @@ mt_gauss_gw_kernel(uint32_t* __restrict__ mt_key, int32_t* __restrict__ mt_pos, 
                 ++step;
                 int wsum = 0, below = 0;
 #pragma unroll
-                for (int j = 0; j < MG_APT; ++j) { wsum += __popc(bal[j]); below += __popc(bal[j] & ((1u << lane) - 1u)); }
+                for (int j = 0; j < MJ_APT; ++j) { wsum += __popc(bal[j]); below += __popc(bal[j] & ((1u << lane) - 1u)); }
                 if (lane == 0) sh.wtot[buf][warp] = wsum;
                 __syncthreads();
                 int scan = (lane < MG_WARPS) ? sh.wtot[buf][lane] : 0;
@@ -454,36 +525,36 @@ mt_gauss_gw_kernel(uint32_t* __restrict__ mt_key, int32_t* __restrict__ mt_pos, 
                 const int before = warp ? __shfl_sync(0xffffffffu, scan, warp - 1) : 0;
                 int rank = before + below;
 #pragma unroll
-                for (int j = 0; j < MG_APT; ++j) {
+                for (int j = 0; j < MJ_APT; ++j) {
                     if (acc[j] && rank < need) {
                         rec[found + rank] = make_uint4(wd[j][0], wd[j][1], wd[j][2], wd[j][3]);
-                        if (rank == need - 1) sh.end = MG_APT * tid + j + 1;
+                        if (rank == need - 1) sh.end = MJ_APT * tid + j + 1;
                     }
                     rank += acc[j] ? 1 : 0;
                 }
                 if (total >= need) {
                     __syncthreads();
-                    cpos += 4 * (size_t)sh.end;
+                    advance(4 * sh.end);
                     need = 0;
                     __syncthreads();
                 } else {
-                    cpos += MG_WIN;
+                    advance(MJ_WIN);
                     need -= total;
                     found += total;
-                    have_next = can_next;
                 }
             }
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (overflow) {                                            // more words than the fill provided: nothing is handed back
         if (tid == 0 && err) *(volatile int*)err = ES_ASYNC_RNG_OVERFLOW;
         return;
     }
     // ---- hand the state back: the raw words behind the tempered words of the cursor's block ----
-    const size_t blk = cpos / MT_NW, off = cpos % MT_NW;
+    const uint32_t blk = cpos / MT_NW, off = cpos % MT_NW;
     const bool at_end = off == 0 && blk > 0;
-    const size_t b_last = at_end ? blk - 1 : blk;
-    for (int i = tid; i < MT_NW; i += MG_THREADS) mt_key[(size_t)sid * MT_NW + i] = mt19937_untemper(__ldg(gw + b_last * MT_NW + i));
+    const uint32_t b_last = at_end ? blk - 1 : blk;
+    for (int i = tid; i < MT_NW; i += MG_THREADS) mt_key[(size_t)sid * MT_NW + i] = mt19937_untemper(__ldg(gw + mj_pos(b_last * MT_NW + i)));
     if (tid == 0) {
         mt_pos[sid] = at_end ? MT_NW : (int32_t)off;
         has_gauss_io[sid] = mg_cached(c0, N, 2 * n_pairs);
@@ -510,7 +581,7 @@ int es_impl_draw_noisy(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int32_t* 
     const double att_mean = n_acc / p_acc, att_sd = sqrt(n_acc * (1.0 - p_acc)) / p_acc;
     const double evals = 2.0 * n_per_stream;
     const double words_max = 624.0 + n_per_stream * (8.0 + 4.0 * coins) + 4.0 * (evals * att_mean + 12.0 * sqrt(evals) * att_sd + 64.0) +
-                             2.0 * MG_WIN + 16.0 * MT_NW;
+                             2.0 * (MJ_WIN > MG_WIN ? MJ_WIN : MG_WIN) + 16.0 * MT_NW;
     const long long blocks_needed = (long long)(words_max / MT_NW) + 1;
     // jump-ahead when a stream is long enough to be worth splitting (ES_MT_JUMP=0 / 1 overrides; ES_MT_JUMP_LB: log2 of the
     // segment length in blocks, for tests)
@@ -526,11 +597,13 @@ int es_impl_draw_noisy(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int32_t* 
         if (lb_log2 > MJ_NPOLY - 1) lb_log2 = MJ_NPOLY - 1;
     }
     const long long n_seg = jump ? (blocks_needed + (1LL << lb_log2) - 1) >> lb_log2 : 0;
-    if (jump && ((n_seg << lb_log2) >> MJ_NPOLY) != 0) {       // the block index of a segment start must fit the available jumps
+    if (jump && (((n_seg << lb_log2) >> MJ_NPOLY) != 0 || (double)(n_seg << lb_log2) * MT_NW > 4.0e9)) {       // the block index of a segment start must fit the available jumps
         es_set_error("es_draw_noisy: %lld blocks per stream exceed the jump-ahead range (2^%d blocks)", n_seg << lb_log2, MJ_NPOLY);
         return ES_ERR_UNSUPPORTED;
     }
-    const size_t stride_words = jump ? (size_t)(1 + (n_seg << lb_log2)) * MT_NW : 0;
+    // (the walk's read-ahead requests whole chunks: round up and pad so that it stays inside the allocation)
+    const size_t gen_words = jump ? (size_t)(1 + (n_seg << lb_log2)) * MT_NW : 0;
+    const size_t stride_words = jump ? ((gen_words + MJ_C - 1) / MJ_C + MJ_NCH + 1) * MJ_C : 0;
     // scratch: [the streams' words (jump-ahead only)] the accepted attempts' words [stream][evaluation][a_max] (16 bytes per two
     // gaussians), the incoming cache per stream
     const int a_max = (N + 1) / 2 > 0 ? (N + 1) / 2 : 1;
@@ -550,9 +623,11 @@ int es_impl_draw_noisy(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int32_t* 
         ES_CHECK_CUDA(cudaFuncSetAttribute(mt_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         mt_fill_kernel<<<(unsigned)(n_streams * n_seg), MG_THREADS, smem, stream>>>(mt_key, (int)n_seg, lb_log2, words, stride_words);
         ES_LAUNCHED(ctx);
-        mt_gauss_gw_kernel<<<n_streams, MG_THREADS, 0, stream>>>(mt_key, mt_pos, has_gauss, gauss, n_per_stream, rng, mask, coins, N,
-                                                               idx_out, extra_out, acc4, a_max, c0, gauss0, words, stride_words,
-                                                               ctx->err_dev);
+        const size_t smem_w = (size_t)MJ_NCH * MJ_C * sizeof(uint32_t);
+        ES_CHECK_CUDA(cudaFuncSetAttribute(mt_gauss_gw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+        mt_gauss_gw_kernel<<<n_streams, MG_THREADS, smem_w, stream>>>(mt_key, mt_pos, has_gauss, gauss, n_per_stream, rng, mask, coins, N,
+                                                                    idx_out, extra_out, acc4, a_max, c0, gauss0, words, stride_words,
+                                                                    (uint32_t)(gen_words - 8), ctx->err_dev);
         ES_LAUNCHED(ctx);
     } else {
         const size_t smem = (size_t)(2 * MG_RING + 1) * MG_N * sizeof(uint32_t);
