@@ -301,33 +301,18 @@ mt_gauss_finish_kernel(const uint4* __restrict__ acc4, int a_max, const int32_t*
 // x[n + i].  So the state 2^r blocks ahead is, word by word, an XOR of ~10 000 words out of the next 20 560: independent per
 // word, no recurrence to follow.  mt_fill_kernel gives every CTA one segment of 2^lb blocks of one stream: it jumps from the
 // stream's current state to its segment's first block (one jump per set bit of the block index), regenerates the segment and
-// writes the TEMPERED words to global memory; mt_gauss_gw_kernel then walks the stream exactly like mt_gauss_kernel, but reads
-// the words instead of regenerating them -- what is left on the sequential path is the accept / reject bookkeeping.
+// writes the TEMPERED words to global memory.  What follows no longer touches the recurrence: mt_flags_kernel computes the accept
+// bit of every possible attempt (all four phases) with per-chunk counts, mt_scan_kernel their prefixes; mt_walk_kernel -- the only
+// sequential step left, one warp per stream -- follows the reference's order with two table look-ups per rollout ("the next
+// `need` accepted attempts of this phase end at word ..."); mt_emit_kernel turns every rollout's accepted attempts into its
+// gaussians, one CTA per rollout.
 // =====================================================================================================================
 constexpr int MJ_NPOLY = 18;
 constexpr int MJ_WIN_BLOCKS = 33;                              // the state block + 32 more: 20 592 words >= 19 937 + 624
-// Layout of a stream's tempered words in global memory: chunks of MJ_C = 4 * MG_THREADS words (one 16-byte cp.async per thread
-// moves a chunk into the walker's shared-memory ring); inside a chunk word k sits at (k % 4) * MJ_C / 4 + k / 4, so that the
-// q-th words of consecutive attempts are consecutive: the attempt windows read shared memory without bank conflicts.
-constexpr int MJ_C = 4 * MG_THREADS, MJ_CQ = MJ_C / 4;
-#ifndef MJ_NCH_T
-#define MJ_NCH_T 16
-#endif
-constexpr int MJ_NCH = MJ_NCH_T;                               // chunks in the walker's ring (11.5 KB each); a power of two
-#ifndef MJ_LOOK_T
-#define MJ_LOOK_T 12
-#endif
-constexpr int MJ_LOOK = MJ_LOOK_T;                             // chunks requested beyond the one a read needs (HBM latency / step time)
-#ifndef MJ_APT_T
-#define MJ_APT_T 2
-#endif
-constexpr int MJ_APT = MJ_APT_T;                               // attempts per thread and step of the walker
-constexpr int MJ_WIN = 4 * MJ_APT * MG_THREADS;                // words per step (MJ_APT chunks)
-static_assert(MJ_APT + 1 + MJ_LOOK <= MJ_NCH, "a window (MJ_APT chunks, unaligned: + 1) and the read-ahead fit the ring");
-__device__ __forceinline__ uint32_t mj_pos(uint32_t w) {       // position of stream word w in the chunked layout
-    const uint32_t c = w / MJ_C, k = w - c * MJ_C;
-    return c * MJ_C + (k & 3u) * MJ_CQ + (k >> 2);
-}
+// Layout in global memory (per stream): the tempered words in stream order; per phase ph = 0..3 (an attempt starts at a word
+// index = ph mod 4) one accept bit per attempt (attempt a of phase ph = words 4 a + ph .. 4 a + ph + 3), in chunks of
+// MJ_CA = 1024 attempts (32 mask words) with the number of accepted attempts of every chunk and its exclusive prefix.
+constexpr int MJ_CA = 1024, MJ_CW = 4 * MJ_CA;                  // attempts / words per chunk
 __device__ const uint32_t mj_polys[MJ_NPOLY][MT_NW] = {
 #include "mt_jump_polys.inc"
 };
@@ -346,7 +331,7 @@ mt_fill_kernel(const uint32_t* __restrict__ mt_key, int n_seg, int lb_log2, uint
     for (int i = tid; i < MT_NW; i += MG_THREADS) {
         const uint32_t y = mt_key[(size_t)sid * MT_NW + i];
         xs[i] = y;
-        if (k == 0) out[mj_pos((uint32_t)i)] = mt19937_temper(y);   // block 0 = the incoming state: its unread words belong to the stream
+        if (k == 0) out[i] = mt19937_temper(y);               // block 0 = the incoming state: its unread words belong to the stream
     }
     if (tid == 0) s_T[MT_NW - 1] = 0;
     __syncthreads();
@@ -357,7 +342,7 @@ mt_fill_kernel(const uint32_t* __restrict__ mt_key, int n_seg, int lb_log2, uint
         if (rg.my_i >= 0) {
             const uint32_t y = rg.word(O, s_T);
             dst[rg.my_i] = y;
-            if (blk >= 0) out[mj_pos((uint32_t)(blk * MT_NW + rg.my_i))] = mt19937_temper(y);
+            if (blk >= 0) out[(size_t)blk * MT_NW + rg.my_i] = mt19937_temper(y);
         }
         __syncthreads();
     };
@@ -393,171 +378,215 @@ mt_fill_kernel(const uint32_t* __restrict__ mt_key, int n_seg, int lb_log2, uint
     }
 }
 
-// mt_gauss_kernel over words in global memory (mt_fill_kernel's output): the same walk, no regeneration.  The words stream
-// through a ring of MJ_NCH chunks in shared memory, MJ_LOOK chunks ahead of the reads (one 16-byte cp.async per thread and chunk).
-__global__ void __launch_bounds__(MG_THREADS, 1)
-mt_gauss_gw_kernel(uint32_t* __restrict__ mt_key, int32_t* __restrict__ mt_pos, int32_t* __restrict__ has_gauss_io,
-                   const double* __restrict__ gauss_io, int n_pairs, uint32_t rng, uint32_t mask, int coins, int N,
-                   int64_t* __restrict__ idx_out, uint32_t* __restrict__ extra_out, uint4* __restrict__ acc4, int a_max,
-                   int32_t* __restrict__ c0_out, double* __restrict__ gauss0_out, const uint32_t* __restrict__ words,
-                   size_t stride_words, uint32_t limit, int* __restrict__ err) {
-    extern __shared__ __align__(16) uint32_t gw_ring[];        // [MJ_NCH][MJ_C]
-    __shared__ MgShared sh;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int sid = blockIdx.x;
+// ---- the accept bit of every possible attempt, in parallel: one CTA per (stream, chunk of 4096 words), thread q looks at the
+//      four attempts that start at words 4 q .. 4 q + 3 of the chunk (one per phase) ----
+__device__ __forceinline__ bool mj_accept(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    // x = 2 u - 1 with u = (a >> 5, b >> 6) / 2^53: the 53-bit integer is exact in float64 and one fused multiply-add rounds
+    // the exact value of 2 u - 1 once, like the reference's (2.0 * u) - 1.0 (2 u is exact); r2 with two roundings as in C
+    const double v1 = fma((double)(w0 >> 5), 67108864.0, (double)(w1 >> 6));
+    const double v2 = fma((double)(w2 >> 5), 67108864.0, (double)(w3 >> 6));
+    const double x1 = fma(v1, 1.0 / 4503599627370496.0, -1.0), x2 = fma(v2, 1.0 / 4503599627370496.0, -1.0);
+    const double r2 = __dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2));
+    return r2 < 1.0 && r2 != 0.0;
+}
+
+__global__ void __launch_bounds__(MJ_CA)
+mt_flags_kernel(const uint32_t* __restrict__ words, size_t stride_words, int n_chunks, uint32_t* __restrict__ masks,
+                uint32_t* __restrict__ counts) {
+    __shared__ int s_cnt[4];
+    const int q = threadIdx.x, c = blockIdx.x, sid = blockIdx.y;
+    if (q < 4) s_cnt[q] = 0;
+    __syncthreads();
+    const uint4* __restrict__ w4 = reinterpret_cast<const uint4*>(words + (size_t)sid * stride_words + (size_t)c * MJ_CW) + q;
+    const uint4 a = __ldg(w4), b = __ldg(w4 + 1);                 // words 4 q .. 4 q + 7 (the buffer is padded past the last chunk)
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t* mk = masks + ((size_t)sid * 4 * n_chunks + c) * 32 + (q >> 5);          // + ph * n_chunks * 32
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph) {
+        const unsigned bal = __ballot_sync(0xffffffffu, mj_accept(w[ph], w[ph + 1], w[ph + 2], w[ph + 3]));
+        if ((q & 31) == 0) {
+            mk[(size_t)ph * n_chunks * 32] = bal;
+            atomicAdd(&s_cnt[ph], __popc(bal));
+        }
+    }
+    __syncthreads();
+    if (q < 4) counts[((size_t)sid * 4 + q) * n_chunks + c] = (uint32_t)s_cnt[q];
+}
+
+// exclusive prefix of the chunk counts of every (stream, phase): one CTA each
+__global__ void __launch_bounds__(1024) mt_scan_kernel(uint32_t* __restrict__ counts, int n_chunks) {
+    __shared__ uint32_t s_part[1024];
+    uint32_t* v = counts + (size_t)blockIdx.x * n_chunks;
+    const int per = (n_chunks + 1023) / 1024, lo = threadIdx.x * per, hi = min(n_chunks, lo + per);
+    uint32_t sum = 0;
+    for (int i = lo; i < hi; ++i) sum += v[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {                          // inclusive scan of the partial sums
+        const uint32_t add = threadIdx.x >= d ? s_part[threadIdx.x - d] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += add;
+        __syncthreads();
+    }
+    uint32_t run = threadIdx.x ? s_part[threadIdx.x - 1] : 0;
+    for (int i = lo; i < hi; ++i) { const uint32_t t = v[i]; v[i] = run; run += t; }
+}
+
+// ---- the walk: ONE WARP per stream follows the reference's order; a rollout's N gaussians are "the next `need` accepted
+//      attempts of phase ph from word s on", i.e. two look-ups in the prefix tables instead of a pass over the words ----
+__global__ void __launch_bounds__(32)
+mt_walk_kernel(uint32_t* __restrict__ mt_key, int32_t* __restrict__ mt_pos, int32_t* __restrict__ has_gauss_io,
+               const double* __restrict__ gauss_io, int n_pairs, uint32_t rng, uint32_t mask, int coins, int N,
+               int64_t* __restrict__ idx_out, uint32_t* __restrict__ extra_out, uint32_t* __restrict__ reg_start,
+               int32_t* __restrict__ c0_out, double* __restrict__ gauss0_out, const uint32_t* __restrict__ words,
+               size_t stride_words, int n_chunks, const uint32_t* __restrict__ masks, const uint32_t* __restrict__ cumul,
+               uint32_t limit, int* __restrict__ err) {
+    const int lane = threadIdx.x, sid = blockIdx.x;
     const uint32_t* __restrict__ gw = words + (size_t)sid * stride_words;
-    const uint32_t cpos0 = (uint32_t)mt_pos[sid];
-    // the cursor: absolute word position (block 0 = the incoming state) as (chunk, offset in the chunk)
-    uint32_t cpos = cpos0;
-    int cch = (int)(cpos0 / MJ_C), cko = (int)(cpos0 % MJ_C);
-    int issued = cch;                                          // chunks [cch0, issued) have been requested
-    int landed = cch - 1;                                      // chunks <= landed are in shared memory and visible to every thread
+    const uint32_t* __restrict__ mk = masks + (size_t)sid * 4 * n_chunks * 32;
+    const uint32_t* __restrict__ cu = cumul + (size_t)sid * 4 * n_chunks;
+    uint32_t cpos = (uint32_t)mt_pos[sid];
     const int c0 = has_gauss_io[sid] ? 1 : 0;
-    if (tid == 0) { c0_out[sid] = c0; gauss0_out[sid] = gauss_io[sid]; }
-    auto advance = [&](int n) {
-        cpos += (uint32_t)n;
-        cko += n;
-        while (cko >= MJ_C) { cko -= MJ_C; ++cch; }
-    };
-    const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(gw_ring) + 16u * (uint32_t)tid;     // (hoisted: the conversion reads a special register)
-    auto ensure = [&](int n) {                                 // the next n words are in the ring (n >= 1, uniform over the CTA)
-        int last = cch, rest = cko + n - 1;
-        while (rest >= MJ_C) { rest -= MJ_C; ++last; }
-        int want = last + 1 + MJ_LOOK;
-        if (want > cch + MJ_NCH) want = cch + MJ_NCH;          // never over a chunk that is still being read
-        while (issued < want) {
-            const uint32_t* src = gw + (size_t)issued * MJ_C + 4 * tid;
-            const uint32_t dst = ring_u32 + (uint32_t)((issued & (MJ_NCH - 1)) * (MJ_C * 4));
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            ++issued;
-        }
-        if (last > landed) {
-            const int pending_ok = issued - 1 - last;          // the most recent groups that may still be in flight
-            switch (pending_ok < 12 ? pending_ok : 12) {
-#define MJ_WAIT_CASE(N) case N: asm volatile("cp.async.wait_group " #N ";" ::: "memory"); break;
-                MJ_WAIT_CASE(12) MJ_WAIT_CASE(11) MJ_WAIT_CASE(10) MJ_WAIT_CASE(9) MJ_WAIT_CASE(8) MJ_WAIT_CASE(7) MJ_WAIT_CASE(6)
-                MJ_WAIT_CASE(5) MJ_WAIT_CASE(4) MJ_WAIT_CASE(3) MJ_WAIT_CASE(2) MJ_WAIT_CASE(1)
-#undef MJ_WAIT_CASE
-                default: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-            }
-            __syncthreads();
-            landed = last;
-        }
-    };
-    auto ring_word = [&](int ko) -> uint32_t {                 // the word at offset ko (>= 0) from the start of the cursor's chunk
-        int c = cch;
-        while (ko >= MJ_C) { ko -= MJ_C; ++c; }
-        return gw_ring[(c % MJ_NCH) * MJ_C + (ko & 3) * MJ_CQ + (ko >> 2)];
-    };
+    if (lane == 0) { c0_out[sid] = c0; gauss0_out[sid] = gauss_io[sid]; }
     int64_t* idx_o = idx_out + (size_t)sid * n_pairs;
     uint32_t* ext_o = extra_out ? extra_out + (size_t)sid * n_pairs * 4 * coins : nullptr;
-    unsigned step = 0;
+    uint32_t* rs = reg_start + (size_t)sid * 2 * n_pairs;
     bool overflow = false;
-
     for (int pair = 0; pair < n_pairs && !overflow; ++pair) {
         uint32_t w;
         do {
             if (cpos + 1 > limit) { overflow = true; break; }
-            ensure(1);
-            w = ring_word(cko) & mask;
-            advance(1);
+            w = __ldg(gw + cpos) & mask;
+            ++cpos;
         } while (w > rng);
         if (overflow) break;
-        if (tid == 0) idx_o[pair] = (int64_t)w;
-        for (int sgn = 0; sgn < 2 && !overflow; ++sgn) {
-            if (cpos + 2 * coins > limit) { overflow = true; break; }
-            if (coins) {
-                ensure(2 * coins);
-                if (ext_o && tid < 2 * coins) ext_o[(size_t)pair * 4 * coins + sgn * 2 * coins + tid] = ring_word(cko + tid);
-                advance(2 * coins);
-            }
+        if (lane == 0) idx_o[pair] = (int64_t)w;
+        for (int sgn = 0; sgn < 2; ++sgn) {
+            if (cpos + 2 * coins + 8 > limit) { overflow = true; break; }
+            if (ext_o && lane < 2 * coins) ext_o[(size_t)pair * 4 * coins + sgn * 2 * coins + lane] = __ldg(gw + cpos + lane);
+            cpos += 2 * coins;
             const int e = pair * 2 + sgn;
-            uint4* rec = acc4 + ((size_t)sid * 2 * n_pairs + e) * a_max;
-            int need = (N - mg_cached(c0, N, e) + 1) >> 1;
-            int found = 0;
-            while (need > 0) {
-                if (cpos + MJ_WIN > limit) { overflow = true; break; }
-                ensure(MJ_WIN);
-                uint32_t wd[MJ_APT][4];
-                bool acc[MJ_APT];
-                unsigned bal[MJ_APT];
-                // Addresses with as little integer work as possible (the first version spent 420 instructions per thread and
-                // window, three quarters of them index arithmetic).  All attempts of a window share the cursor's phase ph: word
-                // q of an attempt sits in quarter (ph + q) % 4 of its chunk, at the attempt's quarter index -- or, for the
-                // words that wrap around the quarter count (ph + q >= 4), at the next quarter index.
-                const int ph = cko & 3;
-                int qoff[4];
+            if (lane == 0) rs[e] = cpos;
+            const int need = (N - mg_cached(c0, N, e) + 1) >> 1;
+            if (need == 0) continue;
+            const int ph = cpos & 3;
+            const uint32_t a0 = cpos >> 2;                        // first attempt of the rollout, in phase ph's numbering
+            const uint32_t* __restrict__ mph = mk + (size_t)ph * n_chunks * 32;
+            const uint32_t* __restrict__ cph = cu + (size_t)ph * n_chunks;
+            // accepted attempts of the phase before a0
+            const uint32_t ch0 = a0 >> 10, r0 = a0 & 1023;
+            const uint32_t m0 = __ldg(mph + (size_t)ch0 * 32 + lane);
+            const uint32_t base0 = __ldg(cph + ch0);
+            int below = (lane < (int)(r0 >> 5)) ? __popc(m0) : (lane == (int)(r0 >> 5) ? __popc(m0 & ((1u << (r0 & 31)) - 1u)) : 0);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) qoff[q] = ((ph + q) & 3) * MJ_CQ;
-#pragma unroll
-                for (int j = 0; j < MJ_APT; ++j) {
-                    int qa = (cko >> 2) + MJ_APT * tid + j, c = cch;           // quarter index of the attempt's first word, its chunk
-#pragma unroll
-                    for (int u = 0; u < MJ_APT; ++u)
-                        if (qa >= MJ_CQ) { qa -= MJ_CQ; ++c; }
-                    int qb = qa + 1, cb = c;                                   // ... of the words behind the wrap
-                    if (qb >= MJ_CQ) { qb = 0; ++cb; }
-                    const int base0 = (c & (MJ_NCH - 1)) * MJ_C + qa, base1 = (cb & (MJ_NCH - 1)) * MJ_C + qb;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) wd[j][q] = gw_ring[qoff[q] + ((ph + q) >= 4 ? base1 : base0)];
-                    const double v1 = fma((double)(wd[j][0] >> 5), 67108864.0, (double)(wd[j][1] >> 6));
-                    const double v2 = fma((double)(wd[j][2] >> 5), 67108864.0, (double)(wd[j][3] >> 6));
-                    const double x1 = fma(v1, 1.0 / 4503599627370496.0, -1.0), x2 = fma(v2, 1.0 / 4503599627370496.0, -1.0);
-                    const double r2 = __dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2));
-                    acc[j] = r2 < 1.0 && r2 != 0.0;
-                    bal[j] = __ballot_sync(0xffffffffu, acc[j]);
+            for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+            const uint32_t target = base0 + (uint32_t)below + (uint32_t)need;      // accepted attempts before the END of the rollout
+            // the chunk that contains the target-th accepted attempt: the last one whose prefix is < target, looked for in a
+            // window of 32 chunks around the expected place (acceptance pi / 4; 32 chunks = 32 768 attempts >> its spread)
+            long long est = ((long long)a0 + (long long)(need * 1.2732395447351628)) >> 10;
+            long long wlo = est - 12;
+            if (wlo < (long long)ch0) wlo = ch0;
+            if (wlo + 32 > n_chunks) wlo = (long long)n_chunks - 32 > 0 ? n_chunks - 32 : 0;
+            long long ci = wlo + lane;
+            uint32_t pre = (ci < n_chunks) ? __ldg(cph + ci) : 0xFFFFFFFFu;
+            unsigned lt = __ballot_sync(0xffffffffu, pre < target);
+            if (lt == 0u || (lt == 0xFFFFFFFFu && wlo + 32 < n_chunks)) {
+                // outside the window (tens of sigma away from the estimate): bisect the prefixes, then look again from there
+                long long lo = ch0, hi = (long long)n_chunks - 1;          // invariant: prefix[lo] < target
+                while (lo < hi) {
+                    const long long mid = (lo + hi + 1) >> 1;
+                    if (__ldg(cph + mid) < target) lo = mid; else hi = mid - 1;
                 }
-                const unsigned buf = step & 1;
-                ++step;
-                int wsum = 0, below = 0;
-#pragma unroll
-                for (int j = 0; j < MJ_APT; ++j) { wsum += __popc(bal[j]); below += __popc(bal[j] & ((1u << lane) - 1u)); }
-                if (lane == 0) sh.wtot[buf][warp] = wsum;
-                __syncthreads();
-                int scan = (lane < MG_WARPS) ? sh.wtot[buf][lane] : 0;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int up = __shfl_up_sync(0xffffffffu, scan, d);
-                    if (lane >= d) scan += up;
-                }
-                const int total = __shfl_sync(0xffffffffu, scan, MG_WARPS - 1);
-                const int before = warp ? __shfl_sync(0xffffffffu, scan, warp - 1) : 0;
-                int rank = before + below;
-#pragma unroll
-                for (int j = 0; j < MJ_APT; ++j) {
-                    if (acc[j] && rank < need) {
-                        rec[found + rank] = make_uint4(wd[j][0], wd[j][1], wd[j][2], wd[j][3]);
-                        if (rank == need - 1) sh.end = MJ_APT * tid + j + 1;
-                    }
-                    rank += acc[j] ? 1 : 0;
-                }
-                if (total >= need) {
-                    __syncthreads();
-                    advance(4 * sh.end);
-                    need = 0;
-                    __syncthreads();
-                } else {
-                    advance(MJ_WIN);
-                    need -= total;
-                    found += total;
-                }
+                wlo = lo;
+                ci = wlo + lane;
+                pre = (ci < n_chunks) ? __ldg(cph + ci) : 0xFFFFFFFFu;
+                lt = __ballot_sync(0xffffffffu, pre < target);
             }
+            const int sel = 31 - __clz((int)lt);                  // last lane with prefix < target (prefixes are non-decreasing)
+            const uint32_t c1 = (uint32_t)(wlo + sel), pre1 = __shfl_sync(0xffffffffu, pre, sel);
+            const uint32_t m1 = __ldg(mph + (size_t)c1 * 32 + lane);
+            int inc = __popc(m1);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += up;
+            }
+            const uint32_t want = target - pre1;                  // the want-th (1-based) accepted attempt of chunk c1 ends the rollout
+            const unsigned ge = __ballot_sync(0xffffffffu, (uint32_t)inc >= want);
+            if (ge == 0u) { overflow = true; break; }
+            const int L = __ffs((int)ge) - 1;
+            const uint32_t mL = __shfl_sync(0xffffffffu, m1, L);
+            const int incL = __shfl_sync(0xffffffffu, inc, L);
+            const int kth = (int)want - (incL - __popc(mL));      // 1-based among the set bits of lane L's word
+            const int bit = __fns(mL, 0, kth);
+            const uint32_t a1 = (c1 << 10) + 32u * (uint32_t)L + (uint32_t)bit;
+            cpos = 4u * (a1 + 1u) + (uint32_t)ph;
+            if (cpos > limit) { overflow = true; break; }
         }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    if (overflow) {                                            // more words than the fill provided: nothing is handed back
-        if (tid == 0 && err) *(volatile int*)err = ES_ASYNC_RNG_OVERFLOW;
+    if (overflow) {
+        if (lane == 0 && err) *(volatile int*)err = ES_ASYNC_RNG_OVERFLOW;
         return;
     }
     // ---- hand the state back: the raw words behind the tempered words of the cursor's block ----
     const uint32_t blk = cpos / MT_NW, off = cpos % MT_NW;
     const bool at_end = off == 0 && blk > 0;
     const uint32_t b_last = at_end ? blk - 1 : blk;
-    for (int i = tid; i < MT_NW; i += MG_THREADS) mt_key[(size_t)sid * MT_NW + i] = mt19937_untemper(__ldg(gw + mj_pos(b_last * MT_NW + i)));
-    if (tid == 0) {
+    for (int i = lane; i < MT_NW; i += 32) mt_key[(size_t)sid * MT_NW + i] = mt19937_untemper(__ldg(gw + (size_t)b_last * MT_NW + i));
+    if (lane == 0) {
         mt_pos[sid] = at_end ? MT_NW : (int32_t)off;
         has_gauss_io[sid] = mg_cached(c0, N, 2 * n_pairs);
+    }
+}
+
+// ---- the gaussians of one rollout per CTA: attempts from the rollout's first word on, accepted ones ranked by a block scan ----
+__global__ void __launch_bounds__(1024)
+mt_emit_kernel(const uint32_t* __restrict__ words, size_t stride_words, const uint32_t* __restrict__ reg_start,
+               const int32_t* __restrict__ c0_in, const double* __restrict__ gauss0, int n_pairs, int N, double scale,
+               float* __restrict__ noise_out, double* __restrict__ gauss_io) {
+    __shared__ int s_wt[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ge = blockIdx.x;                                    // evaluation, stream-major
+    const int e = ge % (2 * n_pairs), sid = ge / (2 * n_pairs);
+    const int c0 = c0_in[sid], ce = mg_cached(c0, N, e);
+    const int need = (N - ce + 1) >> 1;
+    float* out = noise_out + (size_t)ge * N;
+    if (tid == 0) {
+        if (e == 0 && ce && N > 0) out[0] = (float)__dmul_rn(gauss0[sid], scale);          // the stream's incoming cached gaussian
+        if (e == 2 * n_pairs - 1 && !mg_cached(c0, N, 2 * n_pairs)) gauss_io[sid] = 0.0;    // nothing cached afterwards
+        if (N == 0 && e == 0 && c0) gauss_io[sid] = gauss0[sid];
+    }
+    const uint32_t* __restrict__ gw = words + (size_t)sid * stride_words + reg_start[ge];
+    int found = 0;
+    for (unsigned it = 0; found < need; ++it) {
+        const uint32_t* __restrict__ wp = gw + (size_t)4 * (it * 1024u + tid);
+        const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
+        const bool acc = mj_accept(w0, w1, w2, w3);
+        const unsigned bal = __ballot_sync(0xffffffffu, acc);
+        if (lane == 0) s_wt[it & 1][warp] = __popc(bal);
+        __syncthreads();
+        int scan = s_wt[it & 1][lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, scan, d);
+            if (lane >= d) scan += up;
+        }
+        const int total = __shfl_sync(0xffffffffu, scan, 31);
+        const int rank = found + (warp ? __shfl_sync(0xffffffffu, scan, warp - 1) : 0) + __popc(bal & ((1u << lane) - 1u));
+        if (acc && rank < need) {
+            const double v1 = fma((double)(w0 >> 5), 67108864.0, (double)(w1 >> 6));
+            const double v2 = fma((double)(w2 >> 5), 67108864.0, (double)(w3 >> 6));
+            const double x1 = fma(v1, 1.0 / 4503599627370496.0, -1.0), x2 = fma(v2, 1.0 / 4503599627370496.0, -1.0);
+            const double r2 = __dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2));
+            const double f = sqrt(__ddiv_rn(__dmul_rn(-2.0, log(r2)), r2));
+            const int p = ce + 2 * rank;
+            out[p] = (float)__dmul_rn(__dmul_rn(f, x2), scale);
+            const double g2 = __dmul_rn(f, x1);
+            if (p + 1 < N) out[p + 1] = (float)__dmul_rn(g2, scale);
+            else if (e + 1 < 2 * n_pairs) out[N] = (float)__dmul_rn(g2, scale);            // = value 0 of the stream's next evaluation
+            else gauss_io[sid] = g2;                                                        // the cache the stream hands back
+        }
+        found += total;
     }
 }
 
@@ -581,7 +610,7 @@ int es_impl_draw_noisy(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int32_t* 
     const double att_mean = n_acc / p_acc, att_sd = sqrt(n_acc * (1.0 - p_acc)) / p_acc;
     const double evals = 2.0 * n_per_stream;
     const double words_max = 624.0 + n_per_stream * (8.0 + 4.0 * coins) + 4.0 * (evals * att_mean + 12.0 * sqrt(evals) * att_sd + 64.0) +
-                             2.0 * (MJ_WIN > MG_WIN ? MJ_WIN : MG_WIN) + 16.0 * MT_NW;
+                             2.0 * MG_WIN + 16.0 * MT_NW;
     const long long blocks_needed = (long long)(words_max / MT_NW) + 1;
     // jump-ahead when a stream is long enough to be worth splitting (ES_MT_JUMP=0 / 1 overrides; ES_MT_JUMP_LB: log2 of the
     // segment length in blocks, for tests)
@@ -601,35 +630,58 @@ int es_impl_draw_noisy(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int32_t* 
         es_set_error("es_draw_noisy: %lld blocks per stream exceed the jump-ahead range (2^%d blocks)", n_seg << lb_log2, MJ_NPOLY);
         return ES_ERR_UNSUPPORTED;
     }
-    // (the walk's read-ahead requests whole chunks: round up and pad so that it stays inside the allocation)
+    // (whole chunks of MJ_CW words, + one chunk of padding: the flags kernel reads 4 words past every attempt start)
     const size_t gen_words = jump ? (size_t)(1 + (n_seg << lb_log2)) * MT_NW : 0;
-    const size_t stride_words = jump ? ((gen_words + MJ_C - 1) / MJ_C + MJ_NCH + 1) * MJ_C : 0;
-    // scratch: [the streams' words (jump-ahead only)] the accepted attempts' words [stream][evaluation][a_max] (16 bytes per two
-    // gaussians), the incoming cache per stream
+    const long long n_chunks = jump ? (long long)((gen_words + MJ_CW - 1) / MJ_CW) : 0;
+    const size_t stride_words = jump ? (size_t)(n_chunks + 1) * MJ_CW : 0;
     const int a_max = (N + 1) / 2 > 0 ? (N + 1) / 2 : 1;
     const size_t n_eval = (size_t)n_streams * 2 * n_per_stream;
-    const size_t words_bytes = ((size_t)n_streams * stride_words * sizeof(uint32_t) + 255) & ~(size_t)255;
-    const size_t acc_bytes = (n_eval * a_max * sizeof(uint4) + 255) & ~(size_t)255;
-    const size_t c0_bytes = ((size_t)n_streams * sizeof(int32_t) + 255) & ~(size_t)255;
-    void* scratch = nullptr;
-    int rc = es_ctx_scratch(ctx, words_bytes + acc_bytes + c0_bytes + (size_t)n_streams * sizeof(double), &scratch);
-    if (rc) return rc;
-    uint32_t* words = (uint32_t*)scratch;
-    uint4* acc4 = (uint4*)((char*)scratch + words_bytes);
-    int32_t* c0 = (int32_t*)((char*)scratch + words_bytes + acc_bytes);
-    double* gauss0 = (double*)((char*)scratch + words_bytes + acc_bytes + c0_bytes);
+    auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t c0_bytes = pad((size_t)n_streams * sizeof(int32_t)), g0_bytes = pad((size_t)n_streams * sizeof(double));
     if (jump) {
+        // scratch: the streams' words | accept masks [stream][phase][chunk][32] | chunk counts -> prefixes [stream][phase][chunk]
+        //          | first word of every rollout [stream][2 n] | incoming cache per stream
+        const size_t words_bytes = pad((size_t)n_streams * stride_words * sizeof(uint32_t));
+        const size_t mask_bytes = pad((size_t)n_streams * 4 * n_chunks * 32 * sizeof(uint32_t));
+        const size_t cnt_bytes = pad((size_t)n_streams * 4 * n_chunks * sizeof(uint32_t));
+        const size_t reg_bytes = pad(n_eval * sizeof(uint32_t));
+        void* scratch = nullptr;
+        int rc = es_ctx_scratch(ctx, words_bytes + mask_bytes + cnt_bytes + reg_bytes + c0_bytes + g0_bytes, &scratch);
+        if (rc) return rc;
+        char* at = (char*)scratch;
+        uint32_t* words = (uint32_t*)at; at += words_bytes;
+        uint32_t* masks = (uint32_t*)at; at += mask_bytes;
+        uint32_t* counts = (uint32_t*)at; at += cnt_bytes;
+        uint32_t* reg_start = (uint32_t*)at; at += reg_bytes;
+        int32_t* c0 = (int32_t*)at; at += c0_bytes;
+        double* gauss0 = (double*)at;
         const size_t smem = (size_t)(MJ_WIN_BLOCKS + 2) * MT_NW * sizeof(uint32_t);
         ES_CHECK_CUDA(cudaFuncSetAttribute(mt_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         mt_fill_kernel<<<(unsigned)(n_streams * n_seg), MG_THREADS, smem, stream>>>(mt_key, (int)n_seg, lb_log2, words, stride_words);
         ES_LAUNCHED(ctx);
-        const size_t smem_w = (size_t)MJ_NCH * MJ_C * sizeof(uint32_t);
-        ES_CHECK_CUDA(cudaFuncSetAttribute(mt_gauss_gw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
-        mt_gauss_gw_kernel<<<n_streams, MG_THREADS, smem_w, stream>>>(mt_key, mt_pos, has_gauss, gauss, n_per_stream, rng, mask, coins, N,
-                                                                    idx_out, extra_out, acc4, a_max, c0, gauss0, words, stride_words,
-                                                                    (uint32_t)(gen_words - 8), ctx->err_dev);
+        mt_flags_kernel<<<dim3((unsigned)n_chunks, (unsigned)n_streams), MJ_CA, 0, stream>>>(words, stride_words, (int)n_chunks, masks, counts);
         ES_LAUNCHED(ctx);
-    } else {
+        mt_scan_kernel<<<n_streams * 4, 1024, 0, stream>>>(counts, (int)n_chunks);
+        ES_LAUNCHED(ctx);
+        mt_walk_kernel<<<n_streams, 32, 0, stream>>>(mt_key, mt_pos, has_gauss, gauss, n_per_stream, rng, mask, coins, N, idx_out, extra_out,
+                                                     reg_start, c0, gauss0, words, stride_words, (int)n_chunks, masks, counts,
+                                                     (uint32_t)(gen_words - 8), ctx->err_dev);
+        ES_LAUNCHED(ctx);
+        mt_emit_kernel<<<(unsigned)n_eval, 1024, 0, stream>>>(words, stride_words, reg_start, c0, gauss0, n_per_stream, N, scale,
+                                                              noise_out, gauss);
+        ES_LAUNCHED(ctx);
+        return ES_OK;
+    }
+    // sequential kernel.  scratch: the accepted attempts' words [stream][evaluation][a_max] (16 bytes per two gaussians), the
+    // incoming cache per stream
+    const size_t acc_bytes = pad(n_eval * a_max * sizeof(uint4));
+    void* scratch = nullptr;
+    int rc = es_ctx_scratch(ctx, acc_bytes + c0_bytes + g0_bytes, &scratch);
+    if (rc) return rc;
+    uint4* acc4 = (uint4*)scratch;
+    int32_t* c0 = (int32_t*)((char*)scratch + acc_bytes);
+    double* gauss0 = (double*)((char*)scratch + acc_bytes + c0_bytes);
+    {
         const size_t smem = (size_t)(2 * MG_RING + 1) * MG_N * sizeof(uint32_t);
         ES_CHECK_CUDA(cudaFuncSetAttribute(mt_gauss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         mt_gauss_kernel<<<n_streams, MG_THREADS, smem, stream>>>(mt_key, mt_pos, has_gauss, gauss, n_per_stream, rng, mask, coins, N,
