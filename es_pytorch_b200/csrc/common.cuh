@@ -34,6 +34,7 @@ struct es_ctx {
     // by the next entry point
     volatile int* err_host;
     int* err_dev;
+    int mj_lists_ready;     // mt_gauss.cu: the set-bit lists of the jump polynomials have been built on this device
 };
 
 #define ES_ASYNC_BAD_INDEX 1

@@ -33,6 +33,7 @@
 // float32 noise array does not see; the accept/reject arithmetic (the only part that steers the stream) is exact.
 #include <math.h>
 #include <stdlib.h>
+#include <type_traits>
 #include "common.cuh"
 #include "mt19937.cuh"
 
@@ -317,65 +318,157 @@ __device__ const uint32_t mj_polys[MJ_NPOLY][MT_NW] = {
 #include "mt_jump_polys.inc"
 };
 
-__global__ void __launch_bounds__(MG_THREADS, 1)
+// the set bits of every jump polynomial as a list of word offsets (built once per device by mj_lists_kernel): applying a jump
+// is then "XOR the window words at these offsets", 8 offsets per 16-byte load, with independent loads in flight
+constexpr int MJ_BITS = MT_NW * 32;
+__device__ __align__(16) uint16_t mj_idx[MJ_NPOLY][MJ_BITS];
+__device__ int mj_cnt[MJ_NPOLY];
+
+__global__ void __launch_bounds__(640) mj_lists_kernel() {
+    __shared__ int s_w[20];
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t g = tid < MT_NW ? mj_polys[r][tid] : 0u;
+    int inc = __popc(g);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += up;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += s_w[w];
+    int at = before + inc - __popc(g);
+    while (g) {
+        mj_idx[r][at++] = (uint16_t)(tid * 32 + __ffs(g) - 1);
+        g &= g - 1;
+    }
+    if (tid == 639) mj_cnt[r] = before + inc;
+}
+
+// Thread <-> word map of the fill: warp w, lane l looks at word 31 w + l and OWNS it when l < 31 (the last lane of a warp only
+// supplies its word to its neighbour, so no lane has to form a second word); word 623, whose expression differs, sits right
+// after word 622 in warp 20.  One barrier per block: a thread forms its new word N[i] from the old block O and O's twists T
+// (see mt19937.cuh), takes N[i + 1] from the next lane and stores N[i] AND the new block's twist T'[i] = tw(N[i], N[i + 1]) --
+// so the next block can start right after the barrier.  T[623] stays 0 in both twist buffers.  The main loop is unrolled over
+// the two block / twist buffers so that every shared-memory address is a per-thread register plus an immediate (the first
+// version recomputed them and issued ~110 instructions per warp and block; the kernel is issue-bound).
+constexpr int MF_WARPS = 21, MF_THREADS = 32 * MF_WARPS;
+struct MjTaps { int o, a, b, c; };
+__device__ __forceinline__ MjTaps mj_taps(int i) {            // N[i] = O[o] ^ T[a] ^ T[b] ^ T[c], 0 <= i <= 622
+    MjTaps m;
+    m.o = i < MT_DW ? i + MT_MW : (i < 2 * MT_DW ? i + MT_MW - MT_DW : i + MT_MW - 2 * MT_DW);
+    m.a = i;
+    m.b = i >= MT_DW ? i - MT_DW : MT_NW - 1;
+    m.c = i >= 2 * MT_DW ? i - 2 * MT_DW : MT_NW - 1;
+    return m;
+}
+__device__ __forceinline__ uint32_t mj_last_word(const uint32_t* __restrict__ O, const uint32_t* __restrict__ T) {     // N[623]
+    const uint32_t n0 = O[MT_MW] ^ T[0];
+    const uint32_t n396 = O[396 + MT_MW - MT_DW] ^ T[396 - MT_DW] ^ T[396];
+    return n396 ^ mt19937_twist(O[MT_NW - 1], n0);
+}
+
+__global__ void __launch_bounds__(MF_THREADS, 2)
 mt_fill_kernel(const uint32_t* __restrict__ mt_key, int n_seg, int lb_log2, uint32_t* __restrict__ words, size_t stride_words) {
     extern __shared__ uint32_t mj_smem[];
     uint32_t* xs = mj_smem;                                    // [33][624] raw words: the jump window; blocks 0 / 1: ping-pong of the fill
-    uint32_t* s_T = mj_smem + MJ_WIN_BLOCKS * MT_NW;           // [624] twists
-    uint32_t* s_g = s_T + MT_NW;                               // [624] the polynomial of the current jump
-    const int tid = threadIdx.x;
+    uint32_t* s_T = mj_smem + MJ_WIN_BLOCKS * MT_NW;           // [2][624] twists of the block being read / being written
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sid = blockIdx.x / n_seg, k = blockIdx.x % n_seg;
-    Mt19937Regen rg;
-    rg.init(tid);
+    const int iw = 31 * warp + lane;                           // the word this thread looks at
+    const bool last = iw == MT_NW - 1;
+    const bool owner = (lane < 31 && iw < MT_NW - 1) || last;
+    const bool tail_warp = warp == MF_WARPS - 1;
+    const int i = iw < MT_NW - 1 ? iw : MT_NW - 2;             // (clamped: whole warps take part in the shuffle)
+    const MjTaps tp = mj_taps(i);
     uint32_t* __restrict__ out = words + (size_t)sid * stride_words;
-    for (int i = tid; i < MT_NW; i += MG_THREADS) {
-        const uint32_t y = mt_key[(size_t)sid * MT_NW + i];
-        xs[i] = y;
-        if (k == 0) out[i] = mt19937_temper(y);               // block 0 = the incoming state: its unread words belong to the stream
+    for (int j = tid; j < MT_NW; j += MF_THREADS) {
+        const uint32_t y = mt_key[(size_t)sid * MT_NW + j];
+        xs[j] = y;
+        if (k == 0) out[j] = mt19937_temper(y);               // block 0 = the incoming state: its unread words belong to the stream
     }
-    if (tid == 0) s_T[MT_NW - 1] = 0;
+    if (tid < 2) s_T[tid * MT_NW + MT_NW - 1] = 0;
     __syncthreads();
-    // (blk >= 0: the block's index in the stream: its tempered words go to global memory)
-    auto regen = [&](const uint32_t* __restrict__ O, uint32_t* __restrict__ dst, long long blk) {
-        if (tid < MT_NW - 1) s_T[tid] = mt19937_twist(O[tid], O[tid + 1]);
-        __syncthreads();
-        if (rg.my_i >= 0) {
-            const uint32_t y = rg.word(O, s_T);
-            dst[rg.my_i] = y;
-            if (blk >= 0) out[(size_t)blk * MT_NW + rg.my_i] = mt19937_temper(y);
+    // one block: O, T -> D (raw words), Tn (its twists), opw (this thread's tempered word in global memory, when OUT)
+    const bool owner_t = owner && !last;
+    auto regen = [&](auto out_tag, const uint32_t* __restrict__ O, const uint32_t* __restrict__ T, uint32_t* __restrict__ D,
+                     uint32_t* __restrict__ Tn, uint32_t* __restrict__ opw) {
+        constexpr bool OUT = decltype(out_tag)::value;
+        uint32_t n = O[tp.o] ^ T[tp.a] ^ T[tp.b] ^ T[tp.c];
+        if (tail_warp) {
+            if (last) n = mj_last_word(O, T);
+        }
+        const uint32_t nx = __shfl_down_sync(0xffffffffu, n, 1);
+        const uint32_t tw = mt19937_twist(n, nx);
+        if (owner) D[iw] = n;
+        if (owner_t) Tn[iw] = tw;
+        if (OUT) {
+            const uint32_t y = mt19937_temper(n);
+            if (owner) *opw = y;
         }
         __syncthreads();
     };
+    using Yes = std::true_type;
+    using No = std::false_type;
+    auto twists_of = [&](const uint32_t* __restrict__ O, uint32_t* __restrict__ T) {
+        if (tid < MT_NW - 1) T[tid] = mt19937_twist(O[tid], O[tid + 1]);
+        __syncthreads();
+    };
+    uint32_t* const T0 = s_T;
+    uint32_t* const T1 = s_T + MT_NW;
     // ---- jump to block k << lb_log2: one jump per set bit ----
     const unsigned target = (unsigned)k << lb_log2;
     for (int r = MJ_NPOLY - 1; r >= 0; --r) {
         if (!((target >> r) & 1u)) continue;
-        for (int b = 1; b < MJ_WIN_BLOCKS; ++b) regen(xs + (b - 1) * MT_NW, xs + b * MT_NW, -1);
-        for (int i = tid; i < MT_NW; i += MG_THREADS) s_g[i] = mj_polys[r][i];
-        __syncthreads();
-        uint32_t acc = 0;
-        if (tid < MT_NW) {
-            for (int w = 0; w < MT_NW; ++w) {
-                uint32_t gw = s_g[w];
-                const uint32_t* __restrict__ xw = xs + tid + 32 * w;
-                while (gw) {
-                    const int bit = __ffs(gw) - 1;
-                    acc ^= xw[bit];
-                    gw &= gw - 1;
-                }
+        twists_of(xs, T0);
+        for (int b = 1; b < MJ_WIN_BLOCKS; b += 2) {           // 32 more blocks: the window of the jump
+            regen(No(), xs + (b - 1) * MT_NW, T0, xs + b * MT_NW, T1, nullptr);
+            regen(No(), xs + b * MT_NW, T1, xs + (b + 1) * MT_NW, T0, nullptr);
+        }
+        // four output words per thread (j, j + 156, j + 312, j + 468): the offsets are decoded once for four loads
+        uint32_t acc[4] = {0u, 0u, 0u, 0u};
+        if (tid < MT_NW / 4) {
+            const uint16_t* __restrict__ L = mj_idx[r];
+            const int n = mj_cnt[r];
+            const uint32_t* __restrict__ xb = xs + tid;
+            uint32_t alt[4] = {0u, 0u, 0u, 0u};
+            auto tap = [&](uint32_t off, uint32_t* a) {
+                const uint32_t* __restrict__ q = xb + off;
+                a[0] ^= q[0]; a[1] ^= q[MT_NW / 4]; a[2] ^= q[2 * (MT_NW / 4)]; a[3] ^= q[3 * (MT_NW / 4)];
+            };
+            int e = 0;
+            for (; e + 8 <= n; e += 8) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(L + e));
+                tap(q.x & 0xFFFFu, acc); tap(q.x >> 16, alt);
+                tap(q.y & 0xFFFFu, acc); tap(q.y >> 16, alt);
+                tap(q.z & 0xFFFFu, acc); tap(q.z >> 16, alt);
+                tap(q.w & 0xFFFFu, acc); tap(q.w >> 16, alt);
             }
+            for (; e < n; ++e) tap(L[e], acc);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[c] ^= alt[c];
         }
         __syncthreads();
-        if (tid < MT_NW) xs[tid] = acc;                        // (word 0: only its top bit is state, and that bit is right)
+        if (tid < MT_NW / 4) {                                 // (word 0: only its top bit is state, and that bit is right)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) xs[tid + c * (MT_NW / 4)] = acc[c];
+        }
         __syncthreads();
     }
-    // ---- regenerate the segment: blocks target + 1 .. target + 2^lb ----
+    twists_of(xs, T0);
+    // ---- regenerate the segment: blocks target + 1 .. target + 2^lb, two per iteration (buffers 0 -> 1 -> 0) ----
     const int Lb = 1 << lb_log2;
-    int cur = 0;
-    for (int b = 0; b < Lb; ++b) {
-        regen(xs + cur * MT_NW, xs + (cur ^ 1) * MT_NW, (long long)1 + target + b);
-        cur ^= 1;
+    uint32_t* __restrict__ opw = out + (size_t)(1 + target) * MT_NW + iw;
+    uint32_t* const X0 = xs;
+    uint32_t* const X1 = xs + MT_NW;
+    int b = 0;
+    for (; b + 2 <= Lb; b += 2) {
+        regen(Yes(), X0, T0, X1, T1, opw);
+        regen(Yes(), X1, T1, X0, T0, opw + MT_NW);
+        opw += 2 * MT_NW;
     }
+    if (b < Lb) regen(Yes(), X0, T0, X1, T1, opw);
 }
 
 // ---- the accept bit of every possible attempt, in parallel: one CTA per (stream, chunk of 4096 words), thread q looks at the
@@ -390,27 +483,43 @@ __device__ __forceinline__ bool mj_accept(uint32_t w0, uint32_t w1, uint32_t w2,
     return r2 < 1.0 && r2 != 0.0;
 }
 
-__global__ void __launch_bounds__(MJ_CA)
+// One WARP per chunk (4096 words = 1024 attempts of each phase): 32 steps of 128 words; lane l holds words 4 l .. 4 l + 3 of a step
+// (one 16-byte load), takes the next three from lane l + 1 (lane 31: from the next step's first load, which is already in
+// flight), and tests the four attempts that start at its words; lane s keeps the ballots of step s, so the 32 mask words of a
+// phase leave as one 128-byte store and the chunk's counts need no shared memory and no barrier.
+constexpr int MFL_WARPS = 8;
+__global__ void __launch_bounds__(32 * MFL_WARPS)
 mt_flags_kernel(const uint32_t* __restrict__ words, size_t stride_words, int n_chunks, uint32_t* __restrict__ masks,
                 uint32_t* __restrict__ counts) {
-    __shared__ int s_cnt[4];
-    const int q = threadIdx.x, c = blockIdx.x, sid = blockIdx.y;
-    if (q < 4) s_cnt[q] = 0;
-    __syncthreads();
-    const uint4* __restrict__ w4 = reinterpret_cast<const uint4*>(words + (size_t)sid * stride_words + (size_t)c * MJ_CW) + q;
-    const uint4 a = __ldg(w4), b = __ldg(w4 + 1);                 // words 4 q .. 4 q + 7 (the buffer is padded past the last chunk)
-    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    uint32_t* mk = masks + ((size_t)sid * 4 * n_chunks + c) * 32 + (q >> 5);          // + ph * n_chunks * 32
+    const int lane = threadIdx.x & 31, sid = blockIdx.y;
+    const int c = blockIdx.x * MFL_WARPS + (threadIdx.x >> 5);
+    if (c >= n_chunks) return;
+    const uint4* __restrict__ w4 = reinterpret_cast<const uint4*>(words + (size_t)sid * stride_words + (size_t)c * MJ_CW) + lane;
+    uint32_t keep[4] = {0u, 0u, 0u, 0u};
+    uint4 cur = __ldg(w4), nxt1 = __ldg(w4 + 32), nxt2 = __ldg(w4 + 64), nxt3 = __ldg(w4 + 96);   // (the buffer is padded by a chunk)
+#pragma unroll 4
+    for (int s = 0; s < 32; ++s) {
+        const uint4 far = __ldg(w4 + (s + 4) * 32);           // (reads up to 4 steps past the chunk: inside the next chunk / the padding)
+        uint4 b;
+        b.x = __shfl_down_sync(0xffffffffu, cur.x, 1);
+        b.y = __shfl_down_sync(0xffffffffu, cur.y, 1);
+        b.z = __shfl_down_sync(0xffffffffu, cur.z, 1);
+        const uint32_t n0 = __shfl_sync(0xffffffffu, nxt1.x, 0), n1 = __shfl_sync(0xffffffffu, nxt1.y, 0), n2 = __shfl_sync(0xffffffffu, nxt1.z, 0);
+        if (lane == 31) { b.x = n0; b.y = n1; b.z = n2; }
+        const unsigned b0 = __ballot_sync(0xffffffffu, mj_accept(cur.x, cur.y, cur.z, cur.w));
+        const unsigned b1 = __ballot_sync(0xffffffffu, mj_accept(cur.y, cur.z, cur.w, b.x));
+        const unsigned b2 = __ballot_sync(0xffffffffu, mj_accept(cur.z, cur.w, b.x, b.y));
+        const unsigned b3 = __ballot_sync(0xffffffffu, mj_accept(cur.w, b.x, b.y, b.z));
+        if (lane == s) { keep[0] = b0; keep[1] = b1; keep[2] = b2; keep[3] = b3; }
+        cur = nxt1; nxt1 = nxt2; nxt2 = nxt3; nxt3 = far;
+    }
+    uint32_t* mk = masks + ((size_t)sid * 4 * n_chunks + c) * 32 + lane;              // + ph * n_chunks * 32
 #pragma unroll
     for (int ph = 0; ph < 4; ++ph) {
-        const unsigned bal = __ballot_sync(0xffffffffu, mj_accept(w[ph], w[ph + 1], w[ph + 2], w[ph + 3]));
-        if ((q & 31) == 0) {
-            mk[(size_t)ph * n_chunks * 32] = bal;
-            atomicAdd(&s_cnt[ph], __popc(bal));
-        }
+        mk[(size_t)ph * n_chunks * 32] = keep[ph];
+        const int cnt = __reduce_add_sync(0xffffffffu, __popc(keep[ph]));
+        if (lane == 0) counts[((size_t)sid * 4 + ph) * n_chunks + c] = (uint32_t)cnt;
     }
-    __syncthreads();
-    if (q < 4) counts[((size_t)sid * 4 + q) * n_chunks + c] = (uint32_t)s_cnt[q];
 }
 
 // exclusive prefix of the chunk counts of every (stream, phase): one CTA each
@@ -451,15 +560,25 @@ mt_walk_kernel(uint32_t* __restrict__ mt_key, int32_t* __restrict__ mt_pos, int3
     int64_t* idx_o = idx_out + (size_t)sid * n_pairs;
     uint32_t* ext_o = extra_out ? extra_out + (size_t)sid * n_pairs * 4 * coins : nullptr;
     uint32_t* rs = reg_start + (size_t)sid * 2 * n_pairs;
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t nc_u = (uint32_t)n_chunks;                     // (host: n_chunks * 128 < 2^32, every table index fits 32 bits)
     bool overflow = false;
     for (int pair = 0; pair < n_pairs && !overflow; ++pair) {
-        uint32_t w;
-        do {
+        // the index: the first of the next words that passes the masked rejection (32 candidates at a time)
+        uint32_t w = 0;
+        for (;;) {
             if (cpos + 1 > limit) { overflow = true; break; }
-            w = __ldg(gw + cpos) & mask;
-            ++cpos;
-        } while (w > rng);
-        if (overflow) break;
+            const uint32_t v = __ldg(gw + cpos + lane) & mask;          // (the buffer is padded by a chunk past `limit`)
+            const unsigned ok = __ballot_sync(FULL, v <= rng);
+            if (ok) {
+                const int f = __ffs((int)ok) - 1;
+                w = __shfl_sync(FULL, v, f);
+                cpos += (uint32_t)f + 1u;
+                break;
+            }
+            cpos += 32u;
+        }
+        if (overflow || cpos > limit) { overflow = true; break; }
         if (lane == 0) idx_o[pair] = (int64_t)w;
         for (int sgn = 0; sgn < 2; ++sgn) {
             if (cpos + 2 * coins + 8 > limit) { overflow = true; break; }
@@ -473,52 +592,76 @@ mt_walk_kernel(uint32_t* __restrict__ mt_key, int32_t* __restrict__ mt_pos, int3
             const uint32_t a0 = cpos >> 2;                        // first attempt of the rollout, in phase ph's numbering
             const uint32_t* __restrict__ mph = mk + (size_t)ph * n_chunks * 32;
             const uint32_t* __restrict__ cph = cu + (size_t)ph * n_chunks;
-            // accepted attempts of the phase before a0
+            // everything the rollout needs is loaded at once (one memory latency per rollout): the mask row and prefix of the
+            // chunk it starts in, the prefixes of a window of 32 chunks around the expected end (acceptance pi / 4; the spread
+            // of the end is ~sqrt(need) attempts, a window is 32 768), and the mask rows of the three likeliest end chunks.
+            // (32-bit arithmetic throughout: one warp per stream leaves every instruction's latency exposed)
             const uint32_t ch0 = a0 >> 10, r0 = a0 & 1023;
-            const uint32_t m0 = __ldg(mph + (size_t)ch0 * 32 + lane);
+            const uint32_t span = (uint32_t)need + (uint32_t)(((uint64_t)(uint32_t)need * 1173554908u) >> 32);      // need * 4 / pi
+            const uint32_t a_est = a0 + span;
+            uint32_t est = a_est >> 10;
+            if (est > nc_u - 1u) est = nc_u - 1u;
+            uint32_t wlo = est > ch0 + 12u ? est - 12u : ch0;
+            if (wlo + 32u > nc_u) wlo = nc_u > 32u ? nc_u - 32u : 0u;
+            uint32_t ci = wlo + lane;
+            const uint32_t m0 = __ldg(mph + ch0 * 32u + lane);
             const uint32_t base0 = __ldg(cph + ch0);
-            int below = (lane < (int)(r0 >> 5)) ? __popc(m0) : (lane == (int)(r0 >> 5) ? __popc(m0 & ((1u << (r0 & 31)) - 1u)) : 0);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+            uint32_t pre = (ci < nc_u) ? __ldg(cph + ci) : 0xFFFFFFFFu;
+            const uint32_t e0 = est > 0u ? est - 1u : 0u, e2 = est + 1u < nc_u ? est + 1u : est;
+            const uint32_t mc0 = __ldg(mph + e0 * 32u + lane), mc1 = __ldg(mph + est * 32u + lane), mc2 = __ldg(mph + e2 * 32u + lane);
+            // pull what the NEXT draws will touch towards L2 while this rollout is resolved: the words around the expected end
+            // (the next index / coins); for the next rollout, whose phase is not known yet, in all four phases: the mask rows
+            // around its start (= this end) and around its expected end, and the prefix windows around its expected end
+            {
+                const uint32_t a_pf = a_est + (uint32_t)(lane - 12) * 8u;
+                if (a_pf < (limit >> 2)) asm volatile("prefetch.global.L2 [%0];" ::"l"(gw + 4u * a_pf));
+                const uint32_t est2 = (a_est + span) >> 10;
+                if (lane < 24) {
+                    const uint32_t l12 = lane < 12 ? lane : lane - 12;
+                    const uint32_t nc = (lane < 12 ? est : est2) + (l12 % 3u) - 1u;
+                    if (nc < nc_u) asm volatile("prefetch.global.L2 [%0];" ::"l"(mk + ((size_t)(l12 / 3u) * nc_u + nc) * 32));
+                } else {
+                    const uint32_t nc = (est2 > 12u ? est2 - 12u : 0u) + ((lane & 1) ? 31u : 0u);
+                    if (nc < nc_u) asm volatile("prefetch.global.L2 [%0];" ::"l"(cu + (size_t)((lane - 24) >> 1) * nc_u + nc));
+                }
+            }
+            // accepted attempts of the phase before a0
+            const int below = __reduce_add_sync(FULL, (lane < (int)(r0 >> 5)) ? __popc(m0)
+                                                      : (lane == (int)(r0 >> 5) ? __popc(m0 & ((1u << (r0 & 31)) - 1u)) : 0));
             const uint32_t target = base0 + (uint32_t)below + (uint32_t)need;      // accepted attempts before the END of the rollout
-            // the chunk that contains the target-th accepted attempt: the last one whose prefix is < target, looked for in a
-            // window of 32 chunks around the expected place (acceptance pi / 4; 32 chunks = 32 768 attempts >> its spread)
-            long long est = ((long long)a0 + (long long)(need * 1.2732395447351628)) >> 10;
-            long long wlo = est - 12;
-            if (wlo < (long long)ch0) wlo = ch0;
-            if (wlo + 32 > n_chunks) wlo = (long long)n_chunks - 32 > 0 ? n_chunks - 32 : 0;
-            long long ci = wlo + lane;
-            uint32_t pre = (ci < n_chunks) ? __ldg(cph + ci) : 0xFFFFFFFFu;
-            unsigned lt = __ballot_sync(0xffffffffu, pre < target);
-            if (lt == 0u || (lt == 0xFFFFFFFFu && wlo + 32 < n_chunks)) {
+            // the chunk that contains the target-th accepted attempt: the last one whose prefix is < target
+            unsigned lt = __ballot_sync(FULL, pre < target);
+            if (lt == 0u || (lt == 0xFFFFFFFFu && wlo + 32u < nc_u)) {
                 // outside the window (tens of sigma away from the estimate): bisect the prefixes, then look again from there
-                long long lo = ch0, hi = (long long)n_chunks - 1;          // invariant: prefix[lo] < target
+                uint32_t lo = ch0, hi = nc_u - 1u;                          // invariant: prefix[lo] < target
                 while (lo < hi) {
-                    const long long mid = (lo + hi + 1) >> 1;
-                    if (__ldg(cph + mid) < target) lo = mid; else hi = mid - 1;
+                    const uint32_t mid = (lo + hi + 1u) >> 1;
+                    if (__ldg(cph + mid) < target) lo = mid; else hi = mid - 1u;
                 }
                 wlo = lo;
                 ci = wlo + lane;
-                pre = (ci < n_chunks) ? __ldg(cph + ci) : 0xFFFFFFFFu;
-                lt = __ballot_sync(0xffffffffu, pre < target);
+                pre = (ci < nc_u) ? __ldg(cph + ci) : 0xFFFFFFFFu;
+                lt = __ballot_sync(FULL, pre < target);
             }
             const int sel = 31 - __clz((int)lt);                  // last lane with prefix < target (prefixes are non-decreasing)
-            const uint32_t c1 = (uint32_t)(wlo + sel), pre1 = __shfl_sync(0xffffffffu, pre, sel);
-            const uint32_t m1 = __ldg(mph + (size_t)c1 * 32 + lane);
+            const uint32_t c1 = wlo + (uint32_t)sel, pre1 = __shfl_sync(FULL, pre, sel);
+            const uint32_t m1 = c1 == est ? mc1 : (c1 == e0 ? mc0 : (c1 == e2 ? mc2 : __ldg(mph + c1 * 32u + lane)));
             int inc = __popc(m1);
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const int up = __shfl_up_sync(0xffffffffu, inc, d);
+                const int up = __shfl_up_sync(FULL, inc, d);
                 if (lane >= d) inc += up;
             }
             const uint32_t want = target - pre1;                  // the want-th (1-based) accepted attempt of chunk c1 ends the rollout
-            const unsigned ge = __ballot_sync(0xffffffffu, (uint32_t)inc >= want);
+            const unsigned ge = __ballot_sync(FULL, (uint32_t)inc >= want);
             if (ge == 0u) { overflow = true; break; }
             const int L = __ffs((int)ge) - 1;
-            const uint32_t mL = __shfl_sync(0xffffffffu, m1, L);
-            const int incL = __shfl_sync(0xffffffffu, inc, L);
+            const uint32_t mL = __shfl_sync(FULL, m1, L);
+            const int incL = __shfl_sync(FULL, inc, L);
             const int kth = (int)want - (incL - __popc(mL));      // 1-based among the set bits of lane L's word
-            const int bit = __fns(mL, 0, kth);
+            // the kth set bit of mL: the lane whose bit is set with kth - 1 set bits below it
+            const unsigned hit = __ballot_sync(FULL, ((mL >> lane) & 1u) && __popc(mL & ((1u << lane) - 1u)) == kth - 1);
+            const int bit = __ffs((int)hit) - 1;
             const uint32_t a1 = (c1 << 10) + 32u * (uint32_t)L + (uint32_t)bit;
             cpos = 4u * (a1 + 1u) + (uint32_t)ph;
             if (cpos > limit) { overflow = true; break; }
@@ -655,11 +798,17 @@ int es_impl_draw_noisy(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int32_t* 
         uint32_t* reg_start = (uint32_t*)at; at += reg_bytes;
         int32_t* c0 = (int32_t*)at; at += c0_bytes;
         double* gauss0 = (double*)at;
+        if (!ctx->mj_lists_ready) {
+            mj_lists_kernel<<<MJ_NPOLY, 640, 0, stream>>>();
+            ES_LAUNCHED(ctx);
+            ctx->mj_lists_ready = 1;
+        }
         const size_t smem = (size_t)(MJ_WIN_BLOCKS + 2) * MT_NW * sizeof(uint32_t);
         ES_CHECK_CUDA(cudaFuncSetAttribute(mt_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mt_fill_kernel<<<(unsigned)(n_streams * n_seg), MG_THREADS, smem, stream>>>(mt_key, (int)n_seg, lb_log2, words, stride_words);
+        mt_fill_kernel<<<(unsigned)(n_streams * n_seg), MF_THREADS, smem, stream>>>(mt_key, (int)n_seg, lb_log2, words, stride_words);
         ES_LAUNCHED(ctx);
-        mt_flags_kernel<<<dim3((unsigned)n_chunks, (unsigned)n_streams), MJ_CA, 0, stream>>>(words, stride_words, (int)n_chunks, masks, counts);
+        mt_flags_kernel<<<dim3((unsigned)((n_chunks + MFL_WARPS - 1) / MFL_WARPS), (unsigned)n_streams), 32 * MFL_WARPS, 0, stream>>>(
+            words, stride_words, (int)n_chunks, masks, counts);
         ES_LAUNCHED(ctx);
         mt_scan_kernel<<<n_streams * 4, 1024, 0, stream>>>(counts, (int)n_chunks);
         ES_LAUNCHED(ctx);

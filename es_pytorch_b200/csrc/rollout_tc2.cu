@@ -568,6 +568,19 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
                 const int t = m * T2_MT + row;
                 const uint32_t tv_ = tmem + vbuf * C::V_STRIDE + lane_off + cq * CW;            // this warp's V columns
                 const float4* __restrict__ up = reinterpret_cast<const float4*>(p.ubase) + ((size_t)m * 16 + cq * (CW / 4)) * T2_MT + row;
+                if (p.act_noise && cq == 0) {
+                    // action noise of this tile's rows (both signs) towards L2 now; it is read after layer 3 (one warp per lane quarter asks)
+                    const int t0 = m * T2_MT + q * 32;
+                    const int rows = min(32, p.T - t0);
+                    if (rows > 0) {
+                        const char* nb = reinterpret_cast<const char*>(p.act_noise + (((size_t)(blockIdx.x + i * gridDim.x) * 2) * p.T + t0) * p.act);
+                        const int bytes = rows * p.act * 4;
+                        for (int o = lane * 128; o < bytes + 128; o += 32 * 128) {
+                            prefetch_l2(nb + min(o, bytes - 4));
+                            prefetch_l2(nb + (size_t)p.T * p.act * 4 + min(o, bytes - 4));
+                        }
+                    }
+                }
                 mbar_wait(&bars[B2_D1_FULL + vbuf], par_v);
                 tc_fence_after();
                 // ---- epi1: h1+- = tanh(U +- sigma V), 8 columns at a time; the + sign first (its L2 MMA then runs while the - sign
@@ -658,8 +671,18 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
                 const float* nzrow = (p.act_noise && t < p.T)
                     ? p.act_noise + (((size_t)(blockIdx.x + i * gridDim.x) * 2) * p.T + t) * p.act + a_lo : nullptr;
                 float tv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                // the noise values of a sign are in flight before that sign's accumulator is waited for (the - sign's under the
+                // + sign's arithmetic): read inside the tanh groups they cost several exposed memory latencies per tile
+                constexpr int NZ = SPLIT ? 8 : 16;
+                float nz[2][NZ];
+#pragma unroll
+                for (int jj = 0; jj < NZ; ++jj) nz[0][jj] = (nzrow && jj < nj) ? ldg_pinned(nzrow + jj) : 0.f;
 #pragma unroll
                 for (int sgn = 0; sgn < 2; ++sgn) {
+                    if (sgn == 0) {
+#pragma unroll
+                        for (int jj = 0; jj < NZ; ++jj) nz[1][jj] = (nzrow && jj < nj) ? ldg_pinned(nzrow + (size_t)p.T * p.act + jj) : 0.f;
+                    }
                     mbar_wait(&bars[(sgn ? B2_D3N : B2_D3P) + eg], par);
                     tc_fence_after();
                     float r = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
@@ -682,13 +705,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
                                         float a0, a1, a2, a3;
                                         if (SPLIT) { tanh_acc2(z0, z1, a0, a1, (T2_NEWTON_MASK >> 0) & 1); tanh_acc2(z2, z3, a2, a3, (T2_NEWTON_MASK >> 1) & 1); }
                                         else { a0 = tanh_fast(z0); a1 = tanh_fast(z1); a2 = tanh_fast(z2); a3 = tanh_fast(z3); }
-                                        if (nzrow) {              // a += rs.randn(act) * ac_std (src/nn/nn.py:47-48), drawn by mt_gauss.cu
-                                            const float* nq = nzrow + (size_t)sgn * p.T * p.act + gq * 4;
-                                            const int left = nj - gq * 4;
-                                            a0 += ldg_stream(nq);
-                                            if (left > 1) a1 += ldg_stream(nq + 1);
-                                            if (left > 2) a2 += ldg_stream(nq + 2);
-                                            if (left > 3) a3 += ldg_stream(nq + 3);
+                                        if (gq * 4 < NZ) {        // a += rs.randn(act) * ac_std (src/nn/nn.py:47-48), drawn by mt_gauss.cu
+                                            a0 += nz[sgn][(gq * 4 + 0) % NZ]; a1 += nz[sgn][(gq * 4 + 1) % NZ];
+                                            a2 += nz[sgn][(gq * 4 + 2) % NZ]; a3 += nz[sgn][(gq * 4 + 3) % NZ];
                                         }
                                         r = fmaf(a0, cc[gq * 4 + 0], r);
                                         r = fmaf(a1, cc[gq * 4 + 1], r);
