@@ -369,13 +369,29 @@ __device__ __forceinline__ uint32_t mj_last_word(const uint32_t* __restrict__ O,
     return n396 ^ mt19937_twist(O[MT_NW - 1], n0);
 }
 
+// segments in the order the CTAs should start: most jumps (set bits of the segment index) first, so that the long CTAs do not
+// end up in the last wave
+__global__ void __launch_bounds__(1024) mj_order_kernel(int n_seg, uint16_t* __restrict__ order) {
+    for (int k = threadIdx.x; k < n_seg; k += 1024) {
+        const int pc = __popc(k);
+        int rank = 0;
+        for (int j = 0; j < n_seg; ++j) {
+            const int pj = __popc(j);
+            rank += (pj > pc || (pj == pc && j < k)) ? 1 : 0;
+        }
+        order[rank] = (uint16_t)k;
+    }
+}
+
 __global__ void __launch_bounds__(MF_THREADS, 2)
-mt_fill_kernel(const uint32_t* __restrict__ mt_key, int n_seg, int lb_log2, uint32_t* __restrict__ words, size_t stride_words) {
+mt_fill_kernel(const uint32_t* __restrict__ mt_key, int n_streams, int n_seg, int lb_log2, const uint16_t* __restrict__ order,
+               uint32_t* __restrict__ words, size_t stride_words) {
     extern __shared__ uint32_t mj_smem[];
     uint32_t* xs = mj_smem;                                    // [33][624] raw words: the jump window; blocks 0 / 1: ping-pong of the fill
     uint32_t* s_T = mj_smem + MJ_WIN_BLOCKS * MT_NW;           // [2][624] twists of the block being read / being written
+    uint32_t* s_P = s_T + 2 * MT_NW;                           // [4][624] partial sums of a jump (one per quarter of the polynomial)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int sid = blockIdx.x / n_seg, k = blockIdx.x % n_seg;
+    const int sid = blockIdx.x % n_streams, k = order[blockIdx.x / n_streams];
     const int iw = 31 * warp + lane;                           // the word this thread looks at
     const bool last = iw == MT_NW - 1;
     const bool owner = (lane < 31 && iw < MT_NW - 1) || last;
@@ -426,34 +442,35 @@ mt_fill_kernel(const uint32_t* __restrict__ mt_key, int n_seg, int lb_log2, uint
             regen(No(), xs + (b - 1) * MT_NW, T0, xs + b * MT_NW, T1, nullptr);
             regen(No(), xs + b * MT_NW, T1, xs + (b + 1) * MT_NW, T0, nullptr);
         }
-        // four output words per thread (j, j + 156, j + 312, j + 468): the offsets are decoded once for four loads
-        uint32_t acc[4] = {0u, 0u, 0u, 0u};
-        if (tid < MT_NW / 4) {
+        // four output words per thread (j, j + 156, j + 312, j + 468: the offsets are decoded once for four loads), and the
+        // polynomial's set bits in four quarters, one per group of 156 threads; the partial sums meet in shared memory
+        if (tid < MT_NW) {
+            const int grp = tid / (MT_NW / 4), j = tid - grp * (MT_NW / 4);
             const uint16_t* __restrict__ L = mj_idx[r];
             const int n = mj_cnt[r];
-            const uint32_t* __restrict__ xb = xs + tid;
-            uint32_t alt[4] = {0u, 0u, 0u, 0u};
+            const int per = ((n + 3) / 4 + 7) & ~7;            // a quarter of the list, whole 16-byte loads
+            const int lo = min(n, grp * per), hi = min(n, lo + per);
+            const uint32_t* __restrict__ xb = xs + j;
+            uint32_t acc[4] = {0u, 0u, 0u, 0u}, alt[4] = {0u, 0u, 0u, 0u};
             auto tap = [&](uint32_t off, uint32_t* a) {
                 const uint32_t* __restrict__ q = xb + off;
                 a[0] ^= q[0]; a[1] ^= q[MT_NW / 4]; a[2] ^= q[2 * (MT_NW / 4)]; a[3] ^= q[3 * (MT_NW / 4)];
             };
-            int e = 0;
-            for (; e + 8 <= n; e += 8) {
+            int e = lo;
+            for (; e + 8 <= hi; e += 8) {
                 const uint4 q = __ldg(reinterpret_cast<const uint4*>(L + e));
                 tap(q.x & 0xFFFFu, acc); tap(q.x >> 16, alt);
                 tap(q.y & 0xFFFFu, acc); tap(q.y >> 16, alt);
                 tap(q.z & 0xFFFFu, acc); tap(q.z >> 16, alt);
                 tap(q.w & 0xFFFFu, acc); tap(q.w >> 16, alt);
             }
-            for (; e < n; ++e) tap(L[e], acc);
+            for (; e < hi; ++e) tap(L[e], acc);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[c] ^= alt[c];
+            for (int c = 0; c < 4; ++c) s_P[grp * MT_NW + j + c * (MT_NW / 4)] = acc[c] ^ alt[c];
         }
         __syncthreads();
-        if (tid < MT_NW / 4) {                                 // (word 0: only its top bit is state, and that bit is right)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) xs[tid + c * (MT_NW / 4)] = acc[c];
-        }
+        if (tid < MT_NW)                                       // (word 0: only its top bit is state, and that bit is right)
+            xs[tid] = s_P[tid] ^ s_P[MT_NW + tid] ^ s_P[2 * MT_NW + tid] ^ s_P[3 * MT_NW + tid];
         __syncthreads();
     }
     twists_of(xs, T0);
@@ -769,7 +786,7 @@ int es_impl_draw_noisy(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int32_t* 
         if (lb_log2 > MJ_NPOLY - 1) lb_log2 = MJ_NPOLY - 1;
     }
     const long long n_seg = jump ? (blocks_needed + (1LL << lb_log2) - 1) >> lb_log2 : 0;
-    if (jump && (((n_seg << lb_log2) >> MJ_NPOLY) != 0 || (double)(n_seg << lb_log2) * MT_NW > 4.0e9)) {       // the block index of a segment start must fit the available jumps
+    if (jump && (((n_seg << lb_log2) >> MJ_NPOLY) != 0 || (double)(n_seg << lb_log2) * MT_NW > 4.0e9 || n_seg > 65535)) {       // the block index of a segment start must fit the available jumps
         es_set_error("es_draw_noisy: %lld blocks per stream exceed the jump-ahead range (2^%d blocks)", n_seg << lb_log2, MJ_NPOLY);
         return ES_ERR_UNSUPPORTED;
     }
@@ -788,8 +805,9 @@ int es_impl_draw_noisy(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int32_t* 
         const size_t mask_bytes = pad((size_t)n_streams * 4 * n_chunks * 32 * sizeof(uint32_t));
         const size_t cnt_bytes = pad((size_t)n_streams * 4 * n_chunks * sizeof(uint32_t));
         const size_t reg_bytes = pad(n_eval * sizeof(uint32_t));
+        const size_t ord_bytes = pad((size_t)n_seg * sizeof(uint16_t));
         void* scratch = nullptr;
-        int rc = es_ctx_scratch(ctx, words_bytes + mask_bytes + cnt_bytes + reg_bytes + c0_bytes + g0_bytes, &scratch);
+        int rc = es_ctx_scratch(ctx, words_bytes + mask_bytes + cnt_bytes + reg_bytes + c0_bytes + g0_bytes + ord_bytes, &scratch);
         if (rc) return rc;
         char* at = (char*)scratch;
         uint32_t* words = (uint32_t*)at; at += words_bytes;
@@ -797,15 +815,19 @@ int es_impl_draw_noisy(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int32_t* 
         uint32_t* counts = (uint32_t*)at; at += cnt_bytes;
         uint32_t* reg_start = (uint32_t*)at; at += reg_bytes;
         int32_t* c0 = (int32_t*)at; at += c0_bytes;
-        double* gauss0 = (double*)at;
+        double* gauss0 = (double*)at; at += g0_bytes;
+        uint16_t* order = (uint16_t*)at;
         if (!ctx->mj_lists_ready) {
             mj_lists_kernel<<<MJ_NPOLY, 640, 0, stream>>>();
             ES_LAUNCHED(ctx);
             ctx->mj_lists_ready = 1;
         }
-        const size_t smem = (size_t)(MJ_WIN_BLOCKS + 2) * MT_NW * sizeof(uint32_t);
+        mj_order_kernel<<<1, 1024, 0, stream>>>((int)n_seg, order);
+        ES_LAUNCHED(ctx);
+        const size_t smem = (size_t)(MJ_WIN_BLOCKS + 6) * MT_NW * sizeof(uint32_t);
         ES_CHECK_CUDA(cudaFuncSetAttribute(mt_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mt_fill_kernel<<<(unsigned)(n_streams * n_seg), MF_THREADS, smem, stream>>>(mt_key, (int)n_seg, lb_log2, words, stride_words);
+        mt_fill_kernel<<<(unsigned)(n_streams * n_seg), MF_THREADS, smem, stream>>>(mt_key, n_streams, (int)n_seg, lb_log2, order, words,
+                                                                                    stride_words);
         ES_LAUNCHED(ctx);
         mt_flags_kernel<<<dim3((unsigned)((n_chunks + MFL_WARPS - 1) / MFL_WARPS), (unsigned)n_streams), 32 * MFL_WARPS, 0, stream>>>(
             words, stride_words, (int)n_chunks, masks, counts);
