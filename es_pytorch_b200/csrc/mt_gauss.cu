@@ -22,8 +22,9 @@
 // per block with 4 or 10 warps; ONE pass that recomputes up to three twists per word is as slow (~100 instructions per word);
 // sharing the 623 twists through shared memory, warp-aligned ranges, branch-free word expressions and hoisted index arithmetic
 // bring a block to ~450 cycles.  Splitting the CTA into producer and consumer warps did not help (the producer alone sets the
-// pace), neither did moving the float64 math out (it was not the limiter).  A polynomial jump-ahead that spreads one stream's
-// regeneration over many SMs is the known way beyond this; not built.
+// pace), neither did moving the float64 math out (it was not the limiter).  Long streams therefore take the polynomial
+// jump-ahead path in the second half of this file, which spreads one stream's regeneration over the whole GPU (8.4 ms for the
+// same draw); this kernel stays the path for short streams.
 //
 // Output noise[((stream * n_pairs + pair) * 2 + sign) * N + t * act + j] = float32(gauss * scale): the float64 product rounded
 // once; the rollout kernels add it to the float32 action (the reference forms the float64 sum and the env rounds it to
