@@ -185,7 +185,8 @@ def _device_generation(fit_fn, policy: Policy, nt: NoiseTable, streams) -> Devic
                                ob_clip=policy._module.ob_clip, pos_scale=env.pos_scale,
                                coins_per_eval=fit_fn.coins_per_eval, save_obs_chance=fit_fn.save_obs_chance,
                                archive=archive, nov_k=fit_fn.nov_k, rollout_mode=fit_fn.rollout_mode, engine=eng,
-                               ac_std=float(getattr(policy._module, '_action_std', 0.0) or 0.0))
+                               ac_std=float(getattr(policy._module, '_action_std', 0.0) or 0.0),
+                               closed=env.device_closed(eng) if getattr(env, 'is_synthetic_closedloop', False) else None)
         fit_fn._gen = gen
     else:
         gen.load_states(streams)

@@ -246,6 +246,37 @@ int es_rollout_openloop(es_ctx* ctx, const float* table, int64_t table_len, cons
                                      pos_scale, fit_pos, fit_neg, fit_stride, behv_pos, behv_neg, nullptr, mode, stream);
 }
 
+int es_rollout_closedloop(es_ctx* ctx, const float* table, int64_t table_len, const int64_t* idx, int n_pairs, const float* theta,
+                          int P, float sigma, const int* layer_sizes, int n_layers, const double* ob_mean, const double* ob_std,
+                          double ob_clip, const float* obs0, const float* env_a, int band, const float* env_b, const float* rew_vec,
+                          int T, float pos_scale, const uint32_t* coin_words, double save_obs_chance, double* fit_pos,
+                          double* fit_neg, int fit_stride, float* behv_pos, float* behv_neg, double* ob_sum, double* ob_sumsq,
+                          double* ob_count, void* stream) {
+    ES_ENTER(ctx);
+    ES_REQUIRE(table && idx && theta && layer_sizes && ob_mean && ob_std && obs0 && env_a && env_b && rew_vec && fit_pos && fit_neg,
+               "es_rollout_closedloop: NULL pointer");
+    if (n_layers != 3) {
+        es_set_error("es_rollout_closedloop: two hidden layers (n_layers == 3) supported, got %d", n_layers);
+        return ES_ERR_UNSUPPORTED;
+    }
+    ES_REQUIRE(n_pairs >= 0 && T >= 1 && fit_stride >= 1 && band >= 1, "es_rollout_closedloop: bad sizes");
+    ES_REQUIRE((behv_pos == nullptr) == (behv_neg == nullptr), "es_rollout_closedloop: behv_pos/behv_neg must both be set or NULL");
+    ES_REQUIRE((ob_sum == nullptr) == (ob_sumsq == nullptr) && (ob_sum == nullptr) == (ob_count == nullptr),
+               "es_rollout_closedloop: ob_sum/ob_sumsq/ob_count must all be set or NULL");
+    int64_t count = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        ES_REQUIRE(layer_sizes[l] > 0 && layer_sizes[l + 1] > 0, "es_rollout_closedloop: layer size <= 0");
+        count += (int64_t)layer_sizes[l] * layer_sizes[l + 1] + layer_sizes[l + 1];
+    }
+    ES_REQUIRE(count == P, "es_rollout_closedloop: layer sizes give %lld params, P=%d", (long long)count, P);
+    ES_REQUIRE(table_len > P, "es_rollout_closedloop: table smaller than the network");
+    ES_REQUIRE(band <= layer_sizes[0], "es_rollout_closedloop: band wider than the observation");
+    if (n_pairs == 0) return ES_OK;
+    return es_impl_rollout_closed(ctx, table, table_len, idx, n_pairs, theta, P, sigma, layer_sizes, ob_mean, ob_std, ob_clip, obs0,
+                                  env_a, band, env_b, rew_vec, T, pos_scale, coin_words, save_obs_chance, fit_pos, fit_neg, fit_stride,
+                                  behv_pos, behv_neg, ob_sum, ob_sumsq, ob_count, (cudaStream_t)stream);
+}
+
 int es_draw_noisy(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int32_t* has_gauss, double* gauss, int n_streams,
                   int n_per_stream, uint64_t upper_bound, int coins_per_eval, int normals_per_eval, double scale,
                   int64_t* idx_out, uint32_t* coin_out, float* noise_out, void* stream) {

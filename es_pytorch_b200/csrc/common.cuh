@@ -93,6 +93,9 @@ int es_impl_rollout_tc2(es_ctx*, int split, const float*, int64_t, const int64_t
                         int, const float*, const float*, int, float, double*, double*, int, float*, float*, const float*,
                         cudaStream_t);
 void es_tc2_free_shadows(es_ctx* ctx);
+int es_impl_rollout_closed(es_ctx*, const float*, int64_t, const int64_t*, int, const float*, int, float, const int*, const double*,
+                           const double*, double, const float*, const float*, int, const float*, const float*, int, float,
+                           const uint32_t*, double, double*, double*, int, float*, float*, double*, double*, double*, cudaStream_t);
 int es_impl_novelty(es_ctx*, const float*, int, const double*, int, int, double*, int, cudaStream_t);
 int es_impl_rank_transform(es_ctx*, const double*, const double*, int, int, int, double, double, int, int, int,
                            const int64_t*, float*, double*, int32_t*, double*, int32_t*, int64_t*, cudaStream_t);

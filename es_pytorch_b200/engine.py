@@ -277,6 +277,40 @@ class Engine:
                                                  int(fit_stride), _ptr(behv_pos), _ptr(behv_neg), _ptr(act_noise), int(mode),
                                                  self.stream), 'es_rollout_openloop')
 
+    def rollout_closed(self, table, idx, theta, sigma: float, layer_sizes: Sequence[int], ob_mean, ob_std, ob_clip: float,
+                       obs0, env_a, env_b, rew_vec, pos_scale: float, fit_pos, fit_neg, fit_stride: int = 1, behv_pos=None,
+                       behv_neg=None, coin_words=None, save_obs_chance: float = 0.0, ob_sum=None, ob_sumsq=None, ob_count=None):
+        """Antithetic pairs on the closed-loop synthetic env (``gym.synthetic_env.ClosedLoopEnv``): ``env_a`` [band, obs] and
+        ``env_b`` [act, obs] are the transposed transition matrices, ``obs0`` the start observation; the observation
+        normalisation (``ob_mean`` / ``ob_std`` float64, ``ob_clip``) happens inside.  ``coin_words`` [n, 4] + the three
+        float64 statistics buffers: ObStat increments of the evaluations whose save_obs coin fell."""
+        d = self.device
+        _req(table, torch.float32, 'table', d); _req(idx, torch.int64, 'idx', d); _req(theta, torch.float32, 'theta', d)
+        _req(ob_mean, torch.float64, 'ob_mean', d); _req(ob_std, torch.float64, 'ob_std', d)
+        _req(obs0, torch.float32, 'obs0', d); _req(env_a, torch.float32, 'env_a', d); _req(env_b, torch.float32, 'env_b', d)
+        _req(rew_vec, torch.float32, 'rew_vec', d)
+        _req(fit_pos, torch.float64, 'fit_pos', d); _req(fit_neg, torch.float64, 'fit_neg', d)
+        n, T, obs, act = idx.numel(), rew_vec.shape[0], int(layer_sizes[0]), int(layer_sizes[-1])
+        band = env_a.shape[0]
+        assert env_a.shape == (band, obs) and env_b.shape == (act, obs) and obs0.numel() == obs and rew_vec.shape == (T, act)
+        assert ob_mean.numel() == obs and ob_std.numel() == obs
+        assert fit_pos.numel() >= n * fit_stride and fit_neg.numel() >= n * fit_stride
+        if behv_pos is not None:
+            _req(behv_pos, torch.float32, 'behv_pos', d); _req(behv_neg, torch.float32, 'behv_neg', d)
+            assert behv_pos.numel() == 3 * n and behv_neg.numel() == 3 * n
+        if coin_words is not None:
+            assert coin_words.dtype == torch.int32 and coin_words.numel() == 4 * n and coin_words.is_contiguous()
+        if ob_sum is not None:
+            _req(ob_sum, torch.float64, 'ob_sum', d); _req(ob_sumsq, torch.float64, 'ob_sumsq', d); _req(ob_count, torch.float64, 'ob_count', d)
+            assert ob_sum.numel() == obs and ob_sumsq.numel() == obs and ob_count.numel() == 2
+        ls = (C.c_int * len(layer_sizes))(*[int(x) for x in layer_sizes])
+        check(self.lib.es_rollout_closedloop(self._ctx, _ptr(table), table.numel(), _ptr(idx), n, _ptr(theta), theta.numel(),
+                                             float(sigma), ls, len(layer_sizes) - 1, _ptr(ob_mean), _ptr(ob_std), float(ob_clip),
+                                             _ptr(obs0), _ptr(env_a), int(band), _ptr(env_b), _ptr(rew_vec), T, float(pos_scale),
+                                             _ptr(coin_words), float(save_obs_chance), _ptr(fit_pos), _ptr(fit_neg),
+                                             int(fit_stride), _ptr(behv_pos), _ptr(behv_neg), _ptr(ob_sum), _ptr(ob_sumsq),
+                                             _ptr(ob_count), self.stream), 'es_rollout_closedloop')
+
     # ------------------------------------------------------------------ a13
     def novelty(self, behv, archive, k: int, out, out_stride: int = 1):
         d = self.device

@@ -71,8 +71,11 @@ class DeviceGeneration:
                  optim: Optimizer, ob_clip: float = 5.0, pos_scale: float = 0.05, coins_per_eval: int = 0,
                  save_obs_chance: float = 0.0, archive: Optional[torch.Tensor] = None, nov_k: int = 10,
                  moo_w: float = 1.0, rollout_mode: int = ES_ROLLOUT_F32, comm: Optional[dist.Comm] = None,
-                 engine: Optional[Engine] = None, ranker=None, ac_std: float = 0.0):
+                 engine: Optional[Engine] = None, ranker=None, ac_std: float = 0.0, closed=None):
         self.eng = engine or get_engine()
+        # closed-loop variant of the synthetic env (gym.synthetic_env.ClosedLoopEnv): (obs_0 [obs], A^T [band, obs], B^T [act, obs]);
+        # row 0 of obs_stream is then the only one read and the rollout is es_rollout_closedloop
+        self.closed = closed
         self.ranker = ranker                            # a utils.rankers.Ranker; None = Centered / MultiObjective(moo_w)
         e = self.eng
         self.comm = comm or dist.world()
@@ -194,8 +197,40 @@ class DeviceGeneration:
             else:
                 e.draw_indices(self.mt_key, self.mt_pos, n_per_stream, self.table.numel() - self.P, self.extra_words,
                                self.idx, self.extras)
-        e.normalise_obs(self.obs_stream[:self.T], self.ob_mean, self.ob_std, self.ob_clip, self.obsn)
         fp, fn = self.fit_local[0], self.fit_local[1]
+        if self.closed is not None:
+            assert self.ac_std == 0.0, 'the closed-loop variant is defined without action noise'
+            self._gen_stats.zero_()
+            obs0, env_a, env_b = self.closed
+            with self._timed('rollout'):
+                e.rollout_closed(self.table, self.idx, self.theta, self.sigma, self.layer_sizes, self.ob_mean, self.ob_std,
+                                 self.ob_clip, obs0, env_a, env_b, self.rew_vec, self.pos_scale, fp, fn, self.n_obj,
+                                 None if self.behv is None else self.behv[0], None if self.behv is None else self.behv[1],
+                                 coin_words=self.extras if self.extra_words else None, save_obs_chance=self.save_obs_chance,
+                                 ob_sum=self.gen_sum if self.extra_words else None,
+                                 ob_sumsq=self.gen_sumsq if self.extra_words else None,
+                                 ob_count=self.gen_count if self.extra_words else None)
+            if self.n_obj == 2:
+                e.novelty(self.behv.view(-1, 3), self.archive, self.nov_k, self.fit_local.view(-1)[1:], 2)
+        else:
+            self._evaluate_openloop(fp, fn)
+        if self.comm.size > 1:
+            nf = 2 * self.k_local * self.n_obj
+            self.idx_f64.copy_(self.idx)                         # exact: indices < 2^53 (the reference shares them as float64 too)
+            with self._timed('allgather'):
+                self.comm.allgather_into(self.share_all, self.share_local)
+            # [rank][pos|neg][k][obj] -> rank-major [K][obj] per sign (es.py:93-95 ordering)
+            self.fpos_all.view(self.comm.size, self.k_local, self.n_obj).copy_(self.fit_all[:, 0])
+            self.fneg_all.view(self.comm.size, self.k_local, self.n_obj).copy_(self.fit_all[:, 1])
+            self.idx_all.view(self.comm.size, self.k_local).copy_(self.share_all[:, nf:nf + self.k_local])
+            # obs statistics of all processes (rank order: the same float64 sum everywhere), in place of the local ones
+            self._gen_stats.copy_(self.share_all[:, nf + self.k_local:].sum(dim=0))
+            return self.fpos_all, self.fneg_all
+        return fp, fn
+
+    def _evaluate_openloop(self, fp, fn):
+        e = self.eng
+        e.normalise_obs(self.obs_stream[:self.T], self.ob_mean, self.ob_std, self.ob_clip, self.obsn)
         with self._timed('rollout'):
             e.rollout(self.table, self.idx, self.theta, self.sigma, self.layer_sizes, self.obsn, self.rew_vec,
                       self.pos_scale, fp, fn, self.n_obj, None if self.behv is None else self.behv[0],
@@ -215,19 +250,6 @@ class DeviceGeneration:
             s, q = self._colsum
             e.obstat_accumulate_coins(self.gen_sum, self.gen_sumsq, self.gen_count, s, q, self.T,
                                       self.extras.view(-1, 2), self.save_obs_chance)
-        if self.comm.size > 1:
-            nf = 2 * self.k_local * self.n_obj
-            self.idx_f64.copy_(self.idx)                         # exact: indices < 2^53 (the reference shares them as float64 too)
-            with self._timed('allgather'):
-                self.comm.allgather_into(self.share_all, self.share_local)
-            # [rank][pos|neg][k][obj] -> rank-major [K][obj] per sign (es.py:93-95 ordering)
-            self.fpos_all.view(self.comm.size, self.k_local, self.n_obj).copy_(self.fit_all[:, 0])
-            self.fneg_all.view(self.comm.size, self.k_local, self.n_obj).copy_(self.fit_all[:, 1])
-            self.idx_all.view(self.comm.size, self.k_local).copy_(self.share_all[:, nf:nf + self.k_local])
-            # obs statistics of all processes (rank order: the same float64 sum everywhere), in place of the local ones
-            self._gen_stats.copy_(self.share_all[:, nf + self.k_local:].sum(dim=0))
-            return self.fpos_all, self.fneg_all
-        return fp, fn
 
     def update(self, fpos: torch.Tensor, fneg: torch.Tensor, all_weights: bool = False):
         """Ranker.rank + es.approx_grad on the device (rankers.py:46-50, es.py:98-101).  ``all_weights``: finalise the weights
@@ -262,6 +284,11 @@ class DeviceGeneration:
                              torch.zeros(2, 3, dtype=torch.float32, device=e.device),
                              torch.zeros(1, dtype=torch.int64, device=e.device))
         fit0, behv0, idx0 = self._nl_bufs
+        if self.closed is not None:
+            obs0, env_a, env_b = self.closed
+            e.rollout_closed(self.table, idx0, self.theta, 0.0, self.layer_sizes, self.ob_mean, self.ob_std, self.ob_clip, obs0,
+                             env_a, env_b, self.rew_vec, self.pos_scale, fit0[0:1], fit0[1:2], 1, behv0[0].view(-1), behv0[1].view(-1))
+            return fit0, behv0
         e.rollout(self.table, idx0, self.theta, 0.0, self.layer_sizes, self.obsn, self.rew_vec, self.pos_scale,
                   fit0[0:1], fit0[1:2], 1, behv0[0].view(-1), behv0[1].view(-1), ES_ROLLOUT_F32)
         return fit0, behv0

@@ -26,8 +26,8 @@ class BatchedRollout:
                  archive: Optional[np.ndarray] = None, nov_k: int = 10,
                  rank_streams: Optional[Sequence[np.random.RandomState]] = None,
                  rollout_mode: int = _lib.ES_ROLLOUT_F32):
-        if not getattr(env, 'is_synthetic_openloop', False):
-            raise TypeError('BatchedRollout needs the synthetic open-loop env (es_pytorch_b200.gym.synthetic_env)')
+        if not (getattr(env, 'is_synthetic_openloop', False) or getattr(env, 'is_synthetic_closedloop', False)):
+            raise TypeError('BatchedRollout needs a synthetic env (es_pytorch_b200.gym.synthetic_env: open- or closed-loop)')
         self.env = env
         self.max_steps = min(int(max_steps), env.T)
         self.coins_per_eval = int(coins_per_eval)
@@ -65,6 +65,13 @@ class BatchedRollout:
                 for _ in range(self.coins_per_eval):
                     rs.random()
         noise_rs = streams[0] if (use_ac_noise and streams is not None and len(streams)) else None
+        closed = getattr(self.env, 'is_synthetic_closedloop', False)
+        if (closed and hasattr(model, 'is_tanh_mlp') and model.is_tanh_mlp() and len(model.layer_sizes()) == 4
+                and not (noise_rs is not None and float(getattr(model, '_action_std', 0) or 0) != 0)):
+            # the closed-loop episode as one launch (the observations are not returned: this result never carries them)
+            from .gym_runner import _device_episode_closed
+            total, pos, _ = _device_episode_closed(model, self.env, self.max_steps)
+            return self.result_from_device(total, pos)
         rews, behv, obs, steps = run_model(model, self.env, self.max_steps, noise_rs)
         no_obs = np.array([np.zeros(self.env.observation_space.shape)])
         if self.archive is None:

@@ -64,6 +64,27 @@ def _device_episode(model, env, max_steps: int, rs=None):
     return float(fit[0].item()), behv[0].cpu().numpy().astype(np.float64), T
 
 
+def _device_episode_closed(model, env, max_steps: int):
+    """One noise-free episode on the closed-loop synthetic env as one launch of es_rollout_closedloop (sigma = 0)."""
+    from ..engine import get_engine
+    from ..core.policy import Policy
+    eng = get_engine()
+    sizes = model.layer_sizes()
+    T = min(int(max_steps), env.T)
+    _, rew_dev = env.device_arrays(eng)
+    obs0, env_a, env_b = env.device_closed(eng)
+    theta = eng.to_device(Policy.get_flat(model), torch.float32)
+    mean = eng.to_device(np.ascontiguousarray(model._obmean, dtype=np.float64).reshape(-1), torch.float64)
+    std = eng.to_device(np.ascontiguousarray(model._obstd, dtype=np.float64).reshape(-1), torch.float64)
+    table = torch.zeros(theta.numel() + 1, dtype=torch.float32, device=eng.device)      # sigma = 0: the slice is irrelevant
+    idx = torch.zeros(1, dtype=torch.int64, device=eng.device)
+    fit = torch.zeros(2, dtype=torch.float64, device=eng.device)
+    behv = torch.zeros(2, 3, dtype=torch.float32, device=eng.device)
+    eng.rollout_closed(table, idx, theta, 0.0, sizes, mean, std, float(model.ob_clip), obs0, env_a, env_b, rew_dev[:T].contiguous(),
+                       env.pos_scale, fit[0:1], fit[1:2], 1, behv[0:1].view(-1), behv[1:2].view(-1))
+    return float(fit[0].item()), behv[0].cpu().numpy().astype(np.float64), T
+
+
 def run_model(model: torch.nn.Module, env, max_steps: int, rs: np.random.RandomState = None, render: bool = False,
               get_pos_fn: Callable = pybullet_gym_pos) -> Tuple[List[float], List[float], np.ndarray, int]:
     """(rewards, positions padded to max_steps triples, post-step observations, last loop index)."""

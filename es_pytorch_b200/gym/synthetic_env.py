@@ -137,9 +137,55 @@ class SyntheticEnv:
         return self._dev
 
 
+class ClosedLoopEnv(SyntheticEnv):
+    """The closed-loop variant of the synthetic env (optional; reported separately from the open-loop
+    headline): ``obs_{t+1} = tanh(A obs_t + B a_t)`` -- what the policy sees depends on what it did, so the episode cannot
+    be batched over time.  A is banded with wrap-around (``band`` diagonals centred on the main one, gain ``a_gain`` keeps
+    the map contractive), B dense; obs_0 is row 0 of the open-loop stream; reward and position as in the open-loop env.
+    float32 throughout, pre-activation accumulated in index order (A's diagonals, then B's columns)."""
+    is_synthetic_openloop = False
+    is_synthetic_closedloop = True
+
+    def __init__(self, obs_dim: int, act_dim: int, max_episode_steps: int = 1000, band: int = 8, a_seed: int = 17,
+                 b_seed: int = 19, a_gain: float = 0.5, b_gain: float = 0.5, name: str = 'SyntheticClosedLoop-v0', **kwargs):
+        super().__init__(obs_dim, act_dim, max_episode_steps, name=name, **kwargs)
+        self.band = int(band)
+        self.env_a = (np.random.RandomState(a_seed).randn(self.obs_dim, self.band) * (a_gain / np.sqrt(self.band))).astype(np.float32)
+        self.env_b = (np.random.RandomState(b_seed).randn(self.obs_dim, self.act_dim) * (b_gain / np.sqrt(self.act_dim))).astype(np.float32)
+        self.ob = self.obs_stream[0].copy()
+        self._dev_closed = None
+
+    def reset(self):
+        super().reset()
+        self.ob = self.obs_stream[0].copy()
+        return self.ob.copy()
+
+    def step(self, action) -> Tuple[np.ndarray, float, bool, dict]:
+        a = np.asarray(action, dtype=np.float32).reshape(-1)
+        _, rew, done, info = super().step(a)
+        f32, half = np.float32, self.band // 2
+        acc = np.zeros(self.obs_dim, dtype=f32)
+        for d in range(self.band):
+            acc = (acc + (self.env_a[:, d] * np.roll(self.ob, half - d)).astype(f32)).astype(f32)
+        for j in range(self.act_dim):
+            acc = (acc + (self.env_b[:, j] * a[j]).astype(f32)).astype(f32)
+        self.ob = np.tanh(acc).astype(f32)
+        return self.ob.copy(), rew, done, info
+
+    def device_closed(self, engine):
+        """(obs_0 [obs], A transposed [band][obs], B transposed [act][obs]) as float32 tensors in HBM."""
+        if self._dev_closed is None or self._dev_closed[0].device != engine.device:
+            self._dev_closed = (engine.to_device(self.obs_stream[0].copy()),
+                                engine.to_device(np.ascontiguousarray(self.env_a.T)),
+                                engine.to_device(np.ascontiguousarray(self.env_b.T)))
+        return self._dev_closed
+
+
 def make(name: str, **kwargs) -> SyntheticEnv:
     """``gym.make`` replacement: any task name maps to a synthetic env of the matching shape."""
     for frag, (o, a) in KNOWN_SHAPES.items():
         if frag.lower() in name.lower():
+            if 'closedloop' in name.lower().replace('-', '').replace('_', ''):
+                return ClosedLoopEnv(o, a, name=name, **kwargs)
             return SyntheticEnv(o, a, name=name, **kwargs)
     raise ValueError(f'no synthetic shape registered for env {name!r}; known: {sorted(KNOWN_SHAPES)}')

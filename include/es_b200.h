@@ -120,6 +120,27 @@ int es_rollout_openloop_noisy(es_ctx* ctx, const float* table, int64_t table_len
                               double* fit_pos, double* fit_neg, int fit_stride, float* behv_pos, float* behv_neg,
                               const float* act_noise, int mode, void* stream);
 
+/* ---- a3 + a4 + a5 on the CLOSED-LOOP synthetic env (SURVEY.md section 8d's optional variant; never part of the headline) --
+ * obs_{t+1} = tanh(A obs_t + B a_t): the observation depends on the policy's own actions, so the episode runs step by step
+ * with one pair's perturbed weights resident on chip (rollout_closed.cu).  Replaces the same reference loop as
+ * es_rollout_openloop -- Policy.pheno (src/core/policy.py:61-64), FeedForward.forward incl. the observation normalisation
+ * clip((ob - mean) / std) (src/nn/nn.py:42-50), run_model's reward / position / saved observations
+ * (src/gym/gym_runner.py:33-67) -- plus the ObStat increments of the evaluations whose save_obs coin fell
+ * (src/core/es.py:73-74, src/gym/training_result.py:17-21).
+ *   layer_sizes host int [4] (obs, h1, h2, act): two hidden layers <= 64 units, obs <= 384, act <= 64
+ *   ob_mean/ob_std dev double [obs]      obs0 dev float [obs]
+ *   env_a dev float [band][obs] (A's diagonals, transposed: env_a[d][i] multiplies obs[(i + d - band/2) mod obs])
+ *   env_b dev float [act][obs] (B transposed)   rew_vec dev float [T][act]
+ *   coin_words dev uint32 [n_pairs][2 (+,-)][2] (the save_obs coin of every evaluation as drawn by es_draw_indices) or NULL
+ *   ob_sum/ob_sumsq dev double [obs], ob_count dev double [2] (rows, rollouts): incremented atomically; or all NULL   */
+int es_rollout_closedloop(es_ctx* ctx, const float* table, int64_t table_len, const int64_t* idx, int n_pairs,
+                          const float* theta, int P, float sigma, const int* layer_sizes, int n_layers,
+                          const double* ob_mean, const double* ob_std, double ob_clip,
+                          const float* obs0, const float* env_a, int band, const float* env_b, const float* rew_vec, int T,
+                          float pos_scale, const uint32_t* coin_words, double save_obs_chance,
+                          double* fit_pos, double* fit_neg, int fit_stride, float* behv_pos, float* behv_neg,
+                          double* ob_sum, double* ob_sumsq, double* ob_count, void* stream);
+
 /* ---- a2 + a4 with action noise: all draws of a generation in stream order ---------------------------------------------
  * When FeedForward._action_std != 0 every step of every rollout draws rs.randn(act_dim) from the SAME RandomState that
  * draws the noise indices and the save_obs coins (src/nn/nn.py:47-48, src/core/es.py:66-72, simple_example.py:37-40).  Per

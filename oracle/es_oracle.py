@@ -218,6 +218,63 @@ class SyntheticEnvSpec:
         self.rew_vec = np.random.RandomState(self.rew_seed).randn(self.T, self.act_dim).astype(F32)
 
 
+@dataclass
+class ClosedLoopEnvSpec(SyntheticEnvSpec):
+    """The closed-loop variant SURVEY.md section 8d names as optional (labelled separately everywhere):
+    ``obs_{t+1} = tanh(A obs_t + B a_t)`` with a banded, wrap-around A (``band`` diagonals centred on the main one) and a
+    dense B; obs_0 = row 0 of the open-loop stream; reward and position as in the open-loop env.  All float32; the
+    pre-activation is accumulated in index order (A's diagonals, then B's columns), products and sums rounded separately."""
+    band: int = 8
+    a_seed: int = 17
+    b_seed: int = 19
+    a_gain: float = 0.5
+    b_gain: float = 0.5
+    closed_loop: bool = field(init=False, default=True)
+    env_a: np.ndarray = field(init=False, repr=False)        # [obs][band]
+    env_b: np.ndarray = field(init=False, repr=False)        # [obs][act]
+
+    def __post_init__(self):
+        super().__post_init__()
+        self.env_a = (np.random.RandomState(self.a_seed).randn(self.obs_dim, self.band) *
+                      (self.a_gain / np.sqrt(self.band))).astype(F32)
+        self.env_b = (np.random.RandomState(self.b_seed).randn(self.obs_dim, self.act_dim) *
+                      (self.b_gain / np.sqrt(self.act_dim))).astype(F32)
+
+    def step_obs(self, ob: np.ndarray, a: np.ndarray) -> np.ndarray:
+        n, half = self.obs_dim, self.band // 2
+        ob, a = np.asarray(ob, dtype=F32), np.asarray(a, dtype=F32)
+        acc = np.zeros(n, dtype=F32)
+        for d in range(self.band):
+            acc = (acc + (self.env_a[:, d] * np.roll(ob, half - d)).astype(F32)).astype(F32)     # ob[(i + d - half) % n]
+        for j in range(self.act_dim):
+            acc = (acc + (self.env_b[:, j] * a[j]).astype(F32)).astype(F32)
+        return np.tanh(acc).astype(F32)
+
+
+def run_model_closed(env: ClosedLoopEnvSpec, layers, obmean, obstd, ob_clip: float, max_steps: int):
+    """gym_runner.py:33-67 on the closed-loop env (``ac_std == 0``): the literal per-step loop -- normalise the current
+    observation, forward, step the env with the action."""
+    n = min(int(max_steps), env.T)
+    rews, behv, obs = [], [], []
+    pos = np.zeros(3, dtype=F32)
+    ps = F32(env.pos_scale)
+    ob = env.obs_stream[0].copy()
+    for t in range(n):
+        a = mlp_forward(layers, normalise_obs(ob, obmean, obstd, ob_clip)).astype(F32)
+        acc = F32(0.0)
+        for j in range(env.act_dim):           # float32 dot, index order
+            acc = F32(acc + F32(a[j] * env.rew_vec[t, j]))
+        rews.append(float(acc))
+        for j in range(3):
+            pos[j] = F32(pos[j] + F32(ps * a[j % env.act_dim]))
+        behv.extend([float(pos[0]), float(pos[1]), float(pos[2])])
+        ob = env.step_obs(ob, a)
+        obs.append(ob)
+    step = n - 1
+    behv += behv[-3:] * (max_steps - int(len(behv) / 3))
+    return rews, behv, np.stack(obs), step
+
+
 def run_model(env: SyntheticEnvSpec, layers, obmean, obstd, ob_clip: float, max_steps: int,
               batched: bool = False, ac_std: float = 0.0, rs: Optional[np.random.RandomState] = None):
     """gym_runner.py:33-67 on the synthetic env, ``ac_std == 0`` (no RNG consumed in
@@ -232,6 +289,9 @@ def run_model(env: SyntheticEnvSpec, layers, obmean, obstd, ob_clip: float, max_
     step (nn.py:47-48; legacy polar-method gaussians from the SAME RandomState that draws the noise indices and the
     save_obs coins).  ``a += ndarray`` on a float32 tensor yields the float64 sum (numpy's reflected add wraps the
     result back into a tensor), which the env casts to float32 (``np.asarray(action, dtype=float32)``)."""
+    if getattr(env, 'closed_loop', False):
+        assert ac_std == 0, 'the closed-loop variant is defined without action noise'
+        return run_model_closed(env, layers, obmean, obstd, ob_clip, max_steps)
     n = min(int(max_steps), env.T)
     xs = normalise_obs(env.obs_stream[:n], obmean, obstd, ob_clip)
     if batched:

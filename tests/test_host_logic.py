@@ -472,3 +472,24 @@ def test_reporter_set_saves_fits_and_best_policy(tmp_path, monkeypatch):
     assert [s for _, s in Pol.saved] == ['0', '2']                    # generation 1 improved neither reward nor distance
     assert rec.logged['avg-0'] == 5.0 and rec.logged['max-0'] == 8.0 and rec.logged['cum steps'] == 30 and rec.logged['dist'] == 5.0
     assert rec.logged['n fits ranked'] == 4 and 'time' in rec.logged and rec.logged['gen'] == 2
+
+
+def test_closed_loop_env_is_the_oracles_env():
+    """gym.synthetic_env.ClosedLoopEnv (reset / step, what run_model's python loop drives) and the oracle's ClosedLoopEnvSpec are
+    the same transition bit for bit; a perturbed start state is forgotten (the map is contractive: device / oracle rounding
+    differences cannot grow along an episode)."""
+    from oracle import es_oracle as orc
+    from es_pytorch_b200.gym.synthetic_env import ClosedLoopEnv, make
+    env, spec = ClosedLoopEnv(17, 6, 40), orc.ClosedLoopEnvSpec(17, 6, 40)
+    assert np.array_equal(env.env_a, spec.env_a) and np.array_equal(env.env_b, spec.env_b)
+    rs = np.random.RandomState(0)
+    ob, ob_ref, other = env.reset(), spec.obs_stream[0].copy(), spec.obs_stream[0] + np.float32(0.3)
+    for t in range(40):
+        a = np.tanh(rs.randn(6)).astype(np.float32)
+        ob, rew, done, _ = env.step(a)
+        ob_ref = spec.step_obs(ob_ref, a)
+        other = spec.step_obs(other, a)
+        assert np.array_equal(ob, ob_ref) and done == (t == 39)
+    assert np.abs(other - ob_ref).max() < 1e-6
+    assert isinstance(make('HumanoidClosedLoop-v0'), ClosedLoopEnv) and make('HumanoidClosedLoop-v0').obs_dim == 376
+    assert not isinstance(make('Humanoid-v2'), ClosedLoopEnv)
