@@ -361,12 +361,12 @@ def run_ours(args, wl, n_gpus):
     seeds = [1000 + rank * VIRTUAL_RANKS_PER_GPU + r for r in range(VIRTUAL_RANKS_PER_GPU)]
     obs_dev, rew_dev = env.device_arrays(eng)
 
-    def make_gen(mode_name, nsra, n_streams=VIRTUAL_RANKS_PER_GPU):
+    def make_gen(mode_name, nsra, n_streams=VIRTUAL_RANKS_PER_GPU, **kw):
         archive = np.random.RandomState(17).randn(64, 2) if nsra else None
-        return DeviceGeneration(table, eng.to_device(theta0.copy()), sizes, obs_dev, rew_dev,
+        return DeviceGeneration(table, eng.to_device(theta0.copy()), sizes, kw.pop('obs_stream', obs_dev), kw.pop('rew_vec', rew_dev),
                                 [np.random.RandomState(s) for s in seeds[:n_streams]], 0.02, 0.005, Adam(P, 0.01), coins_per_eval=1,
                                 save_obs_chance=0.01, rollout_mode=MODE_ID[mode_name], comm=comm, engine=eng,
-                                archive=None if archive is None else eng.to_device(archive, torch.float64), nov_k=10, moo_w=0.5)
+                                archive=None if archive is None else eng.to_device(archive, torch.float64), nov_k=10, moo_w=0.5, **kw)
 
     def measure(gen, pairs_local, steps, warmup, sampler=None):
         """K-generation timing of ``gen`` at ``pairs_local`` pairs per GPU: max-over-ranks ms per step + per-kernel event
@@ -447,6 +447,33 @@ def run_ours(args, wl, n_gpus):
                                  virtual_mpi_ranks_per_gpu=vr,
                                  kernel_ms=r['kern'], steps=side_steps, warmup=side_warm)
         also['strong'] = strong
+        # two variants that are never part of the headline, same size, same generation otherwise: (1) the action noise every
+        # shipped config sets (ac_std = 0.01: indices, coins and T x act gaussians per rollout drawn on the device in the
+        # reference's stream order), (2) the closed-loop synthetic env (SURVEY 8d's optional variant: no batching
+        # over time, one pair's weights resident per SM)
+        variants = {}
+        try:
+            gv = make_gen(head_mode, False, ac_std=0.01)
+            r = measure(gv, k_local, side_steps, side_warm)
+            variants['action_noise_ac_std_0.01'] = dict(value=K_head / (r['ms_step'] * 1e-3), unit='antithetic pairs/s',
+                                                        ms_per_step=r['ms_step'], kernel_ms=r['kern'], mode=head_mode,
+                                                        steps=side_steps, warmup=side_warm)
+            del gv
+        except _lib.EsLibraryError as ex:
+            variants['action_noise_ac_std_0.01'] = dict(unavailable=str(ex)[:200])
+        try:
+            from es_pytorch_b200.gym.synthetic_env import ClosedLoopEnv
+            cenv = ClosedLoopEnv(wl['obs'], wl['act'], wl['T'])
+            c_obs, c_rew = cenv.device_arrays(eng)
+            gv = make_gen('f32', False, obs_stream=c_obs, rew_vec=c_rew, closed=cenv.device_closed(eng))
+            r = measure(gv, k_local, 2, 1)
+            variants['closed_loop_env'] = dict(value=K_head / (r['ms_step'] * 1e-3), unit='antithetic pairs/s', ms_per_step=r['ms_step'],
+                                               kernel_ms=r['kern'], env='obs\' = tanh(A obs + B a), banded A (8 diagonals), dense B',
+                                               dtype='f32', steps=2, warmup=1)
+            del gv
+        except _lib.EsLibraryError as ex:
+            variants['closed_loop_env'] = dict(unavailable=str(ex)[:200])
+        also['variants'] = variants
 
     # ---------------- the reference-facing API with host buffers: `e2e` ----------------
     e2e = None
