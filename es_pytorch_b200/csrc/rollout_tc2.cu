@@ -383,7 +383,9 @@ __device__ __forceinline__ void issue_ts4(uint32_t d, uint32_t a_tmem, uint64_t 
     umma_ts(d, a_tmem + 24, b_desc + 6, idesc, 1);
 }
 
-template <bool SPLIT>
+// NOISE: the action-noise variant (loads of the noise array in the layer-3 epilogue); a separate instantiation so that the
+// registers it holds across the accumulator wait do not cost the noise-free kernel anything (measured: +6 % when shared)
+template <bool SPLIT, bool NOISE>
 __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid_constant__ T2Params p,
                                                                      const __grid_constant__ T2Maps maps) {
     using C = T2Cfg<SPLIT>;
@@ -568,7 +570,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
                 const int t = m * T2_MT + row;
                 const uint32_t tv_ = tmem + vbuf * C::V_STRIDE + lane_off + cq * CW;            // this warp's V columns
                 const float4* __restrict__ up = reinterpret_cast<const float4*>(p.ubase) + ((size_t)m * 16 + cq * (CW / 4)) * T2_MT + row;
-                if (p.act_noise && cq == 0) {
+                if (NOISE && p.act_noise && cq == 0) {
                     // action noise of this tile's rows (both signs) towards L2 now; it is read after layer 3 (one warp per lane quarter asks)
                     const int t0 = m * T2_MT + q * 32;
                     const int rows = min(32, p.T - t0);
@@ -668,18 +670,20 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
 #pragma unroll
                 for (int jj = 0; jj < 16; ++jj) cc[jj] = (jj < nj) ? ldg_pinned(ccol + jj * T2_MT) : 0.f;
                 // this row's action noise of the + evaluation, columns a_lo.. (the - evaluation: T * act further)
-                const float* nzrow = (p.act_noise && t < p.T)
+                const float* nzrow = (NOISE && p.act_noise && t < p.T)
                     ? p.act_noise + (((size_t)(blockIdx.x + i * gridDim.x) * 2) * p.T + t) * p.act + a_lo : nullptr;
                 float tv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 // the noise values of a sign are in flight before that sign's accumulator is waited for (the - sign's under the
                 // + sign's arithmetic): read inside the tanh groups they cost several exposed memory latencies per tile
-                constexpr int NZ = SPLIT ? 8 : 16;
+                constexpr int NZ = NOISE ? (SPLIT ? 8 : 16) : 1;
                 float nz[2][NZ];
+                if (NOISE) {
 #pragma unroll
-                for (int jj = 0; jj < NZ; ++jj) nz[0][jj] = (nzrow && jj < nj) ? ldg_pinned(nzrow + jj) : 0.f;
+                    for (int jj = 0; jj < NZ; ++jj) nz[0][jj] = (nzrow && jj < nj) ? ldg_pinned(nzrow + jj) : 0.f;
+                }
 #pragma unroll
                 for (int sgn = 0; sgn < 2; ++sgn) {
-                    if (sgn == 0) {
+                    if (NOISE && sgn == 0) {
 #pragma unroll
                         for (int jj = 0; jj < NZ; ++jj) nz[1][jj] = (nzrow && jj < nj) ? ldg_pinned(nzrow + (size_t)p.T * p.act + jj) : 0.f;
                     }
@@ -705,7 +709,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) rollout_tc2_kernel(const __grid
                                         float a0, a1, a2, a3;
                                         if (SPLIT) { tanh_acc2(z0, z1, a0, a1, (T2_NEWTON_MASK >> 0) & 1); tanh_acc2(z2, z3, a2, a3, (T2_NEWTON_MASK >> 1) & 1); }
                                         else { a0 = tanh_fast(z0); a1 = tanh_fast(z1); a2 = tanh_fast(z2); a3 = tanh_fast(z3); }
-                                        if (gq * 4 < NZ) {        // a += rs.randn(act) * ac_std (src/nn/nn.py:47-48), drawn by mt_gauss.cu
+                                        if (NOISE && gq * 4 < NZ) {        // a += rs.randn(act) * ac_std (src/nn/nn.py:47-48), drawn by mt_gauss.cu
                                             a0 += nz[sgn][(gq * 4 + 0) % NZ]; a1 += nz[sgn][(gq * 4 + 1) % NZ];
                                             a2 += nz[sgn][(gq * 4 + 2) % NZ]; a3 += nz[sgn][(gq * 4 + 3) % NZ];
                                         }
@@ -1071,8 +1075,13 @@ int t2_launch(es_ctx* ctx, T2Params& p, const T2Maps& maps, const float* obsn, c
         rollout_tc2_crt_kernel<<<es_div_up(p.n_mtiles * T2_ACT_PAD * T2_MT, 256), 256, 0, stream>>>(rew_vec, T, p.act, p.n_mtiles, crt);
         ES_LAUNCHED(ctx);
     }
-    ES_CHECK_CUDA(cudaFuncSetAttribute(rollout_tc2_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rollout_tc2_kernel<SPLIT><<<grid, T2_THREADS, smem, stream>>>(p, maps);
+    if (p.act_noise) {
+        ES_CHECK_CUDA(cudaFuncSetAttribute(rollout_tc2_kernel<SPLIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rollout_tc2_kernel<SPLIT, true><<<grid, T2_THREADS, smem, stream>>>(p, maps);
+    } else {
+        ES_CHECK_CUDA(cudaFuncSetAttribute(rollout_tc2_kernel<SPLIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rollout_tc2_kernel<SPLIT, false><<<grid, T2_THREADS, smem, stream>>>(p, maps);
+    }
     ES_LAUNCHED(ctx);
     return ES_OK;
 }
