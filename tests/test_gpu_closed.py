@@ -11,13 +11,13 @@ from oracle import es_oracle as orc
 pytestmark = pytest.mark.gpu
 
 
-def _problem(obs_dim, act_dim, T, seed=3, table_extra=120_000, scale=0.1):
-    dims = orc.layer_dims(obs_dim, (64, 64), act_dim)
+def _problem(obs_dim, act_dim, T, seed=3, table_extra=120_000, scale=0.1, hidden=(64, 64), band=8):
+    dims = orc.layer_dims(obs_dim, hidden, act_dim)
     P = orc.n_params(dims)
     rs = np.random.RandomState(seed)
     table = rs.randn(P + table_extra).astype(np.float32)
     theta = (rs.randn(P) * scale).astype(np.float32)
-    return dims, P, table, theta, orc.ClosedLoopEnvSpec(obs_dim, act_dim, T)
+    return dims, P, table, theta, orc.ClosedLoopEnvSpec(obs_dim, act_dim, T, band=band)
 
 
 def _dev_env(eng, spec):
@@ -65,6 +65,46 @@ def test_closed_rollout_matches_the_oracle(eng, obs_dim, act_dim, T, n_pairs):
     assert ocnt.cpu().numpy().tolist() == [float(len(saved) * T), float(len(saved))]
     if n_pairs <= 8:
         assert np.abs(osum.cpu().numpy() - ref_sum).max() <= 1e-4 and np.abs(osq.cpu().numpy() - ref_sq).max() <= 1e-4
+
+
+@pytest.mark.parametrize('obs_dim,act_dim,hidden,band', [(300, 40, (48, 24), 4), (384, 2, (64, 8), 16), (9, 33, (5, 64), 2)])
+def test_closed_rollout_odd_shapes(eng, obs_dim, act_dim, hidden, band):
+    """Shapes off the beaten path: more than 32 actions (two reward registers per lane), hidden layers that do not fill the
+    thread rows, the widest / narrowest band, the largest observation; no ObStat buffers, no behaviour outputs."""
+    T, n_pairs = 21, 3
+    dims, P, table, theta, spec = _problem(obs_dim, act_dim, T, hidden=hidden, band=band)
+    idx = np.random.RandomState(5).randint(0, len(table) - P, size=n_pairs).astype(np.int64)
+    obs0, env_a, env_b = _dev_env(eng, spec)
+    fit = torch.zeros(2, n_pairs, dtype=torch.float64, device=eng.device)
+    eng.rollout_closed(eng.to_device(table), eng.to_device(idx), eng.to_device(theta), 0.05, [obs_dim, *hidden, act_dim],
+                       eng.to_device(np.zeros(obs_dim)), eng.to_device(np.ones(obs_dim)), 5.0, obs0, env_a, env_b,
+                       eng.to_device(spec.rew_vec), spec.pos_scale, fit[0], fit[1])
+    eng.sync()
+    got = fit.cpu().numpy()
+    for k in range(n_pairs):
+        for sgn, sign in enumerate((1.0, -1.0)):
+            layers = orc.unflatten(orc.pheno_params(theta, 0.05, sign * orc.table_get(table, int(idx[k]), P)), dims)
+            rews, _, _, _ = orc.run_model(spec, layers, np.zeros(obs_dim), np.ones(obs_dim), 5.0, T)
+            assert abs(got[sgn, k] - sum(rews)) <= 2e-5 * max(1.0, np.abs(rews).sum()), (k, sgn, got[sgn, k], sum(rews))
+
+
+def test_closed_generation_nsra(eng):
+    """Two objectives on the closed-loop env: the novelty column comes from the final positions the kernel integrates."""
+    from es_pytorch_b200.generation import DeviceGeneration
+    from es_pytorch_b200.nn.optimizers import Adam
+    obs_dim, act_dim, T = 17, 6, 30
+    dims, P, table, theta, spec = _problem(obs_dim, act_dim, T)
+    archive = np.random.RandomState(17).randn(12, 2)
+    seeds = [40, 41]
+    gen = DeviceGeneration(eng.to_device(table), eng.to_device(theta.copy()), [obs_dim, 64, 64, act_dim], eng.to_device(spec.obs_stream),
+                           eng.to_device(spec.rew_vec), [np.random.RandomState(s) for s in seeds], 0.05, 0.005, Adam(P, 0.01),
+                           coins_per_eval=1, engine=eng, closed=_dev_env(eng, spec), archive=eng.to_device(archive, torch.float64),
+                           nov_k=5, moo_w=0.5)
+    fpos, fneg = gen.evaluate(4)
+    pos, neg, inds, _, _ = orc.es_test_params(table, theta, 0.05, dims, spec, seeds, 4, np.zeros(obs_dim), np.ones(obs_dim), 5.0, T,
+                                              coins_per_eval=1, archive=archive, nov_k=5)
+    assert np.array_equal(gen.idx.cpu().numpy(), inds.astype(np.int64))
+    assert np.abs(fpos.cpu().numpy() - pos).max() <= 1e-4 and np.abs(fneg.cpu().numpy() - neg).max() <= 1e-4
 
 
 def test_closed_rollout_rejects_what_it_does_not_cover(eng):
