@@ -19,13 +19,16 @@
 //     (float64 like the reference: a float32 tensor minus a float64 ndarray) and keeps the float32 column sums of the
 //     post-step observations for the ObStat of a rollout whose save_obs coin fell;
 //   * reward (float32 dot in index order, summed in float64 like python's sum) and position by the last warp.
-// Four barriers per step.  Measured (K = 10 000, T = 1 000, Humanoid shapes): 190 ms per generation = 2.8 us per step and SM.
+// Four barriers per step.  Measured (K = 10 000, T = 1 000, Humanoid shapes): 188 ms per generation = 2.8 us per step and SM.
 // On the way (ncu, profiles/README.md): 512 threads with the - weights in shared memory were bound by the shared-memory pipe
-// (4 550 wavefronts per step, mio_throttle); 256 threads x 255 registers removed the wavefronts but left two warps per
-// scheduler waiting on every shared-memory load (short_scoreboard; at the register cap the compiler keeps no load in flight);
-// a row stride of the observation vector that is a multiple of 32 words made every layer-1 load a 4-way bank conflict
-// (371 ms).  What is left is instruction issue: ~9 500 warp instructions per step at an IPC of 2; packed fma.rn.f32x2 on the
-// (+, -) pairs would halve the FMA count -- not built.
+// (4 550 wavefronts per step, mio_throttle, 215 ms); 256 threads x 255 registers removed the wavefronts but left two warps per
+// scheduler waiting on every shared-memory load (218 ms); a row stride of the observation vector that is a multiple of 32
+// words made every layer-1 load a 4-way bank conflict (371 ms); packed fma.rn.f32x2 on the (+, -) pairs (this version) cut
+// layer 1 from 244 to 186 instructions per warp and step for 1 % of time.  What bounds it (source-level samples): layer 1 is
+// 39 % of a step and 3/4 of that is short_scoreboard on the FMA that follows each 16-byte observation load -- the layer-1
+// weights take 96 of the 128 registers, so the compiler keeps no load in flight and 4 warps per scheduler do not cover the
+// shared-memory latency.  The register file is the constraint (2 x 24 064 weights are 73 % of it); the way out is to park the
+// weights in TENSOR MEMORY (384 of the 512 columns hold both signs) and stream them with tcgen05.ld -- not built.
 #include <math.h>
 #include "common.cuh"
 
@@ -104,6 +107,26 @@ __device__ __forceinline__ float cl_tanh(float x) {
     return 1.f - __fdividef(2.f, 1.f + e);
 }
 
+// packed float32 pairs: (+, -) of a weight times (x+, x-) of an input is ONE fma.rn.f32x2 (two independent, identically
+// rounded FMAs per instruction)
+typedef unsigned long long cl_u64;
+__device__ __forceinline__ cl_u64 cl_pk(float lo, float hi) {
+    cl_u64 v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
+}
+__device__ __forceinline__ void cl_unpk(cl_u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ cl_u64 cl_fma2(cl_u64 a, cl_u64 b, cl_u64 c) {
+    cl_u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ cl_u64 cl_add2(cl_u64 a, cl_u64 b) {
+    cl_u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 template <int J>
 __global__ void __launch_bounds__(CL_THREADS, 1) rollout_closed_kernel(const ClParams p) {
     extern __shared__ __align__(16) float cl_smem[];
@@ -161,13 +184,13 @@ __global__ void __launch_bounds__(CL_THREADS, 1) rollout_closed_kernel(const ClP
             wp = __fadd_rn(t, se);
             wm = __fsub_rn(t, se);
         };
-        float wp1[J], wm1[J];
+        cl_u64 w1[J];                                              // (w+, w-) of this thread's layer-1 elements
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const int k = CL_G * j + s;
             float a = 0.f, b = 0.f;
             if (o < h1 && k < obs) wpm(o * obs + k, a, b);
-            wp1[j] = a; wm1[j] = b;
+            w1[j] = cl_pk(a, b);
         }
         for (int j = 0; j < CL_J23; j += 2) {
             float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -220,48 +243,54 @@ __global__ void __launch_bounds__(CL_THREADS, 1) rollout_closed_kernel(const ClP
             // ---- layer 1: weights in registers; observations by 16-byte loads (two elements of both signs), three loads in
             //      flight (with 8 warps nothing else hides the shared-memory latency) ----
             {
-                float zp = 0.f, zm = 0.f, zp1 = 0.f, zm1 = 0.f;
-                const float4* __restrict__ xr = reinterpret_cast<const float4*>(x2 + s * XS);
-                float4 xa = xr[0], xb = xr[1], xc = xr[2];          // (x+[j], x-[j], x+[j+1], x-[j+1]); the row is padded
+                cl_u64 za = 0ull, zb = 0ull;                        // (z+, z-) over the even / the odd elements
+                const ulonglong2* __restrict__ xr = reinterpret_cast<const ulonglong2*>(x2 + s * XS);
+                ulonglong2 xa = xr[0], xb = xr[1], xc = xr[2];      // ((x+, x-)[j], (x+, x-)[j+1]); the row is padded
 #pragma unroll
                 for (int j = 0; j < J; j += 2) {
-                    const float4 xv = xa;
+                    const ulonglong2 xv = xa;
                     xa = xb; xb = xc;
                     if (j + 6 < J + 2) xc = xr[(j >> 1) + 3];
-                    zp = fmaf(wp1[j], xv.x, zp);
-                    zm = fmaf(wm1[j], xv.y, zm);
-                    zp1 = fmaf(wp1[j + 1], xv.z, zp1);
-                    zm1 = fmaf(wm1[j + 1], xv.w, zm1);
+                    za = cl_fma2(w1[j], xv.x, za);
+                    zb = cl_fma2(w1[j + 1], xv.y, zb);
                 }
-                zp = cl_group_sum(zp + zp1); zm = cl_group_sum(zm + zm1);
+                float zp, zm;
+                cl_unpk(cl_add2(za, zb), zp, zm);
+                zp = cl_group_sum(zp); zm = cl_group_sum(zm);
                 if (s == 0) h1v[hslot] = (o < h1) ? make_float2(cl_tanh(zp + bias[o]), cl_tanh(zm + bias[CL_H + o])) : make_float2(0.f, 0.f);
             }
             __syncthreads();
             // ---- layer 2: one 16-byte load brings both signs' weights of two elements, another the two activations ----
             {
-                float zp = 0.f, zm = 0.f, zp1 = 0.f, zm1 = 0.f;
-                const float4* __restrict__ hr = reinterpret_cast<const float4*>(h1v + s * CL_HS);
+                cl_u64 za = 0ull, zb = 0ull;
+                const ulonglong2* __restrict__ hr = reinterpret_cast<const ulonglong2*>(h1v + s * CL_HS);
+                const ulonglong2* __restrict__ wr = reinterpret_cast<const ulonglong2*>(W2) + tid;
 #pragma unroll
                 for (int j = 0; j < CL_J23 / 2; ++j) {
-                    const float4 w = W2[j * CL_THREADS + tid], hv = hr[j];
-                    zp = fmaf(w.x, hv.x, zp); zm = fmaf(w.y, hv.y, zm);
-                    zp1 = fmaf(w.z, hv.z, zp1); zm1 = fmaf(w.w, hv.w, zm1);
+                    const ulonglong2 w = wr[j * CL_THREADS], hv = hr[j];
+                    za = cl_fma2(w.x, hv.x, za);
+                    zb = cl_fma2(w.y, hv.y, zb);
                 }
-                zp = cl_group_sum(zp + zp1); zm = cl_group_sum(zm + zm1);
+                float zp, zm;
+                cl_unpk(cl_add2(za, zb), zp, zm);
+                zp = cl_group_sum(zp); zm = cl_group_sum(zm);
                 if (s == 0) h2v[hslot] = (o < h2) ? make_float2(cl_tanh(zp + bias[2 * CL_H + o]), cl_tanh(zm + bias[3 * CL_H + o])) : make_float2(0.f, 0.f);
             }
             __syncthreads();
             // ---- layer 3 (only the warps that hold its rows; rows >= act of the last such warp hold zero weights) ----
             if (l3_warp) {
-                float zp = 0.f, zm = 0.f, zp1 = 0.f, zm1 = 0.f;
-                const float4* __restrict__ hr = reinterpret_cast<const float4*>(h2v + s * CL_HS);
+                cl_u64 za = 0ull, zb = 0ull;
+                const ulonglong2* __restrict__ hr = reinterpret_cast<const ulonglong2*>(h2v + s * CL_HS);
+                const ulonglong2* __restrict__ wr = reinterpret_cast<const ulonglong2*>(W3) + tid;
 #pragma unroll
                 for (int j = 0; j < CL_J23 / 2; ++j) {
-                    const float4 w = W3[j * CL_THREADS + tid], hv = hr[j];
-                    zp = fmaf(w.x, hv.x, zp); zm = fmaf(w.y, hv.y, zm);
-                    zp1 = fmaf(w.z, hv.z, zp1); zm1 = fmaf(w.w, hv.w, zm1);
+                    const ulonglong2 w = wr[j * CL_THREADS], hv = hr[j];
+                    za = cl_fma2(w.x, hv.x, za);
+                    zb = cl_fma2(w.y, hv.y, zb);
                 }
-                zp = cl_group_sum(zp + zp1); zm = cl_group_sum(zm + zm1);
+                float zp, zm;
+                cl_unpk(cl_add2(za, zb), zp, zm);
+                zp = cl_group_sum(zp); zm = cl_group_sum(zm);
                 if (s == 0 && o < act) a2[o] = make_float2(cl_tanh(zp + bias[4 * CL_H + o]), cl_tanh(zm + bias[5 * CL_H + o]));
             }
             __syncthreads();
