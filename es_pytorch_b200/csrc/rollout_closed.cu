@@ -27,8 +27,9 @@
 // layer 1 from 244 to 186 instructions per warp and step for 1 % of time.  What bounds it (source-level samples): layer 1 is
 // 39 % of a step and 3/4 of that is short_scoreboard on the FMA that follows each 16-byte observation load -- the layer-1
 // weights take 96 of the 128 registers, so the compiler keeps no load in flight and 4 warps per scheduler do not cover the
-// shared-memory latency.  The register file is the constraint (2 x 24 064 weights are 73 % of it); the way out is to park the
-// weights in TENSOR MEMORY (384 of the 512 columns hold both signs) and stream them with tcgen05.ld -- not built.
+// shared-memory latency.  The register file is the constraint (2 x 24 064 weights are 73 % of it).  Parking the weights in
+// tensor memory (both signs fit in 384 of the 512 columns) does not help: tcgen05.ld reads 64 B per cycle, i.e. ~3 000 cycles
+// for the 196 KB a step needs, more than layer 1 takes now.
 #include <math.h>
 #include "common.cuh"
 
