@@ -8,12 +8,13 @@
 // Every step is a batch-1 matrix-vector product per policy, with weights that are unique per pair: the shape that is bound by
 // where the WEIGHTS live.  Re-reading a pair's 117 KB slice from HBM at each of 1 000 steps is 1.2 PB per generation; so one
 // CTA keeps one pair's perturbed weights on chip for the whole episode and the grid is persistent over the pairs:
-//   * layer 1 (82 % of the weights): 512 threads x 128 registers; thread (o = tid / 8, s = tid % 8) owns the elements
-//     k = 8 j + s of row o and keeps BOTH signs' weights in registers (2 x 48), so layer 1 reads only the observations from
-//     shared memory: float2 (x+, x-) in [s][j] order, one 16-byte load per two elements, rows padded so that the eight rows a
-//     warp reads at once sit in different banks; the 8 partial sums of a row meet by three shuffles;
-//   * layers 2 / 3: both signs' weights in shared memory as float4 (w+[j], w-[j], w+[j+1], w-[j+1]), same thread <-> element
-//     map, activations in the same [s][j] float2 layout;
+//   * the three layers share one thread map: warp w owns rows 4 w .. 4 w + 3 of a layer, lane s the elements k = 32 j + s of
+//     each of them.  Layer 1 (82 % of the weights): BOTH signs' weights of a thread's 4 x 12 elements live in registers (96)
+//     as (+, -) pairs, so an fma.rn.f32x2 with the (x+, x-) pair of an input updates both evaluations; a warp reads every
+//     input exactly once per step (one 8-byte load per lane and j -- the 8-lanes-per-row map of the previous version read
+//     each input 64 times and layer 1 was bound by the shared-memory pipe: 1 536 wavefronts per step for the inputs alone);
+//     the eight row sums of a warp meet in a transposing butterfly (9 shuffles).  Layers 2 / 3: the same with the weights in
+//     shared memory, [row][j][lane] pairs;
 //   * the env step: thread i owns observation i of both signs (A's diagonals and B transposed in shared memory; the raw
 //     observations carry a wrap-around halo so the band is a linear read), normalises the new observation with its mean / std
 //     (float64 like the reference: a float32 tensor minus a float64 ndarray) and keeps the float32 column sums of the
@@ -35,11 +36,12 @@
 
 namespace {
 
-constexpr int CL_G = 8;                    // lanes per row of a layer (its elements k = CL_G j + s)
-constexpr int CL_THREADS = 64 * CL_G;
-constexpr int CL_H = 64;                   // hidden units per layer at most (thread rows)
-constexpr int CL_A = 64;                   // action units at most (layer-3 rows)
-constexpr int CL_J23 = CL_H / CL_G;        // elements per thread in layers 2 / 3
+constexpr int CL_THREADS = 512;
+constexpr int CL_WARPS = CL_THREADS / 32;
+constexpr int CL_H = 64;                   // rows per layer at most (4 per warp)
+constexpr int CL_A = 64;                   // action units at most
+constexpr int CL_J23 = CL_H / 32;          // elements per lane and row in layers 2 / 3
+constexpr int CL_HALO = 16;                // the raw observations carry a wrap-around halo of band entries (band <= 16)
 
 struct ClParams {
     const float* table; long long table_len; const int64_t* idx; int n_pairs;
@@ -55,44 +57,32 @@ struct ClParams {
     int* err;
 };
 
-constexpr int CL_HS = CL_J23 + 2;         // row stride (float2) of the [s][j] hidden-activation vectors: 16-byte aligned rows, conflict-free
-constexpr int CL_HALO = 16;                // the raw observations carry a wrap-around halo of band entries (band <= 16)
-
-// row stride (float2) of the [s][j] observation vector: >= J + 2 (the layer-1 loads run two elements past the row), 16-byte
-// aligned rows, and the four rows a warp reads at once in different banks: stride = 2 (mod 4)
-__host__ __device__ constexpr int cl_xs(int J) { return (J % 4 == 0) ? J + 2 : J + 4; }
-
 struct ClLayout {                          // offsets in floats into dynamic shared memory
     int norm, w2, w3, bias, env_a, env_b, x2, o2, h1, h2, a2, prod, stat, racc, total, o2_stride, act_pad;
 };
-__host__ __device__ inline ClLayout cl_layout(int J, int obs, int act, int band) {
+__host__ __device__ inline ClLayout cl_layout(int JL, int obs, int act, int band) {
     ClLayout L;
     int at = 0;
     L.act_pad = (act + 3) & ~3;
     L.o2_stride = obs + CL_HALO;
     L.norm = at; at += 4 * obs;             // double mean[obs], double 1/std[obs]  (first: 8-byte aligned)
     L.racc = at; at += 16;                  // fitness (double x 2) and position (float x 6) of the pair, last warp
-    L.x2 = at; at += 2 * CL_G * cl_xs(J);   // float2 (x+, x-) normalised observations, [s][cl_xs(J)]
-    L.w2 = at; at += 4 * (CL_J23 / 2) * CL_THREADS;      // float4 (w+[j], w-[j], w+[j+1], w-[j+1]) at [j / 2][tid]
-    L.w3 = at; at += 4 * (CL_J23 / 2) * CL_THREADS;
-    L.h1 = at; at += 2 * CL_G * CL_HS;      // float2 (h+, h-), [s][CL_HS]
-    L.h2 = at; at += 2 * CL_G * CL_HS;
+    L.x2 = at; at += 2 * 32 * JL;           // float2 (x+, x-) normalised observations, zero padded to 32 JL
+    L.w2 = at; at += 2 * CL_H * CL_J23 * 32;        // float2 (w+, w-) at [row][j][lane]
+    L.w3 = at; at += 2 * CL_H * CL_J23 * 32;
+    L.h1 = at; at += 2 * CL_H;              // float2 (h+, h-)
+    L.h2 = at; at += 2 * CL_H;
+    L.a2 = at; at += 2 * CL_A;
+    L.prod = at; at += 2 * CL_A;
     L.stat = at; at += 4 * obs;             // float4 (sum+, sumsq+, sum-, sumsq-) of the post-step observations
     L.bias = at; at += 6 * CL_H;            // b1+ b1- b2+ b2- b3+ b3-
     L.o2 = at; at += 2 * 2 * L.o2_stride;   // [2 buffers] float2 raw observations with halo
-    L.a2 = at; at += 2 * CL_A;
-    L.prod = at; at += 2 * CL_A;
     L.env_a = at; at += band * obs;
     L.env_b = at; at += L.act_pad * obs;
     L.total = at;
     return L;
 }
 
-__device__ __forceinline__ float cl_group_sum(float v) {       // sum over the CL_G lanes that share a row
-#pragma unroll
-    for (int m = 1; m < CL_G; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-    return v;
-}
 // clip((ob - mean) / std) in float64 like the reference (a float32 tensor minus a float64 ndarray), the quotient as a product
 // with the rounded reciprocal: the float64 result can differ in its last bit, which survives the rounding to float32 once in
 // ~2^28 values (and then by one float32 ulp) -- far inside the tolerance this variant is held to
@@ -107,7 +97,6 @@ __device__ __forceinline__ float cl_tanh(float x) {
     const float e = __expf(2.f * x);
     return 1.f - __fdividef(2.f, 1.f + e);
 }
-
 // packed float32 pairs: (+, -) of a weight times (x+, x-) of an input is ONE fma.rn.f32x2 (two independent, identically
 // rounded FMAs per instruction)
 typedef unsigned long long cl_u64;
@@ -122,22 +111,42 @@ __device__ __forceinline__ cl_u64 cl_fma2(cl_u64 a, cl_u64 b, cl_u64 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
-__device__ __forceinline__ cl_u64 cl_add2(cl_u64 a, cl_u64 b) {
-    cl_u64 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
+// Transposing butterfly: the warp-wide sums of v[0..7] in 9 shuffles; lane 4 q (and its three neighbours) returns the sum of v[q]
+__device__ __forceinline__ float cl_warp_sum8(const float (&v)[8], int lane) {
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    float a[4], b[2], c;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = (h16 ? v[i + 4] : v[i]) + __shfl_xor_sync(0xffffffffu, h16 ? v[i] : v[i + 4], 16);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) b[i] = (h8 ? a[i + 2] : a[i]) + __shfl_xor_sync(0xffffffffu, h8 ? a[i] : a[i + 2], 8);
+    c = (h4 ? b[1] : b[0]) + __shfl_xor_sync(0xffffffffu, h4 ? b[0] : b[1], 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    return c;
+}
+// the four rows of a warp: z[r] (+, -) -> tanh(z + bias) of row 4 w + r, written by the lane that ends up with that sum
+__device__ __forceinline__ void cl_finish_rows(const cl_u64 (&z)[4], int warp, int lane, int rows, const float* __restrict__ bias_p,
+                                               const float* __restrict__ bias_m, float* __restrict__ out2) {
+    float v[8];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) cl_unpk(z[r], v[2 * r], v[2 * r + 1]);
+    const float c = cl_warp_sum8(v, lane);
+    if ((lane & 3) == 0) {
+        const int q = lane >> 2, o = 4 * warp + (q >> 1), sg = q & 1;
+        out2[2 * o + sg] = (o < rows) ? cl_tanh(c + (sg ? bias_m : bias_p)[o]) : 0.f;
+    }
 }
 
-template <int J>
+template <int JL>
 __global__ void __launch_bounds__(CL_THREADS, 1) rollout_closed_kernel(const ClParams p) {
     extern __shared__ __align__(16) float cl_smem[];
-    const ClLayout L = cl_layout(J, p.obs, p.act, p.band);
+    const ClLayout L = cl_layout(JL, p.obs, p.act, p.band);
     double* __restrict__ nmean = reinterpret_cast<double*>(cl_smem + L.norm);
     double* __restrict__ nrstd = nmean + p.obs;
     double* __restrict__ rfit = reinterpret_cast<double*>(cl_smem + L.racc);        // [2]
     float* __restrict__ rpos = cl_smem + L.racc + 4;                                  // [2][3]
-    float4* __restrict__ W2 = reinterpret_cast<float4*>(cl_smem + L.w2);
-    float4* __restrict__ W3 = reinterpret_cast<float4*>(cl_smem + L.w3);
+    cl_u64* __restrict__ W2 = reinterpret_cast<cl_u64*>(cl_smem + L.w2);
+    cl_u64* __restrict__ W3 = reinterpret_cast<cl_u64*>(cl_smem + L.w3);
     float* __restrict__ bias = cl_smem + L.bias;
     float* __restrict__ envA = cl_smem + L.env_a;
     float* __restrict__ envB = cl_smem + L.env_b;
@@ -148,21 +157,19 @@ __global__ void __launch_bounds__(CL_THREADS, 1) rollout_closed_kernel(const ClP
     float2* __restrict__ a2 = reinterpret_cast<float2*>(cl_smem + L.a2);
     float2* __restrict__ prod = reinterpret_cast<float2*>(cl_smem + L.prod);
     float4* __restrict__ stat = reinterpret_cast<float4*>(cl_smem + L.stat);
-    constexpr int XS = cl_xs(J);
 
-    const int tid = threadIdx.x, o = tid / CL_G, s = tid % CL_G, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int obs = p.obs, h1 = p.h1, h2 = p.h2, act = p.act, T = p.T, band = p.band, half = p.band >> 1;
     const int act_pad = L.act_pad, o2s = L.o2_stride;
     // flat parameter layout (state-dict order, src/core/policy.py:33-35): W1 [h1][obs], b1, W2 [h2][h1], b2, W3 [act][h2], b3
     const int off_b1 = h1 * obs, off_w2 = off_b1 + h1, off_b2 = off_w2 + h2 * h1, off_w3 = off_b2 + h2, off_b3 = off_w3 + act * h2;
-    const bool l3_warp = (tid & ~31) < CL_G * act;              // warps that hold rows of layer 3
-    const bool rew_warp = warp == CL_THREADS / 32 - 1;
-    const int hslot = (o % CL_G) * CL_HS + (o / CL_G);          // where row o's activation goes in a [s][j] vector
+    const bool l3_warp = 4 * warp < act;                        // warps that hold rows of layer 3
+    const bool rew_warp = warp == CL_WARPS - 1;
 
     for (int i = tid; i < band * obs; i += CL_THREADS) envA[i] = p.env_a[i];
     for (int i = tid; i < act_pad * obs; i += CL_THREADS) envB[i] = i < act * obs ? p.env_b[i] : 0.f;
-    for (int i = tid; i < CL_G * XS; i += CL_THREADS) x2[i] = make_float2(0.f, 0.f);
-    for (int i = tid; i < CL_G * CL_HS; i += CL_THREADS) { h1v[i] = make_float2(0.f, 0.f); h2v[i] = make_float2(0.f, 0.f); }
+    for (int i = tid; i < 32 * JL; i += CL_THREADS) x2[i] = make_float2(0.f, 0.f);
+    for (int i = tid; i < CL_H; i += CL_THREADS) { h1v[i] = make_float2(0.f, 0.f); h2v[i] = make_float2(0.f, 0.f); }
     for (int i = tid; i < CL_A; i += CL_THREADS) a2[i] = make_float2(0.f, 0.f);
     for (int i = tid; i < obs; i += CL_THREADS) { nmean[i] = p.ob_mean[i]; nrstd[i] = 1.0 / p.ob_std[i]; }
     __syncthreads();
@@ -180,45 +187,42 @@ __global__ void __launch_bounds__(CL_THREADS, 1) rollout_closed_kernel(const ClP
         const float* __restrict__ th = p.theta;
         const float sg = p.sigma;
         // theta +- sigma * eps: the product and the sum are rounded separately (numpy: flat + std * noise)
-        auto wpm = [&](int at, float& wp, float& wm) {
+        auto wpm = [&](int at) {
             const float t = th[at], se = __fmul_rn(sg, eps[at]);
-            wp = __fadd_rn(t, se);
-            wm = __fsub_rn(t, se);
+            return cl_pk(__fadd_rn(t, se), __fsub_rn(t, se));
         };
-        cl_u64 w1[J];                                              // (w+, w-) of this thread's layer-1 elements
+        cl_u64 w1[4][JL];                                          // (w+, w-) of rows 4 warp + r, elements 32 j + lane
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-            const int k = CL_G * j + s;
-            float a = 0.f, b = 0.f;
-            if (o < h1 && k < obs) wpm(o * obs + k, a, b);
-            w1[j] = cl_pk(a, b);
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int j = 0; j < JL; ++j) {
+                const int o = 4 * warp + r, k = 32 * j + lane;
+                w1[r][j] = (o < h1 && k < obs) ? wpm(o * obs + k) : 0ull;
+            }
         }
-        for (int j = 0; j < CL_J23; j += 2) {
-            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (o < h2 && CL_G * j + s < h1) wpm(off_w2 + o * h1 + CL_G * j + s, w.x, w.y);
-            if (o < h2 && CL_G * (j + 1) + s < h1) wpm(off_w2 + o * h1 + CL_G * (j + 1) + s, w.z, w.w);
-            W2[(j >> 1) * CL_THREADS + tid] = w;
-            w = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (o < act && CL_G * j + s < h2) wpm(off_w3 + o * h2 + CL_G * j + s, w.x, w.y);
-            if (o < act && CL_G * (j + 1) + s < h2) wpm(off_w3 + o * h2 + CL_G * (j + 1) + s, w.z, w.w);
-            W3[(j >> 1) * CL_THREADS + tid] = w;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int j = 0; j < CL_J23; ++j) {
+                const int o = 4 * warp + r, k = 32 * j + lane;
+                W2[(o * CL_J23 + j) * 32 + lane] = (o < h2 && k < h1) ? wpm(off_w2 + o * h1 + k) : 0ull;
+                W3[(o * CL_J23 + j) * 32 + lane] = (o < act && k < h2) ? wpm(off_w3 + o * h2 + k) : 0ull;
+            }
         }
         if (tid < CL_H) {
-            float a = 0.f, b = 0.f;
-            if (tid < h1) wpm(off_b1 + tid, a, b);
+            float a, b;
+            cl_unpk(tid < h1 ? wpm(off_b1 + tid) : 0ull, a, b);
             bias[tid] = a; bias[CL_H + tid] = b;
-            a = 0.f; b = 0.f;
-            if (tid < h2) wpm(off_b2 + tid, a, b);
+            cl_unpk(tid < h2 ? wpm(off_b2 + tid) : 0ull, a, b);
             bias[2 * CL_H + tid] = a; bias[3 * CL_H + tid] = b;
-            a = 0.f; b = 0.f;
-            if (tid < act) wpm(off_b3 + tid, a, b);
+            cl_unpk(tid < act ? wpm(off_b3 + tid) : 0ull, a, b);
             bias[4 * CL_H + tid] = a; bias[5 * CL_H + tid] = b;
         }
         for (int i = tid; i < obs; i += CL_THREADS) {
             const float v = p.obs0[i];
             put_obs(o2, i, make_float2(v, v));
             const float xn = cl_normalise(v, nmean[i], nrstd[i], p.ob_clip);
-            x2[(i % CL_G) * XS + (i / CL_G)] = make_float2(xn, xn);
+            x2[i] = make_float2(xn, xn);
             stat[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (tid < 2) rfit[tid] = 0.0;
@@ -241,58 +245,45 @@ __global__ void __launch_bounds__(CL_THREADS, 1) rollout_closed_kernel(const ClP
                 if (lane < act) crow0 = __ldg(c + lane);
                 if (lane + 32 < act) crow1 = __ldg(c + lane + 32);
             }
-            // ---- layer 1: weights in registers; observations by 16-byte loads (two elements of both signs), three loads in
-            //      flight (with 8 warps nothing else hides the shared-memory latency) ----
+            // ---- layer 1: 4 rows x JL elements per lane, weights in registers, every input read once per warp ----
             {
-                cl_u64 za = 0ull, zb = 0ull;                        // (z+, z-) over the even / the odd elements
-                const ulonglong2* __restrict__ xr = reinterpret_cast<const ulonglong2*>(x2 + s * XS);
-                ulonglong2 xa = xr[0], xb = xr[1], xc = xr[2];      // ((x+, x-)[j], (x+, x-)[j+1]); the row is padded
+                cl_u64 z[4] = {0ull, 0ull, 0ull, 0ull};
+                const cl_u64* __restrict__ xv = reinterpret_cast<const cl_u64*>(x2) + lane;
 #pragma unroll
-                for (int j = 0; j < J; j += 2) {
-                    const ulonglong2 xv = xa;
-                    xa = xb; xb = xc;
-                    if (j + 6 < J + 2) xc = xr[(j >> 1) + 3];
-                    za = cl_fma2(w1[j], xv.x, za);
-                    zb = cl_fma2(w1[j + 1], xv.y, zb);
+                for (int j = 0; j < JL; ++j) {
+                    const cl_u64 x = xv[32 * j];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) z[r] = cl_fma2(w1[r][j], x, z[r]);
                 }
-                float zp, zm;
-                cl_unpk(cl_add2(za, zb), zp, zm);
-                zp = cl_group_sum(zp); zm = cl_group_sum(zm);
-                if (s == 0) h1v[hslot] = (o < h1) ? make_float2(cl_tanh(zp + bias[o]), cl_tanh(zm + bias[CL_H + o])) : make_float2(0.f, 0.f);
+                cl_finish_rows(z, warp, lane, h1, bias, bias + CL_H, reinterpret_cast<float*>(h1v));
             }
             __syncthreads();
-            // ---- layer 2: one 16-byte load brings both signs' weights of two elements, another the two activations ----
+            // ---- layer 2 ----
             {
-                cl_u64 za = 0ull, zb = 0ull;
-                const ulonglong2* __restrict__ hr = reinterpret_cast<const ulonglong2*>(h1v + s * CL_HS);
-                const ulonglong2* __restrict__ wr = reinterpret_cast<const ulonglong2*>(W2) + tid;
+                cl_u64 z[4] = {0ull, 0ull, 0ull, 0ull};
+                const cl_u64* __restrict__ hv = reinterpret_cast<const cl_u64*>(h1v) + lane;
+                const cl_u64* __restrict__ wr = W2 + (size_t)(4 * warp) * CL_J23 * 32 + lane;
 #pragma unroll
-                for (int j = 0; j < CL_J23 / 2; ++j) {
-                    const ulonglong2 w = wr[j * CL_THREADS], hv = hr[j];
-                    za = cl_fma2(w.x, hv.x, za);
-                    zb = cl_fma2(w.y, hv.y, zb);
+                for (int j = 0; j < CL_J23; ++j) {
+                    const cl_u64 x = hv[32 * j];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) z[r] = cl_fma2(wr[(r * CL_J23 + j) * 32], x, z[r]);
                 }
-                float zp, zm;
-                cl_unpk(cl_add2(za, zb), zp, zm);
-                zp = cl_group_sum(zp); zm = cl_group_sum(zm);
-                if (s == 0) h2v[hslot] = (o < h2) ? make_float2(cl_tanh(zp + bias[2 * CL_H + o]), cl_tanh(zm + bias[3 * CL_H + o])) : make_float2(0.f, 0.f);
+                cl_finish_rows(z, warp, lane, h2, bias + 2 * CL_H, bias + 3 * CL_H, reinterpret_cast<float*>(h2v));
             }
             __syncthreads();
-            // ---- layer 3 (only the warps that hold its rows; rows >= act of the last such warp hold zero weights) ----
+            // ---- layer 3 (only the warps that hold its rows) ----
             if (l3_warp) {
-                cl_u64 za = 0ull, zb = 0ull;
-                const ulonglong2* __restrict__ hr = reinterpret_cast<const ulonglong2*>(h2v + s * CL_HS);
-                const ulonglong2* __restrict__ wr = reinterpret_cast<const ulonglong2*>(W3) + tid;
+                cl_u64 z[4] = {0ull, 0ull, 0ull, 0ull};
+                const cl_u64* __restrict__ hv = reinterpret_cast<const cl_u64*>(h2v) + lane;
+                const cl_u64* __restrict__ wr = W3 + (size_t)(4 * warp) * CL_J23 * 32 + lane;
 #pragma unroll
-                for (int j = 0; j < CL_J23 / 2; ++j) {
-                    const ulonglong2 w = wr[j * CL_THREADS], hv = hr[j];
-                    za = cl_fma2(w.x, hv.x, za);
-                    zb = cl_fma2(w.y, hv.y, zb);
+                for (int j = 0; j < CL_J23; ++j) {
+                    const cl_u64 x = hv[32 * j];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) z[r] = cl_fma2(wr[(r * CL_J23 + j) * 32], x, z[r]);
                 }
-                float zp, zm;
-                cl_unpk(cl_add2(za, zb), zp, zm);
-                zp = cl_group_sum(zp); zm = cl_group_sum(zm);
-                if (s == 0 && o < act) a2[o] = make_float2(cl_tanh(zp + bias[4 * CL_H + o]), cl_tanh(zm + bias[5 * CL_H + o]));
+                cl_finish_rows(z, warp, lane, act, bias + 4 * CL_H, bias + 5 * CL_H, reinterpret_cast<float*>(a2));
             }
             __syncthreads();
             // ---- env step: thread i owns observation i; the raw observations carry a wrap-around halo, so the band is a
@@ -303,22 +294,22 @@ __global__ void __launch_bounds__(CL_THREADS, 1) rollout_closed_kernel(const ClP
                 float ap = 0.f, am = 0.f, ap1 = 0.f, am1 = 0.f;
 #pragma unroll 4
                 for (int d = 0; d < band; d += 2) {                 // (band is even, checked on the host)
-                    const float w0 = envA[d * obs + i], w1 = envA[(d + 1) * obs + i];
+                    const float w0 = envA[d * obs + i], w1_ = envA[(d + 1) * obs + i];
                     const float2 u0 = oc[i + d], u1 = oc[i + d + 1];
                     ap = fmaf(w0, u0.x, ap); am = fmaf(w0, u0.y, am);
-                    ap1 = fmaf(w1, u1.x, ap1); am1 = fmaf(w1, u1.y, am1);
+                    ap1 = fmaf(w1_, u1.x, ap1); am1 = fmaf(w1_, u1.y, am1);
                 }
 #pragma unroll 2
                 for (int j = 0; j < act_pad; j += 2) {
-                    const float w0 = envB[j * obs + i], w1 = envB[(j + 1) * obs + i];
+                    const float w0 = envB[j * obs + i], w1_ = envB[(j + 1) * obs + i];
                     const float4 av = *reinterpret_cast<const float4*>(a2 + j);
                     ap = fmaf(w0, av.x, ap); am = fmaf(w0, av.y, am);
-                    ap1 = fmaf(w1, av.z, ap1); am1 = fmaf(w1, av.w, am1);
+                    ap1 = fmaf(w1_, av.z, ap1); am1 = fmaf(w1_, av.w, am1);
                 }
                 const float np_ = cl_tanh(ap + ap1), nm = cl_tanh(am + am1);
                 put_obs(o2 + (cur ^ 1) * o2s, i, make_float2(np_, nm));
                 const double mu = nmean[i], rs_ = nrstd[i];
-                x2[(i % CL_G) * XS + (i / CL_G)] = make_float2(cl_normalise(np_, mu, rs_, p.ob_clip), cl_normalise(nm, mu, rs_, p.ob_clip));
+                x2[i] = make_float2(cl_normalise(np_, mu, rs_, p.ob_clip), cl_normalise(nm, mu, rs_, p.ob_clip));
                 if (keep_stat) {                                    // float32 column sums in step order (numpy's axis-0 reduction)
                     float4 st = stat[i];
                     st.x = __fadd_rn(st.x, np_); st.y = __fadd_rn(st.y, __fmul_rn(np_, np_));
@@ -334,6 +325,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) rollout_closed_kernel(const ClP
                 __syncwarp();
                 if (lane < 2) {
                     float acc = 0.f;
+#pragma unroll 8
                     for (int j = 0; j < act; ++j) {
                         const float2 pv = prod[j];
                         acc = __fadd_rn(acc, lane ? pv.y : pv.x);
@@ -372,18 +364,18 @@ __global__ void __launch_bounds__(CL_THREADS, 1) rollout_closed_kernel(const ClP
     }
 }
 
-template <int J>
+template <int JL>
 int cl_launch(es_ctx* ctx, const ClParams& p, cudaStream_t stream) {
-    const ClLayout L = cl_layout(J, p.obs, p.act, p.band);
+    const ClLayout L = cl_layout(JL, p.obs, p.act, p.band);
     const size_t smem = (size_t)L.total * sizeof(float);
     if (smem > 227 * 1024) {
         es_set_error("es_rollout_closedloop: %zu bytes of shared memory needed (obs %d, act %d, band %d), 227 KB available", smem, p.obs,
                      p.act, p.band);
         return ES_ERR_UNSUPPORTED;
     }
-    ES_CHECK_CUDA(cudaFuncSetAttribute(rollout_closed_kernel<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ES_CHECK_CUDA(cudaFuncSetAttribute(rollout_closed_kernel<JL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = p.n_pairs < ctx->sm_count ? p.n_pairs : ctx->sm_count;
-    rollout_closed_kernel<J><<<grid, CL_THREADS, smem, stream>>>(p);
+    rollout_closed_kernel<JL><<<grid, CL_THREADS, smem, stream>>>(p);
     ES_LAUNCHED(ctx);
     return ES_OK;
 }
@@ -410,7 +402,7 @@ int es_impl_rollout_closed(es_ctx* ctx, const float* table, int64_t table_len, c
                      CL_H, CL_A, CL_HALO, p.obs, p.h1, p.h2, p.act, p.band);
         return ES_ERR_UNSUPPORTED;
     }
-    if (p.obs <= 32) return cl_launch<4>(ctx, p, stream);
-    if (p.obs <= 128) return cl_launch<16>(ctx, p, stream);
-    return cl_launch<48>(ctx, p, stream);
+    if (p.obs <= 32) return cl_launch<1>(ctx, p, stream);
+    if (p.obs <= 128) return cl_launch<4>(ctx, p, stream);
+    return cl_launch<12>(ctx, p, stream);
 }
