@@ -20,17 +20,17 @@
 //     (float64 like the reference: a float32 tensor minus a float64 ndarray) and keeps the float32 column sums of the
 //     post-step observations for the ObStat of a rollout whose save_obs coin fell;
 //   * reward (float32 dot in index order, summed in float64 like python's sum) and position by the last warp.
-// Four barriers per step.  Measured (K = 10 000, T = 1 000, Humanoid shapes): 188 ms per generation = 2.8 us per step and SM.
-// On the way (ncu, profiles/README.md): 512 threads with the - weights in shared memory were bound by the shared-memory pipe
-// (4 550 wavefronts per step, mio_throttle, 215 ms); 256 threads x 255 registers removed the wavefronts but left two warps per
-// scheduler waiting on every shared-memory load (218 ms); a row stride of the observation vector that is a multiple of 32
-// words made every layer-1 load a 4-way bank conflict (371 ms); packed fma.rn.f32x2 on the (+, -) pairs (this version) cut
-// layer 1 from 244 to 186 instructions per warp and step for 1 % of time.  What bounds it (source-level samples): layer 1 is
-// 39 % of a step and 3/4 of that is short_scoreboard on the FMA that follows each 16-byte observation load -- the layer-1
-// weights take 96 of the 128 registers, so the compiler keeps no load in flight and 4 warps per scheduler do not cover the
-// shared-memory latency.  The register file is the constraint (2 x 24 064 weights are 73 % of it).  Parking the weights in
-// tensor memory (both signs fit in 384 of the 512 columns) does not help: tcgen05.ld reads 64 B per cycle, i.e. ~3 000 cycles
-// for the 196 KB a step needs, more than layer 1 takes now.
+// Four barriers per step.  Measured (K = 10 000, T = 1 000, Humanoid shapes): 157 ms per generation = 2.3 us per step and SM.
+// History (ncu pages in profiles/): 512 threads with the - weights in shared memory: shared-memory pipe bound (4 550 wavefronts
+// per step, mio_throttle), 215 ms; 256 threads x 255 registers: every shared load's latency exposed, 218 ms; a 32-word row
+// stride of the input vector: 4-way bank conflicts, 371 ms; both signs' weights in 128 registers with 8 lanes per row: 190 ms
+// (every input was read 64 times per step: 1 536 wavefronts for layer 1 alone; packed fma.rn.f32x2 saved a quarter of its
+// instructions for 1 % of time: not issue-bound); a warp owns whole rows and reads every input once (this version): 157 ms;
+// one EVALUATION per CTA with two CTAs per SM, to fill one CTA's barrier bubbles with the other's phases: 201 ms (the signs no
+// longer share input and env-weight loads, and 376 observations on 256 threads are two passes).  What is left: ~2 000
+// shared-memory wavefronts per step (env weights 340, inputs and activations, layer-2/3 weights 330, shuffles 330) under
+// ~4 400 cycles, the rest is the dependency chain of four short phases (load -> FMA -> 5-level butterfly -> tanh -> store ->
+// barrier).  Tensor memory as a weight store would not help: tcgen05.ld reads 64 B per cycle.
 #include <math.h>
 #include "common.cuh"
 
