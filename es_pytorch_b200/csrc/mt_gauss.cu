@@ -776,7 +776,7 @@ int es_impl_draw_noisy(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int32_t* 
     // jump-ahead when a stream is long enough to be worth splitting (ES_MT_JUMP=0 / 1 overrides; ES_MT_JUMP_LB: log2 of the
     // segment length in blocks, for tests)
     const char* ej = getenv("ES_MT_JUMP");
-    const bool jump = ej ? atoi(ej) != 0 : blocks_needed >= 2048;
+    bool jump = ej ? atoi(ej) != 0 : blocks_needed >= 2048;
     int lb_log2 = 3;
     if (jump) {
         const char* el = getenv("ES_MT_JUMP_LB");
@@ -786,10 +786,16 @@ int es_impl_draw_noisy(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int32_t* 
         if (lb_log2 < 0) lb_log2 = 0;
         if (lb_log2 > MJ_NPOLY - 1) lb_log2 = MJ_NPOLY - 1;
     }
-    const long long n_seg = jump ? (blocks_needed + (1LL << lb_log2) - 1) >> lb_log2 : 0;
-    if (jump && (((n_seg << lb_log2) >> MJ_NPOLY) != 0 || (double)(n_seg << lb_log2) * MT_NW > 4.0e9 || n_seg > 65535)) {       // the block index of a segment start must fit the available jumps
-        es_set_error("es_draw_noisy: %lld blocks per stream exceed the jump-ahead range (2^%d blocks)", n_seg << lb_log2, MJ_NPOLY);
-        return ES_ERR_UNSUPPORTED;
+    long long n_seg = jump ? (blocks_needed + (1LL << lb_log2) - 1) >> lb_log2 : 0;
+    if (jump && (((n_seg << lb_log2) >> MJ_NPOLY) != 0 || (double)(n_seg << lb_log2) * MT_NW > 4.0e9 || n_seg > 65535)) {
+        // the block index of a segment start must fit the available jumps (2^18 blocks = 164 M words per stream) and a
+        // 32-bit word index: longer streams take the sequential kernel unless the jump-ahead path was asked for explicitly
+        if (ej && atoi(ej) != 0) {
+            es_set_error("es_draw_noisy: %lld blocks per stream exceed the jump-ahead range (2^%d blocks)", n_seg << lb_log2, MJ_NPOLY);
+            return ES_ERR_UNSUPPORTED;
+        }
+        jump = false;
+        n_seg = 0;
     }
     // (whole chunks of MJ_CW words, + one chunk of padding: the flags kernel reads 4 words past every attempt start)
     const size_t gen_words = jump ? (size_t)(1 + (n_seg << lb_log2)) * MT_NW : 0;

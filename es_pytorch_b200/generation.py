@@ -199,7 +199,9 @@ class DeviceGeneration:
                                self.idx, self.extras)
         fp, fn = self.fit_local[0], self.fit_local[1]
         if self.closed is not None:
-            assert self.ac_std == 0.0, 'the closed-loop variant is defined without action noise'
+            if self.ac_std != 0.0:
+                raise NotImplementedError('the closed-loop variant of the synthetic env is defined without action noise: set the '
+                                          'network\'s ac_std to 0 (the open-loop env supports ac_std != 0 on the device)')
             self._gen_stats.zero_()
             obs0, env_a, env_b = self.closed
             with self._timed('rollout'):

@@ -157,6 +157,17 @@ def test_closed_generation_matches_the_oracle(eng):
         assert np.abs(gen.theta.cpu().numpy() - flat).max() <= 3e-6
 
 
+def test_closed_generation_refuses_action_noise(eng):
+    from es_pytorch_b200.generation import DeviceGeneration
+    from es_pytorch_b200.nn.optimizers import Adam
+    dims, P, table, theta, spec = _problem(17, 6, 10)
+    gen = DeviceGeneration(eng.to_device(table), eng.to_device(theta.copy()), [17, 64, 64, 6], eng.to_device(spec.obs_stream),
+                           eng.to_device(spec.rew_vec), [np.random.RandomState(1)], 0.05, 0.005, Adam(P, 0.01), coins_per_eval=1,
+                           engine=eng, closed=_dev_env(eng, spec), ac_std=0.01)
+    with pytest.raises(NotImplementedError):
+        gen.evaluate(2)
+
+
 def test_api_step_on_the_closed_loop_env_matches_the_oracle(eng):
     """es.step (single-synchronisation route) with a BatchedRollout over ClosedLoopEnv: two generations incl. the ObStat
     update between them and the noiseless evaluation of the new theta."""
