@@ -547,7 +547,9 @@ def run_ours(args, wl, n_gpus):
     roll_tfs = roll_flop / (kern['rollout'] * 1e-3) / 1e12
     value = K_head / (ms_step * 1e-3)
     default_wl = args.workload == 'humanoid' and not args.pairs_per_gpu and args.scaling == 'weak'
-    roll_regex = {'tc': r'rollout_tc2_kernel<(\(bool\))?(0|false)[,>]', 'tc3': r'rollout_tc2_kernel<(\(bool\))?(1|true)[,>]',
+    # (the second template argument is the action-noise instantiation: not the headline's kernel)
+    nz_off = r'(>|, ?(\(bool\))?(0|false)>)'
+    roll_regex = {'tc': r'rollout_tc2_kernel<(\(bool\))?(0|false)' + nz_off, 'tc3': r'rollout_tc2_kernel<(\(bool\))?(1|true)' + nz_off,
                   'f32': r'rollout_f32x?_kernel'}[head_mode]
     roll_traffic = newest_profile_traffic(roll_regex) if default_wl else None
     rec_traffic = newest_profile_traffic(r'reconstruct_kernel') if default_wl else None
