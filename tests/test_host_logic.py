@@ -493,3 +493,30 @@ def test_closed_loop_env_is_the_oracles_env():
     assert np.abs(other - ob_ref).max() < 1e-6
     assert isinstance(make('HumanoidClosedLoop-v0'), ClosedLoopEnv) and make('HumanoidClosedLoop-v0').obs_dim == 376
     assert not isinstance(make('Humanoid-v2'), ClosedLoopEnv)
+
+
+def test_run_model_python_loop_on_the_closed_loop_env_is_the_oracles_loop():
+    """gym_runner.run_model's python loop (module forward + ClosedLoopEnv.step: the route of an opaque fit_fn, and the
+    reference's own loop shape, src/gym/gym_runner.py:50-54) against the oracle's run_model_closed on the same parameters
+    and a non-trivial observation normalisation: rewards, positions, post-step observations, last index."""
+    import torch
+    from es_pytorch_b200.core.policy import Policy
+    from es_pytorch_b200.gym.gym_runner import run_model
+    from es_pytorch_b200.gym.synthetic_env import ClosedLoopEnv
+    from es_pytorch_b200.nn.nn import FeedForward
+    from es_pytorch_b200.nn.optimizers import Adam
+    obs_dim, act_dim, T = 17, 6, 25
+    env, spec = ClosedLoopEnv(obs_dim, act_dim, T), orc.ClosedLoopEnvSpec(obs_dim, act_dim, T)
+    dims = orc.layer_dims(obs_dim, (64, 64), act_dim)
+    P = orc.n_params(dims)
+    net = FeedForward([64, 64], torch.nn.Tanh(), env, 0.0, 5)
+    pol = Policy(net, 0.02, Adam(P, 0.01))
+    flat = (np.random.RandomState(2).randn(P) * 0.1).astype(np.float32)
+    pol.set_nn_params(flat)
+    mean, std = np.random.RandomState(3).randn(obs_dim) * 0.05, 0.5 + np.random.RandomState(4).rand(obs_dim)
+    net.set_ob_mean_std(mean, std)
+    rews, behv, obs, step = run_model(net, env, T)
+    r_ref, b_ref, o_ref, s_ref = orc.run_model(spec, orc.unflatten(flat, dims), mean, std, 5.0, T)
+    assert step == s_ref == T - 1 and len(rews) == T
+    assert np.allclose(rews, r_ref, rtol=0, atol=2e-6) and np.allclose(behv, b_ref, rtol=0, atol=2e-6)
+    assert np.allclose(obs, o_ref, rtol=0, atol=2e-6)
