@@ -298,18 +298,19 @@ mt_gauss_finish_kernel(const uint4* __restrict__ acc4, int a_max, const int32_t*
 // =====================================================================================================================
 // Jump-ahead: ONE stream regenerated by many CTAs.
 //
-// The state transition of MT19937 is linear over GF(2); with g_r(x) = x^(624 * 2^r) mod phi(x) (phi = its characteristic
-// polynomial, tools/mt_jump/make_jump_polys.py) every word of the raw sequence obeys x[n + 624 * 2^r] = XOR_{i : g_r,i = 1}
+// The state transition of MT19937 is linear over GF(2); with g(x) = x^(624 * B) mod phi(x) (phi = its characteristic
+// polynomial, tools/mt_jump/make_jump_polys.py) every word of the raw sequence obeys x[n + 624 * B] = XOR_{i : g_i = 1}
 // x[n + i].  So the state 2^r blocks ahead is, word by word, an XOR of ~10 000 words out of the next 20 560: independent per
 // word, no recurrence to follow.  mt_fill_kernel gives every CTA one segment of 2^lb blocks of one stream: it jumps from the
-// stream's current state to its segment's first block (one jump per set bit of the block index), regenerates the segment and
+// stream's current state to its segment's first block (one jump per non-zero hexadecimal digit of the block index: the polynomials of B = m * 16^q, m = 1 .. 15, q = 0 .. 4, are precomputed), regenerates the segment and
 // writes the TEMPERED words to global memory.  What follows no longer touches the recurrence: mt_flags_kernel computes the accept
 // bit of every possible attempt (all four phases) with per-chunk counts, mt_scan_kernel their prefixes; mt_walk_kernel -- the only
 // sequential step left, one warp per stream -- follows the reference's order with two table look-ups per rollout ("the next
 // `need` accepted attempts of this phase end at word ..."); mt_emit_kernel turns every rollout's accepted attempts into its
 // gaussians, one CTA per rollout.
 // =====================================================================================================================
-constexpr int MJ_NPOLY = 18;
+constexpr int MJ_NQ = 5, MJ_BITS_RANGE = 4 * MJ_NQ;              // hex digits of a block index that have polynomials: 2^20 blocks
+constexpr int MJ_NPOLY = 15 * MJ_NQ;                            // x^(624 * m * 16^q) mod phi at [q * 15 + m - 1], m = 1 .. 15
 constexpr int MJ_WIN_BLOCKS = 33;                              // the state block + 32 more: 20 592 words >= 19 937 + 624
 // Layout in global memory (per stream): the tempered words in stream order; per phase ph = 0..3 (an attempt starts at a word
 // index = ph mod 4) one accept bit per attempt (attempt a of phase ph = words 4 a + ph .. 4 a + ph + 3), in chunks of
@@ -370,14 +371,18 @@ __device__ __forceinline__ uint32_t mj_last_word(const uint32_t* __restrict__ O,
     return n396 ^ mt19937_twist(O[MT_NW - 1], n0);
 }
 
-// segments in the order the CTAs should start: most jumps (set bits of the segment index) first, so that the long CTAs do not
-// end up in the last wave
-__global__ void __launch_bounds__(1024) mj_order_kernel(int n_seg, uint16_t* __restrict__ order) {
+// segments in the order the CTAs should start: most jumps first, so that the long CTAs do not end up in the last wave
+__device__ __forceinline__ int mj_jumps(unsigned block) {       // non-zero hexadecimal digits = jumps to reach the block
+    int n = 0;
+    for (; block; block >>= 4) n += (block & 15u) ? 1 : 0;
+    return n;
+}
+__global__ void __launch_bounds__(1024) mj_order_kernel(int n_seg, int lb_log2, uint16_t* __restrict__ order) {
     for (int k = threadIdx.x; k < n_seg; k += 1024) {
-        const int pc = __popc(k);
+        const int pc = mj_jumps((unsigned)k << lb_log2);
         int rank = 0;
         for (int j = 0; j < n_seg; ++j) {
-            const int pj = __popc(j);
+            const int pj = mj_jumps((unsigned)j << lb_log2);
             rank += (pj > pc || (pj == pc && j < k)) ? 1 : 0;
         }
         order[rank] = (uint16_t)k;
@@ -434,10 +439,12 @@ mt_fill_kernel(const uint32_t* __restrict__ mt_key, int n_streams, int n_seg, in
     };
     uint32_t* const T0 = s_T;
     uint32_t* const T1 = s_T + MT_NW;
-    // ---- jump to block k << lb_log2: one jump per set bit ----
+    // ---- jump to block k << lb_log2 ----
     const unsigned target = (unsigned)k << lb_log2;
-    for (int r = MJ_NPOLY - 1; r >= 0; --r) {
-        if (!((target >> r) & 1u)) continue;
+    for (int q = MJ_NQ - 1; q >= 0; --q) {                     // (one jump per non-zero hex digit of the first block's index)
+        const unsigned m = (target >> (4 * q)) & 15u;
+        if (m == 0u) continue;
+        const int r = q * 15 + (int)m - 1;
         twists_of(xs, T0);
         for (int b = 1; b < MJ_WIN_BLOCKS; b += 2) {           // 32 more blocks: the window of the jump
             regen(No(), xs + (b - 1) * MT_NW, T0, xs + b * MT_NW, T1, nullptr);
@@ -782,16 +789,16 @@ int es_impl_draw_noisy(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int32_t* 
         const char* el = getenv("ES_MT_JUMP_LB");
         if (el) lb_log2 = atoi(el);
         else
-            while (lb_log2 < MJ_NPOLY - 1 && (long long)n_streams * ((blocks_needed + (1LL << lb_log2) - 1) >> lb_log2) > 4LL * ctx->sm_count) ++lb_log2;
+            while (lb_log2 < MJ_BITS_RANGE - 1 && (long long)n_streams * ((blocks_needed + (1LL << lb_log2) - 1) >> lb_log2) > 4LL * ctx->sm_count) ++lb_log2;
         if (lb_log2 < 0) lb_log2 = 0;
-        if (lb_log2 > MJ_NPOLY - 1) lb_log2 = MJ_NPOLY - 1;
+        if (lb_log2 > MJ_BITS_RANGE - 1) lb_log2 = MJ_BITS_RANGE - 1;
     }
     long long n_seg = jump ? (blocks_needed + (1LL << lb_log2) - 1) >> lb_log2 : 0;
-    if (jump && (((n_seg << lb_log2) >> MJ_NPOLY) != 0 || (double)(n_seg << lb_log2) * MT_NW > 4.0e9 || n_seg > 65535)) {
-        // the block index of a segment start must fit the available jumps (2^18 blocks = 164 M words per stream) and a
+    if (jump && (((n_seg << lb_log2) >> MJ_BITS_RANGE) != 0 || (double)(n_seg << lb_log2) * MT_NW > 4.0e9 || n_seg > 65535)) {
+        // the block index of a segment start must fit the available jumps (2^20 blocks = 654 M words per stream) and a
         // 32-bit word index: longer streams take the sequential kernel unless the jump-ahead path was asked for explicitly
         if (ej && atoi(ej) != 0) {
-            es_set_error("es_draw_noisy: %lld blocks per stream exceed the jump-ahead range (2^%d blocks)", n_seg << lb_log2, MJ_NPOLY);
+            es_set_error("es_draw_noisy: %lld blocks per stream exceed the jump-ahead range (2^%d blocks)", n_seg << lb_log2, MJ_BITS_RANGE);
             return ES_ERR_UNSUPPORTED;
         }
         jump = false;
@@ -829,7 +836,7 @@ int es_impl_draw_noisy(es_ctx* ctx, uint32_t* mt_key, int32_t* mt_pos, int32_t* 
             ES_LAUNCHED(ctx);
             ctx->mj_lists_ready = 1;
         }
-        mj_order_kernel<<<1, 1024, 0, stream>>>((int)n_seg, order);
+        mj_order_kernel<<<1, 1024, 0, stream>>>((int)n_seg, lb_log2, order);
         ES_LAUNCHED(ctx);
         const size_t smem = (size_t)(MJ_WIN_BLOCKS + 6) * MT_NW * sizeof(uint32_t);
         ES_CHECK_CUDA(cudaFuncSetAttribute(mt_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

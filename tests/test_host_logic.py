@@ -520,3 +520,23 @@ def test_run_model_python_loop_on_the_closed_loop_env_is_the_oracles_loop():
     assert step == s_ref == T - 1 and len(rews) == T
     assert np.allclose(rews, r_ref, rtol=0, atol=2e-6) and np.allclose(behv, b_ref, rtol=0, atol=2e-6)
     assert np.allclose(obs, o_ref, rtol=0, atol=2e-6)
+
+
+def test_jump_polynomials_against_numpys_mt19937():
+    """es_pytorch_b200/mt_jump_polys.npy (x^(624 m 16^q) mod phi, what mt_fill_kernel jumps with): for a sample of (q, m) the
+    relation x[n + 624 m 16^q] = XOR_{i : g_i = 1} x[n + i] on the raw words of numpy's own generator, and the C initialisers
+    the kernels compile (csrc/mt_jump_polys.inc) are the same numbers."""
+    sys.path.insert(0, os.path.join(ROOT, 'tools', 'mt_jump'))
+    import make_jump_polys as mjp
+    polys = np.load(os.path.join(ROOT, 'es_pytorch_b200', 'mt_jump_polys.npy'))
+    assert polys.shape == (5, 15, 624) and polys.dtype == np.uint32
+    raw = mjp.numpy_raw_words(77, 15 * 256 * 624 + 2 * mjp.DEG + 2048)
+    for q, m in ((0, 1), (0, 3), (0, 15), (1, 5), (1, 8), (2, 1), (2, 15)):
+        g = sum(int(w) << (32 * i) for i, w in enumerate(polys[q, m - 1]))
+        assert g.bit_length() <= mjp.DEG and mjp.check_against_numpy(g, m * 16 ** q, raw), (q, m)
+    with open(os.path.join(ROOT, 'es_pytorch_b200', 'csrc', 'mt_jump_polys.inc')) as f:
+        rows = [ln for ln in f if ln.startswith('{')]
+    assert len(rows) == 75
+    for r in (0, 17, 74):
+        vals = np.array([int(t.rstrip('u'), 16) for t in rows[r].strip().strip('{},').split(',')], dtype=np.uint64)
+        assert np.array_equal(vals.astype(np.uint32), polys[r // 15, r % 15])
