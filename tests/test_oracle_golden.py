@@ -423,3 +423,23 @@ print('CKPT_OK')
     env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.path.join(root, 'es_pytorch_b200', 'compat'))
     out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0 and 'CKPT_OK' in out.stdout, (out.stdout + out.stderr)[-3000:]
+
+
+def test_closed_loop_oracle_frozen_vectors():
+    """The closed-loop variant has no reference implementation: the oracle is its definition, pinned by vectors frozen at
+    the time the device kernel was validated against it (tests/golden/make_closed_golden.py)."""
+    import importlib.util
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    spec = importlib.util.spec_from_file_location('make_closed_golden', os.path.join(here, 'make_closed_golden.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = np.load(os.path.join(here, 'closed_loop.npz'))
+    got = mod.compute()
+    assert set(got) == set(want.files)
+    for k in want.files:
+        a, b = np.asarray(got[k]), want[k]
+        # (torch's CPU matrix-vector kernels may differ in the last bit between builds: float32 tolerance, indices exact)
+        if k in ('gen_inds', 'gen_steps', 'ob_count', 'env_a', 'env_b'):
+            assert np.array_equal(a, b), k
+        else:
+            assert np.allclose(a, b, rtol=0, atol=5e-6), (k, np.abs(a - b).max())
