@@ -33,6 +33,10 @@ Pinning status:
     plus the real ``test_params`` on two thread-emulated MPI ranks (rank-major ``_share_results`` rows, per-rank RNG streams,
     summed steps, ``ObStat.mpi_inc``): what a process carrying two 'virtual ranks' must reproduce.
 
+  * the CLOSED-LOOP synthetic env (``ClosedLoopEnvSpec`` / ``run_model_closed``) has no reference implementation
+    (SURVEY.md section 8d names only the transition ``obs' = tanh(A obs + B a)``): for that variant this module is the
+    definition -- parity unpinned against the reference by construction; frozen by ``tests/golden/closed_loop.npz``.
+
 Float semantics are those of the reference's pinned stack (numpy 1.18 value-based
 casting): every array op on float32 data stays float32 and python scalars are
 rounded to float32 before the op.  Under numpy 2.x the real ``Adam`` would compute
